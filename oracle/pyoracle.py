@@ -1,0 +1,270 @@
+"""ctypes binding of the CPU oracle (oracle/liborb_oracle.so) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package (slam-module_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_DIR = Path(__file__).resolve().parent
+MAX_LEVELS = 16
+
+
+class Params(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("levels", C.c_int),
+                ("scale_factor", C.c_float), ("max_keypoints", C.c_int),
+                ("ini_fast_thr", C.c_int), ("min_fast_thr", C.c_int)]
+
+
+def make_params(width, height, levels=8, scale_factor=1.2, max_keypoints=2000, ini_fast_thr=20, min_fast_thr=7):
+    return Params(width, height, levels, scale_factor, max_keypoints, ini_fast_thr, min_fast_thr)
+
+
+def build(force=False):
+    so = _DIR / "liborb_oracle.so"
+    if force or not so.exists():
+        subprocess.check_call(["make", "-C", str(_DIR), "all"], stdout=subprocess.DEVNULL)
+    return so
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(str(build()))
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_ic_angle.restype = C.c_float
+        L.orc_util_cos.restype = C.c_float
+        L.orc_util_cos.argtypes = [C.c_float]
+        L.orc_util_sin.restype = C.c_float
+        L.orc_util_sin.argtypes = [C.c_float]
+        L.orc_hamming.restype = C.c_uint
+        L.orc_match_bruteforce.restype = C.c_uint
+        L.orc_angle_bin.argtypes = [C.c_float]
+        L.orc_bench_extract.restype = C.c_double
+        L.orc_bench_match.restype = C.c_double
+        _lib = L
+    return _lib
+
+
+def ref_lib():
+    """The reference's own header-only leaves compiled verbatim (oracle/_ref); None if not built."""
+    global _ref
+    if _ref is None:
+        so = _DIR / "_ref" / "libref_leaves.so"
+        if not so.exists():
+            if os.path.isdir("/root/reference/openvslam"):
+                subprocess.check_call(["make", "-C", str(_DIR), "ref"], stdout=subprocess.DEVNULL)
+            if not so.exists():
+                return None
+        R = C.CDLL(str(so))
+        R.ref_cos.restype = C.c_float
+        R.ref_cos.argtypes = [C.c_float]
+        R.ref_sin.restype = C.c_float
+        R.ref_sin.argtypes = [C.c_float]
+        R.ref_hamming.restype = C.c_uint
+        _ref = R
+    return _ref
+
+
+def geometry(p):
+    s = np.zeros(MAX_LEVELS, np.float32)
+    w = np.zeros(MAX_LEVELS, np.int32)
+    h = np.zeros(MAX_LEVELS, np.int32)
+    b = np.zeros(MAX_LEVELS, np.int32)
+    lib().orc_level_geometry(C.byref(p), s.ctypes, w.ctypes, h.ctypes)
+    lib().orc_level_budgets(C.byref(p), b.ctypes)
+    n = p.levels
+    return s[:n].copy(), w[:n].copy(), h[:n].copy(), b[:n].copy()
+
+
+def resize(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(src.ctypes, src.shape[1], src.shape[0], src.strides[0], dst.ctypes, dw, dh, dw)
+    return dst
+
+
+def gaussian7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().orc_gaussian7_u8(src.ctypes, src.shape[1], src.shape[0], src.strides[0], dst.ctypes, dst.strides[0])
+    return dst
+
+
+def pyramid(p, img):
+    """Returns (levels, blurred) as lists of 2-D uint8 arrays."""
+    img = np.ascontiguousarray(img, np.uint8)
+    _, w, h, _ = geometry(p)
+    total = int((w.astype(np.int64) * h).sum())
+    pyr = np.empty(total, np.uint8)
+    blur = np.empty(total, np.uint8)
+    lib().orc_pyramid(C.byref(p), img.ctypes, img.strides[0], pyr.ctypes, blur.ctypes)
+    lv, bl, off = [], [], 0
+    for l in range(p.levels):
+        n = int(w[l]) * int(h[l])
+        lv.append(pyr[off:off + n].reshape(h[l], w[l]))
+        bl.append(blur[off:off + n].reshape(h[l], w[l]))
+        off += n
+    return lv, bl
+
+
+def cv_fast(img, thr):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = w * h
+    xs = np.empty(cap, np.int32)
+    ys = np.empty(cap, np.int32)
+    rs = np.empty(cap, np.int32)
+    n = lib().orc_cv_fast(img.ctypes, w, h, img.strides[0], int(thr), xs.ctypes, ys.ctypes, rs.ctypes, cap)
+    return xs[:n].copy(), ys[:n].copy(), rs[:n].copy()
+
+
+def fast_response_map(img):
+    """FAST response (cornerScore) of every pixel at least 3 px from the border; -1 elsewhere."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.full((h, w), -1, np.int32)
+    L = lib()
+    base = img.ctypes.data
+    for y in range(3, h - 3):
+        for x in range(3, w - 3):
+            out[y, x] = L.orc_fast_response(C.c_void_p(base + y * img.strides[0] + x), img.strides[0])
+    return out
+
+
+def detect_level(img, budget, ini_thr=20, min_thr=7, with_candidates=False):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = max(budget + 64, 64)
+    ccap = w * h // 4 + 16
+    xs = np.empty(cap, np.int32)
+    ys = np.empty(cap, np.int32)
+    rs = np.empty(cap, np.int32)
+    cx = np.empty(ccap, np.int32)
+    cy = np.empty(ccap, np.int32)
+    cr = np.empty(ccap, np.int32)
+    nc = C.c_int(0)
+    n = lib().orc_detect_level(img.ctypes, w, h, img.strides[0], int(budget), int(ini_thr), int(min_thr),
+                               xs.ctypes, ys.ctypes, rs.ctypes, cap, cx.ctypes, cy.ctypes, cr.ctypes, ccap,
+                               C.byref(nc))
+    assert n <= cap and nc.value <= ccap
+    out = (xs[:n].copy(), ys[:n].copy(), rs[:n].copy())
+    if with_candidates:
+        return out, (cx[:nc.value].copy(), cy[:nc.value].copy(), cr[:nc.value].copy())
+    return out
+
+
+def distribute(cx, cy, cr, area_w, area_h, budget):
+    cx = np.ascontiguousarray(cx, np.int32)
+    cy = np.ascontiguousarray(cy, np.int32)
+    cr = np.ascontiguousarray(cr, np.int32)
+    cap = len(cx) + 1
+    out = np.empty(cap, np.int32)
+    n = lib().orc_distribute(cx.ctypes, cy.ctypes, cr.ctypes, len(cx), int(area_w), int(area_h), int(budget),
+                             out.ctypes, cap)
+    return out[:n].copy()
+
+
+def ic_angle(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    return float(lib().orc_ic_angle(img.ctypes, img.strides[0], int(x), int(y)))
+
+
+def ic_moments(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    a = C.c_int()
+    b = C.c_int()
+    lib().orc_ic_moments(img.ctypes, img.strides[0], int(x), int(y), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def descriptor(blurred, x, y, angle_deg):
+    blurred = np.ascontiguousarray(blurred, np.uint8)
+    d = np.empty(8, np.uint32)
+    lib().orc_descriptor(blurred.ctypes, blurred.strides[0], int(x), int(y), C.c_float(angle_deg), d.ctypes)
+    return d
+
+
+def hamming(a, b):
+    a = np.ascontiguousarray(a, np.uint32)
+    b = np.ascontiguousarray(b, np.uint32)
+    return int(lib().orc_hamming(a.ctypes, b.ctypes))
+
+
+def extract(p, img, tracks=None, track_ids=None, track_level=0):
+    """OrbExtractor::detectAndExtract for one frame; returns a dict of SoA arrays."""
+    img = np.ascontiguousarray(img, np.uint8)
+    nt = 0 if tracks is None else len(tracks)
+    cap = p.max_keypoints + nt + 64
+    x = np.empty(cap, np.float32)
+    y = np.empty(cap, np.float32)
+    a = np.empty(cap, np.float32)
+    o = np.empty(cap, np.int32)
+    d = np.empty((cap, 8), np.uint32)
+    tid = np.empty(cap, np.int32)
+    lx = np.empty(cap, np.int32)
+    ly = np.empty(cap, np.int32)
+    lc = np.zeros(MAX_LEVELS, np.int32)
+    txy = None if nt == 0 else np.ascontiguousarray(tracks, np.float32)
+    tids = None if nt == 0 else np.ascontiguousarray(track_ids if track_ids is not None else np.arange(nt), np.int32)
+    n = lib().orc_extract(C.byref(p), img.ctypes, img.strides[0],
+                          None if txy is None else txy.ctypes, None if tids is None else tids.ctypes,
+                          nt, int(track_level), x.ctypes, y.ctypes, a.ctypes, o.ctypes, d.ctypes, tid.ctypes,
+                          lx.ctypes, ly.ctypes, cap, lc.ctypes)
+    assert n <= cap
+    return dict(n=n, x=x[:n].copy(), y=y[:n].copy(), angle=a[:n].copy(), octave=o[:n].copy(),
+                desc=d[:n].copy(), track_id=tid[:n].copy(), lvl_x=lx[:n].copy(), lvl_y=ly[:n].copy(),
+                level_counts=lc[:p.levels].copy())
+
+
+def match_bruteforce(dA, aA, dB, aB, ratio=0.8, thr=50, check_orientation=True, ratio_is_double=False):
+    dA = np.ascontiguousarray(dA, np.uint32)
+    dB = np.ascontiguousarray(dB, np.uint32)
+    aA = np.ascontiguousarray(aA, np.float32)
+    aB = np.ascontiguousarray(aB, np.float32)
+    m = np.empty(len(dA), np.int32)
+    n = lib().orc_match_bruteforce(dA.ctypes, aA.ctypes, len(dA), dB.ctypes, aB.ctypes, len(dB),
+                                   C.c_float(ratio), C.c_uint(thr), int(check_orientation), int(ratio_is_double),
+                                   m.ctypes)
+    return int(n), m
+
+
+def angle_invalid(deltas, ids):
+    deltas = np.ascontiguousarray(deltas, np.float32)
+    ids = np.ascontiguousarray(ids, np.int32)
+    out = np.empty(len(ids) + 1, np.int32)
+    n = lib().orc_angle_invalid(deltas.ctypes, ids.ctypes, len(ids), out.ctypes)
+    return out[:n].copy()
+
+
+def bin_order(sizes):
+    sizes = np.ascontiguousarray(sizes, np.uint32)
+    out = np.empty(30, np.uint32)
+    lib().orc_bin_order(sizes.ctypes, out.ctypes)
+    return out
+
+
+def bench_extract(p, imgs, threads):
+    imgs = np.ascontiguousarray(imgs, np.uint8)
+    total = C.c_long(0)
+    s = lib().orc_bench_extract(C.byref(p), imgs.ctypes, imgs.shape[0], int(threads), C.byref(total))
+    return float(s), total.value
+
+
+def bench_match(desc, ang, pairs, threads, ratio=0.8, thr=50):
+    desc = np.ascontiguousarray(desc, np.uint32)
+    ang = np.ascontiguousarray(ang, np.float32)
+    pairs = np.ascontiguousarray(pairs, np.int32)
+    total = C.c_long(0)
+    s = lib().orc_bench_match(desc.ctypes, ang.ctypes, desc.shape[0], desc.shape[1], pairs.ctypes, len(pairs),
+                              C.c_float(ratio), C.c_uint(thr), int(threads), C.byref(total))
+    return float(s), total.value

@@ -1,0 +1,104 @@
+// ORACLE (test infrastructure only): Hamming distance, the brute-force degenerate case of
+// matchForLoopClosures, and the angle-consistency histogram.
+// Follows openvslam/match_base.h:18-39, keyframe_matcher.cpp:50-158, and
+// openvslam/match_angle_checker.h:61-134.
+#include "common.h"
+#include <numeric>
+
+namespace orc {
+
+static inline unsigned hamming(const uint32_t *pa, const uint32_t *pb) {
+    constexpr uint32_t m1 = 0x55555555U, m2 = 0x33333333U, m3 = 0x0F0F0F0FU, m4 = 0x01010101U;
+    unsigned dist = 0;
+    for (unsigned i = 0; i < 8; ++i) {
+        uint32_t v = pa[i] ^ pb[i];
+        v -= ((v >> 1) & m1);
+        v = (v & m2) + ((v >> 2) & m2);
+        dist += (((v + (v >> 4)) & m3) * m4) >> 24;
+    }
+    return dist;
+}
+
+struct AngleChecker {  // angle_checker<int>(30, 3)
+    static constexpr unsigned LEN = 30, NUM_VALID = 3;
+    const float inv_len = 1.0f / LEN;
+    std::vector<std::vector<int>> hist{LEN};
+    static int bin_of(float delta, float inv_len) {
+        if (delta < 0.0) delta += 360.0;   // double constants in the reference: float -> double -> float
+        if (360.0 <= delta) delta -= 360.0;
+        return cv_round(delta * inv_len);
+    }
+    void append(float delta, int id) { hist.at((unsigned)bin_of(delta, inv_len)).push_back(id); }
+    std::vector<unsigned> order() const {
+        std::vector<unsigned> idx(LEN);
+        std::iota(idx.begin(), idx.end(), 0);
+        std::sort(idx.begin(), idx.end(),  // unstable, exactly as the reference calls it
+                  [this](const unsigned a, const unsigned b) { return hist.at(a).size() > hist.at(b).size(); });
+        return idx;
+    }
+    std::vector<int> invalid() const {
+        std::vector<int> out;
+        const auto bins = order();
+        for (unsigned b = 0; b < LEN; ++b) {
+            const bool valid = std::any_of(bins.begin(), bins.begin() + NUM_VALID, [b](unsigned i) { return b == i; });
+            if (!valid) out.insert(out.end(), hist[b].begin(), hist[b].end());
+        }
+        return out;
+    }
+};
+
+unsigned match_bruteforce(const uint32_t *dA, const float *aA, int nA, const uint32_t *dB, const float *aB, int nB,
+                          float ratio, unsigned thr, bool check_orientation, bool ratio_is_double, int *matches) {
+    constexpr unsigned MAX_DIST = 256;
+    unsigned num = 0;
+    AngleChecker checker;
+    for (int i = 0; i < nA; ++i) matches[i] = -1;
+    std::vector<bool> taken(nB, false);
+    for (int i1 = 0; i1 < nA; ++i1) {
+        unsigned best = MAX_DIST, second = MAX_DIST;
+        int best_idx = -1;
+        for (int i2 = 0; i2 < nB; ++i2) {
+            if (taken[i2]) continue;
+            const unsigned d = hamming(dA + 8 * i1, dB + 8 * i2);
+            if (d < best) { second = best; best = d; best_idx = i2; }
+            else if (d < second) second = d;
+        }
+        if (thr < best) continue;
+        if (ratio_is_double ? ((double)ratio * second < (double)static_cast<float>(best))
+                            : (ratio * second < static_cast<float>(best))) continue;
+        matches[i1] = best_idx;
+        taken[best_idx] = true;
+        ++num;
+        if (check_orientation) checker.append(aA[i1] - aB[best_idx], i1);
+    }
+    if (check_orientation)
+        for (int idx : checker.invalid()) { matches[idx] = -1; --num; }
+    return num;
+}
+
+}  // namespace orc
+
+using namespace orc;
+
+extern "C" unsigned orc_hamming(const uint32_t *a, const uint32_t *b) { return hamming(a, b); }
+extern "C" unsigned orc_match_bruteforce(const uint32_t *descA, const float *angA, int nA,
+                                         const uint32_t *descB, const float *angB, int nB,
+                                         float ratio, unsigned thr, int check_orientation, int ratio_is_double,
+                                         int *matches) {
+    return match_bruteforce(descA, angA, nA, descB, angB, nB, ratio, thr, check_orientation != 0,
+                            ratio_is_double != 0, matches);
+}
+extern "C" int orc_angle_bin(float delta) { return AngleChecker::bin_of(delta, 1.0f / 30); }
+extern "C" int orc_angle_invalid(const float *deltas, const int *ids, int n, int *invalid_out) {
+    AngleChecker c;
+    for (int i = 0; i < n; ++i) c.append(deltas[i], ids[i]);
+    const auto inv = c.invalid();
+    for (size_t i = 0; i < inv.size(); ++i) invalid_out[i] = inv[i];
+    return (int)inv.size();
+}
+extern "C" void orc_bin_order(const unsigned *sizes30, unsigned *order30) {
+    std::vector<unsigned> idx(30);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::sort(idx.begin(), idx.end(), [sizes30](const unsigned a, const unsigned b) { return sizes30[a] > sizes30[b]; });
+    for (int i = 0; i < 30; ++i) order30[i] = idx[i];
+}
