@@ -1,0 +1,211 @@
+/*
+ * slamgpu.h -- C ABI of libslamgpu.so: the B200 (sm_100a) implementation of the SLAM module's
+ * data-parallel front-end hot path (image pyramid -> FAST + quadtree distribution -> intensity-
+ * centroid orientation -> rBRIEF-256 -> brute-force Hamming matching with ratio / uniqueness /
+ * angle-histogram checks).
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, PODs.  No C++ / torch types cross this boundary.
+ *   - every entry point returns an int status (SG_OK == 0); sg_last_error() gives the text.
+ *   - pointers named h_* are HOST memory, d_* are DEVICE memory of the context's GPU.
+ *   - a context owns every device buffer, table and stream; the caller owns every pointer it
+ *     passes in.  Sizes (image size, levels, budget, frames per batch) are fixed at sg_create,
+ *     mirroring the reference, whose extractor caches a pyramid/detector sized by the first image
+ *     (orb_extractor.cpp:80-81).
+ *   - calls on one context must be serialised by the caller (the reference objects are stateful
+ *     and single-threaded too: orb_extractor.cpp:217-219).  One context per (host thread, GPU).
+ *   - there is NO CPU fallback: without a CUDA device sg_create fails with SG_ERR_CUDA.
+ *
+ * Each entry point cites the reference interface (file:line under the reference tree) it replaces.
+ */
+#ifndef SLAMGPU_H
+#define SLAMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_MAX_LEVELS 16
+#define SG_ABI_VERSION 1
+
+enum {
+    SG_OK = 0,
+    SG_ERR_INVALID = 1,   /* bad argument / size outside what the context was created for */
+    SG_ERR_CUDA = 2,      /* CUDA runtime error (text in sg_last_error)                    */
+    SG_ERR_OVERFLOW = 3,  /* an internal capacity was exceeded (candidate list, node table) */
+    SG_ERR_STATE = 4      /* call order violated (e.g. detect before pyramid update)        */
+};
+
+/* Static configuration: the fields of odometry::ParametersSlam the path reads
+ * (static_settings.cpp:31-32,48; orb_extractor.cpp:91) plus the batch geometry. */
+typedef struct sg_params {
+    int width;            /* level-0 image width  (pixels)                                     */
+    int height;           /* level-0 image height                                              */
+    int levels;           /* slam.orbScaleLevels                                               */
+    float scale_factor;   /* slam.orbScaleFactor                                               */
+    int max_keypoints;    /* slam.maxKeypoints  (budget split by static_settings.cpp:39-60)    */
+    int ini_fast_thr;     /* FAST threshold tried first in every 64-px cell (upstream: 20)     */
+    int min_fast_thr;     /* FAST threshold used when a cell yields nothing (upstream: 7)      */
+    int max_frames;       /* frames per batch the context is sized for (>= 1)                  */
+    int max_tracks;       /* tracker features per frame described besides detected ones (>= 0) */
+    int track_level;      /* slam.orbLkTrackLevel                                              */
+} sg_params;
+
+typedef struct sg_ctx sg_ctx;
+
+/* ---- life cycle ------------------------------------------------------------------------------ */
+/* Replaces OrbExtractor::build / ImagePyramid::build / FeatureDetector::build
+ * (orb_extractor.cpp:356-358, image_pyramid.cpp:209-219, feature_detector.cpp:138-140). */
+int sg_create(int device, const sg_params *params, sg_ctx **out);
+void sg_destroy(sg_ctx *ctx);
+const char *sg_last_error(const sg_ctx *ctx); /* ctx may be NULL: error of the failed sg_create */
+int sg_abi_version(void);
+/* Block until everything queued on the context's stream has finished. */
+int sg_synchronize(sg_ctx *ctx);
+/* The context's cudaStream_t (as void*), so a harness can bracket the launches with its own events. */
+void *sg_stream(sg_ctx *ctx);
+/* Number of kernels this library has launched on the context since creation. */
+unsigned long long sg_launch_count(const sg_ctx *ctx);
+
+/* StaticSettings (static_settings.cpp:9-60) + level sizes (image_pyramid.cpp:76-78).
+ * Any output pointer may be NULL.  Arrays hold `levels` entries. */
+int sg_get_geometry(const sg_ctx *ctx, float *scales, int *widths, int *heights, int *pitches,
+                    int *budgets);
+/* Capacity (per frame) of the keypoint output arrays of sg_extract*. */
+int sg_keypoint_capacity(const sg_ctx *ctx);
+
+/* ---- image pyramid: ImagePyramid::update / getLevel / getBlurredLevel (image_pyramid.hpp:20-27,
+ *      CpuImagePyramid::update image_pyramid.cpp:68-86) --------------------------------------- */
+/* n_frames 8-bit gray images, frame f at h_imgs + f*frame_stride, rows `pitch` bytes apart. */
+int sg_pyramid_update(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames);
+/* Same, images already in device memory (pitch % 16 == 0, base 16-byte aligned). */
+int sg_pyramid_update_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t frame_stride, int n_frames);
+/* Copy one plane (blurred != 0: the Gaussian-blurred one) of one frame to host memory. */
+int sg_pyramid_download(sg_ctx *ctx, int frame, int level, int blurred, uint8_t *h_dst, int dst_pitch);
+/* Device pointer / pitch of a plane of frame 0 (frames follow each other frame_stride bytes apart):
+ * the counterpart of getGpuLevel (image_pyramid.hpp:27). */
+int sg_pyramid_device_plane(sg_ctx *ctx, int level, int blurred, const uint8_t **d_plane, int *pitch,
+                            size_t *frame_stride);
+
+/* ---- detection: FeatureDetector::detect (feature_detector.hpp:20-22, feature_detector.cpp:68-134)
+ *      on the pyramid of the last sg_pyramid_update*.  Per level: FAST-9/16 in 64-px cells
+ *      (ini -> min threshold), NMS, quadtree distribution to the level budget. ---------------- */
+int sg_detect(sg_ctx *ctx);
+/* Keypoints of one (frame, level) in the order of the final quadtree node list: integer level
+ * coordinates and FAST response.  *n receives the count (also when it exceeds cap). */
+int sg_detect_download(sg_ctx *ctx, int frame, int level, int *h_x, int *h_y, int *h_resp, int cap, int *n);
+/* Debug / test hook: the candidates handed to the quadtree (working-area coords), unordered. */
+int sg_detect_download_candidates(sg_ctx *ctx, int frame, int level, int *h_x, int *h_y, int *h_resp,
+                                  int cap, int *n);
+
+/* ---- full extraction: OrbExtractor::detectAndExtract (orb_extractor.hpp:16-20,
+ *      orb_extractor.cpp:73-164), batched over frames ---------------------------------------- */
+/* Output (SoA, host, caller-allocated, `cap` = sg_keypoint_capacity entries per frame; frame f
+ * starts at index f*cap): full-resolution x,y (orb_extractor.cpp:156), angle in degrees, octave,
+ * descriptor 8 x u32, track id (-1 for detected keypoints), integer level coordinates.
+ * Order inside a frame: tracker keypoints, then level 0..levels-1 (orb_extractor.cpp:89-162).
+ * Any array pointer may be NULL (not downloaded). */
+typedef struct sg_keypoints {
+    float *x, *y, *angle;
+    int32_t *octave;
+    uint32_t *desc;     /* 8 words per keypoint */
+    int32_t *track_id;
+    int32_t *lvl_x, *lvl_y;
+    int32_t *count;         /* [n_frames] keypoints per frame                       */
+    int32_t *level_count;   /* [n_frames * levels] detected keypoints per level     */
+} sg_keypoints;
+
+/* Tracker features to describe besides the detected ones (orb_extractor.cpp:89-124): per frame f,
+ * n_tracks[f] points at h_track_xy + 2*f*max_tracks (full-res x,y pairs) with ids at
+ * h_track_ids + f*max_tracks.  Pass NULL / NULL / NULL for none. */
+int sg_extract(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames,
+               const float *h_track_xy, const int32_t *h_track_ids, const int32_t *n_tracks,
+               sg_keypoints *h_out);
+/* Device-resident variant: images in device memory, results stay on the device; fetch them with
+ * sg_extract_download.  This is the call the throughput bench times. */
+int sg_extract_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t frame_stride, int n_frames);
+int sg_extract_download(sg_ctx *ctx, int n_frames, sg_keypoints *h_out);
+/* Device views of the last extraction's results (SoA, `cap` entries per frame). */
+typedef struct sg_keypoints_dev {
+    const float *x, *y, *angle;
+    const int32_t *octave;
+    const uint32_t *desc;
+    const int32_t *count;
+    int cap;
+} sg_keypoints_dev;
+int sg_extract_device_views(sg_ctx *ctx, sg_keypoints_dev *out);
+
+/* ---- Hamming distance: compute_descriptor_distance_32 (openvslam/match_base.h:18-39) --------
+ * n pairs: h_out[i] = popcount(a[i] ^ b[i]) over 256 bits, computed on the GPU. */
+int sg_hamming(sg_ctx *ctx, const uint32_t *h_a, const uint32_t *h_b, int n, uint32_t *h_out);
+
+/* ---- brute-force matcher: the single-BoW-node case of matchForLoopClosures
+ *      (keyframe_matcher.hpp:33-40, keyframe_matcher.cpp:50-158): for every A feature in index
+ *      order, best and second-best Hamming distance over the still-unmatched B features, reject
+ *      when thr < best or ratio*second < best, consume the B feature, then keep only matches in
+ *      the three most populated 30-degree delta-angle bins (match_angle_checker.h:61-134). */
+typedef struct sg_match_params {
+    float ratio;            /* slam.loopClosureFeatureMatchLoweRatio (keyframe_matcher.cpp:120) */
+    uint32_t thr;           /* HAMMING_DIST_THR_LOW = 50 (match_base.h:13, keyframe_matcher.cpp:115) */
+    int check_orientation;  /* keyframe_matcher.cpp:48 (always true in the reference)            */
+    int ratio_is_double;    /* promotion of the ratio test; the parameter's C type is in an absent header */
+} sg_match_params;
+
+/* One pair, host buffers.  h_matches[nA] receives the B index or -1; *n_matches the count. */
+int sg_match_bruteforce(sg_ctx *ctx, const uint32_t *h_descA, const float *h_angA, int nA,
+                        const uint32_t *h_descB, const float *h_angB, int nB,
+                        const sg_match_params *mp, int32_t *h_matches, uint32_t *n_matches);
+
+/* Device-resident descriptor database: n_sets keyframes, set s owns features
+ * [offsets[s], offsets[s+1]) of desc (8 words each) / angle. */
+typedef struct sg_db sg_db;
+int sg_db_create(sg_ctx *ctx, const uint32_t *h_desc, const float *h_angle, const int64_t *h_offsets,
+                 int n_sets, sg_db **out);
+/* Same from device arrays (e.g. the views of sg_extract_device); data is copied. */
+int sg_db_create_device(sg_ctx *ctx, const uint32_t *d_desc, const float *d_angle, const int64_t *h_offsets,
+                        int n_sets, sg_db **out);
+void sg_db_destroy(sg_db *db);
+/* Batched matching of keyframe pairs (h_pairs: n_pairs x {setA, setB}).  h_matches may be NULL;
+ * otherwise row p holds `match_stride` ints (>= size of the largest A set), -1 padded.
+ * h_n_matches[n_pairs] receives the counts. */
+int sg_match_pairs(sg_ctx *ctx, const sg_db *db, const int32_t *h_pairs, int n_pairs,
+                   const sg_match_params *mp, int32_t *h_matches, int match_stride, uint32_t *h_n_matches);
+/* Device-resident variant used by the throughput bench: pairs already on the device, results stay
+ * there (d_matches may be NULL -> only counts). */
+int sg_match_pairs_device(sg_ctx *ctx, const sg_db *db, const int32_t *d_pairs, int n_pairs,
+                          const sg_match_params *mp, int32_t *d_matches, int match_stride,
+                          uint32_t *d_n_matches);
+/* Rows of the last sg_match_* call that needed the exact full-row rescan (diagnostic). */
+unsigned long long sg_match_rescans(const sg_ctx *ctx);
+
+/* ---- angle histogram: angle_checker<int> (openvslam/match_angle_checker.h:72-134) -----------
+ * Test hook for the restated libstdc++ std::sort order of the 30 bins (host code, no GPU). */
+void sg_angle_bin_order(const uint32_t *sizes30, uint32_t *order30);
+/* Same with an explicit introsort depth limit (0 forces the heap-sort branch; std::sort uses 8). */
+void sg_angle_bin_order_depth(const uint32_t *sizes30, int depth_limit, uint32_t *order30);
+int sg_angle_bin(float delta_angle);
+
+/* ---- device helpers for harnesses that must not depend on a CUDA binding of their own ------- */
+int sg_device_count(void);
+int sg_malloc(sg_ctx *ctx, size_t bytes, void **d_ptr);
+int sg_free(sg_ctx *ctx, void *d_ptr);
+int sg_memcpy_h2d(sg_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int sg_memcpy_d2h(sg_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+int sg_host_alloc_pinned(size_t bytes, void **h_ptr);
+int sg_host_free_pinned(void *h_ptr);
+/* CUDA-event timing on the context's stream. */
+int sg_timer_start(sg_ctx *ctx);
+int sg_timer_stop(sg_ctx *ctx, float *ms); /* records, synchronises, returns elapsed ms */
+/* Overwrite a buffer larger than L2 (flushes L2 between timed iterations). */
+int sg_flush_l2(sg_ctx *ctx);
+/* Integer-pipe micro-benchmark: dependent-free POPC.b32 issue rate of the whole chip; returns
+ * popc/s and the kernel time (denominator of the matching roofline). */
+int sg_microbench_popc(sg_ctx *ctx, double *popc_per_s, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAMGPU_H */

@@ -118,6 +118,8 @@ int orc_angle_bin(float delta_angle);
 int orc_angle_invalid(const float *deltas, const int *ids, int n, int *invalid_out);
 /* libstdc++ std::sort order of the 30 histogram bins by size (descending), as the reference calls it. */
 void orc_bin_order(const unsigned *sizes30, unsigned *order30);
+/* std::partial_sort(first, last, last) order of the same bins (std::sort's heap-sort branch). */
+void orc_bin_order_heap(const unsigned *sizes30, unsigned *order30);
 
 /* Threaded drivers for the CPU baseline (frames / keyframe pairs sharded over host threads; the
  * reference itself is single-threaded).  Return wall seconds. */

@@ -253,6 +253,17 @@ def bin_order(sizes):
     return out
 
 
+def bin_order_heap(sizes):
+    sizes = np.ascontiguousarray(sizes, np.uint32)
+    out = np.empty(30, np.uint32)
+    lib().orc_bin_order_heap(sizes.ctypes, out.ctypes)
+    return out
+
+
+def angle_bin(delta):
+    return int(lib().orc_angle_bin(C.c_float(delta)))
+
+
 def bench_extract(p, imgs, threads):
     imgs = np.ascontiguousarray(imgs, np.uint8)
     total = C.c_long(0)

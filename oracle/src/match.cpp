@@ -102,3 +102,12 @@ extern "C" void orc_bin_order(const unsigned *sizes30, unsigned *order30) {
     std::sort(idx.begin(), idx.end(), [sizes30](const unsigned a, const unsigned b) { return sizes30[a] > sizes30[b]; });
     for (int i = 0; i < 30; ++i) order30[i] = idx[i];
 }
+// std::partial_sort(first, last, last) with the same comparator: what std::sort degenerates to when the
+// introsort depth limit is exhausted (checks the heap branch of the GPU library's restated sort).
+extern "C" void orc_bin_order_heap(const unsigned *sizes30, unsigned *order30) {
+    std::vector<unsigned> idx(30);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::partial_sort(idx.begin(), idx.end(), idx.end(),
+                      [sizes30](const unsigned a, const unsigned b) { return sizes30[a] > sizes30[b]; });
+    for (int i = 0; i < 30; ++i) order30[i] = idx[i];
+}

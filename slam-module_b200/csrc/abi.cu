@@ -1,0 +1,623 @@
+// C ABI of libslamgpu.so (include/slamgpu.h): context life cycle, buffer ownership, host <-> device
+// staging and the orchestration of the stage launchers.  No algorithmic work happens here.
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <algorithm>
+#include "ctx.h"
+
+namespace sg {
+
+static thread_local std::string g_create_error;
+
+int fail(sg_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+int grow(sg_ctx *ctx, void **ptr, size_t *cap, size_t need, size_t elem) {
+    if (need <= *cap) return SG_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *cap = 0;
+    SG_CUDA(ctx, cudaMalloc(ptr, need * elem));
+    *cap = need;
+    return SG_OK;
+}
+
+void pyramid_source_extent(const std::vector<ResizeTap> &xt, const std::vector<ResizeTap> &yt, int w, int h,
+                           bool area2x, int sw, int sh, int *tile_w, int *tile_h);
+int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, const sg_match_params &mp,
+              int *d_matches, int match_stride, uint32_t *d_n_matches);
+int match_chunk_pairs(const sg_db *db, bool own_matches);
+int run_hamming(sg_ctx *ctx, const uint32_t *d_a, const uint32_t *d_b, int n, uint32_t *d_out);
+int run_popc_bench(sg_ctx *ctx, double *popc_per_s, float *ms_out);
+size_t distribute_smem_bytes(int node_cap_max);
+
+template <class T>
+static int dev_alloc(sg_ctx *ctx, T **p, size_t n) {
+    SG_CUDA(ctx, cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)));
+    return SG_OK;
+}
+
+static int check_device_error(sg_ctx *ctx) {
+    int e = 0;
+    SG_CUDA(ctx, cudaMemcpyAsync(&e, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (e) {
+        cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream);
+        return fail(ctx, e, "device-side capacity exceeded (candidate list or quadtree node table)");
+    }
+    return SG_OK;
+}
+
+static int build_context(sg_ctx *ctx) {
+    const sg_params &p = ctx->p;
+    make_geometry(p, ctx->lv);
+    GeomDev &g = ctx->geom;
+    memset(&g, 0, sizeof g);
+    g.levels = p.levels;
+    g.max_tracks = p.max_tracks;
+    g.ini_thr = p.ini_fast_thr;
+    g.min_thr = p.min_fast_thr;
+    size_t cand_off = 0;
+    int kp_off = 0, nc_max = 1;
+    const size_t F = p.max_frames;
+    for (int l = 0; l < p.levels; ++l) {
+        Level &L = ctx->lv[l];
+        if (L.w < 8 || L.h < 8) return fail(ctx, SG_ERR_INVALID, "pyramid level %d is %dx%d: too small", l, L.w, L.h);
+        if (L.area_w > 32000 || L.area_h > 32000) return fail(ctx, SG_ERR_INVALID, "image too large");
+        if (L.cells_x > 1023 || L.cells_y > 1023) return fail(ctx, SG_ERR_INVALID, "image too large");
+        L.cand_cap = L.cells_x * L.cells_y * (CELL / 2) * (CELL / 2) + 32;   // NMS: <= one pixel per 2x2 block of a cell
+        L.cand_off = cand_off; cand_off += (size_t)L.cand_cap;
+        L.kp_off = kp_off; kp_off += L.node_cap;
+        nc_max = std::max(nc_max, L.node_cap);
+        if (int r = dev_alloc(ctx, &L.pyr, F * L.frame_stride + 256)) return r;
+        if (int r = dev_alloc(ctx, &L.blur, F * L.frame_stride + 256)) return r;
+        if (l > 0) {
+            const Level &P = ctx->lv[l - 1];
+            std::vector<ResizeTap> xt, yt;
+            make_resize_taps(P.w, L.w, xt, true);
+            make_resize_taps(P.h, L.h, yt, false);
+            L.area2x = is_area2x(P.w, P.h, L.w, L.h);
+            if (L.w == P.w && L.h == P.h) {   // cv::resize copies: identity taps
+                for (int i = 0; i < L.w; ++i) xt[i] = ResizeTap{i, i, 2048, 0};
+                for (int i = 0; i < L.h; ++i) yt[i] = ResizeTap{i, i, 2048, 0};
+            }
+            pyramid_source_extent(xt, yt, L.w, L.h, L.area2x, P.w, P.h, &L.src_tile_w, &L.src_tile_h);
+            if (int r = dev_alloc(ctx, &L.xtab, xt.size())) return r;
+            if (int r = dev_alloc(ctx, &L.ytab, yt.size())) return r;
+            SG_CUDA(ctx, cudaMemcpy(L.xtab, xt.data(), xt.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
+            SG_CUDA(ctx, cudaMemcpy(L.ytab, yt.data(), yt.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
+        }
+        LevelDev &D = g.lv[l];
+        D.w = L.w; D.h = L.h; D.pitch = L.pitch; D.frame_stride = L.frame_stride;
+        D.pyr = L.pyr; D.blur = L.blur; D.scale = L.scale; D.budget = L.budget;
+        D.area_w = L.area_w; D.area_h = L.area_h; D.cells_x = L.cells_x; D.cells_y = L.cells_y;
+        D.cand_cap = L.cand_cap; D.node_cap = L.node_cap; D.init_nx = L.init_nx; D.init_ny = L.init_ny;
+        D.cand_off = L.cand_off; D.kp_off = L.kp_off;
+    }
+    if (distribute_smem_bytes(nc_max) > 200 * 1024)
+        return fail(ctx, SG_ERR_INVALID, "max_keypoints %d needs a quadtree node table larger than shared memory", p.max_keypoints);
+    g.cand_per_frame = cand_off;
+    g.det_cap = kp_off;
+    g.out_cap = kp_off + p.max_tracks;
+
+    if (int r = dev_alloc(ctx, &ctx->d_cand, F * cand_off)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_cand_node, F * cand_off)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_cand_count, F * p.levels)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_kp_xy, F * g.det_cap)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_kp_resp, F * g.det_cap)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_kp_count, F * p.levels)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_err, 1)) return r;
+    SG_CUDA(ctx, cudaMemset(ctx->d_err, 0, sizeof(int)));
+    SG_CUDA(ctx, cudaMemset(ctx->d_kp_count, 0, sizeof(int) * F * p.levels));
+    const size_t T = std::max(p.max_tracks, 1);
+    if (int r = dev_alloc(ctx, &ctx->d_trk_xy, F * T)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_trk_pt, F * T * 2)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_trk_id, F * T)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_trk_count, F)) return r;
+    const size_t O = F * g.out_cap;
+    if (int r = dev_alloc(ctx, &ctx->d_x, O)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_y, O)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_angle, O)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_octave, O)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_track_id, O)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_lvl_x, O)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_lvl_y, O)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_desc, O * 8)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_count, F)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_rescans, 1)) return r;
+    SG_CUDA(ctx, cudaMemset(ctx->d_rescans, 0, sizeof(unsigned long long)));
+    return SG_OK;
+}
+
+static int set_level0(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t stride, int n_frames) {
+    ctx->level0 = d_imgs; ctx->level0_pitch = pitch; ctx->level0_stride = stride;
+    ctx->frames_ready = n_frames;
+    ctx->detected = false;
+    return SG_OK;
+}
+
+static int upload_frames(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames) {
+    const Level &L0 = ctx->lv[0];
+    if (!h_imgs || pitch < L0.w) return fail(ctx, SG_ERR_INVALID, "bad image pointer / pitch");
+    if (n_frames < 1 || n_frames > ctx->p.max_frames) return fail(ctx, SG_ERR_INVALID, "n_frames %d outside [1, %d]", n_frames, ctx->p.max_frames);
+    for (int f = 0; f < n_frames; ++f)
+        SG_CUDA(ctx, cudaMemcpy2DAsync(L0.pyr + (size_t)f * L0.frame_stride, L0.pitch, h_imgs + (size_t)f * frame_stride,
+                                       pitch, L0.w, L0.h, cudaMemcpyHostToDevice, ctx->stream));
+    return set_level0(ctx, L0.pyr, L0.pitch, L0.frame_stride, n_frames);
+}
+
+static int upload_tracks(sg_ctx *ctx, const float *h_xy, const int32_t *h_ids, const int32_t *n_tracks, int n_frames) {
+    ctx->have_tracks = false;
+    if (!h_xy || !n_tracks || ctx->p.max_tracks <= 0) return SG_OK;
+    const int T = ctx->p.max_tracks, lvl = ctx->p.track_level;
+    if (lvl < 0 || lvl >= ctx->p.levels) return fail(ctx, SG_ERR_INVALID, "track_level outside the pyramid");
+    const Level &L = ctx->lv[lvl];
+    std::vector<int> xy((size_t)n_frames * T), ids((size_t)n_frames * T), cnt(n_frames);
+    std::vector<float> pt((size_t)n_frames * T * 2);
+    for (int f = 0; f < n_frames; ++f) {
+        if (n_tracks[f] < 0 || n_tracks[f] > T) return fail(ctx, SG_ERR_INVALID, "n_tracks[%d] outside [0, %d]", f, T);
+        int n = 0;
+        for (int t = 0; t < n_tracks[f]; ++t) {
+            // orb_extractor.cpp:89-104: cvRound(pt / scale), 19-px margin (camera validity is the adapter's job)
+            const float px = h_xy[2 * ((size_t)f * T + t)], py = h_xy[2 * ((size_t)f * T + t) + 1];
+            const int x = (int)lrintf(px / L.scale), y = (int)lrintf(py / L.scale);
+            if (x >= PATCH_RADIUS && y >= PATCH_RADIUS && x < L.w - PATCH_RADIUS && y < L.h - PATCH_RADIUS) {
+                const size_t o = (size_t)f * T + n;
+                xy[o] = x | (y << 16);
+                pt[2 * o] = px; pt[2 * o + 1] = py;
+                ids[o] = h_ids ? h_ids[(size_t)f * T + t] : t;
+                ++n;
+            }
+        }
+        cnt[f] = n;
+    }
+    SG_CUDA(ctx, cudaMemcpyAsync(ctx->d_trk_xy, xy.data(), xy.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(ctx->d_trk_pt, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(ctx->d_trk_id, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(ctx->d_trk_count, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the staging vectors die here
+    ctx->have_tracks = true;
+    return SG_OK;
+}
+
+static int check_device_images(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t frame_stride, int n_frames) {
+    if (!d_imgs || pitch < ctx->lv[0].w || (pitch & 15) || ((uintptr_t)d_imgs & 15) || (frame_stride & 15))
+        return fail(ctx, SG_ERR_INVALID, "device images need a 16-byte aligned base, pitch and frame stride");
+    if (frame_stride < (size_t)pitch * ctx->lv[0].h) return fail(ctx, SG_ERR_INVALID, "frame_stride smaller than one frame");
+    if (n_frames < 1 || n_frames > ctx->p.max_frames) return fail(ctx, SG_ERR_INVALID, "n_frames %d outside [1, %d]", n_frames, ctx->p.max_frames);
+    return SG_OK;
+}
+
+template <class T>
+static int d2h(sg_ctx *ctx, T *h, const T *d, size_t n) {
+    if (!h) return SG_OK;
+    SG_CUDA(ctx, cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    return SG_OK;
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" {
+
+int sg_abi_version(void) { return SG_ABI_VERSION; }
+
+int sg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *sg_last_error(const sg_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int sg_create(int device, const sg_params *params, sg_ctx **out) {
+    if (!params || !out) return fail(nullptr, SG_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const sg_params &p = *params;
+    if (p.width < 64 || p.height < 64 || p.levels < 1 || p.levels > SG_MAX_LEVELS || !(p.scale_factor > 1.0f)
+        || p.max_keypoints < 1 || p.max_frames < 1 || p.max_tracks < 0 || p.min_fast_thr < 1
+        || p.ini_fast_thr < p.min_fast_thr || p.ini_fast_thr > 254
+        || (p.max_tracks > 0 && (p.track_level < 0 || p.track_level >= p.levels)))
+        return fail(nullptr, SG_ERR_INVALID, "invalid sg_params");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, SG_ERR_CUDA, "no CUDA device: %s (libslamgpu has no CPU fallback)", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, SG_ERR_INVALID, "device %d outside [0, %d)", device, n);
+    sg_ctx *ctx = new sg_ctx();
+    ctx->device = device;
+    ctx->p = p;
+    auto bail = [&](int code) { g_create_error = ctx->err; sg_destroy(ctx); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(SG_ERR_CUDA); }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { ctx->err = "cudaGetDeviceProperties failed"; return bail(SG_ERR_CUDA); }
+    if (prop.major < 10) { ctx->err = "libslamgpu is built for sm_100a (B200) only"; return bail(SG_ERR_CUDA); }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess
+        || cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        ctx->err = "stream / event creation failed";
+        return bail(SG_ERR_CUDA);
+    }
+    if (int r = build_context(ctx)) return bail(r);
+    *out = ctx;
+    return SG_OK;
+}
+
+void sg_destroy(sg_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &L : ctx->lv) { cudaFree(L.pyr); cudaFree(L.blur); cudaFree(L.xtab); cudaFree(L.ytab); }
+    void *ptrs[] = {ctx->d_cand, ctx->d_cand_node, ctx->d_cand_count, ctx->d_kp_xy, ctx->d_kp_resp, ctx->d_kp_count,
+                    ctx->d_err, ctx->d_trk_xy, ctx->d_trk_pt, ctx->d_trk_id, ctx->d_trk_count, ctx->d_x, ctx->d_y,
+                    ctx->d_angle, ctx->d_octave, ctx->d_track_id, ctx->d_lvl_x, ctx->d_lvl_y, ctx->d_desc, ctx->d_count,
+                    ctx->d_flush, ctx->d_topk, ctx->d_nseen, ctx->d_pairs, ctx->d_matches, ctx->d_nmatch,
+                    ctx->d_rescans, ctx->d_tmp};
+    for (void *q : ptrs) if (q) cudaFree(q);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int sg_synchronize(sg_ctx *ctx) {
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SG_OK;
+}
+void *sg_stream(sg_ctx *ctx) { return (void *)ctx->stream; }
+unsigned long long sg_launch_count(const sg_ctx *ctx) { return ctx->launches; }
+
+int sg_get_geometry(const sg_ctx *ctx, float *scales, int *widths, int *heights, int *pitches, int *budgets) {
+    for (int l = 0; l < ctx->p.levels; ++l) {
+        const Level &L = ctx->lv[l];
+        if (scales) scales[l] = L.scale;
+        if (widths) widths[l] = L.w;
+        if (heights) heights[l] = L.h;
+        if (pitches) pitches[l] = L.pitch;
+        if (budgets) budgets[l] = L.budget;
+    }
+    return SG_OK;
+}
+int sg_keypoint_capacity(const sg_ctx *ctx) { return ctx->geom.out_cap; }
+
+// ---- pyramid ------------------------------------------------------------------------------------------
+int sg_pyramid_update(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames) {
+    cudaSetDevice(ctx->device);
+    if (int r = upload_frames(ctx, h_imgs, pitch, frame_stride, n_frames)) return r;
+    if (int r = launch_pyramid(ctx, n_frames)) return r;
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SG_OK;
+}
+
+int sg_pyramid_update_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t frame_stride, int n_frames) {
+    cudaSetDevice(ctx->device);
+    if (int r = check_device_images(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
+    set_level0(ctx, d_imgs, pitch, frame_stride, n_frames);
+    return launch_pyramid(ctx, n_frames);
+}
+
+int sg_pyramid_download(sg_ctx *ctx, int frame, int level, int blurred, uint8_t *h_dst, int dst_pitch) {
+    cudaSetDevice(ctx->device);
+    if (frame < 0 || frame >= ctx->frames_ready || level < 0 || level >= ctx->p.levels || !h_dst)
+        return fail(ctx, SG_ERR_INVALID, "bad frame / level");
+    const Level &L = ctx->lv[level];
+    const uint8_t *src;
+    int pitch;
+    if (blurred) { src = L.blur + (size_t)frame * L.frame_stride; pitch = L.pitch; }
+    else if (level == 0) { src = ctx->level0 + (size_t)frame * ctx->level0_stride; pitch = ctx->level0_pitch; }
+    else { src = L.pyr + (size_t)frame * L.frame_stride; pitch = L.pitch; }
+    SG_CUDA(ctx, cudaMemcpy2DAsync(h_dst, dst_pitch, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SG_OK;
+}
+
+int sg_pyramid_device_plane(sg_ctx *ctx, int level, int blurred, const uint8_t **d_plane, int *pitch, size_t *frame_stride) {
+    if (level < 0 || level >= ctx->p.levels) return fail(ctx, SG_ERR_INVALID, "bad level");
+    const Level &L = ctx->lv[level];
+    if (!blurred && level == 0) {
+        if (d_plane) *d_plane = ctx->level0;
+        if (pitch) *pitch = ctx->level0_pitch;
+        if (frame_stride) *frame_stride = ctx->level0_stride;
+    } else {
+        if (d_plane) *d_plane = blurred ? L.blur : L.pyr;
+        if (pitch) *pitch = L.pitch;
+        if (frame_stride) *frame_stride = L.frame_stride;
+    }
+    return SG_OK;
+}
+
+// ---- detection ----------------------------------------------------------------------------------------
+int sg_detect(sg_ctx *ctx) {
+    cudaSetDevice(ctx->device);
+    if (ctx->frames_ready < 1) return fail(ctx, SG_ERR_STATE, "sg_detect before sg_pyramid_update");
+    if (int r = launch_detect(ctx, ctx->frames_ready)) return r;
+    return check_device_error(ctx);
+}
+
+int sg_detect_download(sg_ctx *ctx, int frame, int level, int *h_x, int *h_y, int *h_resp, int cap, int *n) {
+    cudaSetDevice(ctx->device);
+    if (!ctx->detected) return fail(ctx, SG_ERR_STATE, "sg_detect_download before sg_detect");
+    if (frame < 0 || frame >= ctx->frames_ready || level < 0 || level >= ctx->p.levels) return fail(ctx, SG_ERR_INVALID, "bad frame / level");
+    const GeomDev &g = ctx->geom;
+    int cnt = 0;
+    SG_CUDA(ctx, cudaMemcpyAsync(&cnt, ctx->d_kp_count + frame * g.levels + level, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n) *n = cnt;
+    const int m = std::min(cnt, cap);
+    if (m <= 0) return SG_OK;
+    std::vector<int> xy(m), rs(m);
+    const size_t off = (size_t)frame * g.det_cap + g.lv[level].kp_off;
+    SG_CUDA(ctx, cudaMemcpyAsync(xy.data(), ctx->d_kp_xy + off, 4 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(rs.data(), ctx->d_kp_resp + off, 4 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < m; ++i) {
+        if (h_x) h_x[i] = xy[i] & 0xffff;
+        if (h_y) h_y[i] = xy[i] >> 16;
+        if (h_resp) h_resp[i] = rs[i];
+    }
+    return SG_OK;
+}
+
+int sg_detect_download_candidates(sg_ctx *ctx, int frame, int level, int *h_x, int *h_y, int *h_resp, int cap, int *n) {
+    cudaSetDevice(ctx->device);
+    if (!ctx->detected) return fail(ctx, SG_ERR_STATE, "no detection yet");
+    if (frame < 0 || frame >= ctx->frames_ready || level < 0 || level >= ctx->p.levels) return fail(ctx, SG_ERR_INVALID, "bad frame / level");
+    const GeomDev &g = ctx->geom;
+    int cnt = 0;
+    SG_CUDA(ctx, cudaMemcpyAsync(&cnt, ctx->d_cand_count + frame * g.levels + level, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n) *n = cnt;
+    const int m = std::min(cnt, cap);
+    if (m <= 0) return SG_OK;
+    std::vector<unsigned long long> c(m);
+    SG_CUDA(ctx, cudaMemcpyAsync(c.data(), ctx->d_cand + (size_t)frame * g.cand_per_frame + g.lv[level].cand_off,
+                                 8 * (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < m; ++i) {
+        const unsigned key = (unsigned)c[i];
+        if (h_x) h_x[i] = FAST_BORDER + CELL * ((key >> 12) & 1023) + (key & 63);
+        if (h_y) h_y[i] = FAST_BORDER + CELL * (key >> 22) + ((key >> 6) & 63);
+        if (h_resp) h_resp[i] = (int)(c[i] >> 32);
+    }
+    return SG_OK;
+}
+
+// ---- extraction ---------------------------------------------------------------------------------------
+static int extract_launches(sg_ctx *ctx, int n_frames) {
+    if (int r = launch_pyramid(ctx, n_frames)) return r;
+    if (int r = launch_detect(ctx, n_frames)) return r;
+    return launch_describe(ctx, n_frames);
+}
+
+int sg_extract_download(sg_ctx *ctx, int n_frames, sg_keypoints *o) {
+    cudaSetDevice(ctx->device);
+    if (!o || n_frames < 1 || n_frames > ctx->frames_ready) return fail(ctx, SG_ERR_INVALID, "bad n_frames / output");
+    const size_t n = (size_t)n_frames * ctx->geom.out_cap;
+    if (int r = d2h(ctx, o->x, ctx->d_x, n)) return r;
+    if (int r = d2h(ctx, o->y, ctx->d_y, n)) return r;
+    if (int r = d2h(ctx, o->angle, ctx->d_angle, n)) return r;
+    if (int r = d2h(ctx, o->octave, ctx->d_octave, n)) return r;
+    if (int r = d2h(ctx, o->desc, ctx->d_desc, n * 8)) return r;
+    if (int r = d2h(ctx, o->track_id, ctx->d_track_id, n)) return r;
+    if (int r = d2h(ctx, o->lvl_x, ctx->d_lvl_x, n)) return r;
+    if (int r = d2h(ctx, o->lvl_y, ctx->d_lvl_y, n)) return r;
+    if (int r = d2h(ctx, o->count, ctx->d_count, (size_t)n_frames)) return r;
+    if (int r = d2h(ctx, o->level_count, ctx->d_kp_count, (size_t)n_frames * ctx->p.levels)) return r;
+    return check_device_error(ctx);
+}
+
+int sg_extract(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames,
+               const float *h_track_xy, const int32_t *h_track_ids, const int32_t *n_tracks, sg_keypoints *h_out) {
+    cudaSetDevice(ctx->device);
+    if (int r = upload_frames(ctx, h_imgs, pitch, frame_stride, n_frames)) return r;
+    if (int r = upload_tracks(ctx, h_track_xy, h_track_ids, n_tracks, n_frames)) return r;
+    if (int r = extract_launches(ctx, n_frames)) return r;
+    return sg_extract_download(ctx, n_frames, h_out);
+}
+
+int sg_extract_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t frame_stride, int n_frames) {
+    cudaSetDevice(ctx->device);
+    if (int r = check_device_images(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
+    set_level0(ctx, d_imgs, pitch, frame_stride, n_frames);
+    ctx->have_tracks = false;
+    return extract_launches(ctx, n_frames);
+}
+
+int sg_extract_device_views(sg_ctx *ctx, sg_keypoints_dev *out) {
+    if (!out) return fail(ctx, SG_ERR_INVALID, "null argument");
+    out->x = ctx->d_x; out->y = ctx->d_y; out->angle = ctx->d_angle; out->octave = ctx->d_octave;
+    out->desc = ctx->d_desc; out->count = ctx->d_count; out->cap = ctx->geom.out_cap;
+    return SG_OK;
+}
+
+// ---- matching -----------------------------------------------------------------------------------------
+int sg_hamming(sg_ctx *ctx, const uint32_t *h_a, const uint32_t *h_b, int n, uint32_t *h_out) {
+    cudaSetDevice(ctx->device);
+    if (n <= 0) return SG_OK;
+    if (!h_a || !h_b || !h_out) return fail(ctx, SG_ERR_INVALID, "null argument");
+    const size_t bytes = (size_t)n * 32;
+    if (int r = grow(ctx, &ctx->d_tmp, &ctx->tmp_bytes, 2 * bytes + (size_t)n * 4, 1)) return r;
+    uint8_t *base = (uint8_t *)ctx->d_tmp;
+    SG_CUDA(ctx, cudaMemcpyAsync(base, h_a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(base + bytes, h_b, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (int r = run_hamming(ctx, (uint32_t *)base, (uint32_t *)(base + bytes), n, (uint32_t *)(base + 2 * bytes))) return r;
+    SG_CUDA(ctx, cudaMemcpyAsync(h_out, base + 2 * bytes, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SG_OK;
+}
+
+static int db_finish(sg_ctx *ctx, sg_db *db, const int64_t *h_offsets, int n_sets) {
+    db->ctx = ctx;
+    db->n_sets = n_sets;
+    db->offsets.assign(h_offsets, h_offsets + n_sets + 1);
+    db->max_set = 0;
+    for (int s = 0; s < n_sets; ++s) {
+        if (h_offsets[s + 1] < h_offsets[s]) return fail(ctx, SG_ERR_INVALID, "offsets must be non-decreasing");
+        db->max_set = std::max<long long>(db->max_set, h_offsets[s + 1] - h_offsets[s]);
+    }
+    SG_CUDA(ctx, cudaMalloc(&db->d_offsets, sizeof(long long) * (n_sets + 1)));
+    SG_CUDA(ctx, cudaMemcpy(db->d_offsets, db->offsets.data(), sizeof(long long) * (n_sets + 1), cudaMemcpyHostToDevice));
+    return SG_OK;
+}
+
+static int db_create(sg_ctx *ctx, const uint32_t *desc, const float *angle, const int64_t *h_offsets, int n_sets,
+                     sg_db **out, cudaMemcpyKind kind) {
+    cudaSetDevice(ctx->device);
+    if (!desc || !angle || !h_offsets || n_sets < 1 || !out) return fail(ctx, SG_ERR_INVALID, "null / empty database");
+    if (h_offsets[0] != 0) return fail(ctx, SG_ERR_INVALID, "offsets[0] must be 0");
+    sg_db *db = new sg_db();
+    const size_t total = (size_t)h_offsets[n_sets];
+    int r = db_finish(ctx, db, h_offsets, n_sets);
+    if (!r && cudaMalloc(&db->d_desc, std::max<size_t>(total, 1) * 32 + 32) != cudaSuccess) r = fail(ctx, SG_ERR_CUDA, "cudaMalloc failed");
+    if (!r && cudaMalloc(&db->d_angle, std::max<size_t>(total, 1) * 4) != cudaSuccess) r = fail(ctx, SG_ERR_CUDA, "cudaMalloc failed");
+    if (!r && total) {
+        if (cudaMemcpyAsync(db->d_desc, desc, total * 32, kind, ctx->stream) != cudaSuccess
+            || cudaMemcpyAsync(db->d_angle, angle, total * 4, kind, ctx->stream) != cudaSuccess
+            || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            r = fail(ctx, SG_ERR_CUDA, "database upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (r) { sg_db_destroy(db); return r; }
+    *out = db;
+    return SG_OK;
+}
+
+int sg_db_create(sg_ctx *ctx, const uint32_t *h_desc, const float *h_angle, const int64_t *h_offsets, int n_sets, sg_db **out) {
+    return db_create(ctx, h_desc, h_angle, h_offsets, n_sets, out, cudaMemcpyHostToDevice);
+}
+int sg_db_create_device(sg_ctx *ctx, const uint32_t *d_desc, const float *d_angle, const int64_t *h_offsets, int n_sets, sg_db **out) {
+    return db_create(ctx, d_desc, d_angle, h_offsets, n_sets, out, cudaMemcpyDeviceToDevice);
+}
+void sg_db_destroy(sg_db *db) {
+    if (!db) return;
+    if (db->ctx) cudaSetDevice(db->ctx->device);
+    cudaFree(db->d_desc); cudaFree(db->d_angle); cudaFree(db->d_offsets);
+    delete db;
+}
+
+int sg_match_pairs_device(sg_ctx *ctx, const sg_db *db, const int32_t *d_pairs, int n_pairs, const sg_match_params *mp,
+                          int32_t *d_matches, int match_stride, uint32_t *d_n_matches) {
+    cudaSetDevice(ctx->device);
+    if (!db || !d_pairs || !mp || !d_n_matches) return fail(ctx, SG_ERR_INVALID, "null argument");
+    return run_match(ctx, db, d_pairs, n_pairs, *mp, d_matches, match_stride, d_n_matches);
+}
+
+int sg_match_pairs(sg_ctx *ctx, const sg_db *db, const int32_t *h_pairs, int n_pairs, const sg_match_params *mp,
+                   int32_t *h_matches, int match_stride, uint32_t *h_n_matches) {
+    cudaSetDevice(ctx->device);
+    if (!db || !h_pairs || !mp || !h_n_matches) return fail(ctx, SG_ERR_INVALID, "null argument");
+    if (n_pairs <= 0) return SG_OK;
+    for (int i = 0; i < 2 * n_pairs; ++i)
+        if (h_pairs[i] < 0 || h_pairs[i] >= db->n_sets) return fail(ctx, SG_ERR_INVALID, "pair %d names set %d outside the database", i / 2, h_pairs[i]);
+    if (h_matches && match_stride < db->max_set) return fail(ctx, SG_ERR_INVALID, "match_stride smaller than the largest set");
+    if (int r = grow(ctx, (void **)&ctx->d_pairs, &ctx->pairs_cap, 2 * (size_t)n_pairs, sizeof(int))) return r;
+    if (int r = grow(ctx, (void **)&ctx->d_nmatch, &ctx->nmatch_cap, (size_t)n_pairs, sizeof(uint32_t))) return r;
+    SG_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs, h_pairs, 2 * (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // with a host match buffer the pairs are processed in slabs so the device copy stays bounded
+    const int slab = h_matches ? std::min(n_pairs, match_chunk_pairs(db, true)) : n_pairs;
+    for (int p0 = 0; p0 < n_pairs; p0 += slab) {
+        const int np = std::min(slab, n_pairs - p0);
+        if (int r = run_match(ctx, db, ctx->d_pairs + 2 * (size_t)p0, np, *mp, nullptr, 0, ctx->d_nmatch + p0)) return r;
+        if (h_matches) {
+            // run_match left the rows in ctx->d_matches with stride max_set
+            SG_CUDA(ctx, cudaMemcpy2DAsync(h_matches + (size_t)p0 * match_stride, (size_t)match_stride * 4, ctx->d_matches,
+                                           (size_t)db->max_set * 4, (size_t)db->max_set * 4, np, cudaMemcpyDeviceToHost, ctx->stream));
+            SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int p = p0; p < p0 + np; ++p)   // -1 padding behind the largest set
+                for (int i = db->max_set; i < match_stride; ++i) h_matches[(size_t)p * match_stride + i] = -1;
+        }
+    }
+    SG_CUDA(ctx, cudaMemcpyAsync(h_n_matches, ctx->d_nmatch, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(&ctx->rescans, ctx->d_rescans, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SG_OK;
+}
+
+int sg_match_bruteforce(sg_ctx *ctx, const uint32_t *h_descA, const float *h_angA, int nA, const uint32_t *h_descB,
+                        const float *h_angB, int nB, const sg_match_params *mp, int32_t *h_matches, uint32_t *n_matches) {
+    cudaSetDevice(ctx->device);
+    if (nA < 0 || nB < 0 || !mp || !n_matches || (nA && (!h_descA || !h_angA || !h_matches)) || (nB && (!h_descB || !h_angB)))
+        return fail(ctx, SG_ERR_INVALID, "bad argument");
+    *n_matches = 0;
+    if (nA == 0) return SG_OK;
+    if (nB == 0) { for (int i = 0; i < nA; ++i) h_matches[i] = -1; return SG_OK; }
+    std::vector<uint32_t> desc(8 * ((size_t)nA + nB));
+    std::vector<float> ang((size_t)nA + nB);
+    memcpy(desc.data(), h_descA, 32 * (size_t)nA);
+    memcpy(desc.data() + 8 * (size_t)nA, h_descB, 32 * (size_t)nB);
+    memcpy(ang.data(), h_angA, 4 * (size_t)nA);
+    memcpy(ang.data() + nA, h_angB, 4 * (size_t)nB);
+    const int64_t offs[3] = {0, nA, (int64_t)nA + nB};
+    sg_db *db = nullptr;
+    if (int r = sg_db_create(ctx, desc.data(), ang.data(), offs, 2, &db)) return r;
+    const int32_t pair[2] = {0, 1};
+    std::vector<int32_t> m(db->max_set);
+    const int r = sg_match_pairs(ctx, db, pair, 1, mp, m.data(), db->max_set, n_matches);
+    if (!r) memcpy(h_matches, m.data(), 4 * (size_t)nA);
+    sg_db_destroy(db);
+    return r;
+}
+
+unsigned long long sg_match_rescans(const sg_ctx *ctx) { return ctx->rescans; }
+
+// ---- helpers --------------------------------------------------------------------------------------------
+int sg_malloc(sg_ctx *ctx, size_t bytes, void **d_ptr) {
+    cudaSetDevice(ctx->device);
+    SG_CUDA(ctx, cudaMalloc(d_ptr, bytes));
+    return SG_OK;
+}
+int sg_free(sg_ctx *ctx, void *d_ptr) {
+    cudaSetDevice(ctx->device);
+    SG_CUDA(ctx, cudaFree(d_ptr));
+    return SG_OK;
+}
+int sg_memcpy_h2d(sg_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+    cudaSetDevice(ctx->device);
+    SG_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SG_OK;
+}
+int sg_memcpy_d2h(sg_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
+    cudaSetDevice(ctx->device);
+    SG_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SG_OK;
+}
+int sg_host_alloc_pinned(size_t bytes, void **h_ptr) { return cudaMallocHost(h_ptr, bytes) == cudaSuccess ? SG_OK : SG_ERR_CUDA; }
+int sg_host_free_pinned(void *h_ptr) { return cudaFreeHost(h_ptr) == cudaSuccess ? SG_OK : SG_ERR_CUDA; }
+
+int sg_timer_start(sg_ctx *ctx) {
+    SG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    return SG_OK;
+}
+int sg_timer_stop(sg_ctx *ctx, float *ms) {
+    SG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    SG_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    SG_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return SG_OK;
+}
+int sg_flush_l2(sg_ctx *ctx) {
+    cudaSetDevice(ctx->device);
+    const size_t bytes = (size_t)256 << 20;   // 2x the 126 MB L2
+    if (!ctx->d_flush) {
+        SG_CUDA(ctx, cudaMalloc(&ctx->d_flush, bytes));
+        ctx->flush_bytes = bytes;
+    }
+    SG_CUDA(ctx, cudaMemsetAsync(ctx->d_flush, 0x5a, ctx->flush_bytes, ctx->stream));
+    return SG_OK;
+}
+int sg_microbench_popc(sg_ctx *ctx, double *popc_per_s, float *ms) {
+    cudaSetDevice(ctx->device);
+    if (!popc_per_s || !ms) return fail(ctx, SG_ERR_INVALID, "null argument");
+    return run_popc_bench(ctx, popc_per_s, ms);
+}
+
+}  // extern "C"

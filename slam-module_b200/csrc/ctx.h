@@ -1,0 +1,173 @@
+// Internal context of libslamgpu.so (not part of the ABI; see include/slamgpu.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/slamgpu.h"
+
+namespace sg {
+
+constexpr int PATCH_RADIUS = 19;   // StaticSettings::ORB_PATCH_RADIUS (static_settings.hpp:14)
+constexpr int HALF_PATCH = 15;     // ORB_FAST_PATCH_HALF_SIZE (static_settings.hpp:16)
+constexpr int CELL = 64;           // FAST cell size of the upstream detector
+constexpr int FAST_BORDER = 3;     // cv::FAST never evaluates the outer 3 px of (a sub-)image
+constexpr int EVAL_ORIGIN = PATCH_RADIUS + FAST_BORDER;  // first evaluated pixel: 22
+
+// One entry of the horizontal / vertical linear-resize table (cv::resize INTER_LINEAR, 11-bit
+// fixed-point coefficients), precomputed on the host exactly as OpenCV does (tables.cpp).
+struct ResizeTap {
+    int32_t s0, s1;   // source indices (s1 already clipped)
+    int16_t a0, a1;   // coefficients, a0 + a1 == 2048
+};
+
+struct Level {
+    int w = 0, h = 0, pitch = 0;
+    size_t frame_stride = 0;        // bytes between consecutive frames of this level
+    float scale = 1.f;
+    int budget = 0;
+    uint8_t *pyr = nullptr;         // [max_frames][h][pitch]; level 0 may alias an external device image
+    uint8_t *blur = nullptr;
+    ResizeTap *xtab = nullptr;      // [w]   (levels >= 1)
+    ResizeTap *ytab = nullptr;      // [h]
+    bool area2x = false;            // cv::resize switches to INTER_AREA for an exact 2x decimation
+    int src_tile_w = 0, src_tile_h = 0;  // smem extent of the source tile of the resize kernel
+    // detection geometry
+    int area_w = 0, area_h = 0;     // working area (image minus 19-px border)
+    int cells_x = 0, cells_y = 0;   // 64-px cells over the evaluated interior [22, w-22) x [22, h-22)
+    int cand_cap = 0;               // candidate capacity per frame
+    int node_cap = 0;               // quadtree node capacity == keypoint capacity per frame
+    int init_nx = 1, init_ny = 1;   // initial quadtree nodes
+    size_t cand_off = 0;            // offset of this level inside a frame's candidate block
+    int kp_off = 0;                 // offset of this level inside a frame's detected-keypoint block
+};
+
+// Geometry the kernels read (passed by value / __grid_constant__).
+struct LevelDev {
+    int w, h, pitch;
+    unsigned long long frame_stride;
+    const uint8_t *pyr;
+    const uint8_t *blur;
+    float scale;
+    int budget;
+    int area_w, area_h, cells_x, cells_y;
+    int cand_cap, node_cap, init_nx, init_ny;
+    unsigned long long cand_off;
+    int kp_off;
+};
+struct GeomDev {
+    int levels;
+    int det_cap;          // detected keypoints per frame (sum of node_cap)
+    int out_cap;          // output keypoints per frame (max_tracks + det_cap)
+    int max_tracks;
+    unsigned long long cand_per_frame;
+    int ini_thr, min_thr;
+    LevelDev lv[SG_MAX_LEVELS];
+};
+
+}  // namespace sg
+
+struct sg_db {
+    sg_ctx *ctx = nullptr;
+    uint32_t *d_desc = nullptr;
+    float *d_angle = nullptr;
+    long long *d_offsets = nullptr;
+    std::vector<long long> offsets;
+    int n_sets = 0;
+    int max_set = 0;
+};
+
+struct sg_ctx {
+    int device = 0;
+    sg_params p{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    unsigned long long launches = 0;
+    int sm_count = 148;
+
+    std::vector<sg::Level> lv;
+    sg::GeomDev geom{};
+    const uint8_t *level0 = nullptr;   // current level-0 planes (own buffer or caller's device images)
+    int level0_pitch = 0;
+    size_t level0_stride = 0;
+    int frames_ready = 0;              // frames in the current pyramid
+    bool detected = false;
+
+    // detection scratch
+    unsigned long long *d_cand = nullptr;  // [max_frames][cand_per_frame]  resp<<32 | order key
+    uint32_t *d_cand_node = nullptr;       // node id of each candidate during distribution
+    int *d_cand_count = nullptr;           // [max_frames][levels]
+    int *d_kp_xy = nullptr;                // [max_frames][det_cap]  x | y<<16 (level coords)
+    int *d_kp_resp = nullptr;
+    int *d_kp_count = nullptr;             // [max_frames][levels]
+    int *d_err = nullptr;                  // device-side overflow flag
+
+    // tracker points (host-filtered, orb_extractor.cpp:89-104)
+    int *d_trk_xy = nullptr;               // [max_frames][max_tracks]  x | y<<16 at track_level
+    float *d_trk_pt = nullptr;             // [max_frames][max_tracks][2] original full-res point
+    int *d_trk_id = nullptr;
+    int *d_trk_count = nullptr;            // [max_frames]
+    bool have_tracks = false;
+
+    // extraction output (SoA, out_cap per frame)
+    float *d_x = nullptr, *d_y = nullptr, *d_angle = nullptr;
+    int *d_octave = nullptr, *d_track_id = nullptr, *d_lvl_x = nullptr, *d_lvl_y = nullptr;
+    uint32_t *d_desc = nullptr;
+    int *d_count = nullptr;                // [max_frames]
+
+    // staging
+    uint8_t *h_stage = nullptr;            // pinned, one batch of images
+    size_t h_stage_bytes = 0;
+    void *d_flush = nullptr;
+    size_t flush_bytes = 0;
+
+    // matcher scratch (grown on demand)
+    uint32_t *d_topk = nullptr;            // [rows][4] keys
+    uint32_t *d_nseen = nullptr;           // [rows]
+    size_t topk_rows = 0;
+    int *d_pairs = nullptr;
+    size_t pairs_cap = 0;
+    int *d_matches = nullptr;
+    size_t matches_cap = 0;
+    uint32_t *d_nmatch = nullptr;
+    size_t nmatch_cap = 0;
+    unsigned long long *d_rescans = nullptr;
+    unsigned long long rescans = 0;
+    void *d_tmp = nullptr;                 // small uploads for the single-pair entry points
+    size_t tmp_bytes = 0;
+};
+
+namespace sg {
+
+// Error plumbing ---------------------------------------------------------------------------------
+int fail(sg_ctx *ctx, int code, const char *fmt, ...);
+#define SG_CUDA(ctx, call)                                                                        \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return sg::fail((ctx), SG_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                  \
+                            cudaGetErrorString(e_), __FILE__, __LINE__);                          \
+    } while (0)
+#define SG_LAUNCH_CHECK(ctx)                                                                      \
+    do {                                                                                          \
+        ++(ctx)->launches;                                                                        \
+        cudaError_t e_ = cudaGetLastError();                                                      \
+        if (e_ != cudaSuccess)                                                                    \
+            return sg::fail((ctx), SG_ERR_CUDA, "kernel launch failed: %s (%s:%d)",              \
+                            cudaGetErrorString(e_), __FILE__, __LINE__);                          \
+    } while (0)
+
+// Host-side tables (tables.cpp) -----------------------------------------------------------------
+void make_geometry(const sg_params &p, std::vector<Level> &lv);
+void make_resize_taps(int src, int dst, std::vector<ResizeTap> &taps, bool horizontal);
+bool is_area2x(int sw, int sh, int dw, int dh);
+
+// Stage launchers (one per .cu) -----------------------------------------------------------------
+int launch_pyramid(sg_ctx *ctx, int n_frames);
+int launch_detect(sg_ctx *ctx, int n_frames);
+int launch_describe(sg_ctx *ctx, int n_frames);
+int grow(sg_ctx *ctx, void **ptr, size_t *cap, size_t need, size_t elem);
+
+}  // namespace sg

@@ -1,0 +1,504 @@
+// Brute-force Hamming matching with the sequential semantics of matchForLoopClosures
+// (keyframe_matcher.cpp:50-158, single-BoW-node case): for every A feature in index order, best
+// and second-best distance over the B features not yet consumed, reject when thr < best
+// (:115) or ratio * second < best (:120), consume the B feature (:128), finally keep only matches
+// whose delta-angle falls in the three most populated 30-degree bins
+// (openvslam/match_angle_checker.h:61-134).  Distances are compute_descriptor_distance_32
+// (openvslam/match_base.h:18-39) = popcount of the XOR of 256 bits.
+//
+// GPU formulation (exact, not approximate)
+//   hamming_topk_kernel : the O(nA*nB) part.  One thread owns one A descriptor in registers and
+//     streams all B descriptors from a shared-memory tile (broadcast 128-bit reads), 8 XOR + 8 POPC
+//     per pair, and keeps the K = 4 smallest (distance, index) keys with distance <= C, where C is
+//     the largest "second best" that can still change a ratio decision (host, match_cutoff).
+//   match_resolve_kernel: the order-dependent part.  One warp per keyframe pair walks the A rows
+//     in order; best / second are the first two unconsumed entries of a row's list.  When the list
+//     cannot decide (entries consumed and the list was truncated) the warp rescans the whole row
+//     exactly.  Then the angle histogram filter, with libstdc++'s std::sort order of the 30 bins
+//     restated (sort30) so that ties between bins resolve as in the reference.
+#include <algorithm>
+#include "ctx.h"
+
+namespace sg {
+
+constexpr int TOPK = 4;
+constexpr int MT_THREADS = 256;
+constexpr int B_CHUNK = 1024;        // B descriptors per shared-memory tile (32 KB)
+constexpr unsigned EMPTY_KEY = 0xffffffffu;
+constexpr int RES_WARPS = 4;
+
+// ---- libstdc++ std::sort (introsort, _S_threshold 16) restated for 30 bin indices -----------------
+// comp(a, b) == sizes[a] > sizes[b]  (match_angle_checker.h:129-132).  Equal sizes make the result
+// depend on the algorithm, so it is restated step by step: median-of-three to first, unguarded
+// Hoare partition, recursion on the right part, heap sort when the depth limit is hit, final
+// insertion sort (first 16 guarded, rest unguarded).
+struct Sort30 {
+    unsigned v[30];
+    const unsigned *sz;
+    __host__ __device__ bool comp(unsigned a, unsigned b) const { return sz[a] > sz[b]; }
+    __host__ __device__ void swp(int i, int j) { const unsigned t = v[i]; v[i] = v[j]; v[j] = t; }
+
+    __host__ __device__ void median_to_first(int result, int a, int b, int c) {
+        if (comp(v[a], v[b])) {
+            if (comp(v[b], v[c])) swp(result, b);
+            else if (comp(v[a], v[c])) swp(result, c);
+            else swp(result, a);
+        } else if (comp(v[a], v[c])) swp(result, a);
+        else if (comp(v[b], v[c])) swp(result, c);
+        else swp(result, b);
+    }
+    __host__ __device__ int partition(int first, int last, int pivot) {
+        while (true) {
+            while (comp(v[first], v[pivot])) ++first;
+            --last;
+            while (comp(v[pivot], v[last])) --last;
+            if (!(first < last)) return first;
+            swp(first, last);
+            ++first;
+        }
+    }
+    // heap helpers (std::__adjust_heap / __push_heap / __pop_heap / __make_heap) on [first, first+len)
+    __host__ __device__ void adjust_heap(int first, int hole, int len, unsigned value) {
+        const int top = hole;
+        int child = hole;
+        while (child < (len - 1) / 2) {
+            child = 2 * (child + 1);
+            if (comp(v[first + child], v[first + child - 1])) --child;
+            v[first + hole] = v[first + child];
+            hole = child;
+        }
+        if ((len & 1) == 0 && child == (len - 2) / 2) {
+            child = 2 * (child + 1);
+            v[first + hole] = v[first + child - 1];
+            hole = child - 1;
+        }
+        int parent = (hole - 1) / 2;
+        while (hole > top && comp(v[first + parent], value)) {
+            v[first + hole] = v[first + parent];
+            hole = parent;
+            parent = (hole - 1) / 2;
+        }
+        v[first + hole] = value;
+    }
+    __host__ __device__ void heap_sort(int first, int last) {   // std::__partial_sort(first, last, last)
+        const int len = last - first;
+        if (len >= 2)
+            for (int parent = (len - 2) / 2;; --parent) {
+                adjust_heap(first, parent, len, v[first + parent]);
+                if (parent == 0) break;
+            }
+        for (int l = last; l - first > 1;) {
+            --l;
+            const unsigned value = v[l];
+            v[l] = v[first];
+            adjust_heap(first, 0, l - first, value);
+        }
+    }
+    __host__ __device__ void introsort_loop(int first0, int last0, int depth0) {
+        // the recursion on [cut, last) touches a range disjoint from the loop's [first, cut), so an explicit
+        // stack visiting the parts in any order gives the same result
+        int sf[32], sl[32], sd[32], sp = 0;
+        sf[0] = first0; sl[0] = last0; sd[0] = depth0; sp = 1;
+        while (sp) {
+            --sp;
+            int first = sf[sp], last = sl[sp], depth = sd[sp];
+            while (last - first > 16) {
+                if (depth == 0) { heap_sort(first, last); break; }
+                --depth;
+                const int mid = first + (last - first) / 2;
+                median_to_first(first, first + 1, mid, last - 1);
+                const int cut = partition(first + 1, last, first);
+                sf[sp] = cut; sl[sp] = last; sd[sp] = depth; ++sp;
+                last = cut;
+            }
+        }
+    }
+    __host__ __device__ void linear_insert(int last) {
+        const unsigned val = v[last];
+        int next = last - 1;
+        while (comp(val, v[next])) { v[last] = v[next]; last = next; --next; }
+        v[last] = val;
+    }
+    __host__ __device__ void insertion_sort(int first, int last) {
+        if (first == last) return;
+        for (int i = first + 1; i != last; ++i) {
+            if (comp(v[i], v[first])) {
+                const unsigned val = v[i];
+                for (int k = i; k > first; --k) v[k] = v[k - 1];
+                v[first] = val;
+            } else linear_insert(i);
+        }
+    }
+    __host__ __device__ void run(const unsigned *sizes, int depth_limit) {
+        sz = sizes;
+        for (int i = 0; i < 30; ++i) v[i] = i;
+        introsort_loop(0, 30, depth_limit);
+        insertion_sort(0, 16);
+        for (int i = 16; i < 30; ++i) linear_insert(i);
+    }
+};
+
+// angle_checker::append_delta_angle (match_angle_checker.h:72-83): float -> double compare/add -> float
+__host__ __device__ inline int angle_bin(float delta) {
+    if (delta < 0.0) delta = (float)((double)delta + 360.0);
+    if (360.0 <= delta) delta = (float)((double)delta - 360.0);
+#ifdef __CUDA_ARCH__
+    return __float2int_rn(__fmul_rn(delta, 1.0f / 30));
+#else
+    return (int)lrintf(delta * (1.0f / 30));
+#endif
+}
+
+// ---- distance + top-K kernel -----------------------------------------------------------------------
+struct MatchArgs {
+    const uint32_t *desc;      // database descriptors
+    const float *angle;
+    const long long *offsets;  // set offsets
+    const int *pairs;          // {setA, setB} per pair
+    int row_stride;            // rows reserved per pair in the top-K scratch
+    int match_stride;          // ints per pair in the match output
+    unsigned cutoff;           // C
+    unsigned thr;
+    float ratio;
+    int ratio_is_double;
+    int check_orientation;
+};
+
+__device__ __forceinline__ void topk_insert(unsigned (&t)[TOPK], unsigned key) {
+#pragma unroll
+    for (int i = 0; i < TOPK; ++i) {
+        const unsigned lo = min(t[i], key);
+        key = max(t[i], key);
+        t[i] = lo;
+    }
+}
+
+__global__ void __launch_bounds__(MT_THREADS)
+hamming_topk_kernel(const MatchArgs a, uint32_t *topk, uint32_t *nseen_out) {
+    __shared__ uint4 Bs[B_CHUNK * 2];
+    const int tid = threadIdx.x, p = blockIdx.y;
+    const int sa = a.pairs[2 * p], sb = a.pairs[2 * p + 1];
+    const long long oa = a.offsets[sa], ob = a.offsets[sb];
+    const int nA = (int)(a.offsets[sa + 1] - oa), nB = (int)(a.offsets[sb + 1] - ob);
+    if ((int)(blockIdx.x * MT_THREADS) >= nA) return;
+    const int row = blockIdx.x * MT_THREADS + tid;
+    const bool live = row < nA;
+
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    if (live) {
+        const uint4 *pa = reinterpret_cast<const uint4 *>(a.desc + 8 * (oa + row));
+        a0 = __ldg(pa); a1 = __ldg(pa + 1);
+    }
+    unsigned t[TOPK];
+#pragma unroll
+    for (int i = 0; i < TOPK; ++i) t[i] = EMPTY_KEY;
+    unsigned nseen = 0;
+    const unsigned C = a.cutoff;
+    const uint4 *pb = reinterpret_cast<const uint4 *>(a.desc + 8 * ob);
+
+    for (int j0 = 0; j0 < nB; j0 += B_CHUNK) {
+        const int cn = min(B_CHUNK, nB - j0);
+        __syncthreads();
+        for (int i = tid; i < 2 * cn; i += MT_THREADS) Bs[i] = __ldg(pb + 2 * (size_t)j0 + i);
+        __syncthreads();
+        if (live) {
+#pragma unroll 4
+            for (int j = 0; j < cn; ++j) {
+                const uint4 b0 = Bs[2 * j], b1 = Bs[2 * j + 1];
+                const unsigned d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w)
+                                   + __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+                if (d <= C) {
+                    ++nseen;
+                    const unsigned key = (d << 16) | (unsigned)(j0 + j);
+                    if (key < t[TOPK - 1]) topk_insert(t, key);
+                }
+            }
+        }
+    }
+    if (live) {
+        const size_t r = (size_t)p * a.row_stride + row;
+        reinterpret_cast<uint4 *>(topk)[r] = make_uint4(t[0], t[1], t[2], t[3]);
+        nseen_out[r] = nseen;
+    }
+}
+
+// ---- sequential resolve + angle filter -------------------------------------------------------------
+__device__ __forceinline__ bool ratio_rejects(float ratio, unsigned second, unsigned best, int is_double) {
+    // keyframe_matcher.cpp:120  `ratio * second < static_cast<float>(best)`
+    if (is_double) return (double)ratio * (double)second < (double)(float)best;
+    return __fmul_rn(ratio, (float)second) < (float)best;
+}
+
+__global__ void __launch_bounds__(RES_WARPS * 32)
+match_resolve_kernel(const MatchArgs a, int n_pairs, const uint32_t *topk, const uint32_t *nseen_in,
+                     int taken_words, int *matches, uint32_t *n_matches, unsigned long long *rescans) {
+    extern __shared__ uint32_t rsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = blockIdx.x * RES_WARPS + warp;
+    if (p >= n_pairs) return;
+    uint32_t *taken = rsm + warp * (taken_words + 32);
+    uint32_t *hist = taken + taken_words;   // 32 words, 30 used
+
+    const int sa = a.pairs[2 * p], sb = a.pairs[2 * p + 1];
+    const long long oa = a.offsets[sa], ob = a.offsets[sb];
+    const int nA = (int)(a.offsets[sa + 1] - oa), nB = (int)(a.offsets[sb + 1] - ob);
+    const uint32_t *dA = a.desc + 8 * oa, *dB = a.desc + 8 * ob;
+    const float *angA = a.angle + oa, *angB = a.angle + ob;
+    int *mrow = matches + (size_t)p * a.match_stride;
+
+    for (int i = lane; i < taken_words; i += 32) taken[i] = 0;
+    for (int i = nA + lane; i < a.match_stride; i += 32) mrow[i] = -1;   // padding behind the A set
+    hist[lane] = 0;
+    __syncwarp();
+
+    unsigned count = 0, my_bin_count = 0, n_rescan = 0;
+    // the match row is also the record the angle filter re-reads, so it always exists: the caller's
+    // buffer or the context's scratch (run_match)
+    for (int base = 0; base < nA; base += 32) {
+        const int i = base + lane;
+        uint4 keys = make_uint4(EMPTY_KEY, EMPTY_KEY, EMPTY_KEY, EMPTY_KEY);
+        unsigned ns = 0;
+        if (i < nA) {
+            const size_t r = (size_t)p * a.row_stride + i;
+            ns = nseen_in[r];
+            if (ns) keys = reinterpret_cast<const uint4 *>(topk)[r];
+            mrow[i] = -1;
+        }
+        unsigned active = __ballot_sync(0xffffffffu, ns > 0);
+        while (active) {
+            const int src = __ffs(active) - 1;
+            active &= active - 1;
+            const unsigned k[4] = {__shfl_sync(0xffffffffu, keys.x, src), __shfl_sync(0xffffffffu, keys.y, src),
+                                   __shfl_sync(0xffffffffu, keys.z, src), __shfl_sync(0xffffffffu, keys.w, src)};
+            const unsigned rns = __shfl_sync(0xffffffffu, ns, src);
+            const int row = base + src;
+            unsigned u0 = EMPTY_KEY, u1 = EMPTY_KEY, last = EMPTY_KEY;
+#pragma unroll
+            for (int e = 0; e < TOPK; ++e) {
+                if (k[e] == EMPTY_KEY) continue;
+                last = k[e];
+                const unsigned idx = k[e] & 0xffffu;
+                const bool tk = (taken[idx >> 5] >> (idx & 31)) & 1u;
+                if (!tk) {
+                    if (u0 == EMPTY_KEY) u0 = k[e];
+                    else if (u1 == EMPTY_KEY) u1 = k[e];
+                }
+            }
+            const bool complete = rns <= TOPK;
+            const unsigned last_d = last >> 16;
+            int decision;   // 0 reject, 1 accept u0, 2 rescan
+            if (u0 == EMPTY_KEY) {
+                decision = (complete || last_d > a.thr) ? 0 : 2;
+            } else {
+                const unsigned best = u0 >> 16;
+                if (best > a.thr) decision = 0;
+                else if (u1 != EMPTY_KEY) decision = ratio_rejects(a.ratio, u1 >> 16, best, a.ratio_is_double) ? 0 : 1;
+                else if (complete) decision = ratio_rejects(a.ratio, 256u, best, a.ratio_is_double) ? 0 : 1;
+                else decision = ratio_rejects(a.ratio, last_d, best, a.ratio_is_double) ? 2 : 1;
+            }
+            unsigned best_idx = u0 & 0xffffu;
+            if (decision == 2) {
+                // exact full-row scan over the unconsumed B features
+                ++n_rescan;
+                uint32_t ar[8];
+#pragma unroll
+                for (int w = 0; w < 8; ++w) ar[w] = __ldg(dA + 8 * (size_t)row + w);
+                unsigned bkey = (256u << 16) | 0xffffu, sec = 256u;
+                for (int j = lane; j < nB; j += 32) {
+                    if ((taken[j >> 5] >> (j & 31)) & 1u) continue;
+                    const uint4 b0 = __ldg(reinterpret_cast<const uint4 *>(dB + 8 * (size_t)j));
+                    const uint4 b1 = __ldg(reinterpret_cast<const uint4 *>(dB + 8 * (size_t)j) + 1);
+                    const unsigned d = __popc(ar[0] ^ b0.x) + __popc(ar[1] ^ b0.y) + __popc(ar[2] ^ b0.z) + __popc(ar[3] ^ b0.w)
+                                       + __popc(ar[4] ^ b1.x) + __popc(ar[5] ^ b1.y) + __popc(ar[6] ^ b1.z) + __popc(ar[7] ^ b1.w);
+                    const unsigned key = (d << 16) | (unsigned)j;
+                    if (key < bkey) { sec = bkey >> 16; bkey = key; }
+                    else if (d < sec) sec = d;
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    const unsigned ob_ = __shfl_xor_sync(0xffffffffu, bkey, o);
+                    const unsigned os_ = __shfl_xor_sync(0xffffffffu, sec, o);
+                    sec = min(min(sec, os_), max(bkey >> 16, ob_ >> 16));
+                    bkey = min(bkey, ob_);
+                }
+                const unsigned best = bkey >> 16;
+                best_idx = bkey & 0xffffu;
+                decision = (a.thr < best || ratio_rejects(a.ratio, sec, best, a.ratio_is_double)) ? 0 : 1;
+            }
+            if (decision == 1) {
+                ++count;
+                if (lane == 0) {
+                    taken[best_idx >> 5] |= 1u << (best_idx & 31);
+                    mrow[row] = (int)best_idx;
+                }
+                if (a.check_orientation) {
+                    const int bin = angle_bin(angA[row] - angB[best_idx]);
+                    if (lane == bin) ++my_bin_count;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    // ---- angle histogram filter ------------------------------------------------------------------------
+    if (a.check_orientation) {
+        hist[lane] = my_bin_count;
+        __syncwarp();
+        unsigned valid = 0;
+        if (lane == 0) {
+            Sort30 s;
+            s.run(hist, 8);   // depth limit 2 * floor(log2(30))
+            valid = (1u << s.v[0]) | (1u << s.v[1]) | (1u << s.v[2]);
+        }
+        valid = __shfl_sync(0xffffffffu, valid, 0);
+        unsigned removed = 0;
+        for (int i = lane; i < nA; i += 32) {
+            const int m = mrow[i];
+            if (m >= 0) {
+                const int bin = angle_bin(angA[i] - angB[m]);
+                if (!((valid >> bin) & 1u)) { mrow[i] = -1; ++removed; }
+            }
+        }
+        removed = __reduce_add_sync(0xffffffffu, removed);
+        count -= removed;
+    }
+    if (lane == 0) {
+        n_matches[p] = count;
+        if (n_rescan) atomicAdd(rescans, (unsigned long long)n_rescan);
+    }
+}
+
+// Largest second-best distance that can still flip the ratio test for some best <= thr.
+static unsigned match_cutoff(const sg_match_params &mp) {
+    unsigned c = mp.thr;
+    while (c < 256) {
+        const unsigned s = c + 1;
+        const bool rej = mp.ratio_is_double ? ((double)mp.ratio * (double)s < (double)(float)mp.thr)
+                                            : (mp.ratio * (float)s < (float)mp.thr);
+        if (!rej) break;
+        c = s;
+    }
+    return std::min(c, 256u);
+}
+
+// ---- simple kernels: pairwise distances, POPC micro-benchmark ---------------------------------------
+__global__ void hamming_pairs_kernel(const uint32_t *a, const uint32_t *b, int n, uint32_t *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 *pa = reinterpret_cast<const uint4 *>(a) + 2 * (size_t)i, *pb = reinterpret_cast<const uint4 *>(b) + 2 * (size_t)i;
+    const uint4 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1];
+    out[i] = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w)
+             + __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__global__ void popc_bench_kernel(unsigned *out, int iters, unsigned seed) {
+    unsigned x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = seed * (threadIdx.x + 1) + i * 0x9e3779b9u + blockIdx.x;
+    unsigned acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            acc[i] += __popc(x[i]);   // 8 independent POPC per iteration
+            x[i] ^= acc[i] + it;      // keeps the compiler from hoisting; one LOP3/IADD per POPC
+        }
+    }
+    unsigned s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i];
+    if (s == 0xdeadbeefu) out[0] = s;
+}
+
+// Pairs per launch: bounds the top-K (and match-row) scratch to ~256 MB.
+int match_chunk_pairs(const sg_db *db, bool own_matches) {
+    const size_t per_pair = (size_t)std::max(db->max_set, 1) * (TOPK * 4 + 4 + (own_matches ? 4 : 0));
+    return (int)std::max<size_t>(1, ((size_t)256 << 20) / per_pair);
+}
+
+int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, const sg_match_params &mp,
+              int *d_matches, int match_stride, uint32_t *d_n_matches) {
+    if (n_pairs <= 0) return SG_OK;
+    if (db->max_set > 65535) return fail(ctx, SG_ERR_INVALID, "descriptor sets larger than 65535 features are not supported");
+    if (mp.thr > 256) return fail(ctx, SG_ERR_INVALID, "thr must be <= 256");
+    const int stride = db->max_set;
+    if (d_matches && match_stride < stride) return fail(ctx, SG_ERR_INVALID, "match_stride smaller than the largest set");
+    const int chunk = std::min(n_pairs, match_chunk_pairs(db, d_matches == nullptr));
+    {
+        size_t need = (size_t)chunk * stride;
+        if (need > ctx->topk_rows) {
+            if (ctx->d_topk) cudaFree(ctx->d_topk);
+            if (ctx->d_nseen) cudaFree(ctx->d_nseen);
+            ctx->d_topk = nullptr; ctx->d_nseen = nullptr; ctx->topk_rows = 0;
+            SG_CUDA(ctx, cudaMalloc(&ctx->d_topk, need * TOPK * 4));
+            SG_CUDA(ctx, cudaMalloc(&ctx->d_nseen, need * 4));
+            ctx->topk_rows = need;
+        }
+        if (!d_matches) {
+            size_t cap = ctx->matches_cap;
+            int r = grow(ctx, (void **)&ctx->d_matches, &cap, need, sizeof(int));
+            ctx->matches_cap = cap;
+            if (r) return r;
+        }
+    }
+    SG_CUDA(ctx, cudaMemsetAsync(ctx->d_rescans, 0, sizeof(unsigned long long), ctx->stream));
+    MatchArgs a{};
+    a.desc = db->d_desc; a.angle = db->d_angle; a.offsets = db->d_offsets;
+    a.cutoff = match_cutoff(mp); a.thr = mp.thr; a.ratio = mp.ratio;
+    a.ratio_is_double = mp.ratio_is_double; a.check_orientation = mp.check_orientation;
+    const int taken_words = (db->max_set + 31) / 32;
+    const size_t rsmem = (size_t)RES_WARPS * (taken_words + 32) * 4;
+    for (int p0 = 0; p0 < n_pairs; p0 += chunk) {
+        const int np = std::min(chunk, n_pairs - p0);
+        a.pairs = d_pairs + 2 * (size_t)p0;
+        a.row_stride = stride;
+        dim3 grid((stride + MT_THREADS - 1) / MT_THREADS, np);
+        hamming_topk_kernel<<<grid, MT_THREADS, 0, ctx->stream>>>(a, ctx->d_topk, ctx->d_nseen);
+        SG_LAUNCH_CHECK(ctx);
+        a.match_stride = d_matches ? match_stride : stride;
+        int *mout = d_matches ? d_matches + (size_t)p0 * match_stride : ctx->d_matches;
+        match_resolve_kernel<<<(np + RES_WARPS - 1) / RES_WARPS, RES_WARPS * 32, rsmem, ctx->stream>>>(
+            a, np, ctx->d_topk, ctx->d_nseen, taken_words, mout, d_n_matches + p0, ctx->d_rescans);
+        SG_LAUNCH_CHECK(ctx);
+    }
+    return SG_OK;
+}
+
+int run_hamming(sg_ctx *ctx, const uint32_t *d_a, const uint32_t *d_b, int n, uint32_t *d_out) {
+    hamming_pairs_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_a, d_b, n, d_out);
+    SG_LAUNCH_CHECK(ctx);
+    return SG_OK;
+}
+
+int run_popc_bench(sg_ctx *ctx, double *popc_per_s, float *ms_out) {
+    unsigned *d_out = nullptr;
+    SG_CUDA(ctx, cudaMalloc(&d_out, 4));
+    const int iters = 4096, blocks = ctx->sm_count * 8, threads = 256;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        SG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        popc_bench_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 12345u + rep);
+        SG_LAUNCH_CHECK(ctx);
+        SG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        SG_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        SG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaFree(d_out);
+    *popc_per_s = (double)blocks * threads * iters * 8.0 / (best * 1e-3);
+    *ms_out = best;
+    return SG_OK;
+}
+
+}  // namespace sg
+
+extern "C" void sg_angle_bin_order_depth(const uint32_t *sizes30, int depth_limit, uint32_t *order30) {
+    sg::Sort30 s;
+    s.run(sizes30, depth_limit);
+    for (int i = 0; i < 30; ++i) order30[i] = s.v[i];
+}
+extern "C" void sg_angle_bin_order(const uint32_t *sizes30, uint32_t *order30) {
+    sg::Sort30 s;
+    s.run(sizes30, 8);
+    for (int i = 0; i < 30; ++i) order30[i] = s.v[i];
+}
+extern "C" int sg_angle_bin(float delta_angle) { return sg::angle_bin(delta_angle); }

@@ -1,0 +1,252 @@
+// Image pyramid: chained bilinear down-scaling fused with the 7x7 Gaussian blur of every level.
+//
+// Replaces CpuImagePyramid::update (image_pyramid.cpp:68-86): level L = cv::resize(level L-1,
+// INTER_LINEAR), blurred L = cv::GaussianBlur(level L, 7x7, sigma 2, BORDER_REFLECT_101).  Both
+// OpenCV primitives are integer fixed-point on 8-bit data, so the kernel is bit-exact:
+//   resize : 11-bit coefficient taps (host tables, tables.cpp), int32 row sums,
+//            out = (((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2
+//   blur   : kernel {18,34,48,56,48,34,18}/256, horizontal 8.8 sums (u16), vertical 16.16 sums,
+//            out = (v + 32768) >> 16, reflect-101 borders applied to the RESIZED pixels.
+//
+// One CTA produces a 64x32 tile of level L: the source tile of level L-1 is staged in shared
+// memory, the resized tile plus a 3-px halo is produced into shared memory (and its interior
+// written to the pyramid plane), halo pixels outside the image are mirrored in place, then the
+// separable blur runs from shared memory and the blurred tile is written with 32-bit stores.
+// Level L-1 is read once from HBM/L2 and both planes of level L are written once.
+#include "ctx.h"
+
+namespace sg {
+
+constexpr int TW = 64, TH = 32;          // output tile
+constexpr int RW = TW + 8, RH = TH + 6;  // resized tile incl. halo; column 0 <-> x0-4 (word aligned)
+constexpr int PYR_THREADS = 256;
+
+struct PyrArgs {
+    const uint8_t *src;   // level L-1 (or level L itself when !RESIZE)
+    int sw, sh, spitch;
+    unsigned long long sstride;
+    uint8_t *dst;         // pyramid plane of level L (RESIZE only)
+    uint8_t *blur;        // blurred plane of level L
+    int w, h, pitch;
+    unsigned long long dstride;
+    const ResizeTap *xtab, *ytab;
+    int src_tile_w, src_tile_h;  // smem extent of the source tile (bytes per row multiple of 4)
+    int area2x;
+};
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+template <bool RESIZE>
+__global__ void __launch_bounds__(PYR_THREADS) pyr_level_kernel(const PyrArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *R = smem;                                        // [RH][RW]
+    uint16_t *Hs = reinterpret_cast<uint16_t *>(smem + RH * RW);  // [RH][TW]
+    uint8_t *S = smem + RH * RW + RH * TW * 2;                // [src_tile_h][src_tile_w]  (RESIZE)
+    ResizeTap *xt = reinterpret_cast<ResizeTap *>(S + a.src_tile_h * a.src_tile_w);  // [TW+6]
+    ResizeTap *yt = xt + (TW + 6);                                                  // [TH+6]
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, f = blockIdx.z;
+    const int tw = min(TW, a.w - x0), th = min(TH, a.h - y0);
+    // in-image part of the halo window, [xlo, xhi) x [ylo, yhi)
+    const int xlo = max(x0 - 3, 0), xhi = min(x0 + tw + 3, a.w);
+    const int ylo = max(y0 - 3, 0), yhi = min(y0 + th + 3, a.h);
+    const uint8_t *src = a.src + (size_t)f * a.sstride;
+
+    if (RESIZE) {
+        // ---- stage the source tile and the taps ------------------------------------------------
+        const int sx_lo = a.xtab[xlo].s0 & ~3;
+        const int sx_hi = a.area2x ? min(2 * (xhi - 1) + 1, a.sw - 1) : a.xtab[xhi - 1].s1;
+        const int sy_lo = a.area2x ? 2 * ylo : a.ytab[ylo].s0;
+        const int sy_hi = a.area2x ? min(2 * (yhi - 1) + 1, a.sh - 1) : a.ytab[yhi - 1].s1;
+        const int nwords = ((sx_hi - sx_lo) >> 2) + 1, nrows = sy_hi - sy_lo + 1;
+        const int sp = a.src_tile_w;
+        for (int i = tid; i < nwords * nrows; i += PYR_THREADS) {
+            const int r = i / nwords, wd = i - r * nwords;
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(
+                src + (size_t)(sy_lo + r) * a.spitch + sx_lo + 4 * wd));
+            *reinterpret_cast<uint32_t *>(S + r * sp + 4 * wd) = v;
+        }
+        for (int i = tid; i < (xhi - xlo); i += PYR_THREADS) {
+            ResizeTap t = a.xtab[xlo + i];
+            t.s0 -= sx_lo; t.s1 -= sx_lo;
+            xt[i] = t;
+        }
+        for (int i = tid; i < (yhi - ylo); i += PYR_THREADS) {
+            ResizeTap t = a.ytab[ylo + i];
+            t.s0 -= sy_lo; t.s1 -= sy_lo;
+            yt[i] = t;
+        }
+        __syncthreads();
+        // ---- resized pixels of the in-image window -> R ----------------------------------------
+        const int nx = xhi - xlo, ny = yhi - ylo;
+        for (int i = tid; i < nx * ny; i += PYR_THREADS) {
+            const int ry = i / nx, rx = i - ry * nx;
+            int out;
+            if (a.area2x) {
+                const int sx = 2 * (xlo + rx) - sx_lo, sy = 2 * (ylo + ry) - sy_lo;
+                out = (S[sy * sp + sx] + S[sy * sp + sx + 1] + S[(sy + 1) * sp + sx] + S[(sy + 1) * sp + sx + 1] + 2) >> 2;
+            } else {
+                const ResizeTap tx = xt[rx], ty = yt[ry];
+                const uint8_t *r0 = S + ty.s0 * sp, *r1 = S + ty.s1 * sp;
+                const int h0 = r0[tx.s0] * tx.a0 + r0[tx.s1] * tx.a1;
+                const int h1 = r1[tx.s0] * tx.a0 + r1[tx.s1] * tx.a1;
+                out = (((ty.a0 * (h0 >> 4)) >> 16) + ((ty.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                out = min(max(out, 0), 255);
+            }
+            R[(ylo + ry - (y0 - 3)) * RW + (xlo + rx - (x0 - 4))] = (uint8_t)out;
+        }
+    } else {
+        // ---- blur only: the window is read straight from the plane (aligned words) --------------
+        const int ny = yhi - ylo;
+        for (int i = tid; i < ny * (RW / 4); i += PYR_THREADS) {
+            const int ry = i / (RW / 4), wd = i - ry * (RW / 4);
+            const int x = x0 - 4 + 4 * wd;
+            if (x >= 0 && x < a.spitch) {
+                const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)(ylo + ry) * a.spitch + x));
+                *reinterpret_cast<uint32_t *>(R + (ylo + ry - (y0 - 3)) * RW + 4 * wd) = v;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- pyramid plane: interior of R, 32-bit stores ----------------------------------------------
+    if (RESIZE) {
+        uint8_t *dst = a.dst + (size_t)f * a.dstride;
+        for (int i = tid; i < th * (TW / 4); i += PYR_THREADS) {
+            const int r = i / (TW / 4), wd = i - r * (TW / 4);
+            if (4 * wd < tw) {
+                const uint32_t v = *reinterpret_cast<const uint32_t *>(R + (r + 3) * RW + 4 + 4 * wd);
+                *reinterpret_cast<uint32_t *>(dst + (size_t)(y0 + r) * a.pitch + x0 + 4 * wd) = v;
+            }
+        }
+    }
+    // ---- reflect-101: halo entries outside the image mirror resized pixels inside it ------------
+    if (x0 == 0 || y0 == 0 || x0 + tw + 3 > a.w || y0 + th + 3 > a.h) {
+        const int wx = tw + 6, wy = th + 6;
+        for (int i = tid; i < wx * wy; i += PYR_THREADS) {
+            const int ry = i / wx, rx = i - ry * wx;
+            const int x = x0 - 3 + rx, y = y0 - 3 + ry;
+            if (x < 0 || x >= a.w || y < 0 || y >= a.h) {
+                const int mx = reflect101(x, a.w), my = reflect101(y, a.h);
+                R[ry * RW + rx + 1] = R[(my - (y0 - 3)) * RW + (mx - (x0 - 4))];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- horizontal pass: 4 outputs per thread, two dp4a each ------------------------------------
+    {
+        const uint32_t k0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);   // taps 0..3
+        const uint32_t k1 = 48u | (34u << 8) | (18u << 16);                 // taps 4..6
+        for (int i = tid; i < (th + 6) * (TW / 4); i += PYR_THREADS) {
+            const int ry = i / (TW / 4), g = i - ry * (TW / 4);
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(R + ry * RW) + g;
+            const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];   // columns 4g .. 4g+11 of R
+            // output c = 4g + j uses R columns c+1 .. c+7
+            uint32_t o[4];
+            o[0] = __dp4a(__byte_perm(w0, w1, 0x4321), k0, __dp4a(__byte_perm(w1, w2, 0x4321), k1, 0u));
+            o[1] = __dp4a(__byte_perm(w0, w1, 0x5432), k0, __dp4a(__byte_perm(w1, w2, 0x5432), k1, 0u));
+            o[2] = __dp4a(__byte_perm(w0, w1, 0x6543), k0, __dp4a(__byte_perm(w1, w2, 0x6543), k1, 0u));
+            o[3] = __dp4a(w1, k0, __dp4a(w2, k1, 0u));
+            uint2 st;
+            st.x = o[0] | (o[1] << 16);
+            st.y = o[2] | (o[3] << 16);
+            *reinterpret_cast<uint2 *>(Hs + ry * TW + 4 * g) = st;
+        }
+    }
+    __syncthreads();
+
+    // ---- vertical pass: 4 columns x 2 rows per thread, 32-bit stores ------------------------------
+    {
+        uint8_t *bl = a.blur + (size_t)f * a.dstride;
+        const int g = tid & 15, rp = tid >> 4;   // 16 column groups x 16 row pairs
+        const int r0 = 2 * rp;
+        if (r0 < th && 4 * g < tw) {
+            uint32_t hv[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint2 v = *reinterpret_cast<const uint2 *>(Hs + (r0 + j) * TW + 4 * g);
+                hv[j][0] = v.x & 0xffffu; hv[j][1] = v.x >> 16;
+                hv[j][2] = v.y & 0xffffu; hv[j][3] = v.y >> 16;
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                if (r0 + rr < th) {
+                    uint32_t packed = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t v = 18u * (hv[rr][c] + hv[rr + 6][c]) + 34u * (hv[rr + 1][c] + hv[rr + 5][c])
+                                           + 48u * (hv[rr + 2][c] + hv[rr + 4][c]) + 56u * hv[rr + 3][c];
+                        packed |= ((v + 32768u) >> 16) << (8 * c);
+                    }
+                    *reinterpret_cast<uint32_t *>(bl + (size_t)(y0 + r0 + rr) * a.pitch + x0 + 4 * g) = packed;
+                }
+            }
+        }
+    }
+}
+
+static size_t pyr_smem_bytes(const PyrArgs &a, bool resize) {
+    size_t b = RH * RW + RH * TW * 2;
+    if (resize) b += (size_t)a.src_tile_h * a.src_tile_w + sizeof(ResizeTap) * (TW + 6 + TH + 6);
+    return b;
+}
+
+// Largest source-tile extent over all tiles of a level (host, at sg_create).
+void pyramid_source_extent(const std::vector<ResizeTap> &xt, const std::vector<ResizeTap> &yt, int w, int h,
+                           bool area2x, int sw, int sh, int *tile_w, int *tile_h) {
+    int mw = 0, mh = 0;
+    for (int x0 = 0; x0 < w; x0 += TW) {
+        const int tw = std::min(TW, w - x0), xlo = std::max(x0 - 3, 0), xhi = std::min(x0 + tw + 3, w);
+        const int lo = (area2x ? 2 * xlo : xt[xlo].s0) & ~3;
+        const int hi = area2x ? std::min(2 * (xhi - 1) + 1, sw - 1) : xt[xhi - 1].s1;
+        mw = std::max(mw, (((hi - lo) >> 2) + 1) * 4);
+    }
+    for (int y0 = 0; y0 < h; y0 += TH) {
+        const int th = std::min(TH, h - y0), ylo = std::max(y0 - 3, 0), yhi = std::min(y0 + th + 3, h);
+        const int lo = area2x ? 2 * ylo : yt[ylo].s0;
+        const int hi = area2x ? std::min(2 * (yhi - 1) + 1, sh - 1) : yt[yhi - 1].s1;
+        mh = std::max(mh, hi - lo + 1);
+    }
+    *tile_w = mw;
+    *tile_h = mh;
+}
+
+int launch_pyramid(sg_ctx *ctx, int n_frames) {
+    const int levels = ctx->p.levels;
+    for (int l = 0; l < levels; ++l) {
+        const Level &L = ctx->lv[l];
+        PyrArgs a{};
+        a.w = L.w; a.h = L.h; a.pitch = L.pitch; a.dstride = L.frame_stride;
+        a.blur = L.blur;
+        dim3 grid((L.w + TW - 1) / TW, (L.h + TH - 1) / TH, n_frames);
+        if (l == 0) {
+            a.src = ctx->level0; a.sw = L.w; a.sh = L.h; a.spitch = ctx->level0_pitch; a.sstride = ctx->level0_stride;
+            const size_t smem = pyr_smem_bytes(a, false);
+            pyr_level_kernel<false><<<grid, PYR_THREADS, smem, ctx->stream>>>(a);
+        } else {
+            const Level &P = ctx->lv[l - 1];
+            a.src = l == 1 ? ctx->level0 : P.pyr;
+            a.sw = P.w; a.sh = P.h;
+            a.spitch = l == 1 ? ctx->level0_pitch : P.pitch;
+            a.sstride = l == 1 ? ctx->level0_stride : P.frame_stride;
+            a.dst = L.pyr;
+            a.xtab = L.xtab; a.ytab = L.ytab;
+            a.src_tile_w = L.src_tile_w; a.src_tile_h = L.src_tile_h;
+            a.area2x = L.area2x ? 1 : 0;
+            const size_t smem = pyr_smem_bytes(a, true);
+            if (smem > 48 * 1024)
+                SG_CUDA(ctx, cudaFuncSetAttribute(pyr_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            pyr_level_kernel<true><<<grid, PYR_THREADS, smem, ctx->stream>>>(a);
+        }
+        SG_LAUNCH_CHECK(ctx);
+    }
+    return SG_OK;
+}
+
+}  // namespace sg

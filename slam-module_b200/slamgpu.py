@@ -1,0 +1,461 @@
+"""ctypes binding of csrc/libslamgpu.so (C ABI: include/slamgpu.h) plus thin host-side mirrors of
+the reference interfaces this path replaces:
+
+    ImagePyramid.update / get_level / get_blurred_level   (image_pyramid.hpp:16-30)
+    FeatureDetector.detect                                (feature_detector.hpp:15-24)
+    OrbExtractor.detect_and_extract                       (orb_extractor.hpp:11-30)
+    match_for_loop_closures (brute-force case)            (keyframe_matcher.hpp:33-40)
+
+This is harness code for tests and benches: all work happens behind the C ABI on the GPU.  There
+is no CPU fallback -- if the library or a CUDA device is missing, construction raises.
+"""
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_DIR = Path(__file__).resolve().parent
+LIB_PATH = _DIR / "csrc" / "libslamgpu.so"
+MAX_LEVELS = 16
+
+SG_OK, SG_ERR_INVALID, SG_ERR_CUDA, SG_ERR_OVERFLOW, SG_ERR_STATE = 0, 1, 2, 3, 4
+
+
+class SlamGpuError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("libslamgpu error %d: %s" % (code, text))
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("levels", C.c_int), ("scale_factor", C.c_float),
+                ("max_keypoints", C.c_int), ("ini_fast_thr", C.c_int), ("min_fast_thr", C.c_int),
+                ("max_frames", C.c_int), ("max_tracks", C.c_int), ("track_level", C.c_int)]
+
+
+class MatchParams(C.Structure):
+    _fields_ = [("ratio", C.c_float), ("thr", C.c_uint32), ("check_orientation", C.c_int),
+                ("ratio_is_double", C.c_int)]
+
+
+class Keypoints(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("angle", C.c_void_p), ("octave", C.c_void_p),
+                ("desc", C.c_void_p), ("track_id", C.c_void_p), ("lvl_x", C.c_void_p), ("lvl_y", C.c_void_p),
+                ("count", C.c_void_p), ("level_count", C.c_void_p)]
+
+
+class KeypointsDev(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("angle", C.c_void_p), ("octave", C.c_void_p),
+                ("desc", C.c_void_p), ("count", C.c_void_p), ("cap", C.c_int)]
+
+
+# every symbol include/slamgpu.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "sg_create", "sg_destroy", "sg_last_error", "sg_abi_version", "sg_synchronize", "sg_stream",
+    "sg_launch_count", "sg_get_geometry", "sg_keypoint_capacity", "sg_pyramid_update",
+    "sg_pyramid_update_device", "sg_pyramid_download", "sg_pyramid_device_plane", "sg_detect",
+    "sg_detect_download", "sg_detect_download_candidates", "sg_extract", "sg_extract_device",
+    "sg_extract_download", "sg_extract_device_views", "sg_hamming", "sg_match_bruteforce", "sg_db_create",
+    "sg_db_create_device", "sg_db_destroy", "sg_match_pairs", "sg_match_pairs_device", "sg_match_rescans",
+    "sg_angle_bin_order", "sg_angle_bin_order_depth", "sg_angle_bin", "sg_device_count", "sg_malloc", "sg_free",
+    "sg_memcpy_h2d", "sg_memcpy_d2h", "sg_host_alloc_pinned", "sg_host_free_pinned", "sg_timer_start",
+    "sg_timer_stop", "sg_flush_l2", "sg_microbench_popc",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libslamgpu.so.  Raises if it has not been built: there is no other implementation."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise FileNotFoundError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                    "(the CUDA library is the only implementation of this path)" % LIB_PATH)
+        L = C.CDLL(str(LIB_PATH))
+        L.sg_last_error.restype = C.c_char_p
+        L.sg_last_error.argtypes = [C.c_void_p]
+        L.sg_stream.restype = C.c_void_p
+        L.sg_stream.argtypes = [C.c_void_p]
+        L.sg_launch_count.restype = C.c_ulonglong
+        L.sg_launch_count.argtypes = [C.c_void_p]
+        L.sg_match_rescans.restype = C.c_ulonglong
+        L.sg_match_rescans.argtypes = [C.c_void_p]
+        L.sg_angle_bin.argtypes = [C.c_float]
+        L.sg_destroy.argtypes = [C.c_void_p]
+        L.sg_destroy.restype = None
+        L.sg_db_destroy.argtypes = [C.c_void_p]
+        L.sg_db_destroy.restype = None
+        for name in ("sg_create", "sg_synchronize", "sg_get_geometry", "sg_keypoint_capacity", "sg_pyramid_update",
+                     "sg_pyramid_update_device", "sg_pyramid_download", "sg_pyramid_device_plane", "sg_detect",
+                     "sg_detect_download", "sg_detect_download_candidates", "sg_extract", "sg_extract_device",
+                     "sg_extract_download", "sg_extract_device_views", "sg_hamming", "sg_match_bruteforce",
+                     "sg_db_create", "sg_db_create_device", "sg_match_pairs", "sg_match_pairs_device", "sg_malloc",
+                     "sg_free", "sg_memcpy_h2d", "sg_memcpy_d2h", "sg_timer_start", "sg_timer_stop", "sg_flush_l2",
+                     "sg_microbench_popc"):
+            getattr(L, name).restype = C.c_int
+        L.sg_pyramid_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int]
+        L.sg_pyramid_update_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int]
+        L.sg_pyramid_download.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.sg_detect_download.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sg_detect_download_candidates.argtypes = L.sg_detect_download.argtypes
+        L.sg_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]
+        L.sg_extract_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int]
+        L.sg_extract_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.sg_hamming.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sg_match_bruteforce.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sg_db_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sg_db_create_device.argtypes = L.sg_db_create.argtypes
+        L.sg_match_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sg_match_pairs_device.argtypes = L.sg_match_pairs.argtypes
+        L.sg_malloc.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.sg_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.sg_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.sg_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.sg_host_alloc_pinned.argtypes = [C.c_size_t, C.c_void_p]
+        L.sg_host_free_pinned.argtypes = [C.c_void_p]
+        L.sg_timer_start.argtypes = [C.c_void_p]
+        L.sg_timer_stop.argtypes = [C.c_void_p, C.c_void_p]
+        L.sg_flush_l2.argtypes = [C.c_void_p]
+        L.sg_synchronize.argtypes = [C.c_void_p]
+        L.sg_detect.argtypes = [C.c_void_p]
+        L.sg_keypoint_capacity.argtypes = [C.c_void_p]
+        L.sg_microbench_popc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sg_get_geometry.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.sg_extract_device_views.argtypes = [C.c_void_p, C.c_void_p]
+        L.sg_pyramid_device_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def device_count():
+    return int(lib().sg_device_count())
+
+
+def angle_bin_order(sizes, depth_limit=None):
+    sizes = np.ascontiguousarray(sizes, np.uint32)
+    assert sizes.shape == (30,)
+    out = np.empty(30, np.uint32)
+    if depth_limit is None:
+        lib().sg_angle_bin_order(sizes.ctypes, out.ctypes)
+    else:
+        lib().sg_angle_bin_order_depth(sizes.ctypes, int(depth_limit), out.ctypes)
+    return out
+
+
+def angle_bin(delta):
+    return int(lib().sg_angle_bin(C.c_float(delta)))
+
+
+class DeviceBuffer:
+    """A device allocation owned through the C ABI (the harness has no CUDA binding of its own)."""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        p = C.c_void_p()
+        ctx._check(lib().sg_malloc(ctx._h, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        self.ctx._check(lib().sg_memcpy_h2d(self.ctx._h, self.ptr, arr.ctypes.data, arr.nbytes))
+        return self
+
+    def download(self, dtype, count):
+        out = np.empty(count, dtype)
+        assert out.nbytes <= self.nbytes
+        self.ctx._check(lib().sg_memcpy_d2h(self.ctx._h, out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().sg_free(self.ctx._h, self.ptr)
+            self.ptr = None
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory (for end-to-end timing with real H2D / D2H copies)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        if lib().sg_host_alloc_pinned(max(self.nbytes, 1), C.byref(p)) != 0:
+            raise SlamGpuError(SG_ERR_CUDA, "cudaMallocHost failed")
+        self.ptr = p.value
+        buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().sg_host_free_pinned(self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """One sg_ctx: a (host thread, GPU) pair sized for a fixed image size and batch."""
+
+    def __init__(self, width, height, levels=8, scale_factor=1.2, max_keypoints=2000, ini_fast_thr=20,
+                 min_fast_thr=7, max_frames=1, max_tracks=0, track_level=0, device=0):
+        self.params = Params(width, height, levels, scale_factor, max_keypoints, ini_fast_thr, min_fast_thr,
+                             max_frames, max_tracks, track_level)
+        h = C.c_void_p()
+        rc = lib().sg_create(int(device), C.byref(self.params), C.byref(h))
+        if rc != 0:
+            raise SlamGpuError(rc, lib().sg_last_error(None).decode())
+        self._h = h
+        n = levels
+        s = np.zeros(n, np.float32)
+        w, hh, pt, b = (np.zeros(n, np.int32) for _ in range(4))
+        self._check(lib().sg_get_geometry(self._h, s.ctypes, w.ctypes, hh.ctypes, pt.ctypes, b.ctypes))
+        self.scales, self.widths, self.heights, self.pitches, self.budgets = s, w, hh, pt, b
+        self.levels = levels
+        self.cap = int(lib().sg_keypoint_capacity(self._h))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SlamGpuError(rc, lib().sg_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            lib().sg_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing -----------------------------------------------------------------------------
+    def synchronize(self):
+        self._check(lib().sg_synchronize(self._h))
+
+    def launch_count(self):
+        return int(lib().sg_launch_count(self._h))
+
+    def timer_start(self):
+        self._check(lib().sg_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._check(lib().sg_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        self._check(lib().sg_flush_l2(self._h))
+
+    def microbench_popc(self):
+        r, ms = C.c_double(), C.c_float()
+        self._check(lib().sg_microbench_popc(self._h, C.byref(r), C.byref(ms)))
+        return r.value, ms.value
+
+    def device_buffer(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    @staticmethod
+    def _frames(imgs):
+        imgs = np.asarray(imgs)
+        if imgs.ndim == 2:
+            imgs = imgs[None]
+        assert imgs.dtype == np.uint8 and imgs.ndim == 3
+        if imgs.strides[2] != 1 or imgs.strides[1] < imgs.shape[2] or imgs.strides[0] < imgs.strides[1] * imgs.shape[1]:
+            imgs = np.ascontiguousarray(imgs)
+        return imgs
+
+    # ---- ImagePyramid (image_pyramid.hpp:16-30) ------------------------------------------------
+    def pyramid_update(self, imgs):
+        imgs = self._frames(imgs)
+        assert imgs.shape[1] == self.params.height and imgs.shape[2] == self.params.width
+        self._check(lib().sg_pyramid_update(self._h, imgs.ctypes.data, imgs.strides[1], imgs.strides[0], imgs.shape[0]))
+        self._n = imgs.shape[0]
+
+    def pyramid_update_device(self, dptr, pitch, frame_stride, n_frames):
+        self._check(lib().sg_pyramid_update_device(self._h, dptr, pitch, frame_stride, n_frames))
+        self._n = n_frames
+
+    def get_level(self, frame, level, blurred=False):
+        out = np.empty((int(self.heights[level]), int(self.widths[level])), np.uint8)
+        self._check(lib().sg_pyramid_download(self._h, frame, level, int(blurred), out.ctypes.data, out.strides[0]))
+        return out
+
+    def get_blurred_level(self, frame, level):
+        return self.get_level(frame, level, True)
+
+    # ---- FeatureDetector (feature_detector.hpp:15-24) -------------------------------------------
+    def detect(self):
+        self._check(lib().sg_detect(self._h))
+
+    def detected(self, frame, level, candidates=False):
+        fn = lib().sg_detect_download_candidates if candidates else lib().sg_detect_download
+        n = C.c_int()
+        self._check(fn(self._h, frame, level, None, None, None, 0, C.byref(n)))
+        m = n.value
+        x, y, r = (np.empty(max(m, 1), np.int32) for _ in range(3))
+        self._check(fn(self._h, frame, level, x.ctypes.data, y.ctypes.data, r.ctypes.data, m, C.byref(n)))
+        return x[:m], y[:m], r[:m]
+
+    # ---- OrbExtractor (orb_extractor.hpp:11-30) -------------------------------------------------
+    def _alloc_out(self, n_frames, pinned=False):
+        cap, lv = self.cap, self.levels
+        spec = dict(x=((n_frames, cap), np.float32), y=((n_frames, cap), np.float32), angle=((n_frames, cap), np.float32),
+                    octave=((n_frames, cap), np.int32), desc=((n_frames, cap, 8), np.uint32),
+                    track_id=((n_frames, cap), np.int32), lvl_x=((n_frames, cap), np.int32),
+                    lvl_y=((n_frames, cap), np.int32), count=((n_frames,), np.int32),
+                    level_count=((n_frames, lv), np.int32))
+        arrs = {k: np.empty(s, d) for k, (s, d) in spec.items()}
+        ks = Keypoints(*[arrs[k].ctypes.data for k, _ in Keypoints._fields_])
+        return arrs, ks
+
+    @staticmethod
+    def _split(arrs, n_frames):
+        out = []
+        for f in range(n_frames):
+            n = int(arrs["count"][f])
+            d = {k: arrs[k][f, :n].copy() for k in ("x", "y", "angle", "octave", "desc", "track_id", "lvl_x", "lvl_y")}
+            d["n"] = n
+            d["level_counts"] = arrs["level_count"][f].copy()
+            out.append(d)
+        return out
+
+    def detect_and_extract(self, imgs, tracks=None, track_ids=None):
+        """OrbExtractor::detectAndExtract for a batch of frames.  tracks: optional list (one entry per
+        frame) of (n, 2) float arrays of full-resolution tracker points."""
+        imgs = self._frames(imgs)
+        nf = imgs.shape[0]
+        arrs, ks = self._alloc_out(nf)
+        txy = tids = tn = None
+        if tracks is not None and self.params.max_tracks > 0:
+            T = self.params.max_tracks
+            txy = np.zeros((nf, T, 2), np.float32)
+            tids = np.zeros((nf, T), np.int32)
+            tn = np.zeros(nf, np.int32)
+            for f in range(nf):
+                t = np.asarray(tracks[f], np.float32).reshape(-1, 2)
+                tn[f] = len(t)
+                txy[f, :len(t)] = t
+                tids[f, :len(t)] = np.arange(len(t)) if track_ids is None else np.asarray(track_ids[f], np.int32)
+        self._check(lib().sg_extract(self._h, imgs.ctypes.data, imgs.strides[1], imgs.strides[0], nf,
+                                     None if txy is None else txy.ctypes.data, None if tids is None else tids.ctypes.data,
+                                     None if tn is None else tn.ctypes.data, C.byref(ks)))
+        self._n = nf
+        return self._split(arrs, nf)
+
+    def extract_device(self, dptr, pitch, frame_stride, n_frames):
+        self._check(lib().sg_extract_device(self._h, dptr, pitch, frame_stride, n_frames))
+        self._n = n_frames
+
+    def extract_download(self, n_frames, only_counts=False):
+        arrs, ks = self._alloc_out(n_frames)
+        if only_counts:
+            ks = Keypoints(None, None, None, None, None, None, None, None, arrs["count"].ctypes.data,
+                           arrs["level_count"].ctypes.data)
+        self._check(lib().sg_extract_download(self._h, n_frames, C.byref(ks)))
+        if only_counts:
+            return arrs["count"].copy(), arrs["level_count"].copy()
+        return self._split(arrs, n_frames)
+
+    def device_views(self):
+        v = KeypointsDev()
+        self._check(lib().sg_extract_device_views(self._h, C.byref(v)))
+        return v
+
+    # ---- matching -------------------------------------------------------------------------------
+    def hamming(self, a, b):
+        a = np.ascontiguousarray(a, np.uint32).reshape(-1, 8)
+        b = np.ascontiguousarray(b, np.uint32).reshape(-1, 8)
+        out = np.empty(len(a), np.uint32)
+        self._check(lib().sg_hamming(self._h, a.ctypes.data, b.ctypes.data, len(a), out.ctypes.data))
+        return out
+
+    def match_bruteforce(self, dA, aA, dB, aB, ratio=0.8, thr=50, check_orientation=True, ratio_is_double=False):
+        """Brute-force case of matchForLoopClosures: returns (num_matches, matches[nA])."""
+        dA = np.ascontiguousarray(dA, np.uint32).reshape(-1, 8)
+        dB = np.ascontiguousarray(dB, np.uint32).reshape(-1, 8)
+        aA = np.ascontiguousarray(aA, np.float32)
+        aB = np.ascontiguousarray(aB, np.float32)
+        mp = MatchParams(ratio, thr, int(check_orientation), int(ratio_is_double))
+        m = np.empty(max(len(dA), 1), np.int32)
+        n = C.c_uint32()
+        self._check(lib().sg_match_bruteforce(self._h, dA.ctypes.data, aA.ctypes.data, len(dA), dB.ctypes.data,
+                                              aB.ctypes.data, len(dB), C.byref(mp), m.ctypes.data, C.byref(n)))
+        return int(n.value), m[:len(dA)]
+
+    def rescans(self):
+        return int(lib().sg_match_rescans(self._h))
+
+
+class DescriptorDB:
+    """Device-resident descriptor sets (one per keyframe) for batched pair matching."""
+
+    def __init__(self, ctx, desc, angle, offsets=None, device_ptrs=None):
+        self.ctx = ctx
+        h = C.c_void_p()
+        if device_ptrs is not None:
+            d_desc, d_angle = device_ptrs
+            offsets = np.ascontiguousarray(offsets, np.int64)
+            ctx._check(lib().sg_db_create_device(ctx._h, d_desc, d_angle, offsets.ctypes.data, len(offsets) - 1, C.byref(h)))
+        else:
+            desc = np.ascontiguousarray(desc, np.uint32)
+            angle = np.ascontiguousarray(angle, np.float32)
+            if offsets is None:   # (n_sets, n_per_set, 8)
+                n_sets, per = desc.shape[0], desc.shape[1]
+                offsets = np.arange(n_sets + 1, dtype=np.int64) * per
+            offsets = np.ascontiguousarray(offsets, np.int64)
+            ctx._check(lib().sg_db_create(ctx._h, desc.ctypes.data, angle.ctypes.data, offsets.ctypes.data,
+                                          len(offsets) - 1, C.byref(h)))
+        self._h = h
+        self.offsets = offsets
+        self.max_set = int(np.max(np.diff(offsets))) if len(offsets) > 1 else 0
+
+    def match_pairs(self, pairs, ratio=0.8, thr=50, check_orientation=True, ratio_is_double=False, want_matches=True):
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        mp = MatchParams(ratio, thr, int(check_orientation), int(ratio_is_double))
+        n = np.zeros(len(pairs), np.uint32)
+        m = np.empty((len(pairs), max(self.max_set, 1)), np.int32) if want_matches else None
+        self.ctx._check(lib().sg_match_pairs(self.ctx._h, self._h, pairs.ctypes.data, len(pairs), C.byref(mp),
+                                             None if m is None else m.ctypes.data, max(self.max_set, 1), n.ctypes.data))
+        return n, m
+
+    def match_pairs_device(self, d_pairs, n_pairs, d_counts, d_matches=None, ratio=0.8, thr=50, check_orientation=True):
+        mp = MatchParams(ratio, thr, int(check_orientation), 0)
+        self.ctx._check(lib().sg_match_pairs_device(self.ctx._h, self._h, d_pairs, n_pairs, C.byref(mp), d_matches,
+                                                    max(self.max_set, 1), d_counts))
+
+    def close(self):
+        if self._h:
+            lib().sg_db_destroy(self._h)
+            self._h = None
+
+
+# ---- mirrors of the reference's class names (thin; one Context underneath) ------------------------
+class OrbExtractor:
+    """OrbExtractor::build(settings) + detectAndExtract (orb_extractor.hpp:16-22)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    @staticmethod
+    def build(width, height, **kw):
+        return OrbExtractor(Context(width, height, **kw))
+
+    def detect_and_extract(self, imgs, tracks=None, track_ids=None):
+        return self.ctx.detect_and_extract(imgs, tracks, track_ids)
+
+
+def match_for_loop_closures(ctx, kf1, kf2, ratio=0.8, check_orientation=True):
+    """matchForLoopClosures (keyframe_matcher.hpp:33-40) on two extraction results (dicts with `desc` and
+    `angle`), all features in one BoW node and owning triangulated map points."""
+    return ctx.match_bruteforce(kf1["desc"], kf1["angle"], kf2["desc"], kf2["angle"], ratio=ratio, thr=50,
+                                check_orientation=check_orientation)
