@@ -1,0 +1,370 @@
+#!/usr/bin/env python3
+"""Benchmark of the ORB front-end + Hamming matching hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libslamgpu.so)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+One "step" = one pass of the hot path over one batch: ORB extraction (pyramid -> FAST + quadtree ->
+orientation -> rBRIEF) of 256 synthetic 640x480 frames, 8 levels, 2000 keypoints (BASELINE.json
+configs[1]).  `value` = frames/s with the input batch already resident in HBM; `e2e` = the same
+through the C-ABI call that takes HOST buffers (H2D of the frames and D2H of the keypoints inside
+the timed region).  The second half of the metric, Hamming matching (configs[2]: 2000 x 2000
+descriptors per keyframe pair, ratio 0.8, angle histogram), is timed in the same run and reported
+under "matching" with its own roofline (integer POPC issue rate, measured by a micro-benchmark).
+
+Multi-GPU (torchrun, one rank per GPU): frames / keyframe pairs are sharded by rank, no collective
+on the data path; torch.distributed (NCCL) is used only for the barrier and the max-over-ranks.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+W, H, LEVELS, FACTOR, MAXKP = 640, 480, 8, 1.2, 2000
+FRAMES = 256                      # frames per step per GPU
+N_BATCHES = 4                     # rotating input batches: 4 x 78.6 MB > 126 MB of L2
+ALGO_BYTES_PYRAMID = 2208264      # A0 + 2*sum(A_l) per 640x480 frame
+ALGO_BYTES_FAST = 950532          # sum(A_l): every level read once
+MATCH_SETS, MATCH_N, MATCH_PAIRS = 32, 2000, 2048   # descriptor sets, descriptors per set, pairs per step
+METRIC = "ORB frames/sec (640x480, 8 lvls, 2k kp) + Hamming matches/sec at 1/2/4/8 B200"
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        p = json.loads(f.read_text())
+        return float(p["hbm_gbs"]), float(p.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+def make_frames(n, seed0):
+    """n distinct synthetic frames: 32 generated from scratch, the rest rolled / flipped variants."""
+    import slam_module_b200 as sm
+    base = [sm.synth.frame(W, H, seed0 + i) for i in range(min(n, 32))]
+    rng = np.random.default_rng(seed0)
+    out = np.empty((n, H, W), np.uint8)
+    for i in range(n):
+        b = base[i % len(base)]
+        if i >= len(base):
+            b = np.roll(b, (int(rng.integers(1, H)), int(rng.integers(1, W))), axis=(0, 1))
+            if rng.random() < 0.5:
+                b = b[:, ::-1]
+        out[i] = b
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 6:
+                continue
+            try:
+                sm.append(float(c[0]))
+                mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        # median over the samples taken under load (top half of the observed clocks)
+        under = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(under) if under else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    td = None
+    if world > 1:
+        import torch
+        import torch.distributed as td_
+        torch.cuda.set_device(local)
+        td_.init_process_group("nccl", device_id=torch.device("cuda", local))
+        td = td_
+    return rank, world, local, td
+
+
+def barrier_max(td, local, value):
+    """max over ranks of a python float (device tensor all-reduce); identity without a process group."""
+    if td is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=torch.device("cuda", local))
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    return float(t.item())
+
+
+def cpu_extract_baseline(po, frames, threads):
+    p = po.make_params(W, H, levels=LEVELS, scale_factor=FACTOR, max_keypoints=MAXKP)
+    secs, total = po.bench_extract(p, frames, threads)
+    return len(frames) / secs, secs, total
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port: the reference itself cannot be built
+    here) on the host cores, frames sharded over all threads; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    po.build()
+    cores = os.cpu_count() or 1
+    sample = max(16, min(64, 2 * cores))
+    frames = make_frames(sample, 9000)
+    for _ in range(args.warmup):
+        cpu_extract_baseline(po, frames[:max(cores, 4)], cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_extract_baseline(po, frames, cores)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    # matching leg on a few pairs
+    import slam_module_b200 as sm
+    d, a = sm.synth.random_descriptors(8, MATCH_N, 5)
+    pairs = np.array([(i, (i + 1) % 8) for i in range(max(8, cores))], np.int32)
+    msec, _ = po.bench_match(d, a, pairs, cores)
+    desc = "oracle port of the reference CPU path, %d frames per step sharded over %d host threads" % (sample, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "ORB extraction, 640x480 synthetic frames, 8 levels x1.2, 2000 keypoints (configs[1])",
+                   "frames_per_step": sample, "levels": LEVELS, "scale_factor": FACTOR, "max_keypoints": MAXKP},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "matching": {"value": len(pairs) * MATCH_N * MATCH_N / msec, "unit": "descriptor-pair distances/s",
+                     "keyframe_pairs_per_s": len(pairs) / msec, "cores": cores},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local, td = dist_setup(args.gpus)
+    import slam_module_b200 as sm
+    from slam_module_b200 import slamgpu
+
+    if slamgpu.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: libslamgpu has no CPU fallback")
+    hbm_peak, sm_max_mhz, peak_src = peaks()
+
+    ctx = slamgpu.Context(W, H, levels=LEVELS, scale_factor=FACTOR, max_keypoints=MAXKP, max_frames=FRAMES, device=local)
+    frame_bytes = W * H
+    # ---- inputs: rank-specific frames, resident in HBM (N_BATCHES rotating batches) ---------------------
+    host_batches, dev_batches = [], []
+    for b in range(N_BATCHES):
+        pin = slamgpu.PinnedArray((FRAMES, H, W), np.uint8)
+        pin.array[...] = make_frames(FRAMES, 10000 + 1000 * rank + 100 * b)
+        host_batches.append(pin)
+        dev_batches.append(ctx.device_buffer(FRAMES * frame_bytes).upload(pin.array))
+
+    def step_device(i):
+        ctx.extract_device(dev_batches[i % N_BATCHES].ptr, W, frame_bytes, FRAMES)
+
+    # ---- device-resident throughput ----------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_device(i)
+    ctx.synchronize()
+    counts, _ = ctx.extract_download(FRAMES, only_counts=True)
+    kp_per_frame = float(counts.mean())
+    sampler = ClockSampler(local)
+    ctx.set_profiling(True)
+    launches0 = ctx.launch_count()
+    ctx.synchronize()
+    barrier_max(td, local, 0.0)                      # barrier
+    ctx.timer_start()
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+    ms = ctx.timer_stop()                            # records the end event and synchronises
+    ms = barrier_max(td, local, ms)
+    launches = ctx.launch_count() - launches0
+    stage = ctx.stage_ms()
+    ctx.set_profiling(False)
+    value = world * FRAMES * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer entry point (H2D + kernels + D2H) -----------------------------
+    out_arrs, out_struct = ctx._alloc_out(FRAMES)
+    lib = slamgpu.lib()
+    import ctypes as C
+
+    def step_host(i):
+        hb = host_batches[i % N_BATCHES].array
+        ctx._check(lib.sg_extract(ctx._h, hb.ctypes.data, W, frame_bytes, FRAMES, None, None, None, C.byref(out_struct)))
+
+    e2e_steps = max(3, min(args.steps, 10))
+    step_host(0)
+    ctx.synchronize()
+    barrier_max(td, local, 0.0)
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        step_host(1 + i)
+    ctx.synchronize()
+    e2e_s = barrier_max(td, local, time.perf_counter() - t0)
+    e2e_value = world * FRAMES * e2e_steps / e2e_s
+    d2h_bytes = sum(int(a.nbytes) for a in out_arrs.values())
+
+    # ---- matching (configs[2]) ---------------------------------------------------------------------------
+    rngm = np.random.default_rng(77 + rank)
+    dA, aA, dB, aB = sm.synth.correlated_descriptors(MATCH_N, 500 + rank)
+    sets_d, sets_a = [dA, dB], [aA, aB]
+    for s in range(MATCH_SETS - 2):
+        d = sets_d[s % 2].copy()
+        flip = rngm.integers(0, 256, (MATCH_N, 12))
+        for k in range(12):
+            d[np.arange(MATCH_N), flip[:, k] >> 5] ^= (np.uint32(1) << (flip[:, k] & 31).astype(np.uint32))
+        perm = rngm.permutation(MATCH_N)
+        sets_d.append(d[perm])
+        sets_a.append(((sets_a[s % 2] + rngm.normal(0, 3, MATCH_N)) % 360).astype(np.float32)[perm])
+    db = slamgpu.DescriptorDB(ctx, np.stack(sets_d), np.stack(sets_a))
+    pairs = rngm.integers(0, MATCH_SETS, (MATCH_PAIRS, 2)).astype(np.int32)
+    d_pairs = ctx.device_buffer(pairs.nbytes).upload(pairs)
+    d_counts = ctx.device_buffer(4 * MATCH_PAIRS)
+    for _ in range(3):
+        db.match_pairs_device(d_pairs.ptr, MATCH_PAIRS, d_counts.ptr)
+    ctx.synchronize()
+    ctx.set_profiling(True)
+    m_launch0 = ctx.launch_count()
+    barrier_max(td, local, 0.0)
+    m_steps = max(3, min(args.steps, 10))
+    ctx.timer_start()
+    for _ in range(m_steps):
+        db.match_pairs_device(d_pairs.ptr, MATCH_PAIRS, d_counts.ptr)
+    m_ms = barrier_max(td, local, ctx.timer_stop())
+    m_stage = ctx.stage_ms()
+    ctx.set_profiling(False)
+    m_launches = ctx.launch_count() - m_launch0
+    mcounts = d_counts.download(np.uint32, MATCH_PAIRS)
+    pair_dists = float(MATCH_PAIRS) * MATCH_N * MATCH_N
+    match_value = world * pair_dists * m_steps / (m_ms * 1e-3)
+    # host-buffer matching call (pairs up, counts + match rows down)
+    t0 = time.perf_counter()
+    n_host, m_host = db.match_pairs(pairs[:256])
+    match_e2e = world * 256 * MATCH_N * MATCH_N / (time.perf_counter() - t0)
+    popc_peak, _ = ctx.microbench_popc()
+    clocks = sampler.stop()
+
+    # ---- CPU baseline beside it (rank 0, N == 1 only) ----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        from oracle import pyoracle as po
+        po.build()
+        cores = os.cpu_count() or 1
+        sample = max(16, min(64, 2 * cores))
+        v, secs, _ = cpu_extract_baseline(po, host_batches[0].array[:sample], cores)
+        msec, _ = po.bench_match(np.stack(sets_d[:8]), np.stack(sets_a[:8]), pairs[:max(8, cores)] % 8, cores)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "oracle port of the reference CPU path on %d of the step's frames, sharded over %d host "
+                         "threads (%.1f s)" % (sample, cores, secs),
+               "matching_value": max(8, cores) * MATCH_N * MATCH_N / msec, "matching_unit": "descriptor-pair distances/s"}
+
+    if rank == 0:
+        # roofline of the dominant kernel of the step (per-stage CUDA events, averaged over the timed steps)
+        stage_bytes = {"pyramid": ALGO_BYTES_PYRAMID * FRAMES, "fast": ALGO_BYTES_FAST * FRAMES}
+        dom = max(("pyramid", "fast", "distribute", "describe"), key=lambda k: stage[k])
+        stages = {}
+        for k in ("pyramid", "fast", "distribute", "describe"):
+            e = {"ms": stage[k], "share": stage[k] / max(sum(stage[s] for s in ("pyramid", "fast", "distribute", "describe")), 1e-9)}
+            if k in stage_bytes:
+                e["achieved_gbs"] = stage_bytes[k] / (stage[k] * 1e-3) / 1e9
+                e["frac_of_hbm"] = e["achieved_gbs"] / hbm_peak
+            stages[k] = e
+        roof_stage = dom if dom in stage_bytes else "pyramid"
+        roofline = {"kernel": {"pyramid": "pyr_level_kernel (8 launches: blur of level 0 + 7 fused resize+blur levels)",
+                               "fast": "fast_cells_kernel"}[roof_stage],
+                    "bound": "hbm", "achieved": stages[roof_stage]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": stages[roof_stage]["frac_of_hbm"], "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch_group": stage_bytes[roof_stage], "dominant_stage_by_time": dom}
+        topk_ms = m_stage["match_topk"]
+        popc_achieved = 8.0 * min(MATCH_PAIRS, MATCH_PAIRS) * MATCH_N * MATCH_N / (topk_ms * 1e-3) if topk_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "ORB extraction, %d synthetic 640x480 frames per GPU per step, 8 levels x1.2, 2000 keypoints "
+                                   "(BASELINE configs[1])" % FRAMES,
+                       "frames_per_step_per_gpu": FRAMES, "levels": LEVELS, "scale_factor": FACTOR, "max_keypoints": MAXKP,
+                       "keypoints_per_frame": kp_per_frame, "sharding": "frames by rank, no collective",
+                       "l2": "inputs larger than L2: %d rotating batches x %.1f MB" % (N_BATCHES, FRAMES * frame_bytes / 1e6)},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": FRAMES * frame_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "api": "sg_extract (host buffers)"},
+            "gpu_launches": int(launches),
+            "stages": stages,
+            "roofline": roofline,
+            "matching": {"metric": "Hamming matches/sec (2000x2000 per keyframe pair, ratio 0.8, angle histogram; configs[2])",
+                         "value": match_value, "unit": "descriptor-pair distances/s",
+                         "keyframe_pairs_per_s": world * MATCH_PAIRS * m_steps / (m_ms * 1e-3),
+                         "pairs_per_step_per_gpu": MATCH_PAIRS, "steps": m_steps, "ms_per_step": m_ms / m_steps,
+                         "mean_matches_per_pair": float(mcounts.mean()), "gpu_launches": int(m_launches),
+                         "stages_ms": {"topk": m_stage["match_topk"], "resolve": m_stage["match_resolve"]},
+                         "e2e": {"value": match_e2e, "unit": "descriptor-pair distances/s", "api": "sg_match_pairs (host buffers)"},
+                         "roofline": {"kernel": "hamming_topk_kernel", "bound": "int-popc", "achieved": popc_achieved,
+                                      "peak": popc_peak, "unit": "POPC.b32/s",
+                                      "frac": (popc_achieved / popc_peak) if popc_achieved else None,
+                                      "peak_source": "measured live: dependent-free POPC micro-benchmark on this GPU",
+                                      "algorithmic_ops_per_pair": 8}},
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    db.close()
+    ctx.close()
+    if td is not None:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

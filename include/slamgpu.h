@@ -199,6 +199,14 @@ int sg_host_free_pinned(void *h_ptr);
 /* CUDA-event timing on the context's stream. */
 int sg_timer_start(sg_ctx *ctx);
 int sg_timer_stop(sg_ctx *ctx, float *ms); /* records, synchronises, returns elapsed ms */
+/* Per-stage CUDA-event timing on the context's stream.  With profiling on, the stage launchers
+ * record an event after each stage of every call (the last 64 calls are remembered);
+ * sg_get_stage_ms synchronises and returns the AVERAGE duration per call in ms since profiling was
+ * switched on: [0] pyramid (all level kernels), [1] FAST cells, [2] quadtree distribution,
+ * [3] orientation + descriptors, [4] Hamming top-K (first chunk of a call), [5] match resolve
+ * (first chunk); -1 where the stage did not run.  *n_calls (may be NULL): calls averaged. */
+int sg_set_profiling(sg_ctx *ctx, int on);
+int sg_get_stage_ms(sg_ctx *ctx, float *ms6, int *n_calls);
 /* Overwrite a buffer larger than L2 (flushes L2 between timed iterations). */
 int sg_flush_l2(sg_ctx *ctx);
 /* Integer-pipe micro-benchmark: dependent-free POPC.b32 issue rate of the whole chip; returns

@@ -246,6 +246,9 @@ int sg_create(int device, const sg_params *params, sg_ctx **out) {
         ctx->err = "stream / event creation failed";
         return bail(SG_ERR_CUDA);
     }
+    for (auto &slot : ctx->ev_stage)
+        for (auto &e : slot)
+            if (cudaEventCreate(&e) != cudaSuccess) { ctx->err = "event creation failed"; return bail(SG_ERR_CUDA); }
     if (int r = build_context(ctx)) return bail(r);
     *out = ctx;
     return SG_OK;
@@ -263,6 +266,8 @@ void sg_destroy(sg_ctx *ctx) {
                     ctx->d_rescans, ctx->d_tmp};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (auto &slot : ctx->ev_stage)
+        for (auto &e : slot) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -612,6 +617,34 @@ int sg_flush_l2(sg_ctx *ctx) {
         ctx->flush_bytes = bytes;
     }
     SG_CUDA(ctx, cudaMemsetAsync(ctx->d_flush, 0x5a, ctx->flush_bytes, ctx->stream));
+    return SG_OK;
+}
+int sg_set_profiling(sg_ctx *ctx, int on) {
+    ctx->profiling = on != 0;
+    ctx->prof_call = -1;
+    memset(ctx->stage_mark, 0, sizeof ctx->stage_mark);
+    return SG_OK;
+}
+int sg_get_stage_ms(sg_ctx *ctx, float *ms6, int *n_calls) {
+    cudaSetDevice(ctx->device);
+    if (!ms6) return fail(ctx, SG_ERR_INVALID, "null argument");
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int from[6] = {EV_PYR0, EV_PYR1, EV_FAST1, EV_DIST1, EV_MATCH0, EV_TOPK1};
+    const int to[6] = {EV_PYR1, EV_FAST1, EV_DIST1, EV_DESC1, EV_TOPK1, EV_RESOLVE1};
+    const long calls = std::min<long>(ctx->prof_call + 1, sg_ctx::PROF_SLOTS);
+    for (int i = 0; i < 6; ++i) {
+        double sum = 0;
+        int n = 0;
+        for (long c = 0; c < calls; ++c) {
+            if (!ctx->stage_mark[c][from[i]] || !ctx->stage_mark[c][to[i]]) continue;
+            float ms = 0;
+            SG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_stage[c][from[i]], ctx->ev_stage[c][to[i]]));
+            sum += ms;
+            ++n;
+        }
+        ms6[i] = n ? (float)(sum / n) : -1.f;
+    }
+    if (n_calls) *n_calls = (int)calls;
     return SG_OK;
 }
 int sg_microbench_popc(sg_ctx *ctx, double *popc_per_s, float *ms) {

@@ -85,6 +85,13 @@ struct sg_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     unsigned long long launches = 0;
+    // optional per-stage CUDA-event timing (sg_set_profiling): pyramid, fast, distribute, describe,
+    // match top-K, match resolve
+    bool profiling = false;
+    static constexpr int PROF_SLOTS = 64;           // calls remembered (ring)
+    cudaEvent_t ev_stage[PROF_SLOTS][8] = {};
+    unsigned char stage_mark[PROF_SLOTS][8] = {};
+    long prof_call = -1;                             // index of the current call since profiling was switched on
     int sm_count = 148;
 
     std::vector<sg::Level> lv;
@@ -169,5 +176,18 @@ int launch_pyramid(sg_ctx *ctx, int n_frames);
 int launch_detect(sg_ctx *ctx, int n_frames);
 int launch_describe(sg_ctx *ctx, int n_frames);
 int grow(sg_ctx *ctx, void **ptr, size_t *cap, size_t need, size_t elem);
+// Record stage event i on the context's stream when profiling is on.
+inline void mark(sg_ctx *ctx, int i, bool first = false) {
+    if (!ctx->profiling) return;
+    if (first) {   // a new call: take the next ring slot
+        ++ctx->prof_call;
+        for (auto &m : ctx->stage_mark[ctx->prof_call % sg_ctx::PROF_SLOTS]) m = 0;
+    }
+    if (ctx->prof_call < 0) return;
+    const int slot = (int)(ctx->prof_call % sg_ctx::PROF_SLOTS);
+    cudaEventRecord(ctx->ev_stage[slot][i], ctx->stream);
+    ctx->stage_mark[slot][i] = 1;
+}
+enum { EV_PYR0 = 0, EV_PYR1, EV_FAST1, EV_DIST1, EV_DESC1, EV_MATCH0, EV_TOPK1, EV_RESOLVE1 };
 
 }  // namespace sg

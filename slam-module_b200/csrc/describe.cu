@@ -183,6 +183,7 @@ int launch_describe(sg_ctx *ctx, int n_frames) {
         trk ? ctx->d_trk_xy : nullptr, trk ? ctx->d_trk_pt : nullptr, trk ? ctx->d_trk_id : nullptr,
         trk ? ctx->d_trk_count : nullptr, ctx->p.track_level, o);
     SG_LAUNCH_CHECK(ctx);
+    mark(ctx, EV_DESC1);
     return SG_OK;
 }
 

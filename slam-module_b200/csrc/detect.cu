@@ -458,12 +458,14 @@ int launch_detect(sg_ctx *ctx, int n_frames) {
             g, ctx->level0, ctx->level0_pitch, ctx->level0_stride, total_cells, ctx->d_cand, ctx->d_cand_count, ctx->d_err);
         SG_LAUNCH_CHECK(ctx);
     }
+    mark(ctx, EV_FAST1);
     const size_t smem = distribute_smem_bytes(nc_max);
     if (smem > 48 * 1024)
         SG_CUDA(ctx, cudaFuncSetAttribute(distribute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     distribute_kernel<<<dim3(g.levels, n_frames), DIST_THREADS, smem, ctx->stream>>>(
         g, nc_max, ctx->d_cand, ctx->d_cand_node, ctx->d_cand_count, ctx->d_kp_xy, ctx->d_kp_resp, ctx->d_kp_count, ctx->d_err);
     SG_LAUNCH_CHECK(ctx);
+    mark(ctx, EV_DIST1);
     ctx->detected = true;
     return SG_OK;
 }

@@ -448,16 +448,19 @@ int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, con
     const size_t rsmem = (size_t)RES_WARPS * (taken_words + 32) * 4;
     for (int p0 = 0; p0 < n_pairs; p0 += chunk) {
         const int np = std::min(chunk, n_pairs - p0);
+        if (p0 == 0) mark(ctx, EV_MATCH0, true);
         a.pairs = d_pairs + 2 * (size_t)p0;
         a.row_stride = stride;
         dim3 grid((stride + MT_THREADS - 1) / MT_THREADS, np);
         hamming_topk_kernel<<<grid, MT_THREADS, 0, ctx->stream>>>(a, ctx->d_topk, ctx->d_nseen);
         SG_LAUNCH_CHECK(ctx);
+        if (p0 == 0) mark(ctx, EV_TOPK1);
         a.match_stride = d_matches ? match_stride : stride;
         int *mout = d_matches ? d_matches + (size_t)p0 * match_stride : ctx->d_matches;
         match_resolve_kernel<<<(np + RES_WARPS - 1) / RES_WARPS, RES_WARPS * 32, rsmem, ctx->stream>>>(
             a, np, ctx->d_topk, ctx->d_nseen, taken_words, mout, d_n_matches + p0, ctx->d_rescans);
         SG_LAUNCH_CHECK(ctx);
+        if (p0 == 0) mark(ctx, EV_RESOLVE1);
     }
     return SG_OK;
 }

@@ -219,6 +219,7 @@ void pyramid_source_extent(const std::vector<ResizeTap> &xt, const std::vector<R
 
 int launch_pyramid(sg_ctx *ctx, int n_frames) {
     const int levels = ctx->p.levels;
+    mark(ctx, EV_PYR0, true);
     for (int l = 0; l < levels; ++l) {
         const Level &L = ctx->lv[l];
         PyrArgs a{};
@@ -246,6 +247,7 @@ int launch_pyramid(sg_ctx *ctx, int n_frames) {
         }
         SG_LAUNCH_CHECK(ctx);
     }
+    mark(ctx, EV_PYR1);
     return SG_OK;
 }
 

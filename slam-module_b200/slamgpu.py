@@ -60,7 +60,7 @@ ABI_SYMBOLS = [
     "sg_db_create_device", "sg_db_destroy", "sg_match_pairs", "sg_match_pairs_device", "sg_match_rescans",
     "sg_angle_bin_order", "sg_angle_bin_order_depth", "sg_angle_bin", "sg_device_count", "sg_malloc", "sg_free",
     "sg_memcpy_h2d", "sg_memcpy_d2h", "sg_host_alloc_pinned", "sg_host_free_pinned", "sg_timer_start",
-    "sg_timer_stop", "sg_flush_l2", "sg_microbench_popc",
+    "sg_timer_stop", "sg_flush_l2", "sg_microbench_popc", "sg_set_profiling", "sg_get_stage_ms",
 ]
 
 _lib = None
@@ -120,6 +120,10 @@ def lib():
         L.sg_timer_start.argtypes = [C.c_void_p]
         L.sg_timer_stop.argtypes = [C.c_void_p, C.c_void_p]
         L.sg_flush_l2.argtypes = [C.c_void_p]
+        L.sg_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.sg_set_profiling.restype = C.c_int
+        L.sg_get_stage_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sg_get_stage_ms.restype = C.c_int
         L.sg_synchronize.argtypes = [C.c_void_p]
         L.sg_detect.argtypes = [C.c_void_p]
         L.sg_keypoint_capacity.argtypes = [C.c_void_p]
@@ -252,6 +256,18 @@ class Context:
         ms = C.c_float()
         self._check(lib().sg_timer_stop(self._h, C.byref(ms)))
         return ms.value
+
+    STAGES = ("pyramid", "fast", "distribute", "describe", "match_topk", "match_resolve")
+
+    def set_profiling(self, on=True):
+        self._check(lib().sg_set_profiling(self._h, int(on)))
+
+    def stage_ms(self):
+        """Average per-call duration of every stage (ms) since set_profiling(True); -1 = did not run."""
+        ms = (C.c_float * 6)()
+        n = C.c_int()
+        self._check(lib().sg_get_stage_ms(self._h, ms, C.byref(n)))
+        return {k: float(v) for k, v in zip(self.STAGES, ms)}
 
     def flush_l2(self):
         self._check(lib().sg_flush_l2(self._h))
