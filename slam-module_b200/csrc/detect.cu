@@ -28,49 +28,51 @@
 namespace sg {
 
 constexpr int FAST_THREADS = 256;
-constexpr int TP = 80;                 // shared tile pitch (70 px + up to 3 px alignment slack, padded)
+constexpr int TP = 80;                 // shared tile pitch: 3 px alignment slack + 70 px window, padded to words
 constexpr int TILE_ROWS = CELL + 6;    // 70
-constexpr int RP = CELL + 2;           // response map pitch (1-px zero frame)
+constexpr int RPW = CELL + 8;          // response map pitch: 4-byte left pad (word-aligned rows) + 64 + right pad
+constexpr int TILE_SHIFT = 3;          // the window origin 19 + 64*j is always 3 past a word boundary
+static_assert((EVAL_ORIGIN - FAST_BORDER) % 4 == TILE_SHIFT && CELL % 4 == 0, "tile alignment");
+constexpr int MAX_SURVIVORS = CELL * CELL;
 
-// ---- FAST-9/16 corner score, two horizontally adjacent pixels per 32-bit register (s16x2 lanes) ----
-// cornerScore = the largest t for which the pixel is a FAST-9 corner: max over the 16 arcs of 9
-// contiguous ring pixels of min(v - p) (dark arc) and min(p - v) (bright arc), minus one.
-// Ring: Bresenham circle of radius 3, clockwise from (0, 3) -- the order cv::FAST uses.
-// sm_100a has native 16x2 integer min/max (VIMNMX.S16x2, VIMNMX3.S16x2) and VABSDIFF4; the
-// differences (|d| <= 255) fit the s16 lanes exactly.
-// NOTE: a scalar formulation `max(min9, -max9)` is miscompiled by ptxas 12.9 at -O1 and above for
-// sm_100a (wrong scores; correct with -Xptxas -O0).  This formulation avoids the pattern and is
-// checked bit-for-bit against the oracle by the GPU parity tests (candidate responses).
-__device__ __forceinline__ unsigned pack2(const uint8_t *c, int off) {
-    return (unsigned)c[off] | ((unsigned)c[off + 1] << 16);
+// ---- FAST-9/16 in s16x2 lanes -------------------------------------------------------------------------
+// Ring: Bresenham circle of radius 3, clockwise from (0, 3) -- the order cv::FAST uses.  Differences are
+// kept biased, e = 256 + v - p (1..511), two pixels per 32-bit register, so a plain 32-bit subtract
+// never borrows across lanes and unsigned 16x2 min/max (native VIMNMX.U16x2 / VIMNMX3) apply.
+//   corner at threshold t  <=>  some arc of 9 has all e > 256 + t (dark) or all e < 256 - t (bright)
+//   cornerScore            ==   max over arcs of max(min9(e) - 256, 256 - max9(e)) - 1
+// Filter (necessary condition, cheap): every arc of 9 contains one pixel of each of the 8 antipodal
+// pairs, so  min_k max(e_k, e_k+8) > 256 + t  or  max_k min(e_k, e_k+8) < 256 - t  must hold.
+// NOTE: the scalar formulation `max(min9, -max9)` on int is miscompiled by ptxas 12.9 (-O1 and above,
+// sm_100a); the biased unsigned form below avoids the pattern.  Parity is pinned by the GPU tests
+// (candidate positions and responses, bit for bit against the oracle).
+__device__ __forceinline__ unsigned lane_pair(unsigned w, int which) {   // bytes (0,1) or (2,3) -> u16x2
+    return which == 0 ? __byte_perm(w, 0u, 0x4140) : __byte_perm(w, 0u, 0x4342);
 }
 
+// Exact score of two (unrelated) pixels at once: lane lo = pixel at ca, lane hi = pixel at cb.
 template <int P>
-__device__ __forceinline__ unsigned fast_score2(const uint8_t *c, unsigned v, unsigned p0, unsigned p4,
-                                                unsigned p8, unsigned p12) {
-    unsigned d[16];
-    d[0] = __vsub2(v, p0);                     d[1] = __vsub2(v, pack2(c, 3 * P + 1));
-    d[2] = __vsub2(v, pack2(c, 2 * P + 2));    d[3] = __vsub2(v, pack2(c, P + 3));
-    d[4] = __vsub2(v, p4);                     d[5] = __vsub2(v, pack2(c, -P + 3));
-    d[6] = __vsub2(v, pack2(c, -2 * P + 2));   d[7] = __vsub2(v, pack2(c, -3 * P + 1));
-    d[8] = __vsub2(v, p8);                     d[9] = __vsub2(v, pack2(c, -3 * P - 1));
-    d[10] = __vsub2(v, pack2(c, -2 * P - 2));  d[11] = __vsub2(v, pack2(c, -P - 3));
-    d[12] = __vsub2(v, p12);                   d[13] = __vsub2(v, pack2(c, P - 3));
-    d[14] = __vsub2(v, pack2(c, 2 * P - 2));   d[15] = __vsub2(v, pack2(c, 3 * P - 1));
+__device__ __forceinline__ unsigned fast_score_2px(const uint8_t *ca, const uint8_t *cb) {
+    const int off[16] = {3 * P, 3 * P + 1, 2 * P + 2, P + 3, 3, -P + 3, -2 * P + 2, -3 * P + 1,
+                         -3 * P, -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3, 2 * P - 2, 3 * P - 1};
+    const unsigned vb = ((unsigned)ca[0] | ((unsigned)cb[0] << 16)) | 0x01000100u;
+    unsigned e[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) e[k] = vb - ((unsigned)ca[off[k]] | ((unsigned)cb[off[k]] << 16));
     // sliding min / max over windows of 9 of the circular sequence, by doubling: 2, 4, 8, then +1
     unsigned mn2[16], mx2[16], mn4[16], mx4[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { mn2[k] = __vmins2(d[k], d[(k + 1) & 15]); mx2[k] = __vmaxs2(d[k], d[(k + 1) & 15]); }
+    for (int k = 0; k < 16; ++k) { mn2[k] = __vminu2(e[k], e[(k + 1) & 15]); mx2[k] = __vmaxu2(e[k], e[(k + 1) & 15]); }
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { mn4[k] = __vmins2(mn2[k], mn2[(k + 2) & 15]); mx4[k] = __vmaxs2(mx2[k], mx2[(k + 2) & 15]); }
-    unsigned best = 0xff00ff00u;   // (-256, -256)
+    for (int k = 0; k < 16; ++k) { mn4[k] = __vminu2(mn2[k], mn2[(k + 2) & 15]); mx4[k] = __vmaxu2(mx2[k], mx2[(k + 2) & 15]); }
+    unsigned lo = 0u, hi = 0x02000200u;    // running max of min9, running min of max9
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const unsigned mn9 = __vimin3_s16x2(mn4[k], mn4[(k + 4) & 15], d[(k + 8) & 15]);
-        const unsigned mx9 = __vimax3_s16x2(mx4[k], mx4[(k + 4) & 15], d[(k + 8) & 15]);
-        best = __vimax3_s16x2(best, mn9, __vneg2(mx9));
+        lo = __vmaxu2(lo, __vminu2(__vminu2(mn4[k], mn4[(k + 4) & 15]), e[(k + 8) & 15]));
+        hi = __vminu2(hi, __vmaxu2(__vmaxu2(mx4[k], mx4[(k + 4) & 15]), e[(k + 8) & 15]));
     }
-    return __vsub2(best, 0x00010001u);
+    // score + 256 = max(lo, 512 - hi) - 1   (all quantities stay inside 0..511 per lane)
+    return __vmaxu2(lo, 0x02000200u - hi) - 0x00010001u;
 }
 
 __global__ void __launch_bounds__(FAST_THREADS)
@@ -78,8 +80,10 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int 
                   unsigned long long level0_stride, int total_cells, unsigned long long *cand,
                   int *cand_count, int *err) {
     __shared__ __align__(16) uint8_t tile[TILE_ROWS * TP];
-    __shared__ uint8_t resp[RP * RP];
-    __shared__ int s_cnt_ini, s_cnt_min, s_base, s_emit;
+    __shared__ __align__(16) uint8_t resp[(CELL + 2) * RPW];
+    __shared__ unsigned short surv[MAX_SURVIVORS];        // y << 6 | x of the pixels passing the filter
+    __shared__ unsigned short keep[(CELL / 2) * (CELL / 2)];   // NMS winners (at most one per 2x2 block)
+    __shared__ int s_nsurv, s_nkeep, s_base;
 
     const int tid = threadIdx.x, f = blockIdx.y;
     // which level / cell
@@ -96,84 +100,136 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int 
     const int pitch = l == 0 ? level0_pitch : L.pitch;
     const int ex0 = EVAL_ORIGIN + CELL * cj, ey0 = EVAL_ORIGIN + CELL * ci;   // first evaluated pixel
     const int cw = min(CELL, L.w - EVAL_ORIGIN - ex0), ch = min(CELL, L.h - EVAL_ORIGIN - ey0);
-    const int wx0 = ex0 - 3, wy0 = ey0 - 3;         // window origin
-    const int ax0 = wx0 & ~3, shift = wx0 - ax0;    // aligned load origin
+    const int ax0 = ex0 - 3 - TILE_SHIFT, wy0 = ey0 - 3;   // word-aligned window origin
 
-    if (tid == 0) { s_cnt_ini = 0; s_cnt_min = 0; s_emit = 0; }
-    for (int i = tid; i < RP * RP / 4; i += FAST_THREADS) reinterpret_cast<uint32_t *>(resp)[i] = 0;
-    // ---- stage the (cw+6) x (ch+6) window ------------------------------------------------------------
+    // ---- stage the (cw+6) x (ch+6) window: 20 words per row (zero where the cell is narrower) ----------
     {
-        const int nwords = (shift + cw + 6 + 3) >> 2;
-        for (int i = tid; i < nwords * (ch + 6); i += FAST_THREADS) {
-            const int r = i / nwords, wd = i - r * nwords;
-            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)(wy0 + r) * pitch + ax0 + 4 * wd));
+        const int nwords = (TILE_SHIFT + cw + 6 + 3) >> 2;
+        for (int i = tid; i < (TP / 4) * (ch + 6); i += FAST_THREADS) {
+            const int r = i / (TP / 4), wd = i - r * (TP / 4);
+            uint32_t v = 0;
+            if (wd < nwords) v = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)(wy0 + r) * pitch + ax0 + 4 * wd));
             *reinterpret_cast<uint32_t *>(tile + r * TP + 4 * wd) = v;
         }
     }
-    __syncthreads();
 
-    // ---- corner score of every evaluated pixel (only where it reaches min_thr) ------------------------
-    // two pixels per step; a pair is skipped when both fail the antipodal quick test: any arc of 9
-    // contains one pixel of each antipodal pair, so both of a pair inside [v-t, v+t] => no corner
-    const int t = g.min_thr;
-    for (int i = tid; i < (CELL / 2) * ch; i += FAST_THREADS) {
-        const int y = i >> 5, x = (i & 31) * 2;
-        if (x >= cw) continue;
-        const uint8_t *c = tile + (y + 3) * TP + x + 3 + shift;
-        const unsigned v = pack2(c, 0);
-        const unsigned p0 = pack2(c, 3 * TP), p8 = pack2(c, -3 * TP), p4 = pack2(c, 3), p12 = pack2(c, -3);
-        const unsigned m = __vminu2(__vmaxu2(__vabsdiffu4(v, p0), __vabsdiffu4(v, p8)),
-                                    __vmaxu2(__vabsdiffu4(v, p4), __vabsdiffu4(v, p12)));
-        if ((int)(m & 0xffffu) <= t && (int)(m >> 16) <= t) continue;
-        const unsigned sc = fast_score2<TP>(c, v, p0, p4, p8, p12);
-        const int s0 = (short)(sc & 0xffffu), s1 = (short)(sc >> 16);
-        if (s0 >= t) resp[(y + 1) * RP + x + 1] = (uint8_t)s0;
-        if (s1 >= t && x + 1 < cw) resp[(y + 1) * RP + x + 2] = (uint8_t)s1;
-    }
-    __syncthreads();
+    // Two passes at most: threshold ini first; only a cell that yields nothing is redone at min.
+    // A pixel with score >= t is kept by NMS iff it beats its 8 neighbours' scores; neighbours below
+    // t can never beat it, so a response map holding only the scores >= t gives the exact result.
+    int nkeep = 0, t = g.ini_thr;
+    for (int pass = 0; pass < 2; ++pass, t = g.min_thr) {
+        __syncthreads();   // the previous pass has read its counters
+        if (tid == 0) { s_nsurv = 0; s_nkeep = 0; }
+        for (int i = tid; i < (CELL + 2) * RPW / 4; i += FAST_THREADS) reinterpret_cast<uint32_t *>(resp)[i] = 0;
+        __syncthreads();
 
-    // ---- cell-local NMS (strict '>' against the 8 neighbours; outside the cell counts as 0) -----------
-    unsigned keep = 0;   // bit k: pixel (tid + k*256) is a local maximum
-    int n_ini = 0, n_min = 0;
-    for (int k = 0; k * FAST_THREADS < CELL * ch; ++k) {
-        const int i = tid + k * FAST_THREADS;
-        const int y = i >> 6, x = i & 63;
-        if (y >= ch || x >= cw) continue;
-        const uint8_t *s = resp + (y + 1) * RP + x + 1;
-        const int v = s[0];
-        if (v == 0) continue;
-        if (v > s[-1] && v > s[1] && v > s[-RP - 1] && v > s[-RP] && v > s[-RP + 1]
-            && v > s[RP - 1] && v > s[RP] && v > s[RP + 1]) {
-            keep |= 1u << k;
-            ++n_min;
-            if (v >= g.ini_thr) ++n_ini;
+        // ---- filter: 4 pixels (two s16x2 pairs) per step, ring pixels from aligned word loads -------------
+        const unsigned thi = (unsigned)(256 + t) * 0x00010001u, tlo = (unsigned)(256 - t) * 0x00010001u;
+        for (int i = tid; i < (CELL / 4) * ch; i += FAST_THREADS) {
+            const int y = i >> 4, q = i & 15;
+            if (4 * q >= cw) continue;
+            // row pointers as words; pixel x = 4q sits at tile column 4q + 6, i.e. byte 2 of word q + 1
+            const uint32_t *r0 = reinterpret_cast<const uint32_t *>(tile + (y + 3) * TP) + q;
+            const uint32_t *rm3 = r0 - 3 * (TP / 4), *rp3 = r0 + 3 * (TP / 4);
+            // 4-byte windows starting at column 4q+6+dx, built from words q .. q+3 of the row
+            const uint32_t c0 = r0[0], c1 = r0[1], c2 = r0[2], c3 = r0[3];
+            const uint32_t ctr = __funnelshift_r(c1, c2, 16);
+            const uint32_t w4 = __funnelshift_r(c2, c3, 8);          // (3, 0)   k = 4
+            const uint32_t w12 = __funnelshift_r(c0, c1, 24);        // (-3, 0)  k = 12
+            const uint32_t a1 = rp3[1], a2 = rp3[2];
+            const uint32_t w0 = __funnelshift_r(a1, a2, 16);         // (0, 3)   k = 0
+            const uint32_t b1 = rm3[1], b2 = rm3[2];
+            const uint32_t w8 = __funnelshift_r(b1, b2, 16);         // (0, -3)  k = 8
+            // compass test: an arc of 9 contains two adjacent compass points, so two adjacent ones
+            // must both be darker than v - t or both brighter than v + t
+            unsigned vb[2], e0[2], e4[2], e8[2], e12[2];
+            bool any = false;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                vb[h] = lane_pair(ctr, h) | 0x01000100u;
+                e0[h] = vb[h] - lane_pair(w0, h); e4[h] = vb[h] - lane_pair(w4, h);
+                e8[h] = vb[h] - lane_pair(w8, h); e12[h] = vb[h] - lane_pair(w12, h);
+                const unsigned dk = __vmaxu2(__vmaxu2(__vminu2(e0[h], e4[h]), __vminu2(e4[h], e8[h])),
+                                             __vmaxu2(__vminu2(e8[h], e12[h]), __vminu2(e12[h], e0[h])));
+                const unsigned br = __vminu2(__vminu2(__vmaxu2(e0[h], e4[h]), __vmaxu2(e4[h], e8[h])),
+                                             __vminu2(__vmaxu2(e8[h], e12[h]), __vmaxu2(e12[h], e0[h])));
+                any |= (__vcmpgtu2(dk, thi) | __vcmpgtu2(tlo, br)) != 0;
+            }
+            if (!any) continue;
+            const uint32_t *rm2 = r0 - 2 * (TP / 4), *rp2 = r0 + 2 * (TP / 4);
+            const uint32_t *rm1 = r0 - (TP / 4), *rp1 = r0 + (TP / 4);
+            const uint32_t w1 = __funnelshift_r(a1, a2, 24);         // (1, 3)   k = 1
+            const uint32_t w15 = __funnelshift_r(a1, a2, 8);         // (-1, 3)  k = 15
+            const uint32_t w7 = __funnelshift_r(b1, b2, 24);         // (1, -3)  k = 7
+            const uint32_t w9 = __funnelshift_r(b1, b2, 8);          // (-1, -3) k = 9
+            const uint32_t w2 = rp2[2], w14 = rp2[1];                // (2, 2) k = 2, (-2, 2) k = 14
+            const uint32_t w6 = rm2[2], w10 = rm2[1];                // (2, -2) k = 6, (-2, -2) k = 10
+            const uint32_t d0 = rp1[0], d1 = rp1[1], d2 = rp1[2], d3 = rp1[3];
+            const uint32_t w3 = __funnelshift_r(d2, d3, 8);          // (3, 1)   k = 3
+            const uint32_t w13 = __funnelshift_r(d0, d1, 24);        // (-3, 1)  k = 13
+            const uint32_t g0 = rm1[0], g1 = rm1[1], g2 = rm1[2], g3 = rm1[3];
+            const uint32_t w5 = __funnelshift_r(g2, g3, 8);          // (3, -1)  k = 5
+            const uint32_t w11 = __funnelshift_r(g0, g1, 24);        // (-3, -1) k = 11
+            const uint32_t wa[6] = {w1, w2, w3, w5, w6, w7}, wb[6] = {w9, w10, w11, w13, w14, w15};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                // all 8 antipodal pairs: min_k max(e_k, e_k+8) > 256 + t  or  max_k min(e_k, e_k+8) < 256 - t
+                unsigned mn = __vminu2(__vmaxu2(e0[h], e8[h]), __vmaxu2(e4[h], e12[h]));
+                unsigned mx = __vmaxu2(__vminu2(e0[h], e8[h]), __vminu2(e4[h], e12[h]));
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const unsigned ea = vb[h] - lane_pair(wa[k], h), eb = vb[h] - lane_pair(wb[k], h);
+                    mn = __vminu2(mn, __vmaxu2(ea, eb));
+                    mx = __vmaxu2(mx, __vminu2(ea, eb));
+                }
+                const unsigned hit = __vcmpgtu2(mn, thi) | __vcmpgtu2(tlo, mx);   // 0xffff per passing lane
+                const int x = 4 * q + 2 * h;
+                if ((hit & 0xffffu) && x < cw) surv[atomicAdd(&s_nsurv, 1)] = (unsigned short)((y << 6) | x);
+                if ((hit >> 16) && x + 1 < cw) surv[atomicAdd(&s_nsurv, 1)] = (unsigned short)((y << 6) | (x + 1));
+            }
         }
+        __syncthreads();
+
+        // ---- exact corner score of the survivors, two per thread -----------------------------------------
+        const int nsurv = s_nsurv;
+        for (int i = tid; 2 * i < nsurv; i += FAST_THREADS) {
+            const int pa = surv[2 * i], pb = surv[min(2 * i + 1, nsurv - 1)];
+            const uint8_t *ca = tile + ((pa >> 6) + 3) * TP + (pa & 63) + 3 + TILE_SHIFT;
+            const uint8_t *cb = tile + ((pb >> 6) + 3) * TP + (pb & 63) + 3 + TILE_SHIFT;
+            const unsigned sc = fast_score_2px<TP>(ca, cb);
+            const int sa = (int)(sc & 0xffffu) - 256, sb = (int)(sc >> 16) - 256;
+            if (sa >= t) resp[((pa >> 6) + 1) * RPW + (pa & 63) + 4] = (uint8_t)sa;
+            if (sb >= t) resp[((pb >> 6) + 1) * RPW + (pb & 63) + 4] = (uint8_t)sb;
+        }
+        __syncthreads();
+
+        // ---- cell-local NMS over the survivors (strict '>' against the 8 neighbours; outside = 0) --------
+        for (int i = tid; i < nsurv; i += FAST_THREADS) {
+            const int p = surv[i];
+            const uint8_t *s = resp + ((p >> 6) + 1) * RPW + (p & 63) + 4;
+            const int v = s[0];
+            if (v == 0) continue;
+            if (v > s[-1] && v > s[1] && v > s[-RPW - 1] && v > s[-RPW] && v > s[-RPW + 1]
+                && v > s[RPW - 1] && v > s[RPW] && v > s[RPW + 1])
+                keep[atomicAdd(&s_nkeep, 1)] = (unsigned short)p;
+        }
+        __syncthreads();
+        nkeep = s_nkeep;
+        if (nkeep > 0 || g.min_thr == g.ini_thr) break;
     }
-    n_ini = __reduce_add_sync(0xffffffffu, n_ini);
-    n_min = __reduce_add_sync(0xffffffffu, n_min);
-    if ((tid & 31) == 0 && n_min) { atomicAdd(&s_cnt_ini, n_ini); atomicAdd(&s_cnt_min, n_min); }
-    __syncthreads();
-    const bool use_ini = s_cnt_ini > 0;
-    const int n_emit = use_ini ? s_cnt_ini : s_cnt_min;
-    if (n_emit == 0) return;
-    if (tid == 0) s_base = atomicAdd(&cand_count[f * g.levels + l], n_emit);
+    if (nkeep == 0) return;
+    if (tid == 0) s_base = atomicAdd(&cand_count[f * g.levels + l], nkeep);
     __syncthreads();
     const int base = s_base;
-    if (base + n_emit > L.cand_cap) { if (tid == 0) atomicExch(err, SG_ERR_OVERFLOW); return; }
+    if (base + nkeep > L.cand_cap) { if (tid == 0) atomicExch(err, SG_ERR_OVERFLOW); return; }
     unsigned long long *out = cand + (size_t)f * g.cand_per_frame + L.cand_off + base;
-    const int thr_cell = use_ini ? g.ini_thr : 1;
-    while (keep) {
-        const int k = __ffs(keep) - 1;
-        keep &= keep - 1;
-        const int i = tid + k * FAST_THREADS;
-        const int y = i >> 6, x = i & 63;
-        const int v = resp[(y + 1) * RP + x + 1];
-        if (v >= thr_cell) {
-            const int slot = atomicAdd(&s_emit, 1);
-            // order key == position in the sequential candidate list: cell row, cell column, y, x
-            const unsigned key = ((unsigned)ci << 22) | ((unsigned)cj << 12) | ((unsigned)y << 6) | (unsigned)x;
-            out[slot] = ((unsigned long long)v << 32) | key;
-        }
+    for (int i = tid; i < nkeep; i += FAST_THREADS) {
+        const int p = keep[i];
+        const int y = p >> 6, x = p & 63;
+        const int v = resp[(y + 1) * RPW + 4 + x];
+        // order key == position in the sequential candidate list: cell row, cell column, y, x
+        const unsigned key = ((unsigned)ci << 22) | ((unsigned)cj << 12) | ((unsigned)y << 6) | (unsigned)x;
+        out[i] = ((unsigned long long)v << 32) | key;
     }
 }
 
