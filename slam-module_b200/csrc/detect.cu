@@ -50,6 +50,11 @@ __device__ __forceinline__ unsigned lane_pair(unsigned w, int which) {   // byte
     return which == 0 ? __byte_perm(w, 0u, 0x4140) : __byte_perm(w, 0u, 0x4342);
 }
 
+// Per-lane a > b for u16x2 lanes below 32768: bit 15 / 31 of the result (no borrow across lanes).
+__device__ __forceinline__ unsigned gt16x2(unsigned a, unsigned b) {
+    return ~((b | 0x80008000u) - a) & 0x80008000u;
+}
+
 // Exact score of two (unrelated) pixels at once: lane lo = pixel at ca, lane hi = pixel at cb.
 template <int P>
 __device__ __forceinline__ unsigned fast_score_2px(const uint8_t *ca, const uint8_t *cb) {
@@ -83,7 +88,8 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int 
     __shared__ __align__(16) uint8_t resp[(CELL + 2) * RPW];
     __shared__ unsigned short surv[MAX_SURVIVORS];        // y << 6 | x of the pixels passing the filter
     __shared__ unsigned short keep[(CELL / 2) * (CELL / 2)];   // NMS winners (at most one per 2x2 block)
-    __shared__ int s_nsurv, s_nkeep, s_base;
+    __shared__ unsigned short quads[(CELL / 4) * CELL];       // y << 4 | q of the quads passing the compass test
+    __shared__ int s_nsurv, s_nkeep, s_nquad, s_base;
 
     const int tid = threadIdx.x, f = blockIdx.y;
     // which level / cell
@@ -119,72 +125,87 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int 
     int nkeep = 0, t = g.ini_thr;
     for (int pass = 0; pass < 2; ++pass, t = g.min_thr) {
         __syncthreads();   // the previous pass has read its counters
-        if (tid == 0) { s_nsurv = 0; s_nkeep = 0; }
+        if (tid == 0) { s_nsurv = 0; s_nkeep = 0; s_nquad = 0; }
         for (int i = tid; i < (CELL + 2) * RPW / 4; i += FAST_THREADS) reinterpret_cast<uint32_t *>(resp)[i] = 0;
         __syncthreads();
 
-        // ---- filter: 4 pixels (two s16x2 pairs) per step, ring pixels from aligned word loads -------------
+        // ---- compass test, 4 pixels (two s16x2 pairs) per step: an arc of 9 contains two adjacent compass
+        // points (k = 0, 4, 8, 12), so two adjacent ones must both be darker than v - t or both brighter
+        // than v + t.  Passing quads are compacted so that the full filter runs with full warps.
         const unsigned thi = (unsigned)(256 + t) * 0x00010001u, tlo = (unsigned)(256 - t) * 0x00010001u;
         for (int i = tid; i < (CELL / 4) * ch; i += FAST_THREADS) {
             const int y = i >> 4, q = i & 15;
             if (4 * q >= cw) continue;
             // row pointers as words; pixel x = 4q sits at tile column 4q + 6, i.e. byte 2 of word q + 1
             const uint32_t *r0 = reinterpret_cast<const uint32_t *>(tile + (y + 3) * TP) + q;
-            const uint32_t *rm3 = r0 - 3 * (TP / 4), *rp3 = r0 + 3 * (TP / 4);
-            // 4-byte windows starting at column 4q+6+dx, built from words q .. q+3 of the row
             const uint32_t c0 = r0[0], c1 = r0[1], c2 = r0[2], c3 = r0[3];
             const uint32_t ctr = __funnelshift_r(c1, c2, 16);
-            const uint32_t w4 = __funnelshift_r(c2, c3, 8);          // (3, 0)   k = 4
-            const uint32_t w12 = __funnelshift_r(c0, c1, 24);        // (-3, 0)  k = 12
-            const uint32_t a1 = rp3[1], a2 = rp3[2];
-            const uint32_t w0 = __funnelshift_r(a1, a2, 16);         // (0, 3)   k = 0
-            const uint32_t b1 = rm3[1], b2 = rm3[2];
-            const uint32_t w8 = __funnelshift_r(b1, b2, 16);         // (0, -3)  k = 8
-            // compass test: an arc of 9 contains two adjacent compass points, so two adjacent ones
-            // must both be darker than v - t or both brighter than v + t
-            unsigned vb[2], e0[2], e4[2], e8[2], e12[2];
-            bool any = false;
+            const uint32_t w4 = __funnelshift_r(c2, c3, 8), w12 = __funnelshift_r(c0, c1, 24);
+            const uint32_t w0 = __funnelshift_r(r0[3 * (TP / 4) + 1], r0[3 * (TP / 4) + 2], 16);
+            const uint32_t w8 = __funnelshift_r(r0[-3 * (TP / 4) + 1], r0[-3 * (TP / 4) + 2], 16);
+            unsigned hit = 0;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                vb[h] = lane_pair(ctr, h) | 0x01000100u;
-                e0[h] = vb[h] - lane_pair(w0, h); e4[h] = vb[h] - lane_pair(w4, h);
-                e8[h] = vb[h] - lane_pair(w8, h); e12[h] = vb[h] - lane_pair(w12, h);
-                const unsigned dk = __vmaxu2(__vmaxu2(__vminu2(e0[h], e4[h]), __vminu2(e4[h], e8[h])),
-                                             __vmaxu2(__vminu2(e8[h], e12[h]), __vminu2(e12[h], e0[h])));
-                const unsigned br = __vminu2(__vminu2(__vmaxu2(e0[h], e4[h]), __vmaxu2(e4[h], e8[h])),
-                                             __vminu2(__vmaxu2(e8[h], e12[h]), __vmaxu2(e12[h], e0[h])));
-                any |= (__vcmpgtu2(dk, thi) | __vcmpgtu2(tlo, br)) != 0;
+                const unsigned vb = lane_pair(ctr, h) | 0x01000100u;
+                const unsigned e0 = vb - lane_pair(w0, h), e4 = vb - lane_pair(w4, h);
+                const unsigned e8 = vb - lane_pair(w8, h), e12 = vb - lane_pair(w12, h);
+                const unsigned dk = __vmaxu2(__vmaxu2(__vminu2(e0, e4), __vminu2(e4, e8)),
+                                             __vmaxu2(__vminu2(e8, e12), __vminu2(e12, e0)));
+                const unsigned br = __vminu2(__vminu2(__vmaxu2(e0, e4), __vmaxu2(e4, e8)),
+                                             __vminu2(__vmaxu2(e8, e12), __vmaxu2(e12, e0)));
+                hit |= gt16x2(dk, thi) | gt16x2(tlo, br);    // dk > thi  or  br < tlo
             }
-            if (!any) continue;
+            if (hit) quads[atomicAdd(&s_nquad, 1)] = (unsigned short)i;
+        }
+        __syncthreads();
+
+        // ---- full filter on the compacted quads: all 16 ring pixels, 8 antipodal pairs ----------------------
+        const int nquad = s_nquad;
+        for (int n = tid; n < nquad; n += FAST_THREADS) {
+            const int i = quads[n];
+            const int y = i >> 4, q = i & 15;
+            const uint32_t *r0 = reinterpret_cast<const uint32_t *>(tile + (y + 3) * TP) + q;
+            const uint32_t *rm3 = r0 - 3 * (TP / 4), *rp3 = r0 + 3 * (TP / 4);
             const uint32_t *rm2 = r0 - 2 * (TP / 4), *rp2 = r0 + 2 * (TP / 4);
             const uint32_t *rm1 = r0 - (TP / 4), *rp1 = r0 + (TP / 4);
-            const uint32_t w1 = __funnelshift_r(a1, a2, 24);         // (1, 3)   k = 1
-            const uint32_t w15 = __funnelshift_r(a1, a2, 8);         // (-1, 3)  k = 15
-            const uint32_t w7 = __funnelshift_r(b1, b2, 24);         // (1, -3)  k = 7
-            const uint32_t w9 = __funnelshift_r(b1, b2, 8);          // (-1, -3) k = 9
-            const uint32_t w2 = rp2[2], w14 = rp2[1];                // (2, 2) k = 2, (-2, 2) k = 14
-            const uint32_t w6 = rm2[2], w10 = rm2[1];                // (2, -2) k = 6, (-2, -2) k = 10
+            // 4-byte windows starting at column 4q+6+dx, built from words q .. q+3 of the row
+            const uint32_t c0 = r0[0], c1 = r0[1], c2 = r0[2], c3 = r0[3];
+            const uint32_t a1 = rp3[1], a2 = rp3[2], b1 = rm3[1], b2 = rm3[2];
             const uint32_t d0 = rp1[0], d1 = rp1[1], d2 = rp1[2], d3 = rp1[3];
-            const uint32_t w3 = __funnelshift_r(d2, d3, 8);          // (3, 1)   k = 3
-            const uint32_t w13 = __funnelshift_r(d0, d1, 24);        // (-3, 1)  k = 13
             const uint32_t g0 = rm1[0], g1 = rm1[1], g2 = rm1[2], g3 = rm1[3];
-            const uint32_t w5 = __funnelshift_r(g2, g3, 8);          // (3, -1)  k = 5
-            const uint32_t w11 = __funnelshift_r(g0, g1, 24);        // (-3, -1) k = 11
-            const uint32_t wa[6] = {w1, w2, w3, w5, w6, w7}, wb[6] = {w9, w10, w11, w13, w14, w15};
+            const uint32_t ctr = __funnelshift_r(c1, c2, 16);
+            const uint32_t wa[8] = {
+                __funnelshift_r(a1, a2, 16),   // (0, 3)   k = 0
+                __funnelshift_r(a1, a2, 24),   // (1, 3)   k = 1
+                rp2[2],                        // (2, 2)   k = 2
+                __funnelshift_r(d2, d3, 8),    // (3, 1)   k = 3
+                __funnelshift_r(c2, c3, 8),    // (3, 0)   k = 4
+                __funnelshift_r(g2, g3, 8),    // (3, -1)  k = 5
+                rm2[2],                        // (2, -2)  k = 6
+                __funnelshift_r(b1, b2, 24)};  // (1, -3)  k = 7
+            const uint32_t wb[8] = {
+                __funnelshift_r(b1, b2, 16),   // (0, -3)  k = 8
+                __funnelshift_r(b1, b2, 8),    // (-1, -3) k = 9
+                rm2[1],                        // (-2, -2) k = 10
+                __funnelshift_r(g0, g1, 24),   // (-3, -1) k = 11
+                __funnelshift_r(c0, c1, 24),   // (-3, 0)  k = 12
+                __funnelshift_r(d0, d1, 24),   // (-3, 1)  k = 13
+                rp2[1],                        // (-2, 2)  k = 14
+                __funnelshift_r(a1, a2, 8)};   // (-1, 3)  k = 15
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                // all 8 antipodal pairs: min_k max(e_k, e_k+8) > 256 + t  or  max_k min(e_k, e_k+8) < 256 - t
-                unsigned mn = __vminu2(__vmaxu2(e0[h], e8[h]), __vmaxu2(e4[h], e12[h]));
-                unsigned mx = __vmaxu2(__vminu2(e0[h], e8[h]), __vminu2(e4[h], e12[h]));
+                // min_k max(e_k, e_k+8) > 256 + t  or  max_k min(e_k, e_k+8) < 256 - t
+                const unsigned vb = lane_pair(ctr, h) | 0x01000100u;
+                unsigned mn = 0x02000200u, mx = 0u;
 #pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const unsigned ea = vb[h] - lane_pair(wa[k], h), eb = vb[h] - lane_pair(wb[k], h);
+                for (int k = 0; k < 8; ++k) {
+                    const unsigned ea = vb - lane_pair(wa[k], h), eb = vb - lane_pair(wb[k], h);
                     mn = __vminu2(mn, __vmaxu2(ea, eb));
                     mx = __vmaxu2(mx, __vminu2(ea, eb));
                 }
-                const unsigned hit = __vcmpgtu2(mn, thi) | __vcmpgtu2(tlo, mx);   // 0xffff per passing lane
+                const unsigned hit = gt16x2(mn, thi) | gt16x2(tlo, mx);
                 const int x = 4 * q + 2 * h;
-                if ((hit & 0xffffu) && x < cw) surv[atomicAdd(&s_nsurv, 1)] = (unsigned short)((y << 6) | x);
+                if ((hit & 0x8000u) && x < cw) surv[atomicAdd(&s_nsurv, 1)] = (unsigned short)((y << 6) | x);
                 if ((hit >> 16) && x + 1 < cw) surv[atomicAdd(&s_nsurv, 1)] = (unsigned short)((y << 6) | (x + 1));
             }
         }
