@@ -89,6 +89,9 @@ static int build_context(sg_ctx *ctx) {
                 for (int i = 0; i < L.h; ++i) yt[i] = ResizeTap{i, i, 2048, 0};
             }
             pyramid_source_extent(xt, yt, L.w, L.h, L.area2x, P.w, P.h, &L.src_tile_w, &L.src_tile_h);
+            L.fast_resize = !L.area2x && P.h < 32768;
+            for (int i = 0; i + 1 < L.w; ++i)
+                if (xt[i + 1].s0 - xt[i].s0 > 2 || xt[i + 1].s0 < xt[i].s0) L.fast_resize = false;
             if (int r = dev_alloc(ctx, &L.xtab, xt.size())) return r;
             if (int r = dev_alloc(ctx, &L.ytab, yt.size())) return r;
             SG_CUDA(ctx, cudaMemcpy(L.xtab, xt.data(), xt.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));

@@ -32,6 +32,7 @@ struct Level {
     ResizeTap *xtab = nullptr;      // [w]   (levels >= 1)
     ResizeTap *ytab = nullptr;      // [h]
     bool area2x = false;            // cv::resize switches to INTER_AREA for an exact 2x decimation
+    bool fast_resize = false;       // adjacent taps at most 2 source pixels apart: the IDP.2A kernel applies
     int src_tile_w = 0, src_tile_h = 0;  // smem extent of the source tile of the resize kernel
     // detection geometry
     int area_w = 0, area_h = 0;     // working area (image minus 19-px border)

@@ -191,6 +191,175 @@ __global__ void __launch_bounds__(PYR_THREADS) pyr_level_kernel(const PyrArgs a)
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Fast path (scale factor <= 2, no INTER_AREA switch): same arithmetic, restructured for the integer
+// pipes.  Per output pixel the generic kernel above spends ~190 thread instructions (variable
+// divisions, byte loads, scalar multiply-adds); this one ~45:
+//   resize    : 2 px per item; both source bytes of a pixel come from one PRMT on an aligned 8-byte
+//               window, the horizontal interpolation S0*a0 + S1*a1 is one IDP.2A (16-bit coefficient
+//               pair x 8-bit pixel pair); out-of-image window entries use clamped taps (overwritten by
+//               the mirror pass), so there are no guards in the loop
+//   blur H    : IDP.4A on byte windows (two per output), two rows per item, stored as vertical u16
+//               pairs Hp[r/2][c] = H[r][c] | H[r+1][c] << 16
+//   blur V    : IDP.2A on the vertical pairs (3 per output + one scalar tap), 4 columns x 2 rows per
+//               thread, 32-bit stores
+// -------------------------------------------------------------------------------------------------
+constexpr int FW = 80;               // R pitch of the fast kernel (20 words)
+struct XTap { uint32_t coef; int32_t s0; };          // a0 | a1 << 16, source column relative to the tile
+struct YTap { int16_t s0, s1, b0, b1; };
+
+template <bool RESIZE>
+__global__ void __launch_bounds__(PYR_THREADS) pyr_fast_kernel(const PyrArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *R = smem;                                                   // [RH][FW]
+    uint32_t *Hp = reinterpret_cast<uint32_t *>(smem + RH * FW);         // [RH/2][TW]
+    XTap *xt = reinterpret_cast<XTap *>(smem + RH * FW + (RH / 2) * TW * 4);   // [72]
+    YTap *yt = reinterpret_cast<YTap *>(xt + 72);                        // [RH]
+    uint8_t *S = reinterpret_cast<uint8_t *>(yt + RH + 2);               // [src_tile_h][src_tile_w] (16-B aligned)
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, f = blockIdx.z;
+    const int tw = min(TW, a.w - x0), th = min(TH, a.h - y0);
+    const int xlo = max(x0 - 3, 0), xhi = min(x0 + tw + 3, a.w);
+    const int ylo = max(y0 - 3, 0), yhi = min(y0 + th + 3, a.h);
+    const uint8_t *src = a.src + (size_t)f * a.sstride;
+
+    if (RESIZE) {
+        const int sx_lo = a.xtab[xlo].s0 & ~3, sx_hi = a.xtab[xhi - 1].s1;
+        const int sy_lo = a.ytab[ylo].s0, sy_hi = a.ytab[yhi - 1].s1;
+        const int nwords = ((sx_hi - sx_lo) >> 2) + 1, nrows = sy_hi - sy_lo + 1;
+        const int sp = a.src_tile_w;
+        for (int r = tid / 32; r < nrows; r += PYR_THREADS / 32)       // one warp per source row
+            for (int wd = tid & 31; wd < nwords; wd += 32)
+                *reinterpret_cast<uint32_t *>(S + r * sp + 4 * wd) =
+                    __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)(sy_lo + r) * a.spitch + sx_lo + 4 * wd));
+        // taps of every window column / row; outside the image the nearest valid tap (value unused)
+        if (tid < 72) {
+            const ResizeTap t = a.xtab[min(max(x0 - 4 + tid, xlo), xhi - 1)];
+            xt[tid] = XTap{(uint32_t)(uint16_t)t.a0 | ((uint32_t)(uint16_t)t.a1 << 16), t.s0 - sx_lo};
+        } else if (tid >= 128 && tid < 128 + RH) {
+            const ResizeTap t = a.ytab[min(max(y0 - 3 + tid - 128, ylo), yhi - 1)];
+            yt[tid - 128] = YTap{(int16_t)(t.s0 - sy_lo), (int16_t)(t.s1 - sy_lo), t.a0, t.a1};
+        }
+        __syncthreads();
+        for (int i = tid; i < RH * 36; i += PYR_THREADS) {
+            const int ry = i / 36, cp = i - ry * 36;
+            const uint4 tx = *reinterpret_cast<const uint4 *>(xt + 2 * cp);   // {coef_a, s0_a, coef_b, s0_b}
+            const YTap ty = yt[ry];
+            const int base = (int)tx.y >> 2;
+            const unsigned oa = tx.y & 3u, ob = tx.w - 4u * (unsigned)base;     // byte offsets in the 8-byte window
+            const unsigned sel_a = oa * 0x11u + 0x10u, sel_b = ob * 0x11u + 0x10u;
+            const uint32_t *r0 = reinterpret_cast<const uint32_t *>(S + ty.s0 * sp) + base;
+            const uint32_t *r1 = reinterpret_cast<const uint32_t *>(S + ty.s1 * sp) + base;
+            const uint32_t p0 = r0[0], p1 = r0[1], q0 = r1[0], q1 = r1[1];
+            const unsigned ha0 = __dp2a_lo(tx.x, __byte_perm(p0, p1, sel_a), 0u);
+            const unsigned ha1 = __dp2a_lo(tx.x, __byte_perm(q0, q1, sel_a), 0u);
+            const unsigned hb0 = __dp2a_lo(tx.z, __byte_perm(p0, p1, sel_b), 0u);
+            const unsigned hb1 = __dp2a_lo(tx.z, __byte_perm(q0, q1, sel_b), 0u);
+            const unsigned b0 = (unsigned)ty.b0, b1 = (unsigned)ty.b1;
+            const unsigned va = (((b0 * (ha0 >> 4)) >> 16) + ((b1 * (ha1 >> 4)) >> 16) + 2u) >> 2;
+            const unsigned vb = (((b0 * (hb0 >> 4)) >> 16) + ((b1 * (hb1 >> 4)) >> 16) + 2u) >> 2;
+            *reinterpret_cast<uint16_t *>(R + ry * FW + 2 * cp) = (uint16_t)(va | (vb << 8));
+        }
+    } else {
+        for (int i = tid; i < (yhi - ylo) * (FW / 4); i += PYR_THREADS) {
+            const int ry = i / (FW / 4), wd = i - ry * (FW / 4);
+            const int x = x0 - 4 + 4 * wd;
+            if (x >= 0 && x < a.spitch)
+                *reinterpret_cast<uint32_t *>(R + (ylo + ry - (y0 - 3)) * FW + 4 * wd) =
+                    __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)(ylo + ry) * a.spitch + x));
+        }
+    }
+    __syncthreads();
+
+    // ---- pyramid plane: interior of R, 32-bit stores ----------------------------------------------
+    if (RESIZE) {
+        uint8_t *dst = a.dst + (size_t)f * a.dstride;
+        for (int i = tid; i < TH * (TW / 4); i += PYR_THREADS) {
+            const int r = i >> 4, wd = i & 15;
+            if (r < th && 4 * wd < tw)
+                *reinterpret_cast<uint32_t *>(dst + (size_t)(y0 + r) * a.pitch + x0 + 4 * wd) =
+                    *reinterpret_cast<const uint32_t *>(R + (r + 3) * FW + 4 + 4 * wd);
+        }
+    }
+    // ---- reflect-101: halo entries outside the image mirror resized pixels inside it ------------
+    if (x0 == 0 || y0 == 0 || x0 + tw + 3 > a.w || y0 + th + 3 > a.h) {
+        for (int i = tid; i < RH * 72; i += PYR_THREADS) {
+            const int ry = i / 72, rx = i - ry * 72;
+            const int x = x0 - 4 + rx, y = y0 - 3 + ry;
+            if ((x < 0 || x >= a.w || y < 0 || y >= a.h) && rx >= 1 && x < a.w + 3 && y < a.h + 3) {
+                const int mx = reflect101(x, a.w), my = reflect101(y, a.h);
+                R[ry * FW + rx] = R[(my - (y0 - 3)) * FW + (mx - (x0 - 4))];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- horizontal pass: 4 columns x 2 rows per item, stored as vertical u16 pairs ---------------
+    {
+        const uint32_t k0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);   // taps 0..3
+        const uint32_t k1 = 48u | (34u << 8) | (18u << 16);                 // taps 4..6
+        for (int i = tid; i < (RH / 2) * (TW / 4); i += PYR_THREADS) {
+            const int rp = i >> 4, g = i & 15;
+            uint32_t o[2][4];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(R + (2 * rp + rr) * FW) + g;
+                const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];   // columns 4g .. 4g+11 of R
+                // output c = 4g + j uses R columns c+1 .. c+7
+                o[rr][0] = __dp4a(__byte_perm(w0, w1, 0x4321), k0, __dp4a(__byte_perm(w1, w2, 0x4321), k1, 0u));
+                o[rr][1] = __dp4a(__byte_perm(w0, w1, 0x5432), k0, __dp4a(__byte_perm(w1, w2, 0x5432), k1, 0u));
+                o[rr][2] = __dp4a(__byte_perm(w0, w1, 0x6543), k0, __dp4a(__byte_perm(w1, w2, 0x6543), k1, 0u));
+                o[rr][3] = __dp4a(w1, k0, __dp4a(w2, k1, 0u));
+            }
+            *reinterpret_cast<uint4 *>(Hp + rp * TW + 4 * g) =
+                make_uint4(o[0][0] | (o[1][0] << 16), o[0][1] | (o[1][1] << 16), o[0][2] | (o[1][2] << 16), o[0][3] | (o[1][3] << 16));
+        }
+    }
+    __syncthreads();
+
+    // ---- vertical pass: 4 columns x 2 rows per thread; out row r uses H rows r .. r+6 --------------
+    {
+        uint8_t *bl = a.blur + (size_t)f * a.dstride;
+        const int g = tid & 15, rp = tid >> 4;   // 16 column groups x 16 row pairs
+        const int r0 = 2 * rp;
+        if (r0 < th && 4 * g < tw) {
+            const uint4 P0 = *reinterpret_cast<const uint4 *>(Hp + (rp + 0) * TW + 4 * g);
+            const uint4 P1 = *reinterpret_cast<const uint4 *>(Hp + (rp + 1) * TW + 4 * g);
+            const uint4 P2 = *reinterpret_cast<const uint4 *>(Hp + (rp + 2) * TW + 4 * g);
+            const uint4 P3 = *reinterpret_cast<const uint4 *>(Hp + (rp + 3) * TW + 4 * g);
+            const uint32_t kA = 18u | (34u << 8) | (48u << 16) | (56u << 24);   // k0 k1 | k2 k3
+            const uint32_t kB = 48u | (34u << 8);                               // k4 k5
+            const uint32_t kC = 34u | (48u << 8) | (56u << 16) | (48u << 24);   // k1 k2 | k3 k4
+            const uint32_t kD = 34u | (18u << 8);                               // k5 k6
+            const uint32_t p0[4] = {P0.x, P0.y, P0.z, P0.w}, p1[4] = {P1.x, P1.y, P1.z, P1.w};
+            const uint32_t p2[4] = {P2.x, P2.y, P2.z, P2.w}, p3[4] = {P3.x, P3.y, P3.z, P3.w};
+            uint32_t even = 0, odd = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                // even row r0: rows r0..r0+5 are the pairs P0 P1 P2, row r0+6 is the low half of P3
+                uint32_t ve = __dp2a_lo(p0[c], kA, (p3[c] & 0xffffu) * 18u + 32768u);
+                ve = __dp2a_hi(p1[c], kA, ve);
+                ve = __dp2a_lo(p2[c], kB, ve);
+                // odd row r0+1: row r0+1 is the high half of P0, rows r0+2..r0+7 are P1 P2 P3
+                uint32_t vo = __dp2a_lo(p1[c], kC, (p0[c] >> 16) * 18u + 32768u);
+                vo = __dp2a_hi(p2[c], kC, vo);
+                vo = __dp2a_lo(p3[c], kD, vo);
+                even |= (ve >> 16) << (8 * c);
+                odd |= (vo >> 16) << (8 * c);
+            }
+            *reinterpret_cast<uint32_t *>(bl + (size_t)(y0 + r0) * a.pitch + x0 + 4 * g) = even;
+            if (r0 + 1 < th) *reinterpret_cast<uint32_t *>(bl + (size_t)(y0 + r0 + 1) * a.pitch + x0 + 4 * g) = odd;
+        }
+    }
+}
+
+static size_t pyr_fast_smem_bytes(const PyrArgs &a, bool resize) {
+    size_t b = RH * FW + (RH / 2) * TW * 4 + 72 * sizeof(XTap) + (RH + 2) * sizeof(YTap);
+    if (resize) b += (size_t)(a.src_tile_h + 1) * a.src_tile_w + 16;
+    return b;
+}
+
 static size_t pyr_smem_bytes(const PyrArgs &a, bool resize) {
     size_t b = RH * RW + RH * TW * 2;
     if (resize) b += (size_t)a.src_tile_h * a.src_tile_w + sizeof(ResizeTap) * (TW + 6 + TH + 6);
@@ -228,8 +397,7 @@ int launch_pyramid(sg_ctx *ctx, int n_frames) {
         dim3 grid((L.w + TW - 1) / TW, (L.h + TH - 1) / TH, n_frames);
         if (l == 0) {
             a.src = ctx->level0; a.sw = L.w; a.sh = L.h; a.spitch = ctx->level0_pitch; a.sstride = ctx->level0_stride;
-            const size_t smem = pyr_smem_bytes(a, false);
-            pyr_level_kernel<false><<<grid, PYR_THREADS, smem, ctx->stream>>>(a);
+            pyr_fast_kernel<false><<<grid, PYR_THREADS, pyr_fast_smem_bytes(a, false), ctx->stream>>>(a);
         } else {
             const Level &P = ctx->lv[l - 1];
             a.src = l == 1 ? ctx->level0 : P.pyr;
@@ -240,10 +408,15 @@ int launch_pyramid(sg_ctx *ctx, int n_frames) {
             a.xtab = L.xtab; a.ytab = L.ytab;
             a.src_tile_w = L.src_tile_w; a.src_tile_h = L.src_tile_h;
             a.area2x = L.area2x ? 1 : 0;
-            const size_t smem = pyr_smem_bytes(a, true);
-            if (smem > 48 * 1024)
-                SG_CUDA(ctx, cudaFuncSetAttribute(pyr_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            pyr_level_kernel<true><<<grid, PYR_THREADS, smem, ctx->stream>>>(a);
+            const size_t fsmem = pyr_fast_smem_bytes(a, true);
+            if (L.fast_resize && fsmem <= 48 * 1024) {
+                pyr_fast_kernel<true><<<grid, PYR_THREADS, fsmem, ctx->stream>>>(a);
+            } else {   // INTER_AREA switch (exact 2x) or a scale factor above 2: generic kernel
+                const size_t smem = pyr_smem_bytes(a, true);
+                if (smem > 48 * 1024)
+                    SG_CUDA(ctx, cudaFuncSetAttribute(pyr_level_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                pyr_level_kernel<true><<<grid, PYR_THREADS, smem, ctx->stream>>>(a);
+            }
         }
         SG_LAUNCH_CHECK(ctx);
     }
