@@ -90,6 +90,17 @@ static int build_context(sg_ctx *ctx) {
             }
             pyramid_source_extent(xt, yt, L.w, L.h, L.area2x, P.w, P.h, &L.src_tile_w, &L.src_tile_h);
             L.fast_resize = !L.area2x && P.h < 32768;
+            {   // TMA box of the source tile: origin aligned down to 16 bytes (TMA requirement), wide enough
+                // for the 8-byte window the kernel reads at the last column's first tap, rounded to 16
+                int mw = 0;
+                for (int x0 = 0; x0 < L.w; x0 += 64) {
+                    const int tw = std::min(64, L.w - x0), xlo = std::max(x0 - 3, 0), xhi = std::min(x0 + tw + 3, L.w);
+                    mw = std::max(mw, xt[xhi - 1].s0 - (xt[xlo].s0 & ~15) + 8);
+                }
+                L.tma_src_w = (mw + 15) & ~15;
+                L.tma_src_h = L.src_tile_h;
+                if (L.tma_src_w > 256 || L.tma_src_h > 255) L.fast_resize = false;
+            }
             for (int i = 0; i + 1 < L.w; ++i)
                 if (xt[i + 1].s0 - xt[i].s0 > 2 || xt[i + 1].s0 < xt[i].s0) L.fast_resize = false;
             if (int r = dev_alloc(ctx, &L.xtab, xt.size())) return r;
@@ -103,6 +114,14 @@ static int build_context(sg_ctx *ctx) {
         D.area_w = L.area_w; D.area_h = L.area_h; D.cells_x = L.cells_x; D.cells_y = L.cells_y;
         D.cand_cap = L.cand_cap; D.node_cap = L.node_cap; D.init_nx = L.init_nx; D.init_ny = L.init_ny;
         D.cand_off = L.cand_off; D.kp_off = L.kp_off;
+    }
+    // TMA descriptors over the context's own planes (level-0 based ones follow the input: set_level0)
+    for (int l = 1; l < p.levels; ++l) {
+        Level &L = ctx->lv[l];
+        if (int r = encode_plane_map(ctx, &L.map_fast, L.pyr, L.w, L.h, L.pitch, L.frame_stride, p.max_frames, 80, 70)) return r;
+        if (l + 1 < p.levels && ctx->lv[l + 1].fast_resize)
+            if (int r = encode_plane_map(ctx, &ctx->lv[l + 1].map_src, L.pyr, L.w, L.h, L.pitch, L.frame_stride, p.max_frames,
+                                         ctx->lv[l + 1].tma_src_w, ctx->lv[l + 1].tma_src_h)) return r;
     }
     if (distribute_smem_bytes(nc_max) > 200 * 1024)
         return fail(ctx, SG_ERR_INVALID, "max_keypoints %d needs a quadtree node table larger than shared memory", p.max_keypoints);
@@ -140,9 +159,15 @@ static int build_context(sg_ctx *ctx) {
 }
 
 static int set_level0(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t stride, int n_frames) {
+    const bool changed = ctx->level0 != d_imgs || ctx->level0_pitch != pitch || ctx->level0_stride != stride
+                         || ctx->level0_frames < n_frames;
     ctx->level0 = d_imgs; ctx->level0_pitch = pitch; ctx->level0_stride = stride;
     ctx->frames_ready = n_frames;
     ctx->detected = false;
+    if (changed) {
+        ctx->level0_frames = n_frames;
+        return encode_level0_maps(ctx);
+    }
     return SG_OK;
 }
 
@@ -309,7 +334,7 @@ int sg_pyramid_update(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t fram
 int sg_pyramid_update_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t frame_stride, int n_frames) {
     cudaSetDevice(ctx->device);
     if (int r = check_device_images(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
-    set_level0(ctx, d_imgs, pitch, frame_stride, n_frames);
+    if (int r = set_level0(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
     return launch_pyramid(ctx, n_frames);
 }
 
@@ -435,7 +460,7 @@ int sg_extract(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_strid
 int sg_extract_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t frame_stride, int n_frames) {
     cudaSetDevice(ctx->device);
     if (int r = check_device_images(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
-    set_level0(ctx, d_imgs, pitch, frame_stride, n_frames);
+    if (int r = set_level0(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
     ctx->have_tracks = false;
     return extract_launches(ctx, n_frames);
 }

@@ -1,5 +1,6 @@
 // Internal context of libslamgpu.so (not part of the ABI; see include/slamgpu.h).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -33,6 +34,11 @@ struct Level {
     ResizeTap *ytab = nullptr;      // [h]
     bool area2x = false;            // cv::resize switches to INTER_AREA for an exact 2x decimation
     bool fast_resize = false;       // adjacent taps at most 2 source pixels apart: the IDP.2A kernel applies
+    int tma_src_w = 0, tma_src_h = 0;    // TMA box of the source tile of the fast resize kernel
+    // TMA descriptors (3-D: x, y, frame).  map_src: box over the level BELOW (source of this level's
+    // resize; for level 0: box over level 0 itself for the blur-only kernel).  map_fast: 80x70 box over
+    // this level for the FAST cells.  Maps over level 0 are re-encoded when the input pointer changes.
+    CUtensorMap map_src{}, map_fast{};
     int src_tile_w = 0, src_tile_h = 0;  // smem extent of the source tile of the resize kernel
     // detection geometry
     int area_w = 0, area_h = 0;     // working area (image minus 19-px border)
@@ -101,6 +107,7 @@ struct sg_ctx {
     int level0_pitch = 0;
     size_t level0_stride = 0;
     int frames_ready = 0;              // frames in the current pyramid
+    int level0_frames = 0;             // frames the level-0 TMA descriptors cover
     bool detected = false;
 
     // detection scratch
@@ -177,6 +184,10 @@ int launch_pyramid(sg_ctx *ctx, int n_frames);
 int launch_detect(sg_ctx *ctx, int n_frames);
 int launch_describe(sg_ctx *ctx, int n_frames);
 int grow(sg_ctx *ctx, void **ptr, size_t *cap, size_t need, size_t elem);
+// TMA descriptor of an 8-bit plane stack {w, h, frames} with a fixed box (tma.cpp).
+int encode_plane_map(sg_ctx *ctx, CUtensorMap *out, const uint8_t *base, int w, int h, int pitch, size_t frame_stride,
+                     int frames, int box_w, int box_h);
+int encode_level0_maps(sg_ctx *ctx);
 // Record stage event i on the context's stream when profiling is on.
 inline void mark(sg_ctx *ctx, int i, bool first = false) {
     if (!ctx->profiling) return;

@@ -24,6 +24,7 @@
 //     positions come from block-wide scans, so the final node list (and therefore the output
 //     order of the keypoints) is identical to the sequential one.
 #include "ctx.h"
+#include "tma.cuh"
 
 namespace sg {
 
@@ -80,11 +81,13 @@ __device__ __forceinline__ unsigned fast_score_2px(const uint8_t *ca, const uint
     return __vmaxu2(lo, 0x02000200u - hi) - 0x00010001u;
 }
 
+struct FastMaps { CUtensorMap m[SG_MAX_LEVELS]; };   // 80 x 70 box over every pyramid level
+
 __global__ void __launch_bounds__(FAST_THREADS)
-fast_cells_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int level0_pitch,
-                  unsigned long long level0_stride, int total_cells, unsigned long long *cand,
-                  int *cand_count, int *err) {
-    __shared__ __align__(16) uint8_t tile[TILE_ROWS * TP];
+fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ FastMaps maps, int total_cells,
+                  unsigned long long *cand, int *cand_count, int *err) {
+    __shared__ __align__(128) uint8_t tile[TILE_ROWS * TP];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(16) uint8_t resp[(CELL + 2) * RPW];
     __shared__ unsigned short surv[MAX_SURVIVORS];        // y << 6 | x of the pixels passing the filter
     __shared__ unsigned short keep[(CELL / 2) * (CELL / 2)];   // NMS winners (at most one per 2x2 block)
@@ -102,22 +105,18 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int 
     if (l >= g.levels) return;
     const LevelDev &L = g.lv[l];
     const int ci = cell / L.cells_x, cj = cell - ci * L.cells_x;
-    const uint8_t *img = l == 0 ? level0 + (size_t)f * level0_stride : L.pyr + (size_t)f * L.frame_stride;
-    const int pitch = l == 0 ? level0_pitch : L.pitch;
     const int ex0 = EVAL_ORIGIN + CELL * cj, ey0 = EVAL_ORIGIN + CELL * ci;   // first evaluated pixel
     const int cw = min(CELL, L.w - EVAL_ORIGIN - ex0), ch = min(CELL, L.h - EVAL_ORIGIN - ey0);
     const int ax0 = ex0 - 3 - TILE_SHIFT, wy0 = ey0 - 3;   // word-aligned window origin
 
-    // ---- stage the (cw+6) x (ch+6) window: 20 words per row (zero where the cell is narrower) ----------
-    {
-        const int nwords = (TILE_SHIFT + cw + 6 + 3) >> 2;
-        for (int i = tid; i < (TP / 4) * (ch + 6); i += FAST_THREADS) {
-            const int r = i / (TP / 4), wd = i - r * (TP / 4);
-            uint32_t v = 0;
-            if (wd < nwords) v = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)(wy0 + r) * pitch + ax0 + 4 * wd));
-            *reinterpret_cast<uint32_t *>(tile + r * TP + 4 * wd) = v;
-        }
+    // ---- stage the 80 x 70 window with one TMA box load (zero outside the plane) -------------------------
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_expect_tx(&s_bar, TILE_ROWS * TP);
+        tma_load_3d(tile, &maps.m[l], ax0, wy0, f, &s_bar);
     }
+    __syncthreads();
+    mbar_wait(&s_bar, 0);
 
     // Two passes at most: threshold ini first; only a cell that yields nothing is redone at min.
     // A pixel with score >= t is kept by NMS iff it beats its 8 neighbours' scores; neighbours below
@@ -531,8 +530,10 @@ int launch_detect(sg_ctx *ctx, int n_frames) {
         nc_max = std::max(nc_max, g.lv[l].node_cap);
     }
     if (total_cells > 0) {
+        FastMaps maps;
+        for (int l = 0; l < g.levels; ++l) maps.m[l] = ctx->lv[l].map_fast;
         fast_cells_kernel<<<dim3(total_cells, n_frames), FAST_THREADS, 0, ctx->stream>>>(
-            g, ctx->level0, ctx->level0_pitch, ctx->level0_stride, total_cells, ctx->d_cand, ctx->d_cand_count, ctx->d_err);
+            g, maps, total_cells, ctx->d_cand, ctx->d_cand_count, ctx->d_err);
         SG_LAUNCH_CHECK(ctx);
     }
     mark(ctx, EV_FAST1);

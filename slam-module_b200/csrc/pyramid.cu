@@ -14,6 +14,7 @@
 // separable blur runs from shared memory and the blurred tile is written with 32-bit stores.
 // Level L-1 is read once from HBM/L2 and both planes of level L are written once.
 #include "ctx.h"
+#include "tma.cuh"
 
 namespace sg {
 
@@ -204,44 +205,53 @@ __global__ void __launch_bounds__(PYR_THREADS) pyr_level_kernel(const PyrArgs a)
 //   blur V    : IDP.2A on the vertical pairs (3 per output + one scalar tap), 4 columns x 2 rows per
 //               thread, 32-bit stores
 // -------------------------------------------------------------------------------------------------
-constexpr int FW = 80;               // R pitch of the fast kernel (20 words)
+// R geometry of the fast kernel.  RESIZE: R is computed, pitch 80, column 4 <-> x0.  Blur only: R is the
+// TMA box itself; TMA needs the innermost start coordinate to be a multiple of 16 BYTES (anything else
+// raises "illegal instruction" on sm_100a -- measured), so the box starts at x0 - 16: pitch 96, column 16 <-> x0.
+template <bool RESIZE> struct RGeom { static constexpr int FW = RESIZE ? 80 : 96, X0 = RESIZE ? 4 : 16; };
 struct XTap { uint32_t coef; int32_t s0; };          // a0 | a1 << 16, source column relative to the tile
 struct YTap { int16_t s0, s1, b0, b1; };
 
 template <bool RESIZE>
-__global__ void __launch_bounds__(PYR_THREADS) pyr_fast_kernel(const PyrArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t *R = smem;                                                   // [RH][FW]
-    uint32_t *Hp = reinterpret_cast<uint32_t *>(smem + RH * FW);         // [RH/2][TW]
-    XTap *xt = reinterpret_cast<XTap *>(smem + RH * FW + (RH / 2) * TW * 4);   // [72]
-    YTap *yt = reinterpret_cast<YTap *>(xt + 72);                        // [RH]
-    uint8_t *S = reinterpret_cast<uint8_t *>(yt + RH + 2);               // [src_tile_h][src_tile_w] (16-B aligned)
+__global__ void __launch_bounds__(PYR_THREADS)
+pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
+    // [TMA destination: source tile S (RESIZE) or R itself] [R] [Hp] [xt] [yt] [mbarrier]
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int s_bytes = RESIZE ? (((a.src_tile_h + 1) * a.src_tile_w + 127) & ~127) : 0;
+    uint8_t *S = smem;                                                   // [src_tile_h][src_tile_w] (RESIZE)
+    uint8_t *R = smem + s_bytes;                                         // [RH][FW]
+    uint32_t *Hp = reinterpret_cast<uint32_t *>(R + 3712);               // [RH/2][TW]
+    XTap *xt = reinterpret_cast<XTap *>(R + 3712 + (RH / 2) * TW * 4);   // [72]
+    YTap *yt = reinterpret_cast<YTap *>(xt + 72);                        // [RH + 2]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(yt + RH + 2);
 
+    constexpr int FW = RGeom<RESIZE>::FW, X0 = RGeom<RESIZE>::X0;   // R pitch; R column of x0
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, f = blockIdx.z;
     const int tw = min(TW, a.w - x0), th = min(TH, a.h - y0);
     const int xlo = max(x0 - 3, 0), xhi = min(x0 + tw + 3, a.w);
     const int ylo = max(y0 - 3, 0), yhi = min(y0 + th + 3, a.h);
-    const uint8_t *src = a.src + (size_t)f * a.sstride;
 
     if (RESIZE) {
-        const int sx_lo = a.xtab[xlo].s0 & ~3, sx_hi = a.xtab[xhi - 1].s1;
-        const int sy_lo = a.ytab[ylo].s0, sy_hi = a.ytab[yhi - 1].s1;
-        const int nwords = ((sx_hi - sx_lo) >> 2) + 1, nrows = sy_hi - sy_lo + 1;
+        // one thread pulls the source tile with TMA while the others stage the taps
+        const int sx_lo = a.xtab[xlo].s0 & ~15, sy_lo = a.ytab[ylo].s0;   // 16-byte aligned box origin
         const int sp = a.src_tile_w;
-        for (int r = tid / 32; r < nrows; r += PYR_THREADS / 32)       // one warp per source row
-            for (int wd = tid & 31; wd < nwords; wd += 32)
-                *reinterpret_cast<uint32_t *>(S + r * sp + 4 * wd) =
-                    __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)(sy_lo + r) * a.spitch + sx_lo + 4 * wd));
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, (uint32_t)(sp * a.src_tile_h));
+            tma_load_3d(S, &tmap, sx_lo, sy_lo, f, bar);
+        }
         // taps of every window column / row; outside the image the nearest valid tap (value unused)
-        if (tid < 72) {
-            const ResizeTap t = a.xtab[min(max(x0 - 4 + tid, xlo), xhi - 1)];
-            xt[tid] = XTap{(uint32_t)(uint16_t)t.a0 | ((uint32_t)(uint16_t)t.a1 << 16), t.s0 - sx_lo};
+        if (tid >= 32 && tid < 32 + 72) {
+            const int c = tid - 32;
+            const ResizeTap t = a.xtab[min(max(x0 - 4 + c, xlo), xhi - 1)];
+            xt[c] = XTap{(uint32_t)(uint16_t)t.a0 | ((uint32_t)(uint16_t)t.a1 << 16), t.s0 - sx_lo};
         } else if (tid >= 128 && tid < 128 + RH) {
             const ResizeTap t = a.ytab[min(max(y0 - 3 + tid - 128, ylo), yhi - 1)];
             yt[tid - 128] = YTap{(int16_t)(t.s0 - sy_lo), (int16_t)(t.s1 - sy_lo), t.a0, t.a1};
         }
-        __syncthreads();
+        __syncthreads();          // taps staged, barrier initialised
+        mbar_wait(bar, 0);        // source tile landed
         for (int i = tid; i < RH * 36; i += PYR_THREADS) {
             const int ry = i / 36, cp = i - ry * 36;
             const uint4 tx = *reinterpret_cast<const uint4 *>(xt + 2 * cp);   // {coef_a, s0_a, coef_b, s0_b}
@@ -262,13 +272,14 @@ __global__ void __launch_bounds__(PYR_THREADS) pyr_fast_kernel(const PyrArgs a) 
             *reinterpret_cast<uint16_t *>(R + ry * FW + 2 * cp) = (uint16_t)(va | (vb << 8));
         }
     } else {
-        for (int i = tid; i < (yhi - ylo) * (FW / 4); i += PYR_THREADS) {
-            const int ry = i / (FW / 4), wd = i - ry * (FW / 4);
-            const int x = x0 - 4 + 4 * wd;
-            if (x >= 0 && x < a.spitch)
-                *reinterpret_cast<uint32_t *>(R + (ylo + ry - (y0 - 3)) * FW + 4 * wd) =
-                    __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)(ylo + ry) * a.spitch + x));
+        // blur only: the 96 x 38 window of the plane goes straight into R (zero outside the image)
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, (uint32_t)(RH * FW));
+            tma_load_3d(R, &tmap, x0 - X0, y0 - 3, f, bar);
         }
+        __syncthreads();
+        mbar_wait(bar, 0);
     }
     __syncthreads();
 
@@ -279,20 +290,34 @@ __global__ void __launch_bounds__(PYR_THREADS) pyr_fast_kernel(const PyrArgs a) 
             const int r = i >> 4, wd = i & 15;
             if (r < th && 4 * wd < tw)
                 *reinterpret_cast<uint32_t *>(dst + (size_t)(y0 + r) * a.pitch + x0 + 4 * wd) =
-                    *reinterpret_cast<const uint32_t *>(R + (r + 3) * FW + 4 + 4 * wd);
+                    *reinterpret_cast<const uint32_t *>(R + (r + 3) * FW + X0 + 4 * wd);
         }
     }
     // ---- reflect-101: halo entries outside the image mirror resized pixels inside it ------------
-    if (x0 == 0 || y0 == 0 || x0 + tw + 3 > a.w || y0 + th + 3 > a.h) {
-        for (int i = tid; i < RH * 72; i += PYR_THREADS) {
-            const int ry = i / 72, rx = i - ry * 72;
-            const int x = x0 - 4 + rx, y = y0 - 3 + ry;
-            if ((x < 0 || x >= a.w || y < 0 || y >= a.h) && rx >= 1 && x < a.w + 3 && y < a.h + 3) {
-                const int mx = reflect101(x, a.w), my = reflect101(y, a.h);
-                R[ry * FW + rx] = R[(my - (y0 - 3)) * FW + (mx - (x0 - 4))];
-            }
+    // only the (up to) four 3-wide strips outside the image are visited; sources are always inside
+    {
+        const bool left = x0 == 0, right = x0 + tw + 3 > a.w, top = y0 == 0, bottom = y0 + th + 3 > a.h;
+        if (left || right || top || bottom) {
+            if (left || right)
+                for (int i = tid; i < RH * 6; i += PYR_THREADS) {
+                    const int ry = i / 6, k = i - ry * 6;
+                    const int x = k < 3 ? k - 3 : a.w + k - 3, y = y0 - 3 + ry;
+                    if ((k < 3 ? left : right) && y < a.h + 3 && x - x0 < TW + 4) {
+                        const int mx = reflect101(x, a.w), my = reflect101(y, a.h);
+                        R[ry * FW + (x - x0 + X0)] = R[(my - (y0 - 3)) * FW + (mx - x0 + X0)];
+                    }
+                }
+            if (top || bottom)
+                for (int i = tid; i < 6 * 72; i += PYR_THREADS) {
+                    const int k = i / 72, rx = i - k * 72;
+                    const int y = k < 3 ? k - 3 : a.h + k - 3, x = x0 - 4 + rx;
+                    if ((k < 3 ? top : bottom) && x >= 0 && x < a.w && y - (y0 - 3) < RH) {
+                        const int my = reflect101(y, a.h);
+                        R[(y - (y0 - 3)) * FW + rx + X0 - 4] = R[(my - (y0 - 3)) * FW + rx + X0 - 4];
+                    }
+                }
+            __syncthreads();
         }
-        __syncthreads();
     }
 
     // ---- horizontal pass: 4 columns x 2 rows per item, stored as vertical u16 pairs ---------------
@@ -304,8 +329,8 @@ __global__ void __launch_bounds__(PYR_THREADS) pyr_fast_kernel(const PyrArgs a) 
             uint32_t o[2][4];
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
-                const uint32_t *row = reinterpret_cast<const uint32_t *>(R + (2 * rp + rr) * FW) + g;
-                const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];   // columns 4g .. 4g+11 of R
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(R + (2 * rp + rr) * FW + X0 - 4) + g;
+                const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];   // window columns 4g .. 4g+11 (x0-4+4g ..)
                 // output c = 4g + j uses R columns c+1 .. c+7
                 o[rr][0] = __dp4a(__byte_perm(w0, w1, 0x4321), k0, __dp4a(__byte_perm(w1, w2, 0x4321), k1, 0u));
                 o[rr][1] = __dp4a(__byte_perm(w0, w1, 0x5432), k0, __dp4a(__byte_perm(w1, w2, 0x5432), k1, 0u));
@@ -355,8 +380,8 @@ __global__ void __launch_bounds__(PYR_THREADS) pyr_fast_kernel(const PyrArgs a) 
 }
 
 static size_t pyr_fast_smem_bytes(const PyrArgs &a, bool resize) {
-    size_t b = RH * FW + (RH / 2) * TW * 4 + 72 * sizeof(XTap) + (RH + 2) * sizeof(YTap);
-    if (resize) b += (size_t)(a.src_tile_h + 1) * a.src_tile_w + 16;
+    size_t b = 3712 + (RH / 2) * TW * 4 + 72 * sizeof(XTap) + (RH + 2) * sizeof(YTap) + 16;
+    if (resize) b += (((size_t)(a.src_tile_h + 1) * a.src_tile_w + 127) & ~(size_t)127);
     return b;
 }
 
@@ -397,7 +422,7 @@ int launch_pyramid(sg_ctx *ctx, int n_frames) {
         dim3 grid((L.w + TW - 1) / TW, (L.h + TH - 1) / TH, n_frames);
         if (l == 0) {
             a.src = ctx->level0; a.sw = L.w; a.sh = L.h; a.spitch = ctx->level0_pitch; a.sstride = ctx->level0_stride;
-            pyr_fast_kernel<false><<<grid, PYR_THREADS, pyr_fast_smem_bytes(a, false), ctx->stream>>>(a);
+            pyr_fast_kernel<false><<<grid, PYR_THREADS, pyr_fast_smem_bytes(a, false), ctx->stream>>>(a, L.map_src);
         } else {
             const Level &P = ctx->lv[l - 1];
             a.src = l == 1 ? ctx->level0 : P.pyr;
@@ -408,9 +433,11 @@ int launch_pyramid(sg_ctx *ctx, int n_frames) {
             a.xtab = L.xtab; a.ytab = L.ytab;
             a.src_tile_w = L.src_tile_w; a.src_tile_h = L.src_tile_h;
             a.area2x = L.area2x ? 1 : 0;
-            const size_t fsmem = pyr_fast_smem_bytes(a, true);
+            PyrArgs fa = a;
+            fa.src_tile_w = L.tma_src_w; fa.src_tile_h = L.tma_src_h;
+            const size_t fsmem = pyr_fast_smem_bytes(fa, true);
             if (L.fast_resize && fsmem <= 48 * 1024) {
-                pyr_fast_kernel<true><<<grid, PYR_THREADS, fsmem, ctx->stream>>>(a);
+                pyr_fast_kernel<true><<<grid, PYR_THREADS, fsmem, ctx->stream>>>(fa, L.map_src);
             } else {   // INTER_AREA switch (exact 2x) or a scale factor above 2: generic kernel
                 const size_t smem = pyr_smem_bytes(a, true);
                 if (smem > 48 * 1024)
