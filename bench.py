@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--pipe-chunk", type=int, default=0, help="frames per pipeline chunk of sg_extract (0: library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -236,7 +237,9 @@ def main():
     value = world * FRAMES * args.steps / (ms * 1e-3)
 
     # ---- end to end through the host-buffer entry point (H2D + kernels + D2H) -----------------------------
-    out_arrs, out_struct = ctx._alloc_out(FRAMES)
+    out_arrs, out_struct = ctx._alloc_out(FRAMES, pinned=True)   # pinned: the D2H copies overlap the kernels
+    if args.pipe_chunk:
+        ctx.set_pipeline_chunk(args.pipe_chunk)
     lib = slamgpu.lib()
     import ctypes as C
 
@@ -339,7 +342,8 @@ def main():
                        "keypoints_per_frame": kp_per_frame, "sharding": "frames by rank, no collective",
                        "l2": "inputs larger than L2: %d rotating batches x %.1f MB" % (N_BATCHES, FRAMES * frame_bytes / 1e6)},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": FRAMES * frame_bytes,
-                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "api": "sg_extract (host buffers)"},
+                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                    "api": "sg_extract (pinned host buffers; H2D / kernels / D2H pipelined over chunks of the batch)"},
             "gpu_launches": int(launches),
             "stages": stages,
             "roofline": roofline,

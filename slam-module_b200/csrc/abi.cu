@@ -274,6 +274,15 @@ int sg_create(int device, const sg_params *params, sg_ctx **out) {
         ctx->err = "stream / event creation failed";
         return bail(SG_ERR_CUDA);
     }
+    ctx->main_stream = ctx->stream;
+    if (cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) != cudaSuccess
+        || cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) != cudaSuccess
+        || cudaStreamCreateWithFlags(&ctx->s_cmp[0], cudaStreamNonBlocking) != cudaSuccess
+        || cudaStreamCreateWithFlags(&ctx->s_cmp[1], cudaStreamNonBlocking) != cudaSuccess
+        || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
+        ctx->err = "stream / event creation failed";
+        return bail(SG_ERR_CUDA);
+    }
     for (auto &slot : ctx->ev_stage)
         for (auto &e : slot)
             if (cudaEventCreate(&e) != cudaSuccess) { ctx->err = "event creation failed"; return bail(SG_ERR_CUDA); }
@@ -298,6 +307,9 @@ void sg_destroy(sg_ctx *ctx) {
         for (auto &e : slot) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (auto &e : ctx->pipe_ev) cudaEventDestroy(e);
+    for (cudaStream_t q : {ctx->s_in, ctx->s_out, ctx->s_cmp[0], ctx->s_cmp[1]}) if (q) cudaStreamDestroy(q);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -448,13 +460,81 @@ int sg_extract_download(sg_ctx *ctx, int n_frames, sg_keypoints *o) {
     return check_device_error(ctx);
 }
 
+// Host-buffer extraction as a three-stage pipeline over chunks of the batch: H2D of chunk c+1 (copy engine,
+// stream s_in) runs under the kernels of chunk c (alternating compute streams, so the tail of one chunk's
+// small-level kernels overlaps the head of the next) and the D2H of chunk c-1 (second copy engine, s_out).
+// Frames are independent, every per-frame buffer is indexed by the absolute frame number, so the chunks
+// never touch the same memory.
+static int extract_pipelined(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames,
+                             sg_keypoints *o) {
+    const Level &L0 = ctx->lv[0];
+    if (!h_imgs || pitch < L0.w) return fail(ctx, SG_ERR_INVALID, "bad image pointer / pitch");
+    if (n_frames < 1 || n_frames > ctx->p.max_frames) return fail(ctx, SG_ERR_INVALID, "n_frames %d outside [1, %d]", n_frames, ctx->p.max_frames);
+    if (!o) return fail(ctx, SG_ERR_INVALID, "null output");
+    const int C = std::max(1, ctx->pipe_chunk), chunks = (n_frames + C - 1) / C;
+    while ((int)ctx->pipe_ev.size() < 2 * chunks) {
+        cudaEvent_t e;
+        SG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pipe_ev.push_back(e);
+    }
+    if (int r = set_level0(ctx, L0.pyr, L0.pitch, L0.frame_stride, n_frames)) return r;
+    // work queued earlier on the main stream (an un-synchronised sg_extract_device, ...) comes first
+    SG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->main_stream));
+    for (cudaStream_t q : {ctx->s_in, ctx->s_out, ctx->s_cmp[0], ctx->s_cmp[1]}) SG_CUDA(ctx, cudaStreamWaitEvent(q, ctx->ev_fork, 0));
+    const size_t cap = ctx->geom.out_cap;
+    const int levels = ctx->p.levels;
+    int rc = SG_OK;
+    for (int c = 0; c < chunks && rc == SG_OK; ++c) {
+        const int f0 = c * C, n = std::min(C, n_frames - f0);
+        if (pitch == L0.pitch && (n == 1 || frame_stride == L0.frame_stride)) {
+            SG_CUDA(ctx, cudaMemcpyAsync(L0.pyr + (size_t)f0 * L0.frame_stride, h_imgs + (size_t)f0 * frame_stride,
+                                         (size_t)n * L0.frame_stride, cudaMemcpyHostToDevice, ctx->s_in));
+        } else {
+            for (int f = f0; f < f0 + n; ++f)
+                SG_CUDA(ctx, cudaMemcpy2DAsync(L0.pyr + (size_t)f * L0.frame_stride, L0.pitch, h_imgs + (size_t)f * frame_stride,
+                                               pitch, L0.w, L0.h, cudaMemcpyHostToDevice, ctx->s_in));
+        }
+        SG_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_in));
+        cudaStream_t cmp = ctx->s_cmp[c & 1];
+        SG_CUDA(ctx, cudaStreamWaitEvent(cmp, ctx->pipe_ev[2 * c], 0));
+        ctx->stream = cmp; ctx->frame0 = f0; ctx->in_pipeline = true;
+        rc = extract_launches(ctx, n);
+        ctx->stream = ctx->main_stream; ctx->frame0 = 0; ctx->in_pipeline = false;
+        if (rc) break;
+        SG_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[2 * c + 1], cmp));
+        SG_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[2 * c + 1], 0));
+        auto out = [&](auto *h, const auto *d, size_t per_frame) -> int {
+            if (!h) return SG_OK;
+            SG_CUDA(ctx, cudaMemcpyAsync(h + (size_t)f0 * per_frame, d + (size_t)f0 * per_frame,
+                                         (size_t)n * per_frame * sizeof(*h), cudaMemcpyDeviceToHost, ctx->s_out));
+            return SG_OK;
+        };
+        if ((rc = out(o->x, ctx->d_x, cap)) || (rc = out(o->y, ctx->d_y, cap)) || (rc = out(o->angle, ctx->d_angle, cap))
+            || (rc = out(o->octave, ctx->d_octave, cap)) || (rc = out(o->desc, ctx->d_desc, 8 * cap))
+            || (rc = out(o->track_id, ctx->d_track_id, cap)) || (rc = out(o->lvl_x, ctx->d_lvl_x, cap))
+            || (rc = out(o->lvl_y, ctx->d_lvl_y, cap)) || (rc = out(o->count, ctx->d_count, 1))
+            || (rc = out(o->level_count, ctx->d_kp_count, (size_t)levels)))
+            break;
+    }
+    for (cudaStream_t q : {ctx->s_cmp[0], ctx->s_cmp[1], ctx->s_out}) {
+        const cudaError_t e = cudaStreamSynchronize(q);
+        if (e != cudaSuccess && rc == SG_OK) rc = fail(ctx, SG_ERR_CUDA, "pipeline synchronise failed: %s", cudaGetErrorString(e));
+    }
+    if (rc) return rc;
+    return check_device_error(ctx);
+}
+
 int sg_extract(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames,
                const float *h_track_xy, const int32_t *h_track_ids, const int32_t *n_tracks, sg_keypoints *h_out) {
     cudaSetDevice(ctx->device);
-    if (int r = upload_frames(ctx, h_imgs, pitch, frame_stride, n_frames)) return r;
     if (int r = upload_tracks(ctx, h_track_xy, h_track_ids, n_tracks, n_frames)) return r;
-    if (int r = extract_launches(ctx, n_frames)) return r;
-    return sg_extract_download(ctx, n_frames, h_out);
+    return extract_pipelined(ctx, h_imgs, pitch, frame_stride, n_frames, h_out);
+}
+
+int sg_set_pipeline_chunk(sg_ctx *ctx, int frames) {
+    if (frames < 1) return fail(ctx, SG_ERR_INVALID, "chunk must be >= 1 frame");
+    ctx->pipe_chunk = frames;
+    return SG_OK;
 }
 
 int sg_extract_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t frame_stride, int n_frames) {

@@ -70,6 +70,7 @@ struct GeomDev {
     int max_tracks;
     unsigned long long cand_per_frame;
     int ini_thr, min_thr;
+    int frame0;           // first frame of this launch (pipelined sg_extract works on slices of the batch)
     LevelDev lv[SG_MAX_LEVELS];
 };
 
@@ -88,8 +89,13 @@ struct sg_db {
 struct sg_ctx {
     int device = 0;
     sg_params p{};
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr;      // stream the stage launchers use (swapped per chunk by the pipelined sg_extract)
+    cudaStream_t main_stream = nullptr, s_in = nullptr, s_out = nullptr, s_cmp[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> pipe_ev;   // [2 * chunks]: H2D done, compute done
+    int pipe_chunk = 64;                // frames per pipeline chunk of sg_extract
+    int frame0 = 0;                     // first frame the stage launchers work on
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr;
+    bool in_pipeline = false;           // stage events are not recorded inside the pipelined sg_extract
     std::string err;
     unsigned long long launches = 0;
     // optional per-stage CUDA-event timing (sg_set_profiling): pyramid, fast, distribute, describe,
@@ -190,7 +196,7 @@ int encode_plane_map(sg_ctx *ctx, CUtensorMap *out, const uint8_t *base, int w, 
 int encode_level0_maps(sg_ctx *ctx);
 // Record stage event i on the context's stream when profiling is on.
 inline void mark(sg_ctx *ctx, int i, bool first = false) {
-    if (!ctx->profiling) return;
+    if (!ctx->profiling || ctx->in_pipeline) return;
     if (first) {   // a new call: take the next ring slot
         ++ctx->prof_call;
         for (auto &m : ctx->stage_mark[ctx->prof_call % sg_ctx::PROF_SLOTS]) m = 0;

@@ -82,7 +82,7 @@ describe_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int le
                 const int *trk_xy, const float *trk_pt, const int *trk_id, const int *trk_count,
                 int track_level, DescOut o) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int f = blockIdx.y;
+    const int f = blockIdx.y + g.frame0;
     const int slot = blockIdx.x * DESC_WARPS + warp;
     const int n_trk = trk_count ? trk_count[f] : 0;
 
@@ -173,7 +173,8 @@ describe_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int le
 }
 
 int launch_describe(sg_ctx *ctx, int n_frames) {
-    const GeomDev &g = ctx->geom;
+    GeomDev g = ctx->geom;
+    g.frame0 = ctx->frame0;
     DescOut o{ctx->d_x, ctx->d_y, ctx->d_angle, ctx->d_octave, ctx->d_track_id, ctx->d_lvl_x, ctx->d_lvl_y,
               ctx->d_desc, ctx->d_count};
     const bool trk = ctx->have_tracks;

@@ -94,7 +94,7 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
     __shared__ unsigned short quads[(CELL / 4) * CELL];       // y << 4 | q of the quads passing the compass test
     __shared__ int s_nsurv, s_nkeep, s_nquad, s_base;
 
-    const int tid = threadIdx.x, f = blockIdx.y;
+    const int tid = threadIdx.x, f = blockIdx.y + g.frame0;
     // which level / cell
     int cell = blockIdx.x, l = 0;
     for (; l < g.levels; ++l) {
@@ -328,7 +328,7 @@ distribute_kernel(const __grid_constant__ GeomDev g, int node_cap_max, const uns
     __shared__ int tmp[33];
     __shared__ int s_m;
 
-    const int tid = threadIdx.x, l = blockIdx.x, f = blockIdx.y;
+    const int tid = threadIdx.x, l = blockIdx.x, f = blockIdx.y + g.frame0;
     const LevelDev &L = g.lv[l];
     const int N = L.budget;
     int ncand = cand_count[f * g.levels + l];
@@ -522,8 +522,9 @@ size_t distribute_smem_bytes(int node_cap_max) {
 }
 
 int launch_detect(sg_ctx *ctx, int n_frames) {
-    const GeomDev &g = ctx->geom;
-    SG_CUDA(ctx, cudaMemsetAsync(ctx->d_cand_count, 0, sizeof(int) * (size_t)n_frames * g.levels, ctx->stream));
+    GeomDev g = ctx->geom;
+    g.frame0 = ctx->frame0;
+    SG_CUDA(ctx, cudaMemsetAsync(ctx->d_cand_count + (size_t)g.frame0 * g.levels, 0, sizeof(int) * (size_t)n_frames * g.levels, ctx->stream));
     int total_cells = 0, nc_max = 1;
     for (int l = 0; l < g.levels; ++l) {
         total_cells += g.lv[l].cells_x * g.lv[l].cells_y;

@@ -33,6 +33,7 @@ struct PyrArgs {
     const ResizeTap *xtab, *ytab;
     int src_tile_w, src_tile_h;  // smem extent of the source tile (bytes per row multiple of 4)
     int area2x;
+    int f0;               // first frame of the launch
 };
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(PYR_THREADS) pyr_level_kernel(const PyrArgs a)
     ResizeTap *yt = xt + (TW + 6);                                                  // [TH+6]
 
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, f = blockIdx.z;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, f = blockIdx.z + a.f0;
     const int tw = min(TW, a.w - x0), th = min(TH, a.h - y0);
     // in-image part of the halo window, [xlo, xhi) x [ylo, yhi)
     const int xlo = max(x0 - 3, 0), xhi = min(x0 + tw + 3, a.w);
@@ -227,7 +228,7 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
 
     constexpr int FW = RGeom<RESIZE>::FW, X0 = RGeom<RESIZE>::X0;   // R pitch; R column of x0
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, f = blockIdx.z;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, f = blockIdx.z + a.f0;
     const int tw = min(TW, a.w - x0), th = min(TH, a.h - y0);
     const int xlo = max(x0 - 3, 0), xhi = min(x0 + tw + 3, a.w);
     const int ylo = max(y0 - 3, 0), yhi = min(y0 + th + 3, a.h);
@@ -417,6 +418,7 @@ int launch_pyramid(sg_ctx *ctx, int n_frames) {
     for (int l = 0; l < levels; ++l) {
         const Level &L = ctx->lv[l];
         PyrArgs a{};
+        a.f0 = ctx->frame0;
         a.w = L.w; a.h = L.h; a.pitch = L.pitch; a.dstride = L.frame_stride;
         a.blur = L.blur;
         dim3 grid((L.w + TW - 1) / TW, (L.h + TH - 1) / TH, n_frames);

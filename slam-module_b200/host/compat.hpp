@@ -1,0 +1,81 @@
+// Minimal stand-ins for the parent-project types the reference's hot-path interfaces mention but
+// that are NOT part of the reference tree (../tracker/*.hpp, ../odometry/parameters.hpp,
+// accelerated-arrays).  Only the members the hot path reads are present, with the reference's names, so the
+// adapters in slam_frontend.hpp keep the reference's signatures.  A maintainer integrating libslamgpu into
+// the real tree deletes this header and includes the real ones.
+#pragma once
+#include <array>
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace accelerated {
+// accelerated::Image as the hot path uses it: width / height / storageType (image_pyramid.cpp:211,
+// feature_detector.cpp:79) plus, for CPU images, what accelerated::opencv::ref() would expose.
+struct Image {
+    enum class StorageType { CPU, GPU };
+    int width = 0, height = 0;
+    StorageType storageType = StorageType::CPU;
+    // CPU: host pointer; GPU: device pointer of the context's GPU
+    const std::uint8_t *data = nullptr;
+    int stride = 0;   // bytes between rows
+};
+}  // namespace accelerated
+
+namespace tracker {
+// tracker::Feature: id, points[0] (orb_extractor.cpp:90,123), Point{x, y} (key_point.hpp:14)
+struct Feature {
+    struct Point { float x, y; };
+    int id = -1;
+    std::array<Point, 2> points{};
+    float depth = -1;
+};
+
+// tracker::Image: an 8-bit gray frame (orb_extractor.cpp:74, image_pyramid.cpp:69-73)
+struct Image {
+    int width = 0, height = 0;
+    const std::uint8_t *gray = nullptr;   // row-major
+    int stride = 0;
+    accelerated::Image acc;
+    Image() = default;
+    Image(const std::uint8_t *data, int w, int h, int rowStride) : width(w), height(h), gray(data), stride(rowStride) {
+        acc.width = w; acc.height = h; acc.data = data; acc.stride = rowStride;
+    }
+    accelerated::Image &getAccImage() { return acc; }
+};
+
+// tracker::Camera: only isValidPixel is used on the path (orb_extractor.cpp:101,231)
+class Camera {
+public:
+    virtual ~Camera() = default;
+    virtual bool isValidPixel(double x, double y) const { (void)x; (void)y; return true; }
+};
+}  // namespace tracker
+
+namespace odometry {
+// The fields of odometry::ParametersSlam the path reads.
+struct ParametersSlam {
+    unsigned orbScaleLevels = 8;              // static_settings.cpp:31
+    float orbScaleFactor = 1.2f;              // static_settings.cpp:32
+    unsigned maxKeypoints = 1000;             // static_settings.cpp:48
+    unsigned orbLkTrackLevel = 0;             // orb_extractor.cpp:91
+    bool useGpuImagePyramid = true;           // image_pyramid.cpp:211
+    std::string slamFeatureDetector = "FAST"; // feature_detector.cpp:38-41
+    float loopClosureFeatureMatchLoweRatio = 0.8f;     // keyframe_matcher.cpp:120
+    bool requireTringulationForLoopClosures = true;    // keyframe_matcher.cpp:82 (sic)
+    // upstream OpenVSLAM FAST thresholds of the detector the north star names
+    int orbIniFastThreshold = 20, orbMinFastThreshold = 7;
+    // batch geometry of the CUDA context (not in the reference: it handles one frame per call)
+    int cudaDevice = 0, cudaMaxFrames = 1, cudaMaxTracks = 512;
+};
+struct ParametersTracker {
+    int maxTracks = 200;
+    std::string featureDetector = "FAST";
+    double gfttMinDistance = 15;
+};
+struct Parameters {
+    ParametersSlam slam;
+    ParametersTracker tracker;
+};
+}  // namespace odometry

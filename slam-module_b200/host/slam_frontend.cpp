@@ -1,0 +1,389 @@
+// Adapters: the reference's ImagePyramid / FeatureDetector / OrbExtractor / matchForLoopClosures
+// interfaces on top of the C ABI of libslamgpu.so.  They own nothing but a context handle and
+// host-side staging; every computation happens in the CUDA library (there is no CPU fallback:
+// if the context cannot be created the adapters abort like the reference's asserts do).
+#include "slam_frontend.hpp"
+
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "../../include/slamgpu.h"
+
+namespace slam {
+namespace {
+
+[[noreturn]] void die(sg_ctx *ctx, const char *what, int rc) {
+    // the reference has no error codes on this path (asserts only): fail loudly
+    std::fprintf(stderr, "slam-b200: %s failed (%d): %s\n", what, rc, sg_last_error(ctx));
+    std::abort();
+}
+#define SG_CHECK(ctx, call)                          \
+    do {                                             \
+        const int rc_ = (call);                      \
+        if (rc_ != SG_OK) die((ctx), #call, rc_);    \
+    } while (0)
+
+}  // namespace
+
+// ---- StaticSettings (static_settings.cpp:9-60) ---------------------------------------------------------
+StaticSettings::StaticSettings(const odometry::Parameters &p) : parameters(p) {
+    const unsigned n = p.slam.orbScaleLevels;
+    scaleFactors.assign(n, 1.0f);
+    levelSigmaSq.assign(n, 1.0f);
+    for (unsigned l = 1; l < n; ++l) {
+        scaleFactors[l] = p.slam.orbScaleFactor * scaleFactors[l - 1];   // float products
+        levelSigmaSq[l] = scaleFactors[l] * scaleFactors[l];
+    }
+}
+
+std::vector<std::size_t> StaticSettings::maxNumberOfKeypointsPerLevel() const {
+    const auto &s = parameters.slam;
+    std::vector<std::size_t> budget(s.orbScaleLevels, 0);
+    const double inv = 1.0 / s.orbScaleFactor;
+    double want = s.maxKeypoints * (1.0 - inv) / (1.0 - std::pow(inv, static_cast<double>(s.orbScaleLevels)));
+    unsigned total = 0;
+    for (unsigned l = 0; l + 1 < s.orbScaleLevels; ++l, want *= inv) {
+        budget[l] = static_cast<std::size_t>(std::round(want));
+        total += static_cast<unsigned>(budget[l]);
+    }
+    budget[s.orbScaleLevels - 1] = static_cast<std::size_t>(std::max(static_cast<int>(s.maxKeypoints) - static_cast<int>(total), 0));
+    return budget;
+}
+
+// ---- shared CUDA context ----------------------------------------------------------------------------
+struct CudaFrontend {
+    sg_ctx *ctx = nullptr;
+    sg_params params{};
+    int levels = 0, cap = 0;
+    std::vector<float> scales;
+    std::vector<int> widths, heights;
+    ~CudaFrontend() { if (ctx) sg_destroy(ctx); }
+};
+
+std::shared_ptr<CudaFrontend> cudaFrontend(const StaticSettings &settings, int width, int height) {
+    static std::mutex mu;
+    static std::map<std::tuple<const StaticSettings *, int, int>, std::weak_ptr<CudaFrontend>> live;
+    std::lock_guard<std::mutex> lock(mu);
+    auto &slot = live[std::make_tuple(&settings, width, height)];
+    if (auto fe = slot.lock()) return fe;
+    const auto &s = settings.parameters.slam;
+    auto fe = std::make_shared<CudaFrontend>();
+    sg_params &p = fe->params;
+    p.width = width; p.height = height;
+    p.levels = static_cast<int>(s.orbScaleLevels);
+    p.scale_factor = s.orbScaleFactor;
+    p.max_keypoints = static_cast<int>(s.maxKeypoints);
+    p.ini_fast_thr = s.orbIniFastThreshold; p.min_fast_thr = s.orbMinFastThreshold;
+    p.max_frames = std::max(1, s.cudaMaxFrames);
+    p.max_tracks = std::max(0, s.cudaMaxTracks);
+    p.track_level = static_cast<int>(s.orbLkTrackLevel);
+    const int rc = sg_create(s.cudaDevice, &p, &fe->ctx);
+    if (rc != SG_OK) die(nullptr, "sg_create", rc);
+    fe->levels = p.levels;
+    fe->cap = sg_keypoint_capacity(fe->ctx);
+    fe->scales.resize(p.levels); fe->widths.resize(p.levels); fe->heights.resize(p.levels);
+    SG_CHECK(fe->ctx, sg_get_geometry(fe->ctx, fe->scales.data(), fe->widths.data(), fe->heights.data(), nullptr, nullptr));
+    // the adapter's StaticSettings and the library's tables must agree bit for bit
+    for (int l = 0; l < p.levels; ++l) assert(fe->scales[l] == settings.scaleFactors[l]);
+    slot = fe;
+    return fe;
+}
+
+sg_ctx *cudaContext(const std::shared_ptr<CudaFrontend> &fe) { return fe ? fe->ctx : nullptr; }
+
+namespace {
+
+// ---- ImagePyramid -----------------------------------------------------------------------------------
+class CudaImagePyramid : public ImagePyramid {
+public:
+    CudaImagePyramid(const StaticSettings &settings, tracker::Image &model)
+        : fe(cudaFrontend(settings, model.width, model.height)), cpu(fe->levels), blurred(fe->levels), gpu(fe->levels),
+          cpuData(fe->levels), blurData(fe->levels), cpuValid(fe->levels, false), blurValid(fe->levels, false) {}
+
+    void update(tracker::Image &image) final {
+        assert(image.width == fe->params.width && image.height == fe->params.height);
+        auto &acc = image.getAccImage();
+        if (acc.storageType == accelerated::Image::StorageType::GPU)
+            SG_CHECK(fe->ctx, sg_pyramid_update_device(fe->ctx, acc.data, acc.stride, (size_t)acc.stride * acc.height, 1));
+        else
+            SG_CHECK(fe->ctx, sg_pyramid_update(fe->ctx, image.gray, image.stride, 0, 1));
+        std::fill(cpuValid.begin(), cpuValid.end(), false);
+        std::fill(blurValid.begin(), blurValid.end(), false);
+        for (int l = 0; l < fe->levels; ++l) {
+            const std::uint8_t *d = nullptr;
+            int pitch = 0;
+            SG_CHECK(fe->ctx, sg_pyramid_device_plane(fe->ctx, l, 0, &d, &pitch, nullptr));
+            gpu[l].width = fe->widths[l]; gpu[l].height = fe->heights[l];
+            gpu[l].storageType = accelerated::Image::StorageType::GPU;
+            gpu[l].data = d; gpu[l].stride = pitch;
+        }
+        updated = true;
+    }
+    std::size_t numberOfLevels() const final { return fe->levels; }
+    bool isGpu() const final { return true; }
+
+    accelerated::Image &getLevel(std::size_t level) final { return fetch(level, false); }
+    accelerated::Image &getBlurredLevel(std::size_t level) final { return fetch(level, true); }
+    accelerated::Image &getGpuLevel(std::size_t level) final {
+        assert(updated && level < gpu.size());
+        return gpu[level];
+    }
+
+    void debugVisualize(std::vector<std::uint8_t> &target, int &width, int &height) final {
+        // levels side by side, top aligned (the reference draws the same layout into a cv::Mat)
+        width = 0; height = fe->heights[0];
+        for (int l = 0; l < fe->levels; ++l) width += fe->widths[l];
+        target.assign((size_t)width * height, 0);
+        int x0 = 0;
+        for (int l = 0; l < fe->levels; ++l) {
+            const accelerated::Image &im = getLevel(l);
+            for (int y = 0; y < im.height; ++y)
+                std::memcpy(&target[(size_t)y * width + x0], im.data + (size_t)y * im.stride, im.width);
+            x0 += im.width;
+        }
+    }
+
+    std::shared_ptr<CudaFrontend> fe;
+    bool updated = false;
+
+private:
+    accelerated::Image &fetch(std::size_t level, bool blur) {
+        assert(updated && level < cpu.size());
+        auto &img = blur ? blurred[level] : cpu[level];
+        auto &buf = blur ? blurData[level] : cpuData[level];
+        auto valid = blur ? blurValid[level] : cpuValid[level];
+        if (!valid) {
+            const int w = fe->widths[level], h = fe->heights[level];
+            buf.resize((size_t)w * h);
+            SG_CHECK(fe->ctx, sg_pyramid_download(fe->ctx, 0, (int)level, blur ? 1 : 0, buf.data(), w));
+            img.width = w; img.height = h; img.storageType = accelerated::Image::StorageType::CPU;
+            img.data = buf.data(); img.stride = w;
+            (blur ? blurValid : cpuValid)[level] = true;
+        }
+        return img;   // valid until the next update(), like the reference's lazily created refs
+    }
+    std::vector<accelerated::Image> cpu, blurred, gpu;
+    std::vector<std::vector<std::uint8_t>> cpuData, blurData;
+    std::vector<bool> cpuValid, blurValid;
+};
+
+// ---- FeatureDetector --------------------------------------------------------------------------------
+class CudaFeatureDetector : public FeatureDetector {
+public:
+    CudaFeatureDetector(const StaticSettings &settings, tracker::Image &model)
+        : fe(cudaFrontend(settings, model.width, model.height)) {}
+
+    std::size_t detect(ImagePyramid &imagePyramid, std::vector<KeyPointVector> &keypointsPerLevel) final {
+        auto *pyr = dynamic_cast<CudaImagePyramid *>(&imagePyramid);
+        assert(pyr && pyr->fe == fe && "the CUDA detector works on the CUDA pyramid of the same settings");
+        (void)pyr;
+        SG_CHECK(fe->ctx, sg_detect(fe->ctx));
+        keypointsPerLevel.resize(fe->levels);
+        std::size_t total = 0;
+        std::vector<int> xs(fe->cap), ys(fe->cap);
+        for (int l = 0; l < fe->levels; ++l) {
+            int n = 0;
+            SG_CHECK(fe->ctx, sg_detect_download(fe->ctx, 0, l, xs.data(), ys.data(), nullptr, fe->cap, &n));
+            auto &out = keypointsPerLevel[l];
+            out.clear();
+            out.reserve(n);
+            for (int i = 0; i < n; ++i) {
+                KeyPoint kp;
+                kp.pt = {static_cast<float>(xs[i]), static_cast<float>(ys[i])};   // level coordinates
+                kp.angle = 0;                                                     // computed elsewhere
+                kp.octave = l;
+                out.push_back(kp);
+            }
+            total += out.size();
+        }
+        return total;
+    }
+
+private:
+    std::shared_ptr<CudaFrontend> fe;
+};
+
+// ---- OrbExtractor -----------------------------------------------------------------------------------
+class CudaOrbExtractor : public OrbExtractor {
+public:
+    explicit CudaOrbExtractor(const StaticSettings &s) : settings(s), parameters(s.parameters.slam) {}
+
+    void detectAndExtract(tracker::Image &img, const tracker::Camera &camera, const std::vector<tracker::Feature> &tracks,
+                          KeyPointVector &keypts, std::vector<int> &keyptTrackIds) final {
+        ensure(img);
+        keypts.clear();
+        keyptTrackIds.clear();
+        // tracker points: the camera test of orb_extractor.cpp:101 is applied here, the margin test in the library
+        const int T = fe->params.max_tracks;
+        int nTracks = 0;
+        trackXy.clear(); trackIds.clear();
+        for (const auto &track : tracks) {
+            const auto &pt = track.points[0];
+            if (nTracks < T && camera.isValidPixel(pt.x, pt.y)) {
+                trackXy.push_back(pt.x); trackXy.push_back(pt.y);
+                trackIds.push_back(track.id);
+                ++nTracks;
+            }
+        }
+        trackXy.resize(2 * (size_t)std::max(T, 1));
+        trackIds.resize((size_t)std::max(T, 1));
+        sg_keypoints out = outputs(1);
+        SG_CHECK(fe->ctx, sg_extract(fe->ctx, img.gray, img.stride, 0, 1, nTracks ? trackXy.data() : nullptr,
+                                     nTracks ? trackIds.data() : nullptr, nTracks ? &nTracks : nullptr, &out));
+        assemble(0, camera, keypts, &keyptTrackIds);
+    }
+
+    void detectAndExtractBatch(const std::vector<tracker::Image *> &imgs, const tracker::Camera &camera,
+                               std::vector<KeyPointVector> &keyPoints) final {
+        keyPoints.clear();
+        if (imgs.empty()) return;
+        ensure(*imgs[0]);
+        const int n = (int)imgs.size(), w = fe->params.width, h = fe->params.height;
+        assert(n <= fe->params.max_frames);
+        stage.resize((size_t)n * w * h);
+        for (int f = 0; f < n; ++f) {
+            assert(imgs[f]->width == w && imgs[f]->height == h);
+            for (int y = 0; y < h; ++y)
+                std::memcpy(&stage[((size_t)f * h + y) * w], imgs[f]->gray + (size_t)y * imgs[f]->stride, w);
+        }
+        sg_keypoints out = outputs(n);
+        SG_CHECK(fe->ctx, sg_extract(fe->ctx, stage.data(), w, (size_t)w * h, n, nullptr, nullptr, nullptr, &out));
+        keyPoints.resize(n);
+        for (int f = 0; f < n; ++f) assemble(f, camera, keyPoints[f], nullptr);
+    }
+
+    void debugVisualize(const tracker::Image &img, std::vector<std::uint8_t> &target, int &width, int &height,
+                        VisualizationMode mode) const final {
+        assert(mode == VisualizationMode::IMAGE_PYRAMID);
+        (void)img; (void)mode;
+        assert(imagePyramid);
+        imagePyramid->debugVisualize(target, width, height);
+    }
+
+private:
+    void ensure(tracker::Image &img) {
+        if (!fe) {
+            fe = cudaFrontend(settings, img.width, img.height);
+            imagePyramid = ImagePyramid::build(settings, img);
+        }
+        assert(img.width == fe->params.width && img.height == fe->params.height);
+    }
+    sg_keypoints outputs(int n) {
+        const size_t m = (size_t)n * fe->cap;
+        x.resize(m); y.resize(m); angle.resize(m); octave.resize(m); desc.resize(8 * m); trackId.resize(m);
+        count.resize(n);
+        sg_keypoints o{};
+        o.x = x.data(); o.y = y.data(); o.angle = angle.data(); o.octave = octave.data(); o.desc = desc.data();
+        o.track_id = trackId.data(); o.count = count.data();
+        return o;
+    }
+    // output assembly of orb_extractor.cpp:120-124,153-162 + dropInvalidKeypoints (:221-237)
+    void assemble(int f, const tracker::Camera &camera, KeyPointVector &keypts, std::vector<int> *ids) const {
+        const size_t base = (size_t)f * fe->cap;
+        keypts.reserve(count[f]);
+        for (int i = 0; i < count[f]; ++i) {
+            const size_t k = base + i;
+            if (trackId[k] < 0 && !camera.isValidPixel(x[k], y[k])) continue;
+            KeyPoint kp;
+            kp.pt = {x[k], y[k]};
+            kp.angle = angle[k];
+            kp.octave = octave[k];
+            std::memcpy(kp.descriptor.data(), &desc[8 * k], 32);
+            keypts.push_back(kp);
+            if (ids) ids->push_back(trackId[k]);
+        }
+    }
+
+    const StaticSettings &settings;
+    const odometry::ParametersSlam &parameters;
+    std::shared_ptr<CudaFrontend> fe;
+    std::unique_ptr<ImagePyramid> imagePyramid;
+    std::vector<float> x, y, angle, trackXy;
+    std::vector<std::int32_t> octave, trackId, count, trackIds;
+    std::vector<std::uint32_t> desc;
+    std::vector<std::uint8_t> stage;
+};
+
+}  // namespace
+
+std::unique_ptr<ImagePyramid> ImagePyramid::build(const StaticSettings &s, tracker::Image &img) {
+    // image_pyramid.cpp:209-219 picks CPU or GPU here; this build has one implementation and no CPU fallback
+    return std::unique_ptr<ImagePyramid>(new CudaImagePyramid(s, img));
+}
+ImagePyramid::~ImagePyramid() = default;
+
+std::unique_ptr<FeatureDetector> FeatureDetector::build(const StaticSettings &s, tracker::Image &img) {
+    return std::unique_ptr<FeatureDetector>(new CudaFeatureDetector(s, img));
+}
+FeatureDetector::~FeatureDetector() = default;
+
+std::unique_ptr<OrbExtractor> OrbExtractor::build(const StaticSettings &s) {
+    return std::unique_ptr<OrbExtractor>(new CudaOrbExtractor(s));
+}
+
+// ---- matching ---------------------------------------------------------------------------------------
+namespace {
+unsigned int matchSubset(const KeyPointVector &kps1, const std::vector<int> &idx1, const KeyPointVector &kps2,
+                         const std::vector<int> &idx2, std::vector<int> &matched, float ratio, bool checkOrientation,
+                         sg_ctx *ctx) {
+    const int nA = (int)idx1.size(), nB = (int)idx2.size();
+    if (nA == 0 || nB == 0) return 0;
+    std::vector<std::uint32_t> dA(8 * (size_t)nA), dB(8 * (size_t)nB);
+    std::vector<float> aA(nA), aB(nB);
+    for (int i = 0; i < nA; ++i) { std::memcpy(&dA[8 * (size_t)i], kps1[idx1[i]].descriptor.data(), 32); aA[i] = kps1[idx1[i]].angle; }
+    for (int i = 0; i < nB; ++i) { std::memcpy(&dB[8 * (size_t)i], kps2[idx2[i]].descriptor.data(), 32); aB[i] = kps2[idx2[i]].angle; }
+    sg_match_params mp{};
+    mp.ratio = ratio; mp.thr = HAMMING_DIST_THR_LOW; mp.check_orientation = checkOrientation ? 1 : 0; mp.ratio_is_double = 0;
+    std::vector<std::int32_t> m(nA);
+    std::uint32_t n = 0;
+    SG_CHECK(ctx, sg_match_bruteforce(ctx, dA.data(), aA.data(), nA, dB.data(), aB.data(), nB, &mp, m.data(), &n));
+    for (int i = 0; i < nA; ++i)
+        if (m[i] >= 0) matched[idx1[i]] = idx2[m[i]];
+    return n;
+}
+}  // namespace
+
+unsigned int matchForLoopClosures(const Keyframe &kf1, const Keyframe &kf2, const MapDB &mapDB1, const MapDB &mapDB2,
+                                  std::vector<int> &matchedMapPoints, const odometry::ParametersSlam &parameters,
+                                  sg_ctx *ctx) {
+    const auto &kps1 = kf1.shared->keyPoints, &kps2 = kf2.shared->keyPoints;
+    matchedMapPoints.resize(kps1.size(), -1);                       // keyframe_matcher.cpp:61
+    std::vector<int> idx1, idx2;
+    for (size_t i = 0; i < kps1.size(); ++i) {                      // :79-84
+        const MpId id = kf1.mapPoints.at(i);
+        if (id.v == -1) continue;
+        if (parameters.requireTringulationForLoopClosures && mapDB1.mapPoints.at(id.v).status != MapPointStatus::TRIANGULATED) continue;
+        idx1.push_back((int)i);
+    }
+    for (size_t i = 0; i < kps2.size(); ++i) {                      // :93-96
+        const MpId id = kf2.mapPoints.at(i);
+        if (id.v == -1 || mapDB2.mapPoints.at(id.v).status != MapPointStatus::TRIANGULATED) continue;
+        idx2.push_back((int)i);
+    }
+    return matchSubset(kps1, idx1, kps2, idx2, matchedMapPoints, parameters.loopClosureFeatureMatchLoweRatio, true, ctx);
+}
+
+unsigned int bruteForceMatch(const KeyPointVector &kps1, const KeyPointVector &kps2, std::vector<int> &matches,
+                             float loweRatio, bool checkOrientation, sg_ctx *ctx) {
+    matches.assign(kps1.size(), -1);
+    std::vector<int> idx1(kps1.size()), idx2(kps2.size());
+    for (size_t i = 0; i < idx1.size(); ++i) idx1[i] = (int)i;
+    for (size_t i = 0; i < idx2.size(); ++i) idx2[i] = (int)i;
+    return matchSubset(kps1, idx1, kps2, idx2, matches, loweRatio, checkOrientation, ctx);
+}
+
+namespace match {
+void compute_descriptor_distance_32(const std::uint32_t *desc_1, const std::uint32_t *desc_2, int n, unsigned int *out,
+                                    sg_ctx *ctx) {
+    SG_CHECK(ctx, sg_hamming(ctx, desc_1, desc_2, n, out));
+}
+}  // namespace match
+
+}  // namespace slam

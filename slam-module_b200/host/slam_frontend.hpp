@@ -1,0 +1,130 @@
+// Host-side mirror of the reference's front-end interfaces, implemented on top of the C ABI of
+// libslamgpu.so (include/slamgpu.h).  Same names, argument meaning and error behaviour as the
+// reference (asserts, no exceptions, outputs cleared then filled), so that code written against
+//   image_pyramid.hpp:16-30, feature_detector.hpp:15-24, orb_extractor.hpp:11-30,
+//   static_settings.hpp:8-22, key_point.hpp:11-28, keyframe_matcher.hpp:33-40
+// compiles against this header after swapping the include.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <memory>
+#include <utility>
+#include <vector>
+
+#include "compat.hpp"
+
+struct sg_ctx;
+
+namespace slam {
+
+// static_settings.hpp:8-22
+struct StaticSettings {
+    const odometry::Parameters &parameters;
+    std::vector<float> scaleFactors;
+    std::vector<float> levelSigmaSq;
+    explicit StaticSettings(const odometry::Parameters &p);
+
+    static constexpr unsigned ORB_PATCH_RADIUS = 19;
+    static constexpr unsigned ORB_FAST_PATCH_SIZE = 31;
+    static constexpr unsigned ORB_FAST_PATCH_HALF_SIZE = ORB_FAST_PATCH_SIZE / 2;
+
+    std::vector<std::size_t> maxNumberOfKeypointsPerLevel() const;
+};
+
+// key_point.hpp:11-28 (Eigen::Vector3d bearing -> three doubles; filled later by keyframe.cpp:67)
+struct KeyPoint {
+    tracker::Feature::Point pt{0, 0};
+    float angle = 0;
+    int octave = 0;
+    std::array<double, 3> bearing{{0, 0, 0}};
+    using Descriptor = std::array<std::uint32_t, 8>;
+    Descriptor descriptor{};
+};
+using KeyPointVector = std::vector<KeyPoint>;
+
+// The CUDA context shared by the pyramid, the detector and the extractor built from the same
+// StaticSettings + model image (the reference builds them lazily from the first image too,
+// orb_extractor.cpp:80-81).
+struct CudaFrontend;
+std::shared_ptr<CudaFrontend> cudaFrontend(const StaticSettings &settings, int width, int height);
+sg_ctx *cudaContext(const std::shared_ptr<CudaFrontend> &fe);
+
+// image_pyramid.hpp:16-30
+struct ImagePyramid {
+    static std::unique_ptr<ImagePyramid> build(const StaticSettings &settings, tracker::Image &modelImage);
+    virtual ~ImagePyramid();
+
+    virtual void update(tracker::Image &image) = 0;
+    virtual std::size_t numberOfLevels() const = 0;
+    virtual bool isGpu() const = 0;
+
+    virtual accelerated::Image &getLevel(std::size_t level) = 0;         // CPU (downloaded on demand)
+    virtual accelerated::Image &getBlurredLevel(std::size_t level) = 0;  // CPU (downloaded on demand)
+    virtual accelerated::Image &getGpuLevel(std::size_t level) = 0;      // GPU, not blurred
+
+    // for debugging: all levels side by side in one 8-bit image (the reference renders a cv::Mat)
+    virtual void debugVisualize(std::vector<std::uint8_t> &target, int &width, int &height) = 0;
+};
+
+// feature_detector.hpp:15-24
+struct FeatureDetector {
+    static std::unique_ptr<FeatureDetector> build(const StaticSettings &settings, tracker::Image &modelImage);
+    virtual ~FeatureDetector();
+
+    /** @return the total number of detected keypoints */
+    virtual std::size_t detect(ImagePyramid &imagePyramid, std::vector<KeyPointVector> &keypointsPerLevel) = 0;
+};
+
+// orb_extractor.hpp:11-30
+struct OrbExtractor {
+    constexpr static int DESCRIPTOR_COLS = 32;
+    virtual ~OrbExtractor() {}
+
+    virtual void detectAndExtract(tracker::Image &img, const tracker::Camera &camera,
+                                  const std::vector<tracker::Feature> &tracks, KeyPointVector &keyPoints,
+                                  std::vector<int> &keyPointTrackIds) = 0;
+
+    // Batched form (not in the reference): frames of one size, one call, results per frame.
+    virtual void detectAndExtractBatch(const std::vector<tracker::Image *> &imgs, const tracker::Camera &camera,
+                                       std::vector<KeyPointVector> &keyPoints) = 0;
+
+    static std::unique_ptr<OrbExtractor> build(const StaticSettings &settings);
+
+    enum class VisualizationMode { IMAGE_PYRAMID };
+    virtual void debugVisualize(const tracker::Image &img, std::vector<std::uint8_t> &target, int &width, int &height,
+                                VisualizationMode mode) const = 0;
+};
+
+// ---- matching (keyframe_matcher.hpp:10-12,33-40; openvslam/match_base.h:13-39) -------------------
+constexpr unsigned int HAMMING_DIST_THR_LOW = 50;
+constexpr unsigned int HAMMING_DIST_THR_HIGH = 100;
+constexpr unsigned int MAX_HAMMING_DIST = 256;
+
+// The slice of Keyframe / MapDB that matchForLoopClosures reads (keyframe_matcher.cpp:50-158):
+// keypoints with descriptors and angles, the map point id of every keypoint and its status.
+enum class MapPointStatus { NOT_TRIANGULATED, TRIANGULATED, BAD };
+struct MpId { int v = -1; };
+struct MapPoint { MapPointStatus status = MapPointStatus::NOT_TRIANGULATED; };
+struct MapDB { std::vector<MapPoint> mapPoints; };   // indexed by MpId::v
+struct KeyframeShared { KeyPointVector keyPoints; };
+struct Keyframe {
+    std::shared_ptr<KeyframeShared> shared;
+    std::vector<MpId> mapPoints;   // per keypoint, v == -1: none
+};
+
+/** keyframe_matcher.hpp:33-40 with every feature in ONE BoW node (brute force, BASELINE.json north star):
+ *  `matchedMapPoints[i]` = keypoint index of kf2 matched to keypoint i of kf1, or -1.  @return match count */
+unsigned int matchForLoopClosures(const Keyframe &kf1, const Keyframe &kf2, const MapDB &mapDB1, const MapDB &mapDB2,
+                                  std::vector<int> &matchedMapPoints, const odometry::ParametersSlam &parameters,
+                                  sg_ctx *ctx);
+
+/** The same loop on bare keypoint vectors (every feature eligible). */
+unsigned int bruteForceMatch(const KeyPointVector &kps1, const KeyPointVector &kps2, std::vector<int> &matches,
+                             float loweRatio, bool checkOrientation, sg_ctx *ctx);
+
+namespace match {
+/** openvslam/match_base.h:18-39, evaluated on the GPU for n descriptor pairs. */
+void compute_descriptor_distance_32(const std::uint32_t *desc_1, const std::uint32_t *desc_2, int n,
+                                    unsigned int *out, sg_ctx *ctx);
+}
+}  // namespace slam

@@ -61,6 +61,7 @@ ABI_SYMBOLS = [
     "sg_angle_bin_order", "sg_angle_bin_order_depth", "sg_angle_bin", "sg_device_count", "sg_malloc", "sg_free",
     "sg_memcpy_h2d", "sg_memcpy_d2h", "sg_host_alloc_pinned", "sg_host_free_pinned", "sg_timer_start",
     "sg_timer_stop", "sg_flush_l2", "sg_microbench_popc", "sg_set_profiling", "sg_get_stage_ms",
+    "sg_set_pipeline_chunk",
 ]
 
 _lib = None
@@ -125,6 +126,8 @@ def lib():
         L.sg_get_stage_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.sg_get_stage_ms.restype = C.c_int
         L.sg_synchronize.argtypes = [C.c_void_p]
+        L.sg_set_pipeline_chunk.argtypes = [C.c_void_p, C.c_int]
+        L.sg_set_pipeline_chunk.restype = C.c_int
         L.sg_detect.argtypes = [C.c_void_p]
         L.sg_keypoint_capacity.argtypes = [C.c_void_p]
         L.sg_microbench_popc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -330,9 +333,17 @@ class Context:
                     track_id=((n_frames, cap), np.int32), lvl_x=((n_frames, cap), np.int32),
                     lvl_y=((n_frames, cap), np.int32), count=((n_frames,), np.int32),
                     level_count=((n_frames, lv), np.int32))
-        arrs = {k: np.empty(s, d) for k, (s, d) in spec.items()}
+        if pinned:   # page-locked host memory: the D2H copies of sg_extract run asynchronously
+            pins = {k: PinnedArray(s, d) for k, (s, d) in spec.items()}
+            arrs = {k: v.array for k, v in pins.items()}
+            self._pins = pins   # keeps the allocations alive as long as the context
+        else:
+            arrs = {k: np.empty(s, d) for k, (s, d) in spec.items()}
         ks = Keypoints(*[arrs[k].ctypes.data for k, _ in Keypoints._fields_])
         return arrs, ks
+
+    def set_pipeline_chunk(self, frames):
+        self._check(lib().sg_set_pipeline_chunk(self._h, int(frames)))
 
     @staticmethod
     def _split(arrs, n_frames):

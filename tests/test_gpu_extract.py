@@ -148,6 +148,20 @@ def test_extract_batch_matches_single_frames(slamgpu, oracle, synth):
             _assert_same_extraction(got2[f], got[3 + f])
 
 
+def test_extract_pipeline_chunks_agree(slamgpu, oracle, synth):
+    """sg_extract pipelines H2D / kernels / D2H over chunks of the batch; any chunking gives the same result."""
+    imgs = synth.frames(640, 480, 7, 2300)
+    ref = [oracle.extract(oracle.make_params(640, 480), imgs[f]) for f in range(7)]
+    with slamgpu.Context(640, 480, max_frames=7) as ctx:
+        for chunk in (1, 2, 3, 7, 64):
+            ctx.set_pipeline_chunk(chunk)
+            got = ctx.detect_and_extract(imgs)
+            for f in range(7):
+                _assert_same_extraction(got[f], ref[f])
+        with pytest.raises(slamgpu.SlamGpuError):
+            ctx.set_pipeline_chunk(0)
+
+
 def test_extract_with_tracker_features(slamgpu, oracle, synth):
     img = synth.frame(640, 480, 3100)
     rng = np.random.default_rng(5)

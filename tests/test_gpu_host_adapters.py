@@ -1,0 +1,107 @@
+"""The C++ adapters (slam-module_b200/host/: ImagePyramid, FeatureDetector, OrbExtractor,
+matchForLoopClosures with the reference's signatures) driven by tests/cpp/host_adapter_main.cpp the way
+the reference's own callers drive the original classes; every dumped artefact is compared bit for bit
+with the CPU oracle."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+HOST = ROOT / "slam-module_b200" / "host"
+
+
+def _build():
+    subprocess.check_call(["make", "-C", str(HOST), "all"], stdout=subprocess.DEVNULL)
+    return HOST / "host_adapter_main"
+
+
+def test_host_adapter_library_builds_and_exports():
+    """CPU check: the adapter library builds with plain g++ and exports the reference's entry points."""
+    _build()
+    syms = subprocess.check_output(["nm", "-DC", str(HOST / "libslam_frontend.so")], text=True)
+    for s in ("slam::ImagePyramid::build(", "slam::FeatureDetector::build(", "slam::OrbExtractor::build(",
+              "slam::matchForLoopClosures(", "slam::StaticSettings::maxNumberOfKeypointsPerLevel()",
+              "slam::match::compute_descriptor_distance_32("):
+        assert s in syms, s
+
+
+def _kps(prefix):
+    xya = np.fromfile(str(prefix) + "_xya.f32", np.float32).reshape(-1, 3)
+    return dict(x=xya[:, 0], y=xya[:, 1], angle=xya[:, 2], octave=np.fromfile(str(prefix) + "_octave.i32", np.int32),
+                desc=np.fromfile(str(prefix) + "_desc.u32", np.uint32).reshape(-1, 8))
+
+
+def _same(got, ref, keep=None):
+    keep = np.ones(ref["n"], bool) if keep is None else keep
+    assert len(got["x"]) == int(keep.sum())
+    for k in ("x", "y", "angle", "octave", "desc"):
+        assert np.array_equal(got[k], ref[k][keep]), k
+
+
+@pytest.mark.gpu
+def test_host_adapters_match_oracle(tmp_path, oracle, synth):
+    exe = _build()
+    w, h, maxkp = 640, 480, 1000
+    a, b = synth.frame(w, h, 7100), synth.frame(w, h, 7101)
+    a.tofile(tmp_path / "a.raw")
+    b.tofile(tmp_path / "b.raw")
+    r = subprocess.run([str(exe), str(w), str(h), str(tmp_path / "a.raw"), str(tmp_path / "b.raw"), str(tmp_path), str(maxkp)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    p = oracle.make_params(w, h, max_keypoints=maxkp)
+    _, _, _, budgets = oracle.geometry(p)
+
+    # ImagePyramid::update / getLevel / getBlurredLevel
+    lv, bl = oracle.pyramid(p, a)
+    dims = np.fromfile(tmp_path / "dims.i32", np.int32).reshape(-1, 2)
+    for l in range(8):
+        assert tuple(dims[l]) == (lv[l].shape[1], lv[l].shape[0])
+        assert np.array_equal(np.fromfile(tmp_path / ("pyr_%d.u8" % l), np.uint8).reshape(lv[l].shape), lv[l]), l
+        assert np.array_equal(np.fromfile(tmp_path / ("blur_%d.u8" % l), np.uint8).reshape(bl[l].shape), bl[l]), l
+
+    # FeatureDetector::detect: per-level keypoints in level coordinates, in the oracle's order
+    det = np.fromfile(tmp_path / "detect.i32", np.int32).reshape(-1, 3)
+    for l in range(8):
+        ox, oy, _ = oracle.detect_level(lv[l], int(budgets[l]))
+        d = det[det[:, 0] == l]
+        assert d[:, 1].tolist() == ox.tolist() and d[:, 2].tolist() == oy.tolist(), l
+
+    # OrbExtractor::detectAndExtract with tracker features (level 1) and a camera rejecting x >= w - 40
+    tracks = np.array([[(7 + (i * 37) % (w - 3)) + 0.25 * (i % 4), (5 + (i * 53) % (h - 3)) + 0.5 * (i % 2)] for i in range(40)],
+                      np.float32)
+    ids = (100 + np.arange(40)).astype(np.int32)
+    ok = tracks[:, 0].astype(np.float64) < w - 40.0           # camera.isValidPixel on the tracker points
+    ref = oracle.extract(p, a, tracks=tracks[ok], track_ids=ids[ok], track_level=1)
+    keep = (ref["track_id"] >= 0) | (ref["x"].astype(np.float64) < w - 40.0)   # dropInvalidKeypoints on detected ones
+    got = _kps(tmp_path / "kpsA")
+    _same(got, ref, keep)
+    assert np.array_equal(np.fromfile(tmp_path / "idsA.i32", np.int32), ref["track_id"][keep])
+    assert (ref["track_id"] >= 0).sum() > 10 and (~keep).sum() > 0
+
+    refB = oracle.extract(p, b)
+    gotB = _kps(tmp_path / "kpsB")
+    _same(gotB, refB)
+    refA = oracle.extract(p, a)
+    _same(_kps(tmp_path / "batch0"), refB)
+    _same(_kps(tmp_path / "batch1"), refA)
+
+    # matchForLoopClosures with map-point filters == brute force on the eligible subsets
+    n1, n2 = refA["n"], refB["n"]
+    i1 = np.array([i for i in range(n1) if i % 5 != 4 and i % 7 != 6])
+    i2 = np.array([i for i in range(n2) if i % 3 != 2])
+    n, m = oracle.match_bruteforce(refA["desc"][i1], refA["angle"][i1], refB["desc"][i2], refB["angle"][i2])
+    want = np.full(n1, -1, np.int32)
+    want[i1[m >= 0]] = i2[m[m >= 0]]
+    lm = np.fromfile(tmp_path / "loop_matches.i32", np.int32)
+    assert lm[-1] == n and np.array_equal(lm[:-1], want)
+    assert n > 0
+
+    nb, mb = oracle.match_bruteforce(refA["desc"], refA["angle"], refB["desc"], refB["angle"])
+    bf = np.fromfile(tmp_path / "bf_matches.i32", np.int32)
+    assert bf[-1] == nb and np.array_equal(bf[:-1], mb)
+
+    k = min(len(got["x"]), n2)
+    hd = np.fromfile(tmp_path / "hamming.u32", np.uint32)
+    assert hd.tolist() == [oracle.hamming(got["desc"][i], refB["desc"][i]) for i in range(k)]
