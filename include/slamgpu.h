@@ -124,7 +124,7 @@ typedef struct sg_keypoints {
 int sg_extract(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames,
                const float *h_track_xy, const int32_t *h_track_ids, const int32_t *n_tracks,
                sg_keypoints *h_out);
-/* sg_extract pipelines the batch in chunks of `frames` frames (default 64): the host->device copy of chunk
+/* sg_extract pipelines the batch in chunks of `frames` frames (default 32): the host->device copy of chunk
  * c+1 and the device->host copy of chunk c-1 run under the kernels of chunk c.  Pass pinned host memory
  * (sg_host_alloc_pinned) for the copies to be asynchronous. */
 int sg_set_pipeline_chunk(sg_ctx *ctx, int frames);

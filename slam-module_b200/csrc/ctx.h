@@ -92,7 +92,7 @@ struct sg_ctx {
     cudaStream_t stream = nullptr;      // stream the stage launchers use (swapped per chunk by the pipelined sg_extract)
     cudaStream_t main_stream = nullptr, s_in = nullptr, s_out = nullptr, s_cmp[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> pipe_ev;   // [2 * chunks]: H2D done, compute done
-    int pipe_chunk = 64;                // frames per pipeline chunk of sg_extract
+    int pipe_chunk = 32;                // frames per pipeline chunk of sg_extract
     int frame0 = 0;                     // first frame the stage launchers work on
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr;
     bool in_pipeline = false;           // stage events are not recorded inside the pipelined sg_extract

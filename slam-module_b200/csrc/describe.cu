@@ -9,6 +9,7 @@
 // round-to-nearest mul / add / sub / div intrinsics in the reference's evaluation order (no FMA
 // contraction), cvRound is round-half-even (__float2int_rn), the degree -> radian conversion is
 // done in double like orb_extractor.cpp:286.
+#include <algorithm>
 #include "ctx.h"
 
 namespace sg {
@@ -76,99 +77,212 @@ struct DescOut {
     int *count;
 };
 
+// ---- kernel geometry ------------------------------------------------------------------------------------
+// A warp owns a GROUP of 32 consecutive output slots of one frame and runs three phases over it:
+//   A  moments, warp-cooperative per keypoint: 3 patch rows per step, lane = (row, aligned word), the row
+//      sums  sum(u*I)  and  sum(I)  are one IDP.4A each against per-(alignment, |v|) weight words in shared
+//      memory (the disc mask u_max_ is folded into the weights);
+//   B  lane j finishes keypoint j: fastAtan2, degree -> radian (double), util::cos / util::sin, and the
+//      coalesced stores of x, y, angle, octave, track id, level coordinates;
+//   C  descriptor, warp-cooperative per keypoint: the 37x37 window of the blurred plane is staged in shared
+//      memory with aligned word loads, lane = descriptor byte samples its 8 point pairs from there; the 32
+//      pattern floats of a lane live in registers for the whole (persistent) kernel; cvRound is the
+//      1.5*2^23 magic-number add (exact round-half-even for |v| < 2^22) instead of the quarter-rate F2I.
+constexpr int MOM_WORDS = 9;            // aligned words covering the 31 columns of the moment disc
+constexpr int BLUR_R = 18;              // max |rotated pattern coordinate| (pattern radius 18.38, |cos|,|sin| <= 1.001)
+constexpr int BLUR_ROWS = 2 * BLUR_R + 1, BLUR_WORDS = 10, BLUR_PITCH = 44;   // bytes per staged row (11 words: odd)
+constexpr float ROUND_MAGIC = 12582912.f;        // 1.5 * 2^23
+constexpr int ROUND_MAGIC_BITS = 0x4B400000;
+
+struct KpInfo { int ix, iy, l, tid; float ox, oy; };
+
+// unsigned pixel bytes x signed weight bytes (IDP.4A.U8.S8)
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int rint_magic_bits(float v) { return __float_as_int(__fadd_rn(v, ROUND_MAGIC)); }
+
 __global__ void __launch_bounds__(DESC_WARPS * 32)
 describe_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int level0_pitch,
                 unsigned long long level0_stride, const int *kp_xy, const int *kp_count,
                 const int *trk_xy, const float *trk_pt, const int *trk_id, const int *trk_count,
-                int track_level, DescOut o) {
+                int track_level, int n_frames, DescOut o) {
+    __shared__ uint32_t s_wu[4][16][MOM_WORDS];    // u weights (signed bytes) per (alignment, |v|, word)
+    __shared__ uint32_t s_wm[4][16][MOM_WORDS];    // disc mask (0 / 1 bytes)
+    __shared__ __align__(16) uint8_t s_patch[DESC_WARPS][BLUR_ROWS * BLUR_PITCH];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int f = blockIdx.y + g.frame0;
-    const int slot = blockIdx.x * DESC_WARPS + warp;
-    const int n_trk = trk_count ? trk_count[f] : 0;
 
-    // which keypoint is this slot: tracker points first, then level 0, 1, ... (orb_extractor.cpp:89-162)
-    int l, ix, iy, tid_out = -1;
-    float ox, oy;
-    int total = n_trk;
-    for (int k = 0; k < g.levels; ++k) total += kp_count[f * g.levels + k];
-    if (slot == 0 && lane == 0) o.count[f] = total;
-    if (slot >= total) return;
-    if (slot < n_trk) {
-        l = track_level;
-        const int p = trk_xy[f * g.max_tracks + slot];
-        ix = p & 0xffff; iy = p >> 16;
-        ox = trk_pt[2 * (f * g.max_tracks + slot)];
-        oy = trk_pt[2 * (f * g.max_tracks + slot) + 1];
-        tid_out = trk_id[f * g.max_tracks + slot];
-    } else {
-        int t = slot - n_trk;
-        for (l = 0; l < g.levels; ++l) {
-            const int c = kp_count[f * g.levels + l];
-            if (t < c) break;
-            t -= c;
+    // ---- per-CTA tables --------------------------------------------------------------------------------
+    for (int i = threadIdx.x; i < 4 * 16 * MOM_WORDS; i += DESC_WARPS * 32) {
+        const int w = i % MOM_WORDS, av = (i / MOM_WORDS) % 16, off = i / (MOM_WORDS * 16);
+        uint32_t wu = 0, wm = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int u = 4 * w + j - HALF_PATCH - off;
+            if (abs(u) <= c_umax[av]) { wu |= (uint32_t)(uint8_t)(int8_t)u << (8 * j); wm |= 1u << (8 * j); }
         }
-        const int p = kp_xy[(size_t)f * g.det_cap + g.lv[l].kp_off + t];
-        ix = p & 0xffff; iy = p >> 16;
-        ox = __fmul_rn((float)ix, g.lv[l].scale);   // kp.pt * scale_at_level (orb_extractor.cpp:156)
-        oy = __fmul_rn((float)iy, g.lv[l].scale);
+        (&s_wu[0][0][0])[i] = wu;
+        (&s_wm[0][0][0])[i] = wm;
     }
-    const LevelDev &L = g.lv[l];
-    const uint8_t *img = l == 0 ? level0 + (size_t)f * level0_stride : L.pyr + (size_t)f * L.frame_stride;
-    const int pitch = l == 0 ? level0_pitch : L.pitch;
-    const uint8_t *blur = L.blur + (size_t)f * L.frame_stride;
-
-    // ---- intensity-centroid moments over the radius-15 disc: lane = column u ---------------------------
-    int m10 = 0, m01 = 0;
+    // ---- this lane's 8 point pairs (descriptor byte = lane), as floats in registers -------------------------
+    float px0[8], py0[8], px1[8], py1[8];
     {
-        const int u = lane - HALF_PATCH;
-        const uint8_t *c = img + (size_t)iy * pitch + ix;
-        if (lane < 31) {
-            const int au = abs(u);
-#pragma unroll 1
-            for (int v = -HALF_PATCH; v <= HALF_PATCH; ++v) {
-                if (au <= c_umax[abs(v)]) {
-                    const int val = __ldg(c + v * pitch + u);
-                    m10 += u * val;
-                    m01 += v * val;
+        const int4 *pat = reinterpret_cast<const int4 *>(d_pattern) + 2 * lane;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int4 w = __ldg(pat + h);
+            const int ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                px0[4 * h + k] = (float)(int8_t)(ws[k] & 0xff); py0[4 * h + k] = (float)(int8_t)((ws[k] >> 8) & 0xff);
+                px1[4 * h + k] = (float)(int8_t)((ws[k] >> 16) & 0xff); py1[4 * h + k] = (float)(int8_t)((ws[k] >> 24) & 0xff);
+            }
+        }
+    }
+    __syncthreads();
+
+    const int groups_per_frame = (g.out_cap + 31) >> 5;
+    const int n_groups = groups_per_frame * n_frames;
+    const int mrow = lane / MOM_WORDS, mword = lane - mrow * MOM_WORDS;        // lanes 0..26: 3 rows x 9 words
+    const int brow = lane / BLUR_WORDS, bword = lane - brow * BLUR_WORDS;      // lanes 0..29: 3 rows x 10 words
+    uint8_t *patch = s_patch[warp];
+
+    for (int grp = blockIdx.x * DESC_WARPS + warp; grp < n_groups; grp += gridDim.x * DESC_WARPS) {
+        const int f = g.frame0 + grp / groups_per_frame;
+        const int slot0 = (grp % groups_per_frame) << 5;
+        const int n_trk = trk_count ? trk_count[f] : 0;
+        // which keypoints: tracker points first, then level 0, 1, ... (orb_extractor.cpp:89-162)
+        int cnt = lane < g.levels ? kp_count[f * g.levels + lane] : 0;
+        int incl = cnt;                                    // inclusive scan over the levels
+#pragma unroll
+        for (int d = 1; d < SG_MAX_LEVELS; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int total = n_trk + __shfl_sync(0xffffffffu, incl, SG_MAX_LEVELS - 1);
+        if (slot0 == 0 && lane == 0) o.count[f] = total;
+        if (slot0 >= total) continue;
+        const int n_here = min(32, total - slot0);
+
+        // ---- lane j looks up keypoint slot0 + j -------------------------------------------------------------
+        KpInfo k{0, 0, 0, -1, 0.f, 0.f};
+        const int slot = slot0 + lane;
+        {
+            const int t = slot - n_trk;
+            // level of a detected keypoint: number of levels whose inclusive count is <= t
+            int l = 0;
+#pragma unroll
+            for (int q = 0; q < SG_MAX_LEVELS; ++q) {
+                const int iq = __shfl_sync(0xffffffffu, incl, q);
+                l += (q < g.levels && iq <= t) ? 1 : 0;
+            }
+            if (slot < total) {
+                if (slot < n_trk) {
+                    k.l = track_level;
+                    const int p = trk_xy[f * g.max_tracks + slot];
+                    k.ix = p & 0xffff; k.iy = p >> 16;
+                    k.ox = trk_pt[2 * (f * g.max_tracks + slot)];
+                    k.oy = trk_pt[2 * (f * g.max_tracks + slot) + 1];
+                    k.tid = trk_id[f * g.max_tracks + slot];
+                } else {
+                    k.l = l;
                 }
             }
         }
-        m10 = __reduce_add_sync(0xffffffffu, m10);
-        m01 = __reduce_add_sync(0xffffffffu, m01);
-    }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-
-    // ---- rBRIEF: lane = descriptor byte, 8 point pairs each ---------------------------------------------
-    const float rad = (float)((double)angle * 3.14159265358979323846 / 180.0);
-    const float cs = util_cos(rad), sn = util_sin(rad);
-    const uint8_t *cb = blur + (size_t)iy * L.pitch + ix;
-    const int4 *pat = reinterpret_cast<const int4 *>(d_pattern) + 2 * lane;
-    unsigned byte = 0;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int4 w = __ldg(pat + h);
-        const int ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float x0 = (float)(int8_t)(ws[k] & 0xff), y0 = (float)(int8_t)((ws[k] >> 8) & 0xff);
-            const float x1 = (float)(int8_t)((ws[k] >> 16) & 0xff), y1 = (float)(int8_t)((ws[k] >> 24) & 0xff);
-            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(y0, cs)));
-            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(y0, sn)));
-            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sn), __fmul_rn(y1, cs)));
-            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, cs), __fmul_rn(y1, sn)));
-            const int v0 = __ldg(cb + r0 * L.pitch + c0), v1 = __ldg(cb + r1 * L.pitch + c1);
-            byte |= (v0 < v1 ? 1u : 0u) << (4 * h + k);
+        // exclusive count of the lane's level (second pass: shuffles must be warp-uniform)
+        {
+            const int lsel = (slot < total && slot >= n_trk) ? k.l : 0;
+            const int excl = __shfl_sync(0xffffffffu, incl - cnt, lsel);
+            if (slot < total && slot >= n_trk) {
+                const int t = slot - n_trk - excl;
+                const int p = kp_xy[(size_t)f * g.det_cap + g.lv[k.l].kp_off + t];
+                k.ix = p & 0xffff; k.iy = p >> 16;
+                k.ox = __fmul_rn((float)k.ix, g.lv[k.l].scale);   // kp.pt * scale_at_level (orb_extractor.cpp:156)
+                k.oy = __fmul_rn((float)k.iy, g.lv[k.l].scale);
+            }
         }
-    }
-    unsigned word = byte << (8 * (lane & 3));
-    word |= __shfl_xor_sync(0xffffffffu, word, 1);
-    word |= __shfl_xor_sync(0xffffffffu, word, 2);
 
-    const size_t oi = (size_t)f * g.out_cap + slot;
-    if ((lane & 3) == 0) o.desc[8 * oi + (lane >> 2)] = word;
-    if (lane == 0) {
-        o.x[oi] = ox; o.y[oi] = oy; o.angle[oi] = angle; o.octave[oi] = l;
-        o.track_id[oi] = tid_out; o.lvl_x[oi] = ix; o.lvl_y[oi] = iy;
+        // ---- phase A: intensity-centroid moments (un-blurred level) ----------------------------------------
+        int my_m10 = 0, my_m01 = 0;
+        for (int j = 0; j < n_here; ++j) {
+            const int ix = __shfl_sync(0xffffffffu, k.ix, j), iy = __shfl_sync(0xffffffffu, k.iy, j);
+            const int l = __shfl_sync(0xffffffffu, k.l, j);
+            const uint8_t *img = l == 0 ? level0 + (size_t)f * level0_stride : g.lv[l].pyr + (size_t)f * g.lv[l].frame_stride;
+            const int pitch = l == 0 ? level0_pitch : g.lv[l].pitch;
+            const int off = (ix - HALF_PATCH) & 3;
+            const uint8_t *c = img + (size_t)iy * pitch + (ix - HALF_PATCH - off) + 4 * mword;
+            int m10 = 0, m01 = 0;
+            if (lane < 3 * MOM_WORDS) {
+#pragma unroll
+                for (int i = 0; i < 11; ++i) {
+                    const int v = 3 * i + mrow - HALF_PATCH;
+                    if (v <= HALF_PATCH) {
+                        const uint32_t pix = __ldg(reinterpret_cast<const uint32_t *>(c + v * pitch));
+                        const int av = abs(v);
+                        m10 = dp4a_us(pix, (int)s_wu[off][av][mword], m10);
+                        m01 += v * (int)__dp4a(pix, s_wm[off][av][mword], 0u);
+                    }
+                }
+            }
+            m10 = __reduce_add_sync(0xffffffffu, m10);
+            m01 = __reduce_add_sync(0xffffffffu, m01);
+            if (lane == j) { my_m10 = m10; my_m01 = m01; }
+        }
+
+        // ---- phase B: lane j finishes keypoint j ---------------------------------------------------------------
+        const float angle = fast_atan2_deg((float)my_m01, (float)my_m10);
+        const float rad = (float)((double)angle * 3.14159265358979323846 / 180.0);
+        const float cs = util_cos(rad), sn = util_sin(rad);
+        const size_t oi0 = (size_t)f * g.out_cap + slot0;
+        if (lane < n_here) {
+            const size_t oi = oi0 + lane;
+            o.x[oi] = k.ox; o.y[oi] = k.oy; o.angle[oi] = angle; o.octave[oi] = k.l;
+            o.track_id[oi] = k.tid; o.lvl_x[oi] = k.ix; o.lvl_y[oi] = k.iy;
+        }
+
+        // ---- phase C: rBRIEF on the blurred level -----------------------------------------------------------
+        for (int j = 0; j < n_here; ++j) {
+            const int ix = __shfl_sync(0xffffffffu, k.ix, j), iy = __shfl_sync(0xffffffffu, k.iy, j);
+            const int l = __shfl_sync(0xffffffffu, k.l, j);
+            const float c_ = __shfl_sync(0xffffffffu, cs, j), s_ = __shfl_sync(0xffffffffu, sn, j);
+            const int pitch = g.lv[l].pitch;
+            const int off = (ix - BLUR_R) & 3;
+            const uint8_t *src = g.lv[l].blur + (size_t)f * g.lv[l].frame_stride + (size_t)(iy - BLUR_R) * pitch
+                                 + (ix - BLUR_R - off) + 4 * bword;
+            __syncwarp();   // the previous keypoint's samples have been read
+            if (lane < 3 * BLUR_WORDS) {
+#pragma unroll
+                for (int i = 0; i < 13; ++i) {
+                    const int r = 3 * i + brow;
+                    if (r < BLUR_ROWS)
+                        *reinterpret_cast<uint32_t *>(patch + r * BLUR_PITCH + 4 * bword) =
+                            __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)r * pitch));
+                }
+            }
+            __syncwarp();
+            // sample index = (r + 18) * 44 + (c + 18 + off); r, c arrive as MAGIC_BITS + integer
+            // (unsigned arithmetic: the magic offsets cancel modulo 2^32)
+            const unsigned bias = (unsigned)(BLUR_R * BLUR_PITCH + BLUR_R + off) - (unsigned)ROUND_MAGIC_BITS * (unsigned)(BLUR_PITCH + 1);
+            unsigned bits = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r0 = rint_magic_bits(__fadd_rn(__fmul_rn(px0[q], s_), __fmul_rn(py0[q], c_)));
+                const int c0 = rint_magic_bits(__fsub_rn(__fmul_rn(px0[q], c_), __fmul_rn(py0[q], s_)));
+                const int r1 = rint_magic_bits(__fadd_rn(__fmul_rn(px1[q], s_), __fmul_rn(py1[q], c_)));
+                const int c1 = rint_magic_bits(__fsub_rn(__fmul_rn(px1[q], c_), __fmul_rn(py1[q], s_)));
+                const int v0 = patch[(unsigned)r0 * BLUR_PITCH + (unsigned)c0 + bias];
+                const int v1 = patch[(unsigned)r1 * BLUR_PITCH + (unsigned)c1 + bias];
+                bits |= (v0 < v1 ? 1u : 0u) << q;
+            }
+            unsigned word = bits << (8 * (lane & 3));
+            word |= __shfl_xor_sync(0xffffffffu, word, 1);
+            word |= __shfl_xor_sync(0xffffffffu, word, 2);
+            // 8 words per descriptor: lanes 0, 4, 8, ... hold words 0..7
+            const unsigned wsel = __shfl_sync(0xffffffffu, word, (lane & 7) << 2);
+            if (lane < 8) o.desc[8 * (oi0 + j) + lane] = wsel;
+        }
     }
 }
 
@@ -178,11 +292,17 @@ int launch_describe(sg_ctx *ctx, int n_frames) {
     DescOut o{ctx->d_x, ctx->d_y, ctx->d_angle, ctx->d_octave, ctx->d_track_id, ctx->d_lvl_x, ctx->d_lvl_y,
               ctx->d_desc, ctx->d_count};
     const bool trk = ctx->have_tracks;
-    dim3 grid((g.out_cap + DESC_WARPS - 1) / DESC_WARPS, n_frames);
-    describe_kernel<<<grid, DESC_WARPS * 32, 0, ctx->stream>>>(
+    const int groups = ((g.out_cap + 31) / 32) * n_frames;
+    static int per_sm = 0;   // resident CTAs per SM of this (persistent) kernel
+    if (!per_sm) {
+        SG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, describe_kernel, DESC_WARPS * 32, 0));
+        per_sm = std::max(per_sm, 1);
+    }
+    const int blocks = std::max(1, std::min((groups + DESC_WARPS - 1) / DESC_WARPS, ctx->sm_count * per_sm));
+    describe_kernel<<<blocks, DESC_WARPS * 32, 0, ctx->stream>>>(
         g, ctx->level0, ctx->level0_pitch, ctx->level0_stride, ctx->d_kp_xy, ctx->d_kp_count,
         trk ? ctx->d_trk_xy : nullptr, trk ? ctx->d_trk_pt : nullptr, trk ? ctx->d_trk_id : nullptr,
-        trk ? ctx->d_trk_count : nullptr, ctx->p.track_level, o);
+        trk ? ctx->d_trk_count : nullptr, ctx->p.track_level, n_frames, o);
     SG_LAUNCH_CHECK(ctx);
     mark(ctx, EV_DESC1);
     return SG_OK;
