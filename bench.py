@@ -181,6 +181,116 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def extra_configs(slamgpu, sm, sh, rank, world, local, barrier_max_, td):
+    """The remaining BASELINE.json configs, each on a bounded sample, reported beside the headline
+    (configs[1]) and the matching leg (configs[2]):
+      configs[0]  one 640x480 frame, 1000 keypoints: latency of sg_extract (host buffers) and of the kernels;
+      configs[3]  1280x720 stereo pairs: extract L and R, match L -> R (M1 semantics), pairs sharded by rank;
+      configs[4]  loop-closure scale: 10 000 keyframes x 2000 descriptors resident per GPU (640 MB), the
+                  all-pairs candidate list block-sharded over the ranks, a bounded block of it timed."""
+    import ctypes as C
+    lib = slamgpu.lib()
+    out = {}
+    # ---- configs[0]: single-frame latency -------------------------------------------------------------
+    with slamgpu.Context(W, H, levels=LEVELS, scale_factor=FACTOR, max_keypoints=1000, max_frames=1, device=local) as c1:
+        pin = slamgpu.PinnedArray((1, H, W), np.uint8)
+        pin.array[0] = sm.synth.frame(W, H, 1000)
+        arrs, ks = c1._alloc_out(1, pinned=True)
+        lat = []
+        for i in range(25):
+            t0 = time.perf_counter()
+            c1._check(lib.sg_extract(c1._h, pin.array.ctypes.data, W, W * H, 1, None, None, None, C.byref(ks)))
+            lat.append(time.perf_counter() - t0)
+        dbuf = c1.device_buffer(W * H).upload(pin.array)
+        for _ in range(3):
+            c1.extract_device(dbuf.ptr, W, W * H, 1)
+        c1.synchronize()
+        c1.timer_start()
+        for _ in range(20):
+            c1.extract_device(dbuf.ptr, W, W * H, 1)
+        dev_us = c1.timer_stop() * 1e3 / 20
+        out["config0_single_frame"] = {"workload": "1 frame 640x480, 8 levels, 1000 keypoints", "keypoints": int(arrs["count"][0]),
+                                       "latency_us_host_call_median": 1e6 * statistics.median(lat[5:]),
+                                       "latency_us_kernels_only": dev_us}
+    # ---- configs[3]: 1280x720 stereo stream --------------------------------------------------------------
+    SW, SH, PAIRS = 1280, 720, 16
+    with slamgpu.Context(SW, SH, levels=LEVELS, scale_factor=FACTOR, max_keypoints=MAXKP, max_frames=2 * PAIRS, device=local) as c4:
+        left = [sm.synth.frame(SW, SH, 4000 + 10 * rank + i) for i in range(4)]
+        frames = np.empty((2 * PAIRS, SH, SW), np.uint8)
+        for i in range(PAIRS):
+            frames[2 * i] = left[i % 4]
+            frames[2 * i + 1] = np.roll(left[i % 4], -6 - (i % 3), axis=1)      # right view: horizontal disparity
+        dfr = c4.device_buffer(frames.nbytes).upload(frames)
+        cap = c4.cap
+        pairs = np.array([(4 * i, 4 * i + 2) for i in range(PAIRS)], np.int32)   # sets 2f (keypoints) / 2f+1 (padding)
+        d_pairs = c4.device_buffer(pairs.nbytes).upload(pairs)
+        d_counts = c4.device_buffer(4 * PAIRS)
+
+        def stereo_step():
+            c4.extract_device(dfr.ptr, SW, SW * SH, 2 * PAIRS)
+            counts, _ = c4.extract_download(2 * PAIRS, only_counts=True)          # host gather of the counts
+            offs = np.zeros(4 * PAIRS + 1, np.int64)
+            offs[1::2] = np.arange(2 * PAIRS) * cap + counts
+            offs[2::2] = (np.arange(2 * PAIRS) + 1) * cap
+            v = c4.device_views()
+            db = slamgpu.DescriptorDB(c4, None, None, offsets=offs, device_ptrs=(v.desc, v.angle))
+            db.match_pairs_device(d_pairs.ptr, PAIRS, d_counts.ptr)
+            c4.synchronize()
+            db.close()
+            return counts
+
+        for _ in range(2):
+            counts = stereo_step()
+        barrier_max_(td, local, 0.0)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            stereo_step()
+        dt = barrier_max_(td, local, time.perf_counter() - t0)
+        nm = d_counts.download(np.uint32, PAIRS)
+        out["config3_stereo_stream"] = {"workload": "1280x720 stereo pairs: extract L+R (2000 kp) and match L->R, %d pairs per step per GPU" % PAIRS,
+                                        "stereo_pairs_per_s": world * PAIRS * 5 / dt, "frames_per_s": world * 2 * PAIRS * 5 / dt,
+                                        "keypoints_per_frame": float(counts.mean()), "matches_per_pair": float(nm.mean()),
+                                        "sharding": "stereo pairs by rank; L and R of a pair stay on one GPU"}
+    # ---- configs[4]: loop-closure scale --------------------------------------------------------------------
+    KF, N, SAMPLE = 10000, MATCH_N, 4096
+    rng = np.random.default_rng(99)
+    base = rng.integers(0, 2 ** 32, (64, N, 8), dtype=np.uint32)                 # 64 distinct places
+    noise = np.ones((157, N, 8), np.uint32) * np.uint32(0xffffffff)
+    for _ in range(4):                                                           # each bit flipped with p = 1/16
+        noise &= rng.integers(0, 2 ** 32, (157, N, 8), dtype=np.uint32)
+    ang_base = rng.uniform(0, 360, (64, N)).astype(np.float32)
+    with slamgpu.Context(W, H, max_frames=1, device=local) as c5:
+        desc = np.empty((KF, N, 8), np.uint32)
+        ang = np.empty((KF, N), np.float32)
+        for k0 in range(0, KF, 64):
+            n = min(64, KF - k0)
+            desc[k0:k0 + n] = base[:n] ^ noise[(k0 // 64) % 157][None]
+            ang[k0:k0 + n] = ang_base[:n]
+        db = slamgpu.DescriptorDB(c5, desc, ang)                                 # replicated on every GPU
+        total = sh.n_unordered_pairs(KF)
+        lo, hi = sh.block_range(total, rank, world)
+        # a bounded block of this rank's share of the all-pairs list, taken where every 64th pair revisits a place
+        blk = sh.pair_block(KF, rank, world, limit=SAMPLE)
+        d_blk = c5.device_buffer(blk.nbytes).upload(blk)
+        d_cnt = c5.device_buffer(4 * SAMPLE)
+        db.match_pairs_device(d_blk.ptr, len(blk), d_cnt.ptr)
+        c5.synchronize()
+        barrier_max_(td, local, 0.0)
+        c5.timer_start()
+        db.match_pairs_device(d_blk.ptr, len(blk), d_cnt.ptr)
+        ms = barrier_max_(td, local, c5.timer_stop())
+        cnt = d_cnt.download(np.uint32, len(blk))
+        rate = world * len(blk) / (ms * 1e-3)
+        out["config4_loop_closure_scale"] = {
+            "workload": "10000 keyframes x 2000 descriptors resident per GPU (%.0f MB), all %d unordered pairs block-sharded over %d rank(s); "
+                        "timed sample: the first %d pairs of each rank's block" % (desc.nbytes / 1e6, total, world, len(blk)),
+            "keyframe_pairs_per_s": rate, "descriptor_pair_distances_per_s": rate * N * N,
+            "projected_full_job_s": total / rate, "pairs_in_rank_block": int(hi - lo),
+            "pairs_with_matches_in_sample": int((cnt > 0).sum())}
+        db.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,6 +298,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extra-configs", action="store_true")
     ap.add_argument("--pipe-chunk", type=int, default=0, help="frames per pipeline chunk of sg_extract (0: library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -298,6 +409,10 @@ def main():
     match_e2e = world * 256 * MATCH_N * MATCH_N / (time.perf_counter() - t0)
     popc_peak, _ = ctx.microbench_popc()
     clocks = sampler.stop()
+    extras = None
+    if not args.skip_extra_configs:
+        from slam_module_b200 import sharding as sh
+        extras = extra_configs(slamgpu, sm, sh, rank, world, local, barrier_max, td)
 
     # ---- CPU baseline beside it (rank 0, N == 1 only) ----------------------------------------------------
     cpu = None
@@ -361,6 +476,8 @@ def main():
                                       "algorithmic_ops_per_pair": 8}},
             "clocks": clocks,
         }
+        if extras is not None:
+            line["other_configs"] = extras
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
