@@ -151,7 +151,7 @@ def run_reference(args):
     from oracle import pyoracle as po
     po.build()
     cores = os.cpu_count() or 1
-    sample = max(16, min(64, 2 * cores))
+    sample = FRAMES            # the whole step: 256 frames (about 1-2 s on a 16-core host)
     frames = make_frames(sample, 9000)
     for _ in range(args.warmup):
         cpu_extract_baseline(po, frames[:max(cores, 4)], cores)
@@ -163,7 +163,7 @@ def run_reference(args):
     # matching leg on a few pairs
     import slam_module_b200 as sm
     d, a = sm.synth.random_descriptors(8, MATCH_N, 5)
-    pairs = np.array([(i, (i + 1) % 8) for i in range(max(8, cores))], np.int32)
+    pairs = np.array([(i % 8, (i + 1) % 8) for i in range(16 * max(8, cores))], np.int32)
     msec, _ = po.bench_match(d, a, pairs, cores)
     desc = "oracle port of the reference CPU path, %d frames per step sharded over %d host threads" % (sample, cores)
     line = {
@@ -420,13 +420,18 @@ def main():
         from oracle import pyoracle as po
         po.build()
         cores = os.cpu_count() or 1
-        sample = max(16, min(64, 2 * cores))
+        sample = FRAMES
         v, secs, _ = cpu_extract_baseline(po, host_batches[0].array[:sample], cores)
-        msec, _ = po.bench_match(np.stack(sets_d[:8]), np.stack(sets_a[:8]), pairs[:max(8, cores)] % 8, cores)
+        v2, secs2, _ = cpu_extract_baseline(po, host_batches[1].array[:sample], cores)   # second pass: warm caches, take the better
+        if v2 > v:
+            v, secs = v2, secs2
+        n_cpu_pairs = 16 * max(8, cores)
+        msec, _ = po.bench_match(np.stack(sets_d[:8]), np.stack(sets_a[:8]), pairs[:n_cpu_pairs] % 8, cores)
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": "oracle port of the reference CPU path on %d of the step's frames, sharded over %d host "
-                         "threads (%.1f s)" % (sample, cores, secs),
-               "matching_value": max(8, cores) * MATCH_N * MATCH_N / msec, "matching_unit": "descriptor-pair distances/s"}
+               "sample": "oracle port of the reference CPU path on the %d frames of one step, sharded over %d host "
+                         "threads (%.1f s per pass, best of 2)" % (sample, cores, secs),
+               "matching_value": n_cpu_pairs * MATCH_N * MATCH_N / msec, "matching_unit": "descriptor-pair distances/s",
+               "matching_sample": "%d keyframe pairs over %d threads (%.1f s)" % (n_cpu_pairs, cores, msec)}
 
     if rank == 0:
         # roofline of the dominant kernel of the step (per-stage CUDA events, averaged over the timed steps)
