@@ -121,7 +121,19 @@ def dist_setup(n_gpus):
         import torch
         import torch.distributed as td_
         torch.cuda.set_device(local)
-        td_.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the communicator comes up: keep stdout for the ONE json line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            td_.init_process_group("nccl", device_id=torch.device("cuda", local))
+            t = torch.zeros(1, device=torch.device("cuda", local))
+            td_.all_reduce(t)                      # forces communicator creation inside the redirected region
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
         td = td_
     return rank, world, local, td
 
