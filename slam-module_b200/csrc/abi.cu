@@ -31,6 +31,7 @@ int grow(sg_ctx *ctx, void **ptr, size_t *cap, size_t need, size_t elem) {
 
 void pyramid_source_extent(const std::vector<ResizeTap> &xt, const std::vector<ResizeTap> &yt, int w, int h,
                            bool area2x, int sw, int sh, int *tile_w, int *tile_h);
+int pyramid_fast_source_rows(const std::vector<ResizeTap> &yt, int h);
 int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, const sg_match_params &mp,
               int *d_matches, int match_stride, uint32_t *d_n_matches);
 int match_chunk_pairs(const sg_db *db, bool own_matches);
@@ -98,8 +99,9 @@ static int build_context(sg_ctx *ctx) {
                     mw = std::max(mw, xt[xhi - 1].s0 - (xt[xlo].s0 & ~15) + 8);
                 }
                 L.tma_src_w = (mw + 15) & ~15;
-                L.tma_src_h = L.src_tile_h;
-                if (L.tma_src_w > 256 || L.tma_src_h > 255) L.fast_resize = false;
+                L.tma_src_h = pyramid_fast_source_rows(yt, L.h);
+                // YTap keeps row * (pitch / 4) in 16 bits
+                if (L.tma_src_w > 256 || L.tma_src_h > 255 || (L.tma_src_h + 1) * (L.tma_src_w / 4) > 32767) L.fast_resize = false;
             }
             for (int i = 0; i + 1 < L.w; ++i)
                 if (xt[i + 1].s0 - xt[i].s0 > 2 || xt[i + 1].s0 < xt[i].s0) L.fast_resize = false;

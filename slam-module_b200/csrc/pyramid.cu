@@ -195,23 +195,28 @@ __global__ void __launch_bounds__(PYR_THREADS) pyr_level_kernel(const PyrArgs a)
 
 // -------------------------------------------------------------------------------------------------
 // Fast path (scale factor <= 2, no INTER_AREA switch): same arithmetic, restructured for the integer
-// pipes.  Per output pixel the generic kernel above spends ~190 thread instructions (variable
-// divisions, byte loads, scalar multiply-adds); this one ~45:
-//   resize    : 2 px per item; both source bytes of a pixel come from one PRMT on an aligned 8-byte
-//               window, the horizontal interpolation S0*a0 + S1*a1 is one IDP.2A (16-bit coefficient
-//               pair x 8-bit pixel pair); out-of-image window entries use clamped taps (overwritten by
-//               the mirror pass), so there are no guards in the loop
+// pipes, 64 x 64 output tiles (halo work 70/64 instead of 38/32, half the per-CTA fixed cost per pixel):
+//   resize    : a thread owns one PAIR of window columns and walks down 10 window rows, so the column
+//               taps (16-bit coefficient pair, byte selectors into an aligned 8-byte source window)
+//               are loop invariants; per row: 4 LDS, 4 PRMT, 4 IDP.2A (S0*a0 + S1*a1 of both columns
+//               and both source rows), then the two truncating vertical products.  Out-of-image
+//               window entries use clamped taps (overwritten by the mirror pass): no guards in the loop
 //   blur H    : IDP.4A on byte windows (two per output), two rows per item, stored as vertical u16
 //               pairs Hp[r/2][c] = H[r][c] | H[r+1][c] << 16
-//   blur V    : IDP.2A on the vertical pairs (3 per output + one scalar tap), 4 columns x 2 rows per
-//               thread, 32-bit stores
+//   blur V    : IDP.2A on the vertical pairs (4 per output, rounding constant in the accumulator),
+//               4 columns x 4 rows per thread from 5 LDS.128, 32-bit stores
 // -------------------------------------------------------------------------------------------------
 // R geometry of the fast kernel.  RESIZE: R is computed, pitch 80, column 4 <-> x0.  Blur only: R is the
 // TMA box itself; TMA needs the innermost start coordinate to be a multiple of 16 BYTES (anything else
 // raises "illegal instruction" on sm_100a -- measured), so the box starts at x0 - 16: pitch 96, column 16 <-> x0.
+constexpr int FTH = 64, FRH = FTH + 6;       // output tile rows, window rows (incl. the 3-px blur halo)
+constexpr int FR_BYTES = 6784;               // >= FRH * 96, multiple of 128
+constexpr int COLP = 36;                     // window column pairs (72 columns: x0 - 4 .. x0 + 67)
+constexpr int ROWG = 7, ROWS_PER_G = FRH / ROWG;   // 7 row groups x 10 rows; 7 * 36 = 252 threads busy
+static_assert(ROWG * ROWS_PER_G == FRH && ROWG * COLP <= PYR_THREADS, "resize work split");
 template <bool RESIZE> struct RGeom { static constexpr int FW = RESIZE ? 80 : 96, X0 = RESIZE ? 4 : 16; };
 struct XTap { uint32_t coef; int32_t s0; };          // a0 | a1 << 16, source column relative to the tile
-struct YTap { int16_t s0, s1, b0, b1; };
+struct YTap { int16_t w0, w1, b0, b1; };             // source row word offsets (row * pitch / 4), coefficients
 
 template <bool RESIZE>
 __global__ void __launch_bounds__(PYR_THREADS)
@@ -220,63 +225,69 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int s_bytes = RESIZE ? (((a.src_tile_h + 1) * a.src_tile_w + 127) & ~127) : 0;
     uint8_t *S = smem;                                                   // [src_tile_h][src_tile_w] (RESIZE)
-    uint8_t *R = smem + s_bytes;                                         // [RH][FW]
-    uint32_t *Hp = reinterpret_cast<uint32_t *>(R + 3712);               // [RH/2][TW]
-    XTap *xt = reinterpret_cast<XTap *>(R + 3712 + (RH / 2) * TW * 4);   // [72]
-    YTap *yt = reinterpret_cast<YTap *>(xt + 72);                        // [RH + 2]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(yt + RH + 2);
+    uint8_t *R = smem + s_bytes;                                         // [FRH][FW]
+    uint32_t *Hp = reinterpret_cast<uint32_t *>(R + FR_BYTES);           // [FRH/2][TW]
+    XTap *xt = reinterpret_cast<XTap *>(R + FR_BYTES + (FRH / 2) * TW * 4);   // [72]
+    YTap *yt = reinterpret_cast<YTap *>(xt + 2 * COLP);                  // [FRH + 2]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(yt + FRH + 2);
 
     constexpr int FW = RGeom<RESIZE>::FW, X0 = RGeom<RESIZE>::X0;   // R pitch; R column of x0
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, f = blockIdx.z + a.f0;
-    const int tw = min(TW, a.w - x0), th = min(TH, a.h - y0);
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * FTH, f = blockIdx.z + a.f0;
+    const int tw = min(TW, a.w - x0), th = min(FTH, a.h - y0);
     const int xlo = max(x0 - 3, 0), xhi = min(x0 + tw + 3, a.w);
     const int ylo = max(y0 - 3, 0), yhi = min(y0 + th + 3, a.h);
 
     if (RESIZE) {
         // one thread pulls the source tile with TMA while the others stage the taps
         const int sx_lo = a.xtab[xlo].s0 & ~15, sy_lo = a.ytab[ylo].s0;   // 16-byte aligned box origin
-        const int sp = a.src_tile_w;
+        const int sp = a.src_tile_w, spw = sp >> 2;
         if (tid == 0) {
             mbar_init(bar, 1);
             mbar_expect_tx(bar, (uint32_t)(sp * a.src_tile_h));
             tma_load_3d(S, &tmap, sx_lo, sy_lo, f, bar);
         }
         // taps of every window column / row; outside the image the nearest valid tap (value unused)
-        if (tid >= 32 && tid < 32 + 72) {
+        if (tid >= 32 && tid < 32 + 2 * COLP) {
             const int c = tid - 32;
             const ResizeTap t = a.xtab[min(max(x0 - 4 + c, xlo), xhi - 1)];
             xt[c] = XTap{(uint32_t)(uint16_t)t.a0 | ((uint32_t)(uint16_t)t.a1 << 16), t.s0 - sx_lo};
-        } else if (tid >= 128 && tid < 128 + RH) {
+        } else if (tid >= 128 && tid < 128 + FRH) {
             const ResizeTap t = a.ytab[min(max(y0 - 3 + tid - 128, ylo), yhi - 1)];
-            yt[tid - 128] = YTap{(int16_t)(t.s0 - sy_lo), (int16_t)(t.s1 - sy_lo), t.a0, t.a1};
+            yt[tid - 128] = YTap{(int16_t)((t.s0 - sy_lo) * spw), (int16_t)((t.s1 - sy_lo) * spw), t.a0, t.a1};
         }
         __syncthreads();          // taps staged, barrier initialised
+        const int cp = tid % COLP, rg = tid / COLP;
+        // column taps of this thread's pair: loop invariants
+        const uint4 tx = *reinterpret_cast<const uint4 *>(xt + 2 * cp);   // {coef_a, s0_a, coef_b, s0_b}
+        const int base = (int)tx.y >> 2;
+        const unsigned oa = tx.y & 3u, ob = tx.w - 4u * (unsigned)base;     // byte offsets in the 8-byte window
+        const unsigned sel_a = oa * 0x11u + 0x10u, sel_b = ob * 0x11u + 0x10u;
+        const uint32_t *Sw = reinterpret_cast<const uint32_t *>(S) + base;
+        uint8_t *Rc = R + 2 * cp;
         mbar_wait(bar, 0);        // source tile landed
-        for (int i = tid; i < RH * 36; i += PYR_THREADS) {
-            const int ry = i / 36, cp = i - ry * 36;
-            const uint4 tx = *reinterpret_cast<const uint4 *>(xt + 2 * cp);   // {coef_a, s0_a, coef_b, s0_b}
-            const YTap ty = yt[ry];
-            const int base = (int)tx.y >> 2;
-            const unsigned oa = tx.y & 3u, ob = tx.w - 4u * (unsigned)base;     // byte offsets in the 8-byte window
-            const unsigned sel_a = oa * 0x11u + 0x10u, sel_b = ob * 0x11u + 0x10u;
-            const uint32_t *r0 = reinterpret_cast<const uint32_t *>(S + ty.s0 * sp) + base;
-            const uint32_t *r1 = reinterpret_cast<const uint32_t *>(S + ty.s1 * sp) + base;
-            const uint32_t p0 = r0[0], p1 = r0[1], q0 = r1[0], q1 = r1[1];
-            const unsigned ha0 = __dp2a_lo(tx.x, __byte_perm(p0, p1, sel_a), 0u);
-            const unsigned ha1 = __dp2a_lo(tx.x, __byte_perm(q0, q1, sel_a), 0u);
-            const unsigned hb0 = __dp2a_lo(tx.z, __byte_perm(p0, p1, sel_b), 0u);
-            const unsigned hb1 = __dp2a_lo(tx.z, __byte_perm(q0, q1, sel_b), 0u);
-            const unsigned b0 = (unsigned)ty.b0, b1 = (unsigned)ty.b1;
-            const unsigned va = (((b0 * (ha0 >> 4)) >> 16) + ((b1 * (ha1 >> 4)) >> 16) + 2u) >> 2;
-            const unsigned vb = (((b0 * (hb0 >> 4)) >> 16) + ((b1 * (hb1 >> 4)) >> 16) + 2u) >> 2;
-            *reinterpret_cast<uint16_t *>(R + ry * FW + 2 * cp) = (uint16_t)(va | (vb << 8));
+        if (rg < ROWG) {
+#pragma unroll 5
+            for (int k = 0; k < ROWS_PER_G; ++k) {
+                const int ry = rg * ROWS_PER_G + k;
+                const YTap ty = yt[ry];
+                const uint32_t *r0 = Sw + ty.w0, *r1 = Sw + ty.w1;
+                const uint32_t p0 = r0[0], p1 = r0[1], q0 = r1[0], q1 = r1[1];
+                const unsigned ha0 = __dp2a_lo(tx.x, __byte_perm(p0, p1, sel_a), 0u);
+                const unsigned ha1 = __dp2a_lo(tx.x, __byte_perm(q0, q1, sel_a), 0u);
+                const unsigned hb0 = __dp2a_lo(tx.z, __byte_perm(p0, p1, sel_b), 0u);
+                const unsigned hb1 = __dp2a_lo(tx.z, __byte_perm(q0, q1, sel_b), 0u);
+                const unsigned b0 = (unsigned)ty.b0, b1 = (unsigned)ty.b1;
+                const unsigned va = (((b0 * (ha0 >> 4)) >> 16) + ((b1 * (ha1 >> 4)) >> 16) + 2u) >> 2;
+                const unsigned vb = (((b0 * (hb0 >> 4)) >> 16) + ((b1 * (hb1 >> 4)) >> 16) + 2u) >> 2;
+                *reinterpret_cast<uint16_t *>(Rc + ry * FW) = (uint16_t)(va | (vb << 8));
+            }
         }
     } else {
-        // blur only: the 96 x 38 window of the plane goes straight into R (zero outside the image)
+        // blur only: the 96 x 70 window of the plane goes straight into R (zero outside the image)
         if (tid == 0) {
             mbar_init(bar, 1);
-            mbar_expect_tx(bar, (uint32_t)(RH * FW));
+            mbar_expect_tx(bar, (uint32_t)(FRH * FW));
             tma_load_3d(R, &tmap, x0 - X0, y0 - 3, f, bar);
         }
         __syncthreads();
@@ -286,11 +297,12 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
 
     // ---- pyramid plane: interior of R, 32-bit stores ----------------------------------------------
     if (RESIZE) {
-        uint8_t *dst = a.dst + (size_t)f * a.dstride;
-        for (int i = tid; i < TH * (TW / 4); i += PYR_THREADS) {
-            const int r = i >> 4, wd = i & 15;
-            if (r < th && 4 * wd < tw)
-                *reinterpret_cast<uint32_t *>(dst + (size_t)(y0 + r) * a.pitch + x0 + 4 * wd) =
+        uint8_t *dst = a.dst + (size_t)f * a.dstride + (size_t)y0 * a.pitch + x0;
+        const int wd = tid & 15;
+        if (4 * wd < tw) {
+#pragma unroll 4
+            for (int r = tid >> 4; r < th; r += PYR_THREADS / 16)
+                *reinterpret_cast<uint32_t *>(dst + (size_t)r * a.pitch + 4 * wd) =
                     *reinterpret_cast<const uint32_t *>(R + (r + 3) * FW + X0 + 4 * wd);
         }
     }
@@ -300,7 +312,7 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
         const bool left = x0 == 0, right = x0 + tw + 3 > a.w, top = y0 == 0, bottom = y0 + th + 3 > a.h;
         if (left || right || top || bottom) {
             if (left || right)
-                for (int i = tid; i < RH * 6; i += PYR_THREADS) {
+                for (int i = tid; i < FRH * 6; i += PYR_THREADS) {
                     const int ry = i / 6, k = i - ry * 6;
                     const int x = k < 3 ? k - 3 : a.w + k - 3, y = y0 - 3 + ry;
                     if ((k < 3 ? left : right) && y < a.h + 3 && x - x0 < TW + 4) {
@@ -312,7 +324,7 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
                 for (int i = tid; i < 6 * 72; i += PYR_THREADS) {
                     const int k = i / 72, rx = i - k * 72;
                     const int y = k < 3 ? k - 3 : a.h + k - 3, x = x0 - 4 + rx;
-                    if ((k < 3 ? top : bottom) && x >= 0 && x < a.w && y - (y0 - 3) < RH) {
+                    if ((k < 3 ? top : bottom) && x >= 0 && x < a.w && y - (y0 - 3) < FRH) {
                         const int my = reflect101(y, a.h);
                         R[(y - (y0 - 3)) * FW + rx + X0 - 4] = R[(my - (y0 - 3)) * FW + rx + X0 - 4];
                     }
@@ -325,8 +337,8 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
     {
         const uint32_t k0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);   // taps 0..3
         const uint32_t k1 = 48u | (34u << 8) | (18u << 16);                 // taps 4..6
-        for (int i = tid; i < (RH / 2) * (TW / 4); i += PYR_THREADS) {
-            const int rp = i >> 4, g = i & 15;
+        const int g = tid & 15;
+        for (int rp = tid >> 4; rp < FRH / 2; rp += PYR_THREADS / 16) {
             uint32_t o[2][4];
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
@@ -339,52 +351,72 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
                 o[rr][3] = __dp4a(w1, k0, __dp4a(w2, k1, 0u));
             }
             *reinterpret_cast<uint4 *>(Hp + rp * TW + 4 * g) =
-                make_uint4(o[0][0] | (o[1][0] << 16), o[0][1] | (o[1][1] << 16), o[0][2] | (o[1][2] << 16), o[0][3] | (o[1][3] << 16));
+                make_uint4(__byte_perm(o[0][0], o[1][0], 0x5410), __byte_perm(o[0][1], o[1][1], 0x5410),
+                           __byte_perm(o[0][2], o[1][2], 0x5410), __byte_perm(o[0][3], o[1][3], 0x5410));
         }
     }
     __syncthreads();
 
-    // ---- vertical pass: 4 columns x 2 rows per thread; out row r uses H rows r .. r+6 --------------
+    // ---- vertical pass: 4 columns x 4 rows per thread; out row r uses H rows r .. r+6 --------------
     {
-        uint8_t *bl = a.blur + (size_t)f * a.dstride;
-        const int g = tid & 15, rp = tid >> 4;   // 16 column groups x 16 row pairs
-        const int r0 = 2 * rp;
+        const int g = tid & 15, strip = tid >> 4;   // 16 column groups x 16 strips of 2 row pairs
+        const int r0 = 4 * strip;
         if (r0 < th && 4 * g < tw) {
-            const uint4 P0 = *reinterpret_cast<const uint4 *>(Hp + (rp + 0) * TW + 4 * g);
-            const uint4 P1 = *reinterpret_cast<const uint4 *>(Hp + (rp + 1) * TW + 4 * g);
-            const uint4 P2 = *reinterpret_cast<const uint4 *>(Hp + (rp + 2) * TW + 4 * g);
-            const uint4 P3 = *reinterpret_cast<const uint4 *>(Hp + (rp + 3) * TW + 4 * g);
+            uint8_t *bl = a.blur + (size_t)f * a.dstride + (size_t)(y0 + r0) * a.pitch + x0 + 4 * g;
+            uint4 P[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) P[j] = *reinterpret_cast<const uint4 *>(Hp + (2 * strip + j) * TW + 4 * g);
             const uint32_t kA = 18u | (34u << 8) | (48u << 16) | (56u << 24);   // k0 k1 | k2 k3
             const uint32_t kB = 48u | (34u << 8);                               // k4 k5
             const uint32_t kC = 34u | (48u << 8) | (56u << 16) | (48u << 24);   // k1 k2 | k3 k4
             const uint32_t kD = 34u | (18u << 8);                               // k5 k6
-            const uint32_t p0[4] = {P0.x, P0.y, P0.z, P0.w}, p1[4] = {P1.x, P1.y, P1.z, P1.w};
-            const uint32_t p2[4] = {P2.x, P2.y, P2.z, P2.w}, p3[4] = {P3.x, P3.y, P3.z, P3.w};
-            uint32_t even = 0, odd = 0;
+            const uint32_t kE = 18u;                                            // k6 on the low half
+            const uint32_t kF = 18u << 8;                                       // k0 on the high half
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                // even row r0: rows r0..r0+5 are the pairs P0 P1 P2, row r0+6 is the low half of P3
-                uint32_t ve = __dp2a_lo(p0[c], kA, (p3[c] & 0xffffu) * 18u + 32768u);
-                ve = __dp2a_hi(p1[c], kA, ve);
-                ve = __dp2a_lo(p2[c], kB, ve);
-                // odd row r0+1: row r0+1 is the high half of P0, rows r0+2..r0+7 are P1 P2 P3
-                uint32_t vo = __dp2a_lo(p1[c], kC, (p0[c] >> 16) * 18u + 32768u);
-                vo = __dp2a_hi(p2[c], kC, vo);
-                vo = __dp2a_lo(p3[c], kD, vo);
-                even |= (ve >> 16) << (8 * c);
-                odd |= (vo >> 16) << (8 * c);
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t p0[4] = {P[h].x, P[h].y, P[h].z, P[h].w}, p1[4] = {P[h + 1].x, P[h + 1].y, P[h + 1].z, P[h + 1].w};
+                const uint32_t p2[4] = {P[h + 2].x, P[h + 2].y, P[h + 2].z, P[h + 2].w}, p3[4] = {P[h + 3].x, P[h + 3].y, P[h + 3].z, P[h + 3].w};
+                uint32_t ve[4], vo[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    // even row: rows r..r+5 are the pairs p0 p1 p2, row r+6 is the low half of p3
+                    uint32_t e = __dp2a_lo(p0[c], kA, 32768u);
+                    e = __dp2a_hi(p1[c], kA, e);
+                    e = __dp2a_lo(p2[c], kB, e);
+                    ve[c] = __dp2a_lo(p3[c], kE, e);
+                    // odd row: row r+1 is the high half of p0, rows r+2..r+7 are p1 p2 p3
+                    uint32_t o = __dp2a_lo(p0[c], kF, 32768u);
+                    o = __dp2a_lo(p1[c], kC, o);
+                    o = __dp2a_hi(p2[c], kC, o);
+                    vo[c] = __dp2a_lo(p3[c], kD, o);
+                }
+                // byte 2 of every sum (v >> 16 fits 8 bits): two PRMTs gather four of them
+                const uint32_t even = __byte_perm(__byte_perm(ve[0], ve[1], 0x0062), __byte_perm(ve[2], ve[3], 0x0062), 0x5410);
+                const uint32_t odd = __byte_perm(__byte_perm(vo[0], vo[1], 0x0062), __byte_perm(vo[2], vo[3], 0x0062), 0x5410);
+                const int r = r0 + 2 * h;
+                if (r < th) *reinterpret_cast<uint32_t *>(bl + (size_t)(2 * h) * a.pitch) = even;
+                if (r + 1 < th) *reinterpret_cast<uint32_t *>(bl + (size_t)(2 * h + 1) * a.pitch) = odd;
             }
-            *reinterpret_cast<uint32_t *>(bl + (size_t)(y0 + r0) * a.pitch + x0 + 4 * g) = even;
-            if (r0 + 1 < th) *reinterpret_cast<uint32_t *>(bl + (size_t)(y0 + r0 + 1) * a.pitch + x0 + 4 * g) = odd;
         }
     }
 }
 
 static size_t pyr_fast_smem_bytes(const PyrArgs &a, bool resize) {
-    size_t b = 3712 + (RH / 2) * TW * 4 + 72 * sizeof(XTap) + (RH + 2) * sizeof(YTap) + 16;
+    size_t b = FR_BYTES + (FRH / 2) * TW * 4 + 2 * COLP * sizeof(XTap) + (FRH + 2) * sizeof(YTap) + 16;
     if (resize) b += (((size_t)(a.src_tile_h + 1) * a.src_tile_w + 127) & ~(size_t)127);
     return b;
 }
+
+// Source rows one 64-row tile of the fast kernel needs (TMA box height), host, at sg_create.
+int pyramid_fast_source_rows(const std::vector<ResizeTap> &yt, int h) {
+    int mh = 0;
+    for (int y0 = 0; y0 < h; y0 += FTH) {
+        const int th = std::min(FTH, h - y0), ylo = std::max(y0 - 3, 0), yhi = std::min(y0 + th + 3, h);
+        mh = std::max(mh, yt[yhi - 1].s1 - yt[ylo].s0 + 1);
+    }
+    return mh;
+}
+int pyramid_fast_tile_rows() { return FTH; }
 
 static size_t pyr_smem_bytes(const PyrArgs &a, bool resize) {
     size_t b = RH * RW + RH * TW * 2;
@@ -422,9 +454,10 @@ int launch_pyramid(sg_ctx *ctx, int n_frames) {
         a.w = L.w; a.h = L.h; a.pitch = L.pitch; a.dstride = L.frame_stride;
         a.blur = L.blur;
         dim3 grid((L.w + TW - 1) / TW, (L.h + TH - 1) / TH, n_frames);
+        const dim3 fgrid((L.w + TW - 1) / TW, (L.h + FTH - 1) / FTH, n_frames);
         if (l == 0) {
             a.src = ctx->level0; a.sw = L.w; a.sh = L.h; a.spitch = ctx->level0_pitch; a.sstride = ctx->level0_stride;
-            pyr_fast_kernel<false><<<grid, PYR_THREADS, pyr_fast_smem_bytes(a, false), ctx->stream>>>(a, L.map_src);
+            pyr_fast_kernel<false><<<fgrid, PYR_THREADS, pyr_fast_smem_bytes(a, false), ctx->stream>>>(a, L.map_src);
         } else {
             const Level &P = ctx->lv[l - 1];
             a.src = l == 1 ? ctx->level0 : P.pyr;
@@ -439,7 +472,7 @@ int launch_pyramid(sg_ctx *ctx, int n_frames) {
             fa.src_tile_w = L.tma_src_w; fa.src_tile_h = L.tma_src_h;
             const size_t fsmem = pyr_fast_smem_bytes(fa, true);
             if (L.fast_resize && fsmem <= 48 * 1024) {
-                pyr_fast_kernel<true><<<grid, PYR_THREADS, fsmem, ctx->stream>>>(fa, L.map_src);
+                pyr_fast_kernel<true><<<fgrid, PYR_THREADS, fsmem, ctx->stream>>>(fa, L.map_src);
             } else {   // INTER_AREA switch (exact 2x) or a scale factor above 2: generic kernel
                 const size_t smem = pyr_smem_bytes(a, true);
                 if (smem > 48 * 1024)

@@ -42,7 +42,7 @@ int encode_level0_maps(sg_ctx *ctx) {
     const Level &L0 = ctx->lv[0];
     const int frames = ctx->frames_ready > 0 ? ctx->frames_ready : 1;
     if (int r = encode_plane_map(ctx, &ctx->lv[0].map_src, ctx->level0, L0.w, L0.h, ctx->level0_pitch, ctx->level0_stride,
-                                 frames, 96, 38)) return r;
+                                 frames, 96, 70)) return r;   // window of the blur-only kernel: 64 + 32 x 64 + 6
     if (int r = encode_plane_map(ctx, &ctx->lv[0].map_fast, ctx->level0, L0.w, L0.h, ctx->level0_pitch, ctx->level0_stride,
                                  frames, 80, 70)) return r;
     if (ctx->p.levels > 1 && ctx->lv[1].fast_resize)
