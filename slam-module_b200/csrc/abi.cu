@@ -100,8 +100,7 @@ static int build_context(sg_ctx *ctx) {
                 }
                 L.tma_src_w = (mw + 15) & ~15;
                 L.tma_src_h = pyramid_fast_source_rows(yt, L.h);
-                // YTap keeps row * (pitch / 4) in 16 bits
-                if (L.tma_src_w > 256 || L.tma_src_h > 255 || (L.tma_src_h + 1) * (L.tma_src_w / 4) > 32767) L.fast_resize = false;
+                if (L.tma_src_w > 256 || L.tma_src_h > 255) L.fast_resize = false;
             }
             for (int i = 0; i + 1 < L.w; ++i)
                 if (xt[i + 1].s0 - xt[i].s0 > 2 || xt[i + 1].s0 < xt[i].s0) L.fast_resize = false;

@@ -216,7 +216,7 @@ constexpr int ROWG = 7, ROWS_PER_G = FRH / ROWG;   // 7 row groups x 10 rows; 7 
 static_assert(ROWG * ROWS_PER_G == FRH && ROWG * COLP <= PYR_THREADS, "resize work split");
 template <bool RESIZE> struct RGeom { static constexpr int FW = RESIZE ? 80 : 96, X0 = RESIZE ? 4 : 16; };
 struct XTap { uint32_t coef; int32_t s0; };          // a0 | a1 << 16, source column relative to the tile
-struct YTap { int16_t w0, w1, b0, b1; };             // source row word offsets (row * pitch / 4), coefficients
+struct YTap { uint32_t o0, o1, b0s, b1s; };          // byte offsets of the two source rows in S, coefficients << 12
 
 template <bool RESIZE>
 __global__ void __launch_bounds__(PYR_THREADS)
@@ -254,7 +254,8 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
             xt[c] = XTap{(uint32_t)(uint16_t)t.a0 | ((uint32_t)(uint16_t)t.a1 << 16), t.s0 - sx_lo};
         } else if (tid >= 128 && tid < 128 + FRH) {
             const ResizeTap t = a.ytab[min(max(y0 - 3 + tid - 128, ylo), yhi - 1)];
-            yt[tid - 128] = YTap{(int16_t)((t.s0 - sy_lo) * spw), (int16_t)((t.s1 - sy_lo) * spw), t.a0, t.a1};
+            yt[tid - 128] = YTap{(uint32_t)((t.s0 - sy_lo) * sp), (uint32_t)((t.s1 - sy_lo) * sp),
+                                 (uint32_t)(uint16_t)t.a0 << 12, (uint32_t)(uint16_t)t.a1 << 12};
         }
         __syncthreads();          // taps staged, barrier initialised
         const int cp = tid % COLP, rg = tid / COLP;
@@ -262,25 +263,24 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
         const uint4 tx = *reinterpret_cast<const uint4 *>(xt + 2 * cp);   // {coef_a, s0_a, coef_b, s0_b}
         const int base = (int)tx.y >> 2;
         const unsigned oa = tx.y & 3u, ob = tx.w - 4u * (unsigned)base;     // byte offsets in the 8-byte window
-        const unsigned sel_a = oa * 0x11u + 0x10u, sel_b = ob * 0x11u + 0x10u;
-        const uint32_t *Sw = reinterpret_cast<const uint32_t *>(S) + base;
-        uint8_t *Rc = R + 2 * cp;
+        // one PRMT gathers {S[a], S[a+1], S[b], S[b+1]} of a source row from its aligned 8-byte window
+        const unsigned sel = (oa * 0x11u + 0x10u) | ((ob * 0x11u + 0x10u) << 8);
+        const uint32_t s_col = smem_u32(S) + 4u * (unsigned)base;          // shared-space address of the window column
+        uint32_t r_addr = smem_u32(R) + 2u * cp + (unsigned)(rg * ROWS_PER_G) * FW;
+        const uint32_t yt_addr = smem_u32(yt) + (unsigned)(rg * ROWS_PER_G) * (unsigned)sizeof(YTap);
         mbar_wait(bar, 0);        // source tile landed
         if (rg < ROWG) {
-#pragma unroll 5
+#pragma unroll
             for (int k = 0; k < ROWS_PER_G; ++k) {
-                const int ry = rg * ROWS_PER_G + k;
-                const YTap ty = yt[ry];
-                const uint32_t *r0 = Sw + ty.w0, *r1 = Sw + ty.w1;
-                const uint32_t p0 = r0[0], p1 = r0[1], q0 = r1[0], q1 = r1[1];
-                const unsigned ha0 = __dp2a_lo(tx.x, __byte_perm(p0, p1, sel_a), 0u);
-                const unsigned ha1 = __dp2a_lo(tx.x, __byte_perm(q0, q1, sel_a), 0u);
-                const unsigned hb0 = __dp2a_lo(tx.z, __byte_perm(p0, p1, sel_b), 0u);
-                const unsigned hb1 = __dp2a_lo(tx.z, __byte_perm(q0, q1, sel_b), 0u);
-                const unsigned b0 = (unsigned)ty.b0, b1 = (unsigned)ty.b1;
-                const unsigned va = (((b0 * (ha0 >> 4)) >> 16) + ((b1 * (ha1 >> 4)) >> 16) + 2u) >> 2;
-                const unsigned vb = (((b0 * (hb0 >> 4)) >> 16) + ((b1 * (hb1 >> 4)) >> 16) + 2u) >> 2;
-                *reinterpret_cast<uint16_t *>(Rc + ry * FW) = (uint16_t)(va | (vb << 8));
+                const uint4 ty = lds128(yt_addr + k * (unsigned)sizeof(YTap));
+                const uint32_t a0 = s_col + ty.x, a1 = s_col + ty.y;
+                const uint32_t g0 = __byte_perm(lds32(a0), lds32(a0 + 4), sel), g1 = __byte_perm(lds32(a1), lds32(a1 + 4), sel);
+                const unsigned ha0 = __dp2a_lo(tx.x, g0, 0u), hb0 = __dp2a_hi(tx.z, g0, 0u);
+                const unsigned ha1 = __dp2a_lo(tx.x, g1, 0u), hb1 = __dp2a_hi(tx.z, g1, 0u);
+                // ((b * (h >> 4)) >> 16) == umulhi(b << 12, h & ~15): one LOP3 + one IMAD.HI per product
+                const unsigned va = (__umulhi(ty.w, ha1 & ~15u) + __umulhi(ty.z, ha0 & ~15u) + 2u) >> 2;
+                const unsigned vb = (__umulhi(ty.w, hb1 & ~15u) + __umulhi(ty.z, hb0 & ~15u) + 2u) >> 2;
+                sts16(r_addr + k * FW, va | (vb << 8));
             }
         }
     } else {
@@ -334,9 +334,21 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
     }
 
     // ---- horizontal pass: 4 columns x 2 rows per item, stored as vertical u16 pairs ---------------
+    // Output c = 4g + j is sum_i k[i] * R[c + 1 + i] over the 12 window bytes w0 w1 w2 = R[4g .. 4g + 11]:
+    // the kernel is shifted inside the coefficient words instead of shifting the data, so the pass is
+    // IDP.4A only (10 per 4 outputs, FMA pipe) with no PRMT on the ALU pipe.
     {
-        const uint32_t k0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);   // taps 0..3
-        const uint32_t k1 = 48u | (34u << 8) | (18u << 16);                 // taps 4..6
+        constexpr uint32_t K0 = 18, K1 = 34, K2 = 48, K3 = 56;                      // k[0..3]; k[4..6] = k[2..0]
+        constexpr uint32_t A0 = (K0 << 8) | (K1 << 16) | (K2 << 24);                // j = 0: w0 bytes 1..3
+        constexpr uint32_t A1 = K3 | (K2 << 8) | (K1 << 16) | (K0 << 24);           //        w1 bytes 0..3
+        constexpr uint32_t B0 = (K0 << 16) | (K1 << 24);                            // j = 1: w0 bytes 2..3
+        constexpr uint32_t B1 = K2 | (K3 << 8) | (K2 << 16) | (K1 << 24);           //        w1
+        constexpr uint32_t B2 = K0;                                                 //        w2 byte 0
+        constexpr uint32_t C0 = K0 << 24;                                           // j = 2: w0 byte 3
+        constexpr uint32_t C1 = K1 | (K2 << 8) | (K3 << 16) | (K2 << 24);           //        w1
+        constexpr uint32_t C2 = K1 | (K0 << 8);                                     //        w2 bytes 0..1
+        constexpr uint32_t D1 = K0 | (K1 << 8) | (K2 << 16) | (K3 << 24);           // j = 3: w1
+        constexpr uint32_t D2 = K2 | (K1 << 8) | (K0 << 16);                        //        w2 bytes 0..2
         const int g = tid & 15;
         for (int rp = tid >> 4; rp < FRH / 2; rp += PYR_THREADS / 16) {
             uint32_t o[2][4];
@@ -344,15 +356,15 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
             for (int rr = 0; rr < 2; ++rr) {
                 const uint32_t *row = reinterpret_cast<const uint32_t *>(R + (2 * rp + rr) * FW + X0 - 4) + g;
                 const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];   // window columns 4g .. 4g+11 (x0-4+4g ..)
-                // output c = 4g + j uses R columns c+1 .. c+7
-                o[rr][0] = __dp4a(__byte_perm(w0, w1, 0x4321), k0, __dp4a(__byte_perm(w1, w2, 0x4321), k1, 0u));
-                o[rr][1] = __dp4a(__byte_perm(w0, w1, 0x5432), k0, __dp4a(__byte_perm(w1, w2, 0x5432), k1, 0u));
-                o[rr][2] = __dp4a(__byte_perm(w0, w1, 0x6543), k0, __dp4a(__byte_perm(w1, w2, 0x6543), k1, 0u));
-                o[rr][3] = __dp4a(w1, k0, __dp4a(w2, k1, 0u));
+                o[rr][0] = __dp4a(w1, A1, __dp4a(w0, A0, 0u));
+                o[rr][1] = __dp4a(w2, B2, __dp4a(w1, B1, __dp4a(w0, B0, 0u)));
+                o[rr][2] = __dp4a(w2, C2, __dp4a(w1, C1, __dp4a(w0, C0, 0u)));
+                o[rr][3] = __dp4a(w2, D2, __dp4a(w1, D1, 0u));
             }
+            // H[r] | H[r+1] << 16 as a multiply-add (FMA pipe); both halves are below 65536
             *reinterpret_cast<uint4 *>(Hp + rp * TW + 4 * g) =
-                make_uint4(__byte_perm(o[0][0], o[1][0], 0x5410), __byte_perm(o[0][1], o[1][1], 0x5410),
-                           __byte_perm(o[0][2], o[1][2], 0x5410), __byte_perm(o[0][3], o[1][3], 0x5410));
+                make_uint4(o[1][0] * 65536u + o[0][0], o[1][1] * 65536u + o[0][1],
+                           o[1][2] * 65536u + o[0][2], o[1][3] * 65536u + o[0][3]);
         }
     }
     __syncthreads();
