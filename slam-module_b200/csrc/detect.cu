@@ -34,67 +34,50 @@ constexpr int TILE_ROWS = CELL + 6;    // 70
 constexpr int RPW = CELL + 8;          // response map pitch: 4-byte left pad (word-aligned rows) + 64 + right pad
 constexpr int TILE_SHIFT = 3;          // the window origin 19 + 64*j is always 3 past a word boundary
 static_assert((EVAL_ORIGIN - FAST_BORDER) % 4 == TILE_SHIFT && CELL % 4 == 0, "tile alignment");
-constexpr int MAX_SURVIVORS = CELL * CELL;
+constexpr int WP = TP / 2;             // pair-word pitch: 40 words per row
+constexpr int MAX_ENTRIES = CELL * CELL;   // 2048 pixel pairs, each at most twice (both polarities)
+constexpr int WARP_Q = MAX_ENTRIES / (FAST_THREADS / 32);   // per-warp queue: 8 rows x 32 pairs x 2
+constexpr int MAX_SCORED = 1024;           // list of scored pixels (NMS candidates); beyond it the map is scanned
 
-// ---- FAST-9/16 in s16x2 lanes -------------------------------------------------------------------------
-// Ring: Bresenham circle of radius 3, clockwise from (0, 3) -- the order cv::FAST uses.  Differences are
-// kept biased, e = 256 + v - p (1..511), two pixels per 32-bit register, so a plain 32-bit subtract
-// never borrows across lanes and unsigned 16x2 min/max (native VIMNMX.U16x2 / VIMNMX3) apply.
-//   corner at threshold t  <=>  some arc of 9 has all e > 256 + t (dark) or all e < 256 - t (bright)
-//   cornerScore            ==   max over arcs of max(min9(e) - 256, 256 - max9(e)) - 1
-// Filter (necessary condition, cheap): every arc of 9 contains one pixel of each of the 8 antipodal
-// pairs, so  min_k max(e_k, e_k+8) > 256 + t  or  max_k min(e_k, e_k+8) < 256 - t  must hold.
+// ---- FAST-9/16 in u16x2 lanes ---------------------------------------------------------------------------
+// Ring: Bresenham circle of radius 3, clockwise from (0, 3) -- the order cv::FAST uses.  Two horizontally
+// adjacent pixels (x, x+1) are processed per 32-bit register, one per 16-bit lane.  The cell window is kept in
+// shared memory as PAIR WORDS: We[y][i] = p(2i) | p(2i+1) << 16 and Wo[y][i] = p(2i+1) | p(2i+2) << 16, so the
+// ring pixel of both lanes at any offset (dx, dy) is ONE aligned 32-bit load (We for even dx, Wo for odd dx):
+// no per-use byte permutes.  Differences are kept biased, e = 256 + v - p (1..511), so a plain 32-bit subtract
+// never borrows across lanes and the native 16x2 min / max (VIMNMX.U16x2, VIMNMX3) apply.
+//   corner at threshold t (dark)  <=>  some arc of 9 has all e > 256 + t
+//   dark score                    ==   max over arcs of min9(e) - 257        (cv::cornerScore convention)
+// The bright polarity is the dark polarity of the complemented image (p -> 255 - p), so a lane that needs the
+// bright test XORs its pixels with 0xff and runs the same code.
+// Stage 1 (every pair): an arc of 9 contains one pixel of each antipodal pair, so for the compass pairs
+//   (e0 or e8 dark) and (e4 or e12 dark)  <=>  min(max(e0, e8), max(e4, e12)) > 256 + t   is necessary.
+// Stage 2 (pairs that pass, compacted): exact one-sided score of both lanes for the polarity stage 1 left
+// possible (a pixel can be a corner of one polarity only; a lane that passes both is queued twice).
 // NOTE: the scalar formulation `max(min9, -max9)` on int is miscompiled by ptxas 12.9 (-O1 and above,
-// sm_100a); the biased unsigned form below avoids the pattern.  Parity is pinned by the GPU tests
-// (candidate positions and responses, bit for bit against the oracle).
-__device__ __forceinline__ unsigned lane_pair(unsigned w, int which) {   // bytes (0,1) or (2,3) -> u16x2
-    return which == 0 ? __byte_perm(w, 0u, 0x4140) : __byte_perm(w, 0u, 0x4342);
-}
+// sm_100a); the biased unsigned form avoids the pattern.  Parity is pinned by the GPU tests (candidate
+// positions and responses, bit for bit against the oracle).
 
 // Per-lane a > b for u16x2 lanes below 32768: bit 15 / 31 of the result (no borrow across lanes).
 __device__ __forceinline__ unsigned gt16x2(unsigned a, unsigned b) {
     return ~((b | 0x80008000u) - a) & 0x80008000u;
 }
 
-// Exact score of two (unrelated) pixels at once: lane lo = pixel at ca, lane hi = pixel at cb.
-template <int P>
-__device__ __forceinline__ unsigned fast_score_2px(const uint8_t *ca, const uint8_t *cb) {
-    const int off[16] = {3 * P, 3 * P + 1, 2 * P + 2, P + 3, 3, -P + 3, -2 * P + 2, -3 * P + 1,
-                         -3 * P, -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3, 2 * P - 2, 3 * P - 1};
-    const unsigned vb = ((unsigned)ca[0] | ((unsigned)cb[0] << 16)) | 0x01000100u;
-    unsigned e[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) e[k] = vb - ((unsigned)ca[off[k]] | ((unsigned)cb[off[k]] << 16));
-    // sliding min / max over windows of 9 of the circular sequence, by doubling: 2, 4, 8, then +1
-    unsigned mn2[16], mx2[16], mn4[16], mx4[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { mn2[k] = __vminu2(e[k], e[(k + 1) & 15]); mx2[k] = __vmaxu2(e[k], e[(k + 1) & 15]); }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { mn4[k] = __vminu2(mn2[k], mn2[(k + 2) & 15]); mx4[k] = __vmaxu2(mx2[k], mx2[(k + 2) & 15]); }
-    unsigned lo = 0u, hi = 0x02000200u;    // running max of min9, running min of max9
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        lo = __vmaxu2(lo, __vminu2(__vminu2(mn4[k], mn4[(k + 4) & 15]), e[(k + 8) & 15]));
-        hi = __vminu2(hi, __vmaxu2(__vmaxu2(mx4[k], mx4[(k + 4) & 15]), e[(k + 8) & 15]));
-    }
-    // score + 256 = max(lo, 512 - hi) - 1   (all quantities stay inside 0..511 per lane)
-    return __vmaxu2(lo, 0x02000200u - hi) - 0x00010001u;
-}
-
 struct FastMaps { CUtensorMap m[SG_MAX_LEVELS]; };   // 80 x 70 box over every pyramid level
 
-__global__ void __launch_bounds__(FAST_THREADS)
+__global__ void __launch_bounds__(FAST_THREADS, 4)
 fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ FastMaps maps, int total_cells,
                   unsigned long long *cand, int *cand_count, int *err) {
-    __shared__ __align__(128) uint8_t tile[TILE_ROWS * TP];
+    __shared__ __align__(128) uint8_t tile[TILE_ROWS * TP + 16];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(16) uint32_t We[TILE_ROWS * WP], Wo[TILE_ROWS * WP];
     __shared__ __align__(16) uint8_t resp[(CELL + 2) * RPW];
-    __shared__ unsigned short surv[MAX_SURVIVORS];        // y << 6 | x of the pixels passing the filter
+    __shared__ unsigned short ent[MAX_ENTRIES];                // k | y << 5 | side_a << 11 | side_b << 13 | dup << 15
     __shared__ unsigned short keep[(CELL / 2) * (CELL / 2)];   // NMS winners (at most one per 2x2 block)
-    __shared__ unsigned short quads[(CELL / 4) * CELL];       // y << 4 | q of the quads passing the compass test
-    __shared__ int s_nsurv, s_nkeep, s_nquad, s_base;
+    __shared__ unsigned short scored[MAX_SCORED];              // y << 6 | x of the pixels with a score >= t
+    __shared__ int s_nscored, s_nkeep, s_base;
 
-    const int tid = threadIdx.x, f = blockIdx.y + g.frame0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, f = blockIdx.y + g.frame0;
     // which level / cell
     int cell = blockIdx.x, l = 0;
     for (; l < g.levels; ++l) {
@@ -114,128 +97,128 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
         mbar_init(&s_bar, 1);
         mbar_expect_tx(&s_bar, TILE_ROWS * TP);
         tma_load_3d(tile, &maps.m[l], ax0, wy0, f, &s_bar);
+        s_nscored = 0; s_nkeep = 0;
     }
+    for (int i = tid; i < (CELL + 2) * RPW / 4; i += FAST_THREADS) reinterpret_cast<uint32_t *>(resp)[i] = 0;
     __syncthreads();
     mbar_wait(&s_bar, 0);
+
+    // ---- pair words: 4 per aligned tile word ----------------------------------------------------------------
+    for (int i = tid; i < TILE_ROWS * (TP / 4); i += FAST_THREADS) {
+        const uint32_t w = reinterpret_cast<const uint32_t *>(tile)[i], nx = reinterpret_cast<const uint32_t *>(tile)[i + 1];
+        // row r, word j of the row: i = r * 20 + j; pair index 2j, 2j + 1 of the row: 2 * i overall
+        *reinterpret_cast<uint2 *>(We + 2 * i) = make_uint2(__byte_perm(w, 0u, 0x4140), __byte_perm(w, 0u, 0x4342));
+        *reinterpret_cast<uint2 *>(Wo + 2 * i) = make_uint2(__byte_perm(w, 0u, 0x4241), __byte_perm(w, nx, 0x0403) & 0x00ff00ffu);
+    }
+    __syncthreads();
 
     // Two passes at most: threshold ini first; only a cell that yields nothing is redone at min.
     // A pixel with score >= t is kept by NMS iff it beats its 8 neighbours' scores; neighbours below
     // t can never beat it, so a response map holding only the scores >= t gives the exact result.
+    // (Scores written by the ini pass are a subset of the min pass's, with the same values: no re-zeroing.)
     int nkeep = 0, t = g.ini_thr;
     for (int pass = 0; pass < 2; ++pass, t = g.min_thr) {
-        __syncthreads();   // the previous pass has read its counters
-        if (tid == 0) { s_nsurv = 0; s_nkeep = 0; s_nquad = 0; }
-        for (int i = tid; i < (CELL + 2) * RPW / 4; i += FAST_THREADS) reinterpret_cast<uint32_t *>(resp)[i] = 0;
-        __syncthreads();
-
-        // ---- compass test, 4 pixels (two s16x2 pairs) per step: an arc of 9 contains two adjacent compass
-        // points (k = 0, 4, 8, 12), so two adjacent ones must both be darker than v - t or both brighter
-        // than v + t.  Passing quads are compacted so that the full filter runs with full warps.
         const unsigned thi = (unsigned)(256 + t) * 0x00010001u, tlo = (unsigned)(256 - t) * 0x00010001u;
-        for (int i = tid; i < (CELL / 4) * ch; i += FAST_THREADS) {
-            const int y = i >> 4, q = i & 15;
-            if (4 * q >= cw) continue;
-            // row pointers as words; pixel x = 4q sits at tile column 4q + 6, i.e. byte 2 of word q + 1
-            const uint32_t *r0 = reinterpret_cast<const uint32_t *>(tile + (y + 3) * TP) + q;
-            const uint32_t c0 = r0[0], c1 = r0[1], c2 = r0[2], c3 = r0[3];
-            const uint32_t ctr = __funnelshift_r(c1, c2, 16);
-            const uint32_t w4 = __funnelshift_r(c2, c3, 8), w12 = __funnelshift_r(c0, c1, 24);
-            const uint32_t w0 = __funnelshift_r(r0[3 * (TP / 4) + 1], r0[3 * (TP / 4) + 2], 16);
-            const uint32_t w8 = __funnelshift_r(r0[-3 * (TP / 4) + 1], r0[-3 * (TP / 4) + 2], 16);
-            unsigned hit = 0;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const unsigned vb = lane_pair(ctr, h) | 0x01000100u;
-                const unsigned e0 = vb - lane_pair(w0, h), e4 = vb - lane_pair(w4, h);
-                const unsigned e8 = vb - lane_pair(w8, h), e12 = vb - lane_pair(w12, h);
-                const unsigned dk = __vmaxu2(__vmaxu2(__vminu2(e0, e4), __vminu2(e4, e8)),
-                                             __vmaxu2(__vminu2(e8, e12), __vminu2(e12, e0)));
-                const unsigned br = __vminu2(__vminu2(__vmaxu2(e0, e4), __vmaxu2(e4, e8)),
-                                             __vminu2(__vmaxu2(e8, e12), __vmaxu2(e12, e0)));
-                hit |= gt16x2(dk, thi) | gt16x2(tlo, br);    // dk > thi  or  br < tlo
-            }
-            if (hit) quads[atomicAdd(&s_nquad, 1)] = (unsigned short)i;
-        }
-        __syncthreads();
-
-        // ---- full filter on the compacted quads: all 16 ring pixels, 8 antipodal pairs ----------------------
-        const int nquad = s_nquad;
-        for (int n = tid; n < nquad; n += FAST_THREADS) {
-            const int i = quads[n];
-            const int y = i >> 4, q = i & 15;
-            const uint32_t *r0 = reinterpret_cast<const uint32_t *>(tile + (y + 3) * TP) + q;
-            const uint32_t *rm3 = r0 - 3 * (TP / 4), *rp3 = r0 + 3 * (TP / 4);
-            const uint32_t *rm2 = r0 - 2 * (TP / 4), *rp2 = r0 + 2 * (TP / 4);
-            const uint32_t *rm1 = r0 - (TP / 4), *rp1 = r0 + (TP / 4);
-            // 4-byte windows starting at column 4q+6+dx, built from words q .. q+3 of the row
-            const uint32_t c0 = r0[0], c1 = r0[1], c2 = r0[2], c3 = r0[3];
-            const uint32_t a1 = rp3[1], a2 = rp3[2], b1 = rm3[1], b2 = rm3[2];
-            const uint32_t d0 = rp1[0], d1 = rp1[1], d2 = rp1[2], d3 = rp1[3];
-            const uint32_t g0 = rm1[0], g1 = rm1[1], g2 = rm1[2], g3 = rm1[3];
-            const uint32_t ctr = __funnelshift_r(c1, c2, 16);
-            const uint32_t wa[8] = {
-                __funnelshift_r(a1, a2, 16),   // (0, 3)   k = 0
-                __funnelshift_r(a1, a2, 24),   // (1, 3)   k = 1
-                rp2[2],                        // (2, 2)   k = 2
-                __funnelshift_r(d2, d3, 8),    // (3, 1)   k = 3
-                __funnelshift_r(c2, c3, 8),    // (3, 0)   k = 4
-                __funnelshift_r(g2, g3, 8),    // (3, -1)  k = 5
-                rm2[2],                        // (2, -2)  k = 6
-                __funnelshift_r(b1, b2, 24)};  // (1, -3)  k = 7
-            const uint32_t wb[8] = {
-                __funnelshift_r(b1, b2, 16),   // (0, -3)  k = 8
-                __funnelshift_r(b1, b2, 8),    // (-1, -3) k = 9
-                rm2[1],                        // (-2, -2) k = 10
-                __funnelshift_r(g0, g1, 24),   // (-3, -1) k = 11
-                __funnelshift_r(c0, c1, 24),   // (-3, 0)  k = 12
-                __funnelshift_r(d0, d1, 24),   // (-3, 1)  k = 13
-                rp2[1],                        // (-2, 2)  k = 14
-                __funnelshift_r(a1, a2, 8)};   // (-1, 3)  k = 15
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                // min_k max(e_k, e_k+8) > 256 + t  or  max_k min(e_k, e_k+8) < 256 - t
-                const unsigned vb = lane_pair(ctr, h) | 0x01000100u;
-                unsigned mn = 0x02000200u, mx = 0u;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const unsigned ea = vb - lane_pair(wa[k], h), eb = vb - lane_pair(wb[k], h);
-                    mn = __vminu2(mn, __vmaxu2(ea, eb));
-                    mx = __vmaxu2(mx, __vminu2(ea, eb));
+        // ---- stage 1: compass test, one warp per row, lane = pixel pair (2k, 2k + 1) ------------------------
+        // Passing pairs go to a queue PRIVATE to the warp (ballot + prefix popc, no atomics, no CTA barrier):
+        // a warp owns rows warp, warp + 8, ... and scores its own queue right after.
+        unsigned short *q = ent + warp * WARP_Q;
+        int nq = 0;
+        const unsigned lt = (1u << lane) - 1u;
+        const unsigned okmask = (2 * lane < cw ? 3u : 0u) | (2 * lane + 1 < cw ? 12u : 0u);   // pixels outside the cell never count
+        for (int y = warp; y < ch; y += FAST_THREADS / 32) {
+            const uint32_t *we = We + (y + 3) * WP + lane + 3, *wo = Wo + (y + 3) * WP + lane;
+            const unsigned vb = we[0] | 0x01000100u;
+            const unsigned e0 = vb - we[3 * WP], e8 = vb - we[-3 * WP], e4 = vb - wo[4], e12 = vb - wo[1];
+            const unsigned dk = __vminu2(__vmaxu2(e0, e8), __vmaxu2(e4, e12));
+            const unsigned br = __vmaxu2(__vminu2(e0, e8), __vminu2(e4, e12));
+            // per-lane dk > thi -> bits 0 / 16, br < tlo -> bits 1 / 17
+            const unsigned tt = ((~((thi | 0x80008000u) - dk) & 0x80008000u) >> 15) | ((~((br | 0x80008000u) - tlo) & 0x80008000u) >> 14);
+            const unsigned nib = ((tt & 3u) | ((tt >> 14) & 12u)) & okmask;      // lane a dark / bright, lane b dark / bright
+            const unsigned m = __ballot_sync(0xffffffffu, nib != 0u);
+            if (m) {
+                const unsigned fa = nib & 3u, fbb = nib >> 2;
+                const unsigned pos = (unsigned)lane | ((unsigned)y << 5);
+                if (nib) {
+                    const unsigned sa = (fa & 1u) ? 1u : fa, sb = (fbb & 1u) ? 1u : fbb;      // dark first
+                    q[nq + __popc(m & lt)] = (unsigned short)(pos | (sa << 11) | (sb << 13));
                 }
-                const unsigned hit = gt16x2(mn, thi) | gt16x2(tlo, mx);
-                const int x = 4 * q + 2 * h;
-                if ((hit & 0x8000u) && x < cw) surv[atomicAdd(&s_nsurv, 1)] = (unsigned short)((y << 6) | x);
-                if ((hit >> 16) && x + 1 < cw) surv[atomicAdd(&s_nsurv, 1)] = (unsigned short)((y << 6) | (x + 1));
+                nq += __popc(m);
+                const unsigned m2 = __ballot_sync(0xffffffffu, fa == 3u || fbb == 3u);        // both polarities: rare
+                if (m2) {
+                    if (fa == 3u || fbb == 3u)
+                        q[nq + __popc(m2 & lt)] = (unsigned short)(pos | ((fa == 3u ? 2u : 0u) << 11) | ((fbb == 3u ? 2u : 0u) << 13) | 0x8000u);
+                    nq += __popc(m2);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- stage 2: exact one-sided score of both lanes of every queued pair ----------------------------
+        for (int i = lane; i < nq; i += 32) {
+            const unsigned e = q[i];
+            const int k = e & 31, y = (e >> 5) & 63;
+            const unsigned sa = (e >> 11) & 3u, sb = (e >> 13) & 3u;
+            const unsigned cm = (sa == 2u ? 0x000000ffu : 0u) | (sb == 2u ? 0x00ff0000u : 0u);   // complement -> bright test
+            const uint32_t *we = We + (y + 3) * WP + k + 3, *wo = Wo + (y + 3) * WP + k;
+            const unsigned vb = (we[0] ^ cm) | 0x01000100u;
+            unsigned r[16];
+            r[0] = we[3 * WP];      r[1] = wo[3 * WP + 3];  r[2] = we[2 * WP + 1];   r[3] = wo[WP + 4];
+            r[4] = wo[4];           r[5] = wo[-WP + 4];     r[6] = we[-2 * WP + 1];  r[7] = wo[-3 * WP + 3];
+            r[8] = we[-3 * WP];     r[9] = wo[-3 * WP + 2]; r[10] = we[-2 * WP - 1]; r[11] = wo[-WP + 1];
+            r[12] = wo[1];          r[13] = wo[WP + 1];     r[14] = we[2 * WP - 1];  r[15] = wo[3 * WP + 2];
+            unsigned d[16], m2[16], m4[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) d[j] = vb - (r[j] ^ cm);
+            // sliding min over windows of 9 of the circular sequence, by doubling: 2, 4, 8, then +1
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m2[j] = __vminu2(d[j], d[(j + 1) & 15]);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m4[j] = __vminu2(m2[j], m2[(j + 2) & 15]);
+            unsigned lo = 0u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) lo = __vmaxu2(lo, __vminu2(__vminu2(m4[j], m4[(j + 4) & 15]), d[(j + 8) & 15]));
+            const int s0 = (int)(lo & 0xffffu) - 257, s1 = (int)(lo >> 16) - 257;
+            const bool w0 = sa && s0 >= t, w1 = sb && s1 >= t;
+            if (w0 || w1) {
+                uint8_t *rp = resp + (y + 1) * RPW + 4 + 2 * k;
+                if (w0) rp[0] = (uint8_t)s0;
+                if (w1) rp[1] = (uint8_t)s1;
+                // pixels with a score are the only NMS candidates (a pixel scores in at most one of its entries)
+                int at = atomicAdd(&s_nscored, (w0 ? 1 : 0) + (w1 ? 1 : 0));
+                if (w0 && at < MAX_SCORED) scored[at] = (unsigned short)((y << 6) | (2 * k));
+                at += w0 ? 1 : 0;
+                if (w1 && at < MAX_SCORED) scored[at] = (unsigned short)((y << 6) | (2 * k + 1));
             }
         }
         __syncthreads();
 
-        // ---- exact corner score of the survivors, two per thread -----------------------------------------
-        const int nsurv = s_nsurv;
-        for (int i = tid; 2 * i < nsurv; i += FAST_THREADS) {
-            const int pa = surv[2 * i], pb = surv[min(2 * i + 1, nsurv - 1)];
-            const uint8_t *ca = tile + ((pa >> 6) + 3) * TP + (pa & 63) + 3 + TILE_SHIFT;
-            const uint8_t *cb = tile + ((pb >> 6) + 3) * TP + (pb & 63) + 3 + TILE_SHIFT;
-            const unsigned sc = fast_score_2px<TP>(ca, cb);
-            const int sa = (int)(sc & 0xffffu) - 256, sb = (int)(sc >> 16) - 256;
-            if (sa >= t) resp[((pa >> 6) + 1) * RPW + (pa & 63) + 4] = (uint8_t)sa;
-            if (sb >= t) resp[((pb >> 6) + 1) * RPW + (pb & 63) + 4] = (uint8_t)sb;
-        }
-        __syncthreads();
-
-        // ---- cell-local NMS over the survivors (strict '>' against the 8 neighbours; outside = 0) --------
-        for (int i = tid; i < nsurv; i += FAST_THREADS) {
-            const int p = surv[i];
-            const uint8_t *s = resp + ((p >> 6) + 1) * RPW + (p & 63) + 4;
-            const int v = s[0];
-            if (v == 0) continue;
-            if (v > s[-1] && v > s[1] && v > s[-RPW - 1] && v > s[-RPW] && v > s[-RPW + 1]
-                && v > s[RPW - 1] && v > s[RPW] && v > s[RPW + 1])
-                keep[atomicAdd(&s_nkeep, 1)] = (unsigned short)p;
+        // ---- cell-local NMS (strict '>' against the 8 neighbours; outside the cell = 0) --------------------
+        const int nscored = s_nscored;
+        if (nscored <= MAX_SCORED) {
+            for (int i = tid; i < nscored; i += FAST_THREADS) {
+                const int p = scored[i];
+                const uint8_t *sp = resp + ((p >> 6) + 1) * RPW + 4 + (p & 63);
+                const int v = sp[0];
+                if (v > sp[-1] && v > sp[1] && v > sp[-RPW - 1] && v > sp[-RPW] && v > sp[-RPW + 1]
+                    && v > sp[RPW - 1] && v > sp[RPW] && v > sp[RPW + 1])
+                    keep[atomicAdd(&s_nkeep, 1)] = (unsigned short)p;
+            }
+        } else {
+            // more scored pixels than the list holds (very dense corners): scan the response map instead
+            for (int p = tid; p < CELL * CELL; p += FAST_THREADS) {
+                const uint8_t *sp = resp + ((p >> 6) + 1) * RPW + 4 + (p & 63);
+                const int v = sp[0];
+                if (v != 0 && v > sp[-1] && v > sp[1] && v > sp[-RPW - 1] && v > sp[-RPW] && v > sp[-RPW + 1]
+                    && v > sp[RPW - 1] && v > sp[RPW] && v > sp[RPW + 1])
+                    keep[atomicAdd(&s_nkeep, 1)] = (unsigned short)p;
+            }
         }
         __syncthreads();
         nkeep = s_nkeep;
         if (nkeep > 0 || g.min_thr == g.ini_thr) break;
+        if (tid == 0) s_nscored = 0;
+        __syncthreads();
     }
     if (nkeep == 0) return;
     if (tid == 0) s_base = atomicAdd(&cand_count[f * g.levels + l], nkeep);
@@ -256,7 +239,7 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
 // ------------------------------------------------------------------------------------------------
 // Quadtree distribution
 // ------------------------------------------------------------------------------------------------
-constexpr int DIST_THREADS = 512;
+constexpr int DIST_THREADS = 256;
 
 struct NodeBox { short bx, by, ex, ey; };
 
