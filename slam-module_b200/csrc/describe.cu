@@ -111,7 +111,7 @@ describe_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int le
                 int track_level, int n_frames, DescOut o) {
     __shared__ uint32_t s_wu[4][16][MOM_WORDS];    // u weights (signed bytes) per (alignment, |v|, word)
     __shared__ uint32_t s_wm[4][16][MOM_WORDS];    // disc mask (0 / 1 bytes)
-    __shared__ __align__(16) uint8_t s_patch[DESC_WARPS][BLUR_ROWS * BLUR_PITCH];
+    __shared__ __align__(16) uint8_t s_patch[DESC_WARPS][2 * BLUR_ROWS * BLUR_PITCH];   // two buffers per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // ---- per-CTA tables --------------------------------------------------------------------------------
@@ -205,30 +205,46 @@ describe_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int le
         }
 
         // ---- phase A: intensity-centroid moments (un-blurred level) ----------------------------------------
+        // software pipelined: the 11 words of keypoint j + 1 are in flight while keypoint j is summed
         int my_m10 = 0, my_m01 = 0;
-        for (int j = 0; j < n_here; ++j) {
-            const int ix = __shfl_sync(0xffffffffu, k.ix, j), iy = __shfl_sync(0xffffffffu, k.iy, j);
-            const int l = __shfl_sync(0xffffffffu, k.l, j);
-            const uint8_t *img = l == 0 ? level0 + (size_t)f * level0_stride : g.lv[l].pyr + (size_t)f * g.lv[l].frame_stride;
-            const int pitch = l == 0 ? level0_pitch : g.lv[l].pitch;
-            const int off = (ix - HALF_PATCH) & 3;
-            const uint8_t *c = img + (size_t)iy * pitch + (ix - HALF_PATCH - off) + 4 * mword;
-            int m10 = 0, m01 = 0;
-            if (lane < 3 * MOM_WORDS) {
+        {
+            uint32_t pix[11], nxt[11];
+            int off = 0, off_n = 0;
+            auto issue = [&](int j, uint32_t (&dst)[11], int &o_) {
+                const int ix = __shfl_sync(0xffffffffu, k.ix, j), iy = __shfl_sync(0xffffffffu, k.iy, j);
+                const int l = __shfl_sync(0xffffffffu, k.l, j);
+                const uint8_t *img = l == 0 ? level0 + (size_t)f * level0_stride : g.lv[l].pyr + (size_t)f * g.lv[l].frame_stride;
+                const int pitch = l == 0 ? level0_pitch : g.lv[l].pitch;
+                o_ = (ix - HALF_PATCH) & 3;
+                const uint8_t *c = img + (size_t)(iy - HALF_PATCH + mrow) * pitch + (ix - HALF_PATCH - o_) + 4 * mword;
+                if (lane < 3 * MOM_WORDS) {
 #pragma unroll
-                for (int i = 0; i < 11; ++i) {
-                    const int v = 3 * i + mrow - HALF_PATCH;
-                    if (v <= HALF_PATCH) {
-                        const uint32_t pix = __ldg(reinterpret_cast<const uint32_t *>(c + v * pitch));
-                        const int av = abs(v);
-                        m10 = dp4a_us(pix, (int)s_wu[off][av][mword], m10);
-                        m01 += v * (int)__dp4a(pix, s_wm[off][av][mword], 0u);
+                    for (int i = 0; i < 11; ++i)
+                        if (3 * i + mrow <= 2 * HALF_PATCH) dst[i] = __ldg(reinterpret_cast<const uint32_t *>(c + (size_t)(3 * i) * pitch));
+                }
+            };
+            issue(0, pix, off);
+            for (int j = 0; j < n_here; ++j) {
+                if (j + 1 < n_here) issue(j + 1, nxt, off_n);
+                int m10 = 0, m01 = 0;
+                if (lane < 3 * MOM_WORDS) {
+#pragma unroll
+                    for (int i = 0; i < 11; ++i) {
+                        const int v = 3 * i + mrow - HALF_PATCH;
+                        if (v <= HALF_PATCH) {
+                            const int av = abs(v);
+                            m10 = dp4a_us(pix[i], (int)s_wu[off][av][mword], m10);
+                            m01 += v * (int)__dp4a(pix[i], s_wm[off][av][mword], 0u);
+                        }
                     }
                 }
+                m10 = __reduce_add_sync(0xffffffffu, m10);
+                m01 = __reduce_add_sync(0xffffffffu, m01);
+                if (lane == j) { my_m10 = m10; my_m01 = m01; }
+#pragma unroll
+                for (int i = 0; i < 11; ++i) pix[i] = nxt[i];
+                off = off_n;
             }
-            m10 = __reduce_add_sync(0xffffffffu, m10);
-            m01 = __reduce_add_sync(0xffffffffu, m01);
-            if (lane == j) { my_m10 = m10; my_m01 = m01; }
         }
 
         // ---- phase B: lane j finishes keypoint j ---------------------------------------------------------------
@@ -243,25 +259,40 @@ describe_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int le
         }
 
         // ---- phase C: rBRIEF on the blurred level -----------------------------------------------------------
-        for (int j = 0; j < n_here; ++j) {
+        // software pipelined over two patch buffers: the 37 x 40-byte window of keypoint j + 1 is loaded into
+        // registers before keypoint j is sampled, and stored to the other buffer afterwards
+        uint32_t win[13];
+        auto fetch = [&](int j) {
             const int ix = __shfl_sync(0xffffffffu, k.ix, j), iy = __shfl_sync(0xffffffffu, k.iy, j);
             const int l = __shfl_sync(0xffffffffu, k.l, j);
-            const float c_ = __shfl_sync(0xffffffffu, cs, j), s_ = __shfl_sync(0xffffffffu, sn, j);
             const int pitch = g.lv[l].pitch;
             const int off = (ix - BLUR_R) & 3;
-            const uint8_t *src = g.lv[l].blur + (size_t)f * g.lv[l].frame_stride + (size_t)(iy - BLUR_R) * pitch
+            const uint8_t *src = g.lv[l].blur + (size_t)f * g.lv[l].frame_stride + (size_t)(iy - BLUR_R + brow) * pitch
                                  + (ix - BLUR_R - off) + 4 * bword;
-            __syncwarp();   // the previous keypoint's samples have been read
             if (lane < 3 * BLUR_WORDS) {
 #pragma unroll
-                for (int i = 0; i < 13; ++i) {
-                    const int r = 3 * i + brow;
-                    if (r < BLUR_ROWS)
-                        *reinterpret_cast<uint32_t *>(patch + r * BLUR_PITCH + 4 * bword) =
-                            __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)r * pitch));
-                }
+                for (int i = 0; i < 13; ++i)
+                    if (3 * i + brow < BLUR_ROWS) win[i] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)(3 * i) * pitch));
             }
-            __syncwarp();
+        };
+        auto stash = [&](uint8_t *dst) {
+            if (lane < 3 * BLUR_WORDS) {
+#pragma unroll
+                for (int i = 0; i < 13; ++i)
+                    if (3 * i + brow < BLUR_ROWS) *reinterpret_cast<uint32_t *>(dst + (3 * i + brow) * BLUR_PITCH + 4 * bword) = win[i];
+            }
+        };
+        fetch(0);
+        __syncwarp();       // the previous group's samples have been read
+        stash(patch);
+        for (int j = 0; j < n_here; ++j) {
+            uint8_t *cur = patch + (j & 1) * (BLUR_ROWS * BLUR_PITCH);
+            if (j + 1 < n_here) fetch(j + 1);
+            __syncwarp();   // buffer j is complete
+            const int ix = __shfl_sync(0xffffffffu, k.ix, j);
+            const float c_ = __shfl_sync(0xffffffffu, cs, j), s_ = __shfl_sync(0xffffffffu, sn, j);
+            const int off = (ix - BLUR_R) & 3;
+            const uint8_t *patch_j = cur;
             // sample index = (r + 18) * 44 + (c + 18 + off); r, c arrive as MAGIC_BITS + integer
             // (unsigned arithmetic: the magic offsets cancel modulo 2^32)
             const unsigned bias = (unsigned)(BLUR_R * BLUR_PITCH + BLUR_R + off) - (unsigned)ROUND_MAGIC_BITS * (unsigned)(BLUR_PITCH + 1);
@@ -272,8 +303,8 @@ describe_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int le
                 const int c0 = rint_magic_bits(__fsub_rn(__fmul_rn(px0[q], c_), __fmul_rn(py0[q], s_)));
                 const int r1 = rint_magic_bits(__fadd_rn(__fmul_rn(px1[q], s_), __fmul_rn(py1[q], c_)));
                 const int c1 = rint_magic_bits(__fsub_rn(__fmul_rn(px1[q], c_), __fmul_rn(py1[q], s_)));
-                const int v0 = patch[(unsigned)r0 * BLUR_PITCH + (unsigned)c0 + bias];
-                const int v1 = patch[(unsigned)r1 * BLUR_PITCH + (unsigned)c1 + bias];
+                const int v0 = patch_j[(unsigned)r0 * BLUR_PITCH + (unsigned)c0 + bias];
+                const int v1 = patch_j[(unsigned)r1 * BLUR_PITCH + (unsigned)c1 + bias];
                 bits |= (v0 < v1 ? 1u : 0u) << q;
             }
             unsigned word = bits << (8 * (lane & 3));
@@ -282,6 +313,8 @@ describe_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int le
             // 8 words per descriptor: lanes 0, 4, 8, ... hold words 0..7
             const unsigned wsel = __shfl_sync(0xffffffffu, word, (lane & 7) << 2);
             if (lane < 8) o.desc[8 * (oi0 + j) + lane] = wsel;
+            // the other buffer was last read for keypoint j - 1: every lane is past that (syncwarp above)
+            if (j + 1 < n_here) stash(patch + ((j + 1) & 1) * (BLUR_ROWS * BLUR_PITCH));
         }
     }
 }
