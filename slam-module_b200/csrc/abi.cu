@@ -1,6 +1,8 @@
 // C ABI of libslamgpu.so (include/slamgpu.h): context life cycle, buffer ownership, host <-> device
 // staging and the orchestration of the stage launchers.  No algorithmic work happens here.
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstring>
 #include <algorithm>
@@ -276,10 +278,13 @@ int sg_create(int device, const sg_params *params, sg_ctx **out) {
         return bail(SG_ERR_CUDA);
     }
     ctx->main_stream = ctx->stream;
+    if (const char *e = getenv("SG_PIPE_STREAMS")) ctx->pipe_streams = std::min(4, std::max(1, atoi(e)));   // tuning knob (default 4)
     if (cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) != cudaSuccess
         || cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) != cudaSuccess
         || cudaStreamCreateWithFlags(&ctx->s_cmp[0], cudaStreamNonBlocking) != cudaSuccess
         || cudaStreamCreateWithFlags(&ctx->s_cmp[1], cudaStreamNonBlocking) != cudaSuccess
+        || cudaStreamCreateWithFlags(&ctx->s_cmp[2], cudaStreamNonBlocking) != cudaSuccess
+        || cudaStreamCreateWithFlags(&ctx->s_cmp[3], cudaStreamNonBlocking) != cudaSuccess
         || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
         ctx->err = "stream / event creation failed";
         return bail(SG_ERR_CUDA);
@@ -310,7 +315,7 @@ void sg_destroy(sg_ctx *ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (auto &e : ctx->pipe_ev) cudaEventDestroy(e);
-    for (cudaStream_t q : {ctx->s_in, ctx->s_out, ctx->s_cmp[0], ctx->s_cmp[1]}) if (q) cudaStreamDestroy(q);
+    for (cudaStream_t q : {ctx->s_in, ctx->s_out, ctx->s_cmp[0], ctx->s_cmp[1], ctx->s_cmp[2], ctx->s_cmp[3]}) if (q) cudaStreamDestroy(q);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -472,7 +477,22 @@ static int extract_pipelined(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size
     if (!h_imgs || pitch < L0.w) return fail(ctx, SG_ERR_INVALID, "bad image pointer / pitch");
     if (n_frames < 1 || n_frames > ctx->p.max_frames) return fail(ctx, SG_ERR_INVALID, "n_frames %d outside [1, %d]", n_frames, ctx->p.max_frames);
     if (!o) return fail(ctx, SG_ERR_INVALID, "null output");
-    const int C = std::max(1, ctx->pipe_chunk), chunks = (n_frames + C - 1) / C;
+    // chunk schedule: small chunks at both ends (short pipeline fill and drain: the first kernels start after a
+    // short copy, the last copy-out is short), full chunks in between (efficient grids)
+    std::vector<int> sched;
+    {
+        const int C = std::max(1, ctx->pipe_chunk), q = std::max(1, C / 4), h = std::max(1, C / 2);
+        int rest = n_frames;
+        if (n_frames >= 2 * (q + h) + C) {
+            sched.push_back(q); sched.push_back(h);
+            rest -= 2 * (q + h);
+            while (rest > 0) { const int n = std::min(C, rest); sched.push_back(n); rest -= n; }
+            sched.push_back(h); sched.push_back(q);
+        } else {
+            while (rest > 0) { const int n = std::min(C, rest); sched.push_back(n); rest -= n; }
+        }
+    }
+    const int chunks = (int)sched.size();
     while ((int)ctx->pipe_ev.size() < 2 * chunks) {
         cudaEvent_t e;
         SG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -481,12 +501,16 @@ static int extract_pipelined(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size
     if (int r = set_level0(ctx, L0.pyr, L0.pitch, L0.frame_stride, n_frames)) return r;
     // work queued earlier on the main stream (an un-synchronised sg_extract_device, ...) comes first
     SG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->main_stream));
-    for (cudaStream_t q : {ctx->s_in, ctx->s_out, ctx->s_cmp[0], ctx->s_cmp[1]}) SG_CUDA(ctx, cudaStreamWaitEvent(q, ctx->ev_fork, 0));
+    for (cudaStream_t q : {ctx->s_in, ctx->s_out, ctx->s_cmp[0], ctx->s_cmp[1], ctx->s_cmp[2], ctx->s_cmp[3]}) SG_CUDA(ctx, cudaStreamWaitEvent(q, ctx->ev_fork, 0));
     const size_t cap = ctx->geom.out_cap;
     const int levels = ctx->p.levels;
     int rc = SG_OK;
+    int f_next = 0;
+    static const bool dbg = getenv("SG_DEBUG_TIMING") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
     for (int c = 0; c < chunks && rc == SG_OK; ++c) {
-        const int f0 = c * C, n = std::min(C, n_frames - f0);
+        const int f0 = f_next, n = sched[c];
+        f_next += n;
         if (pitch == L0.pitch && (n == 1 || frame_stride == L0.frame_stride)) {
             SG_CUDA(ctx, cudaMemcpyAsync(L0.pyr + (size_t)f0 * L0.frame_stride, h_imgs + (size_t)f0 * frame_stride,
                                          (size_t)n * L0.frame_stride, cudaMemcpyHostToDevice, ctx->s_in));
@@ -496,7 +520,7 @@ static int extract_pipelined(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size
                                                pitch, L0.w, L0.h, cudaMemcpyHostToDevice, ctx->s_in));
         }
         SG_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_in));
-        cudaStream_t cmp = ctx->s_cmp[c & 1];
+        cudaStream_t cmp = ctx->s_cmp[c % ctx->pipe_streams];
         SG_CUDA(ctx, cudaStreamWaitEvent(cmp, ctx->pipe_ev[2 * c], 0));
         ctx->stream = cmp; ctx->frame0 = f0; ctx->in_pipeline = true;
         rc = extract_launches(ctx, n);
@@ -517,9 +541,16 @@ static int extract_pipelined(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size
             || (rc = out(o->level_count, ctx->d_kp_count, (size_t)levels)))
             break;
     }
-    for (cudaStream_t q : {ctx->s_cmp[0], ctx->s_cmp[1], ctx->s_out}) {
+    const auto t_submitted = std::chrono::steady_clock::now();
+    for (cudaStream_t q : {ctx->s_cmp[0], ctx->s_cmp[1], ctx->s_cmp[2], ctx->s_cmp[3], ctx->s_out}) {
         const cudaError_t e = cudaStreamSynchronize(q);
         if (e != cudaSuccess && rc == SG_OK) rc = fail(ctx, SG_ERR_CUDA, "pipeline synchronise failed: %s", cudaGetErrorString(e));
+    }
+    if (dbg) {
+        const auto t_done = std::chrono::steady_clock::now();
+        fprintf(stderr, "sg_extract: %d chunks, submit %.3f ms, wait %.3f ms\n", chunks,
+                std::chrono::duration<double, std::milli>(t_submitted - t_begin).count(),
+                std::chrono::duration<double, std::milli>(t_done - t_submitted).count());
     }
     if (rc) return rc;
     return check_device_error(ctx);
