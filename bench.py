@@ -300,6 +300,37 @@ def extra_configs(slamgpu, sm, sh, rank, world, local, barrier_max_, td):
             "projected_full_job_s": total / rate, "pairs_in_rank_block": int(hi - lo),
             "pairs_with_matches_in_sample": int((cnt > 0).sum())}
         db.close()
+    # ---- candidate-list matchers and descriptor medoid (host-buffer calls) -------------
+    with slamgpu.Context(W, H, max_frames=1, device=local) as c6:
+        rng = np.random.default_rng(5)
+        nk, nq = 2000, 1500
+        kx = rng.uniform(0, W, nk).astype(np.float32); ky = rng.uniform(0, H, nk).astype(np.float32)
+        koct = rng.integers(0, 8, nk).astype(np.int32)
+        kdesc = rng.integers(0, 2 ** 32, (nk, 8), dtype=np.uint32)
+        src = rng.integers(0, nk, nq)
+        qx = (kx[src] + rng.normal(0, 3, nq)).astype(np.float32); qy = (ky[src] + rng.normal(0, 3, nq)).astype(np.float32)
+        qr = np.full(nq, 20, np.float32)
+        qdesc = kdesc[src] ^ (np.uint32(1) << rng.integers(0, 32, (nq, 8)).astype(np.uint32))
+        sizes = rng.integers(2, 30, 4000)
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        mdesc = rng.integers(0, 2 ** 32, (int(offs[-1]), 8), dtype=np.uint32)
+        def timed(fn, n=5):
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                r = fn()
+            return (time.perf_counter() - t0) / n, r
+        t_proj, (n_proj, _, _) = timed(lambda: c6.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=1, thr=100,
+                                                                    taken=np.zeros(nk, np.uint8)))
+        t_dup, (n_dup, _, _) = timed(lambda: c6.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=0, thr=50))
+        t_med, _ = timed(lambda: c6.medoid(mdesc, offs))
+        out["next_rows"] = {
+            "search_by_projection": {"workload": "%d projected map points against %d keypoints, radius 20 px (keyframe_matcher.cpp:295-414 inner loop)" % (nq, nk),
+                                     "ms_per_call_host_buffers": t_proj * 1e3, "matches": n_proj},
+            "replace_duplication": {"workload": "same queries, best only, thr 50 (keyframe_matcher.cpp:482-499)",
+                                    "ms_per_call_host_buffers": t_dup * 1e3, "matches": n_dup},
+            "map_point_medoid": {"workload": "%d map points, 2..29 observations each (map_point.cpp:75-116)" % len(sizes),
+                                 "ms_per_call_host_buffers": t_med * 1e3, "map_points_per_s": len(sizes) / t_med}}
     return out
 
 

@@ -185,6 +185,29 @@ int sg_match_pairs_device(sg_ctx *ctx, const sg_db *db, const int32_t *d_pairs, 
 /* Rows of the last sg_match_* call that needed the exact full-row rescan (diagnostic). */
 unsigned long long sg_match_rescans(const sg_ctx *ctx);
 
+/* ---- candidate-list matchers: FeatureSearch radius query (feature_search.cpp:22-48) + the
+ *      descriptor loops of searchByProjection (keyframe_matcher.cpp:356-386), replaceDuplication (:482-499)
+ *      and findMatchesTranformedMps (:604-627).  The caller projects the map points (kf.reproject, viewing
+ *      distance, predictScaleLevel stay host geometry) and passes point, radius and descriptor per query.
+ *   keypoints : h_kx, h_ky (the coordinates FeatureSearch indexes), h_koct, h_kdesc (8 words each), nK <= 65535;
+ *               h_order = FeatureSearch's Y-sorted keypoint indices or NULL (the library runs the same std::sort)
+ *   mode 0    : best only; match when best <= thr; with h_qlevel != NULL only octaves in [level-1, level] count
+ *   mode 1    : searchByProjection: keypoints with h_taken[i] != 0 are skipped (:358), best and second best with
+ *               their octaves, match when best <= thr and not (same octave and best > 0.8 * second); queries
+ *               are resolved IN ORDER and a matched keypoint becomes taken (h_taken is updated in place)
+ *   outputs   : h_idx[q] = matched keypoint or -1, h_dist[q] = its distance (256 when unmatched), *n_matched */
+int sg_search_candidates(sg_ctx *ctx, const float *h_kx, const float *h_ky, const int32_t *h_koct,
+                         const uint32_t *h_kdesc, int nK, const int32_t *h_order, uint8_t *h_taken,
+                         const float *h_qx, const float *h_qy, const float *h_qr, const uint32_t *h_qdesc,
+                         const int32_t *h_qlevel, int nQ, int mode, uint32_t thr, int32_t *h_idx, uint32_t *h_dist,
+                         uint32_t *n_matched);
+/* FeatureSearch constructor (feature_search.cpp:22-31): keypoint indices sorted by y (host code, no GPU). */
+int sg_feature_index(const float *h_x, const float *h_y, int n, int32_t *h_order);
+/* MapPoint::updateDescriptor (map_point.cpp:75-116), batched: segment s owns descriptors
+ * [offsets[s], offsets[s+1]) (at most 1024); h_best[s] = index inside the segment of the descriptor whose
+ * median Hamming distance to the segment is smallest (first wins; 0 for an empty segment). */
+int sg_medoid(sg_ctx *ctx, const uint32_t *h_desc, const int64_t *h_offsets, int n_seg, int32_t *h_best);
+
 /* ---- angle histogram: angle_checker<int> (openvslam/match_angle_checker.h:72-134) -----------
  * Test hook for the restated libstdc++ std::sort order of the 30 bins (host code, no GPU). */
 void sg_angle_bin_order(const uint32_t *sizes30, uint32_t *order30);

@@ -123,6 +123,19 @@ void orc_bin_order_heap(const unsigned *sizes30, unsigned *order30);
 
 /* Threaded drivers for the CPU baseline (frames / keyframe pairs sharded over host threads; the
  * reference itself is single-threaded).  Return wall seconds. */
+/* ---- "next" rows ---------------------------------------------------------------- */
+/* MapPoint::updateDescriptor (map_point.cpp:75-116): medoid index of every descriptor segment. */
+void orc_medoid(const uint32_t *desc, const long long *offsets, int n_seg, int *best);
+/* FeatureSearch (feature_search.cpp:22-48): the Y-sorted order and one radius query. */
+void orc_feature_index(const float *x, const float *y, int n, int *order);
+int orc_features_around(const float *x, const float *y, int n, float qx, float qy, float r, int *out);
+/* Candidate loops of searchByProjection / replaceDuplication / findMatchesTranformedMps
+ * (keyframe_matcher.cpp:356-386, 482-499, 604-627); see oracle/src/search.cpp. */
+int orc_search_candidates(const float *kx, const float *ky, const int *koct, const uint32_t *kdesc, int nK,
+                          unsigned char *taken, const float *qx, const float *qy, const float *qr,
+                          const uint32_t *qdesc, const int *q_pred_level, int nQ, int mode, unsigned thr,
+                          int *out_idx, unsigned *out_dist);
+
 double orc_bench_extract(const orc_params *p, const uint8_t *imgs, int n_frames, int threads, long *total_kp);
 double orc_bench_match(const uint32_t *desc, const float *ang, int n_sets, int n_per_set,
                        const int *pairs, int n_pairs, float ratio, unsigned thr, int threads, long *total_matches);

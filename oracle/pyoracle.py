@@ -264,6 +264,48 @@ def angle_bin(delta):
     return int(lib().orc_angle_bin(C.c_float(delta)))
 
 
+def medoid(desc, offsets):
+    desc = np.ascontiguousarray(desc, np.uint32).reshape(-1, 8)
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    best = np.zeros(max(len(offsets) - 1, 1), np.int32)
+    lib().orc_medoid(C.c_void_p(desc.ctypes.data), C.c_void_p(offsets.ctypes.data), len(offsets) - 1, C.c_void_p(best.ctypes.data))
+    return best[:len(offsets) - 1]
+
+
+def feature_index(x, y):
+    x = np.ascontiguousarray(x, np.float32); y = np.ascontiguousarray(y, np.float32)
+    order = np.zeros(max(len(x), 1), np.int32)
+    lib().orc_feature_index(C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), len(x), C.c_void_p(order.ctypes.data))
+    return order[:len(x)]
+
+
+def features_around(x, y, qx, qy, r):
+    x = np.ascontiguousarray(x, np.float32); y = np.ascontiguousarray(y, np.float32)
+    out = np.zeros(max(len(x), 1), np.int32)
+    n = lib().orc_features_around(C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), len(x), C.c_float(qx), C.c_float(qy),
+                                  C.c_float(r), C.c_void_p(out.ctypes.data))
+    return out[:n].copy()
+
+
+def search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=0, thr=50, taken=None, qlevel=None):
+    kx = np.ascontiguousarray(kx, np.float32); ky = np.ascontiguousarray(ky, np.float32)
+    koct = np.ascontiguousarray(koct, np.int32); kdesc = np.ascontiguousarray(kdesc, np.uint32).reshape(-1, 8)
+    qx = np.ascontiguousarray(qx, np.float32); qy = np.ascontiguousarray(qy, np.float32)
+    qr = np.ascontiguousarray(qr, np.float32); qdesc = np.ascontiguousarray(qdesc, np.uint32).reshape(-1, 8)
+    ql = None if qlevel is None else np.ascontiguousarray(qlevel, np.int32)
+    tk = np.zeros(max(len(kx), 1), np.uint8) if taken is None else taken
+    idx = np.zeros(max(len(qx), 1), np.int32)
+    dist = np.zeros(max(len(qx), 1), np.uint32)
+    L = lib()
+    L.orc_search_candidates.restype = C.c_int
+    n = L.orc_search_candidates(C.c_void_p(kx.ctypes.data), C.c_void_p(ky.ctypes.data), C.c_void_p(koct.ctypes.data),
+                                C.c_void_p(kdesc.ctypes.data), len(kx), C.c_void_p(tk.ctypes.data),
+                                C.c_void_p(qx.ctypes.data), C.c_void_p(qy.ctypes.data), C.c_void_p(qr.ctypes.data),
+                                C.c_void_p(qdesc.ctypes.data), None if ql is None else C.c_void_p(ql.ctypes.data),
+                                len(qx), int(mode), C.c_uint(thr), C.c_void_p(idx.ctypes.data), C.c_void_p(dist.ctypes.data))
+    return int(n), idx[:len(qx)], dist[:len(qx)]
+
+
 def bench_extract(p, imgs, threads):
     imgs = np.ascontiguousarray(imgs, np.uint8)
     total = C.c_long(0)

@@ -1,0 +1,381 @@
+// "Next" rows of the hot path: the candidate-list matchers and the descriptor medoid.
+//
+//   FeatureSearch                 feature_search.cpp:22-48   Y-sorted index + radius query
+//   searchByProjection            keyframe_matcher.cpp:356-386  best / second best over the query result, level-aware
+//                                                             ratio rule, accepted keypoints are consumed
+//   replaceDuplication            keyframe_matcher.cpp:482-499  best only, threshold 50
+//   findMatchesTranformedMps      keyframe_matcher.cpp:604-627  best only, threshold 100, octave window [pred-1, pred]
+//   MapPoint::updateDescriptor    map_point.cpp:75-116       Hamming medoid (median-of-distances arg-min)
+//
+// The geometry in front of the loops (reprojection, viewing distance, scale prediction) is the caller's: the
+// kernels take the projected point, the search radius and the query descriptor.
+//
+// GPU formulation (exact):
+//   search_topk_kernel    one warp per query: two binary searches bound the Y range, lanes test the circle
+//                         (fp32 mul / add without contraction, like the x86 reference), compute the Hamming
+//                         distance of the eligible candidates and keep the 4 smallest (distance, sorted position)
+//                         keys of the warp -- ties resolve to the earlier position, i.e. the reference's scan order.
+//   search_resolve_kernel mode 0: one thread per query (no interaction between queries).
+//                         mode 1: one warp walks the queries in order; best / second are the first two unconsumed
+//                         keys; when a truncated list cannot decide, the warp rescans the query's range exactly.
+//   medoid_kernel         one CTA per map point: descriptors in shared memory, one warp per row of the distance
+//                         matrix, the row median by bisection on the value range 0..256 with warp-wide counts.
+#include <algorithm>
+#include <vector>
+#include "ctx.h"
+
+namespace sg {
+
+constexpr int SK = 4;                       // keys kept per query
+constexpr unsigned NOKEY = 0xffffffffu;
+constexpr int SEARCH_WARPS = 8;
+constexpr int MED_THREADS = 128, MED_MAX = 1024;   // descriptors per map point the medoid kernel stages
+
+struct SearchArgs {
+    const float *sx, *sy;        // keypoint coordinates in Y-sorted order
+    const int *sidx;             // keypoint index of every sorted position
+    const int *soct;             // octave of every sorted position
+    const uint32_t *sdesc;       // descriptors in sorted order
+    const unsigned char *elig0;  // per sorted position: 1 = not eligible from the start (mode 1: already matched)
+    int nK;
+    const float *qx, *qy, *qr;
+    const uint32_t *qdesc;
+    const int *qlevel;           // predicted scale level per query or nullptr (octave window off)
+    int nQ, mode;
+    unsigned thr;
+};
+
+__device__ __forceinline__ unsigned hamming8(const uint32_t (&a)[8], const uint32_t *b) {
+    const uint4 b0 = __ldg(reinterpret_cast<const uint4 *>(b)), b1 = __ldg(reinterpret_cast<const uint4 *>(b) + 1);
+    return __popc(a[0] ^ b0.x) + __popc(a[1] ^ b0.y) + __popc(a[2] ^ b0.z) + __popc(a[3] ^ b0.w)
+           + __popc(a[4] ^ b1.x) + __popc(a[5] ^ b1.y) + __popc(a[6] ^ b1.z) + __popc(a[7] ^ b1.w);
+}
+
+// first position with !(sy[p] < v)
+__device__ __forceinline__ int lower_bound_y(const float *sy, int n, float v) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(sy + mid) < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// first position with sy[p] > v   (the scan stops at the first element with !(y <= v))
+__device__ __forceinline__ int upper_bound_y(const float *sy, int n, float v) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(sy + mid) <= v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ bool in_circle(float qx, float qy, float r, float x, float y) {
+    const float dx = __fsub_rn(qx, x), dy = __fsub_rn(qy, y);
+    return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(r, r);   // feature_search.cpp:42-44
+}
+
+__device__ __forceinline__ bool level_ok(const SearchArgs &a, int q, int oct) {
+    if (!a.qlevel) return true;
+    const int pl = a.qlevel[q];
+    return !(oct < pl - 1 || oct > pl);                                          // keyframe_matcher.cpp:611
+}
+
+__device__ __forceinline__ void insert4(unsigned (&t)[SK], unsigned key) {
+#pragma unroll
+    for (int i = 0; i < SK; ++i) {
+        const unsigned lo = min(t[i], key);
+        key = max(t[i], key);
+        t[i] = lo;
+    }
+}
+
+__global__ void __launch_bounds__(SEARCH_WARPS * 32)
+search_topk_kernel(const SearchArgs a, uint32_t *keys, int2 *range, uint32_t *nseen_out) {
+    const int lane = threadIdx.x & 31, q = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5);
+    if (q >= a.nQ) return;
+    const float qx = a.qx[q], qy = a.qy[q], r = a.qr[q];
+    const int lo = lower_bound_y(a.sy, a.nK, __fsub_rn(qy, r)), hi = upper_bound_y(a.sy, a.nK, __fadd_rn(qy, r));
+    uint32_t d[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) d[w] = __ldg(a.qdesc + 8 * (size_t)q + w);
+    unsigned t[SK] = {NOKEY, NOKEY, NOKEY, NOKEY};
+    unsigned nseen = 0;
+    for (int p = lo + lane; p < hi; p += 32) {
+        if (a.mode == 1 && a.elig0[p]) continue;
+        if (!in_circle(qx, qy, r, __ldg(a.sx + p), __ldg(a.sy + p))) continue;
+        if (!level_ok(a, q, __ldg(a.soct + p))) continue;
+        ++nseen;
+        insert4(t, (hamming8(d, a.sdesc + 8 * (size_t)p) << 16) | (unsigned)p);
+    }
+    nseen = __reduce_add_sync(0xffffffffu, nseen);
+    // the 4 smallest keys of the warp: pop the minimum head four times
+    unsigned out[SK];
+#pragma unroll
+    for (int k = 0; k < SK; ++k) {
+        const unsigned m = __reduce_min_sync(0xffffffffu, t[0]);
+        out[k] = m;
+        if (m != NOKEY && t[0] == m) { t[0] = t[1]; t[1] = t[2]; t[2] = t[3]; t[3] = NOKEY; }   // keys are unique (position)
+    }
+    if (lane == 0) {
+        reinterpret_cast<uint4 *>(keys)[q] = make_uint4(out[0], out[1], out[2], out[3]);
+        range[q] = make_int2(lo, hi);
+        nseen_out[q] = nseen;
+    }
+}
+
+__global__ void search_resolve_independent_kernel(const SearchArgs a, const uint32_t *keys, int *out_idx, unsigned *out_dist,
+                                                  unsigned *n_matched) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.nQ) return;
+    const unsigned k0 = keys[4 * (size_t)q];
+    int idx = -1;
+    unsigned dist = 256;
+    if (k0 != NOKEY && (k0 >> 16) <= a.thr) { idx = a.sidx[k0 & 0xffffu]; dist = k0 >> 16; }
+    out_idx[q] = idx;
+    out_dist[q] = dist;
+    if (idx >= 0) atomicAdd(n_matched, 1u);
+}
+
+// searchByProjection semantics: queries in order, accepted keypoints are consumed (keyframe_matcher.cpp:356-386).
+__global__ void __launch_bounds__(32)
+search_resolve_sequential_kernel(const SearchArgs a, const uint32_t *keys, const int2 *range, const uint32_t *nseen,
+                                 unsigned char *taken_pos, int *out_idx, unsigned *out_dist, unsigned *n_matched,
+                                 unsigned long long *rescans) {
+    const int lane = threadIdx.x;
+    unsigned count = 0, n_rescan = 0;
+    for (int q = 0; q < a.nQ; ++q) {
+        const uint4 kk = reinterpret_cast<const uint4 *>(keys)[q];
+        const unsigned k[SK] = {kk.x, kk.y, kk.z, kk.w};
+        const bool complete = nseen[q] <= SK;
+        unsigned u0 = NOKEY, u1 = NOKEY, last = NOKEY;
+#pragma unroll
+        for (int e = 0; e < SK; ++e) {
+            if (k[e] == NOKEY) continue;
+            last = k[e];
+            if (!taken_pos[k[e] & 0xffffu]) {
+                if (u0 == NOKEY) u0 = k[e];
+                else if (u1 == NOKEY) u1 = k[e];
+            }
+        }
+        bool need_scan = false;
+        if (u0 == NOKEY) need_scan = !complete && (last >> 16) <= a.thr;          // an unconsumed candidate <= thr may exist
+        else if ((u0 >> 16) <= a.thr && u1 == NOKEY && !complete) need_scan = true;   // the second best decides the ratio rule
+        if (need_scan) {
+            ++n_rescan;
+            uint32_t d[8];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) d[w] = __ldg(a.qdesc + 8 * (size_t)q + w);
+            const float qx = a.qx[q], qy = a.qy[q], r = a.qr[q];
+            unsigned b0 = NOKEY, b1 = NOKEY;
+            for (int p = range[q].x + lane; p < range[q].y; p += 32) {
+                if (taken_pos[p] || !in_circle(qx, qy, r, a.sx[p], a.sy[p]) || !level_ok(a, q, a.soct[p])) continue;
+                const unsigned key = (hamming8(d, a.sdesc + 8 * (size_t)p) << 16) | (unsigned)p;
+                if (key < b0) { b1 = b0; b0 = key; } else if (key < b1) b1 = key;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const unsigned o0 = __shfl_xor_sync(0xffffffffu, b0, o), o1 = __shfl_xor_sync(0xffffffffu, b1, o);
+                const unsigned lo = min(b0, o0), hi = max(b0, o0);
+                b1 = min(min(b1, o1), hi);
+                b0 = lo;
+            }
+            u0 = b0; u1 = b1;
+        }
+        int idx = -1;
+        unsigned dist = 256;
+        if (u0 != NOKEY && (u0 >> 16) <= a.thr) {
+            const int best = (int)(u0 >> 16), lvl = a.soct[u0 & 0xffffu];
+            const int best2 = u1 != NOKEY ? (int)(u1 >> 16) : 256, lvl2 = u1 != NOKEY ? a.soct[u1 & 0xffffu] : -1;
+            if (!(lvl == lvl2 && (double)best > 0.8 * (double)best2)) {          // keyframe_matcher.cpp:384-386
+                idx = a.sidx[u0 & 0xffffu];
+                dist = (unsigned)best;
+                if (lane == 0) taken_pos[u0 & 0xffffu] = 1;
+                ++count;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { out_idx[q] = idx; out_dist[q] = dist; }
+    }
+    if (lane == 0) { *n_matched = count; *rescans = n_rescan; }
+}
+
+// ---- medoid ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MED_THREADS)
+medoid_kernel(const uint32_t *desc, const long long *offsets, int *best_out) {
+    __shared__ uint4 sd[2 * MED_MAX];                       // the segment's descriptors
+    __shared__ unsigned short drow[MED_THREADS / 32][MED_MAX];
+    __shared__ unsigned short med[MED_MAX];
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long o = offsets[s];
+    const int n = (int)(offsets[s + 1] - o);
+    if (n <= 0) { if (tid == 0) best_out[s] = 0; return; }
+    const uint4 *src = reinterpret_cast<const uint4 *>(desc + 8 * o);
+    for (int i = tid; i < 2 * n; i += MED_THREADS) sd[i] = __ldg(src + i);
+    __syncthreads();
+    const int kth = (n - 1) / 2;                            // static_cast<unsigned>(0.5 * (n - 1)), map_point.cpp:107
+    for (int i = warp; i < n; i += MED_THREADS / 32) {
+        const uint4 a0 = sd[2 * i], a1 = sd[2 * i + 1];
+        for (int j = lane; j < n; j += 32) {
+            const uint4 b0 = sd[2 * j], b1 = sd[2 * j + 1];
+            drow[warp][j] = (unsigned short)(__popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w)
+                                             + __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w));
+        }
+        __syncwarp();
+        // the (kth + 1)-th smallest = the smallest v with #(d <= v) > kth
+        int lo = 0, hi = 256;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            int c = 0;
+            for (int j = lane; j < n; j += 32) c += drow[warp][j] <= mid ? 1 : 0;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c > kth) hi = mid; else lo = mid + 1;
+        }
+        if (lane == 0) med[i] = (unsigned short)lo;
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned best = 0xffffffffu;
+        for (int i = lane; i < n; i += 32) best = min(best, ((unsigned)med[i] << 16) | (unsigned)i);
+        best = __reduce_min_sync(0xffffffffu, best);
+        // `median_dist < best_median_dist` starts from 256 (map_point.cpp:99,109): a median of 256 never wins
+        if (lane == 0) best_out[s] = (best >> 16) < 256u ? (int)(best & 0xffffu) : 0;
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+template <class T>
+static int up(sg_ctx *ctx, T **d, const T *h, size_t n) {
+    SG_CUDA(ctx, cudaMalloc((void **)d, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) SG_CUDA(ctx, cudaMemcpyAsync(*d, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return SG_OK;
+}
+
+struct DevBufs {
+    std::vector<void *> p;
+    ~DevBufs() { for (void *q : p) cudaFree(q); }
+    template <class T> T *keep(T *q) { p.push_back((void *)q); return q; }
+};
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" int sg_medoid(sg_ctx *ctx, const uint32_t *h_desc, const int64_t *h_offsets, int n_seg, int32_t *h_best) {
+    cudaSetDevice(ctx->device);
+    if (n_seg <= 0) return SG_OK;
+    if (!h_desc || !h_offsets || !h_best) return fail(ctx, SG_ERR_INVALID, "null argument");
+    for (int s = 0; s < n_seg; ++s) {
+        const long long n = h_offsets[s + 1] - h_offsets[s];
+        if (n < 0 || n > MED_MAX) return fail(ctx, SG_ERR_INVALID, "segment %d has %lld descriptors (supported: 0..%d)", s, n, MED_MAX);
+    }
+    DevBufs bufs;
+    uint32_t *d_desc = nullptr;
+    long long *d_off = nullptr;
+    int *d_best = nullptr;
+    const size_t total = (size_t)h_offsets[n_seg];
+    if (int r = up(ctx, &d_desc, h_desc, 8 * total)) return r;
+    bufs.keep(d_desc);
+    if (int r = up(ctx, &d_off, (const long long *)h_offsets, (size_t)n_seg + 1)) return r;
+    bufs.keep(d_off);
+    SG_CUDA(ctx, cudaMalloc((void **)&d_best, sizeof(int) * (size_t)n_seg));
+    bufs.keep(d_best);
+    medoid_kernel<<<n_seg, MED_THREADS, 0, ctx->stream>>>(d_desc, d_off, d_best);
+    SG_LAUNCH_CHECK(ctx);
+    SG_CUDA(ctx, cudaMemcpyAsync(h_best, d_best, sizeof(int) * (size_t)n_seg, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SG_OK;
+}
+
+extern "C" int sg_search_candidates(sg_ctx *ctx, const float *h_kx, const float *h_ky, const int32_t *h_koct,
+                                    const uint32_t *h_kdesc, int nK, const int32_t *h_order, uint8_t *h_taken,
+                                    const float *h_qx, const float *h_qy, const float *h_qr, const uint32_t *h_qdesc,
+                                    const int32_t *h_qlevel, int nQ, int mode, uint32_t thr, int32_t *h_idx,
+                                    uint32_t *h_dist, uint32_t *n_matched) {
+    cudaSetDevice(ctx->device);
+    if (n_matched) *n_matched = 0;
+    if (nQ <= 0) return SG_OK;
+    if (!h_qx || !h_qy || !h_qr || !h_qdesc || !h_idx || !h_dist) return fail(ctx, SG_ERR_INVALID, "null argument");
+    if (mode != 0 && mode != 1) return fail(ctx, SG_ERR_INVALID, "mode must be 0 or 1");
+    if (nK < 0 || nK > 65535) return fail(ctx, SG_ERR_INVALID, "keypoint sets larger than 65535 are not supported");
+    if (nK && (!h_kx || !h_ky || !h_koct || !h_kdesc)) return fail(ctx, SG_ERR_INVALID, "null keypoint arrays");
+    // FeatureSearch index (feature_search.cpp:22-31): keypoints sorted by y with the very same std::sort call
+    std::vector<int> order(nK);
+    if (h_order) std::copy(h_order, h_order + nK, order.begin());
+    else {
+        struct Node { float x, y; int idx; };
+        std::vector<Node> v(nK);
+        for (int i = 0; i < nK; ++i) v[i] = Node{h_kx[i], h_ky[i], i};
+        std::sort(v.begin(), v.end(), [](const Node &a, const Node &b) { return a.y < b.y; });
+        for (int i = 0; i < nK; ++i) order[i] = v[i].idx;
+    }
+    std::vector<float> sx(nK), sy(nK);
+    std::vector<int> soct(nK);
+    std::vector<uint32_t> sdesc(8 * (size_t)nK);
+    std::vector<unsigned char> tk(std::max(nK, 1), 0);
+    for (int p = 0; p < nK; ++p) {
+        const int i = order[p];
+        if (i < 0 || i >= nK) return fail(ctx, SG_ERR_INVALID, "order[%d] = %d outside the keypoint set", p, i);
+        sx[p] = h_kx[i]; sy[p] = h_ky[i]; soct[p] = h_koct[i];
+        std::copy(h_kdesc + 8 * (size_t)i, h_kdesc + 8 * (size_t)i + 8, sdesc.begin() + 8 * (size_t)p);
+        if (mode == 1 && h_taken) tk[p] = h_taken[i] ? 1 : 0;
+    }
+    DevBufs bufs;
+    SearchArgs a{};
+    float *d_sx, *d_sy, *d_qx, *d_qy, *d_qr;
+    int *d_sidx, *d_soct, *d_ql = nullptr;
+    uint32_t *d_sdesc, *d_qdesc;
+    unsigned char *d_tk;
+    if (int r = up(ctx, &d_sx, sx.data(), (size_t)nK)) return r; bufs.keep(d_sx);
+    if (int r = up(ctx, &d_sy, sy.data(), (size_t)nK)) return r; bufs.keep(d_sy);
+    if (int r = up(ctx, &d_sidx, order.data(), (size_t)nK)) return r; bufs.keep(d_sidx);
+    if (int r = up(ctx, &d_soct, soct.data(), (size_t)nK)) return r; bufs.keep(d_soct);
+    if (int r = up(ctx, &d_sdesc, sdesc.data(), 8 * (size_t)nK)) return r; bufs.keep(d_sdesc);
+    if (int r = up(ctx, &d_tk, tk.data(), tk.size())) return r; bufs.keep(d_tk);
+    if (int r = up(ctx, &d_qx, h_qx, (size_t)nQ)) return r; bufs.keep(d_qx);
+    if (int r = up(ctx, &d_qy, h_qy, (size_t)nQ)) return r; bufs.keep(d_qy);
+    if (int r = up(ctx, &d_qr, h_qr, (size_t)nQ)) return r; bufs.keep(d_qr);
+    if (int r = up(ctx, &d_qdesc, h_qdesc, 8 * (size_t)nQ)) return r; bufs.keep(d_qdesc);
+    if (h_qlevel) { if (int r = up(ctx, &d_ql, (const int *)h_qlevel, (size_t)nQ)) return r; bufs.keep(d_ql); }
+    uint32_t *d_keys, *d_nseen, *d_dist, *d_nm;
+    int2 *d_range;
+    int *d_idx;
+    unsigned long long *d_resc;
+    SG_CUDA(ctx, cudaMalloc((void **)&d_keys, 16 * (size_t)nQ)); bufs.keep(d_keys);
+    SG_CUDA(ctx, cudaMalloc((void **)&d_nseen, 4 * (size_t)nQ)); bufs.keep(d_nseen);
+    SG_CUDA(ctx, cudaMalloc((void **)&d_range, 8 * (size_t)nQ)); bufs.keep(d_range);
+    SG_CUDA(ctx, cudaMalloc((void **)&d_idx, 4 * (size_t)nQ)); bufs.keep(d_idx);
+    SG_CUDA(ctx, cudaMalloc((void **)&d_dist, 4 * (size_t)nQ)); bufs.keep(d_dist);
+    SG_CUDA(ctx, cudaMalloc((void **)&d_nm, 4)); bufs.keep(d_nm);
+    SG_CUDA(ctx, cudaMalloc((void **)&d_resc, 8)); bufs.keep(d_resc);
+    SG_CUDA(ctx, cudaMemsetAsync(d_nm, 0, 4, ctx->stream));
+    SG_CUDA(ctx, cudaMemsetAsync(d_resc, 0, 8, ctx->stream));
+    a.sx = d_sx; a.sy = d_sy; a.sidx = d_sidx; a.soct = d_soct; a.sdesc = d_sdesc; a.elig0 = d_tk; a.nK = nK;
+    a.qx = d_qx; a.qy = d_qy; a.qr = d_qr; a.qdesc = d_qdesc; a.qlevel = d_ql; a.nQ = nQ; a.mode = mode; a.thr = thr;
+    search_topk_kernel<<<(nQ + SEARCH_WARPS - 1) / SEARCH_WARPS, SEARCH_WARPS * 32, 0, ctx->stream>>>(a, d_keys, d_range, d_nseen);
+    SG_LAUNCH_CHECK(ctx);
+    if (mode == 0) search_resolve_independent_kernel<<<(nQ + 255) / 256, 256, 0, ctx->stream>>>(a, d_keys, d_idx, d_dist, d_nm);
+    else search_resolve_sequential_kernel<<<1, 32, 0, ctx->stream>>>(a, d_keys, d_range, d_nseen, d_tk, d_idx, d_dist, d_nm, d_resc);
+    SG_LAUNCH_CHECK(ctx);
+    SG_CUDA(ctx, cudaMemcpyAsync(h_idx, d_idx, 4 * (size_t)nQ, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(h_dist, d_dist, 4 * (size_t)nQ, cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t nm = 0;
+    SG_CUDA(ctx, cudaMemcpyAsync(&nm, d_nm, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(&ctx->rescans, d_resc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mode == 1 && h_taken) SG_CUDA(ctx, cudaMemcpyAsync(tk.data(), d_tk, tk.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (mode == 1 && h_taken)
+        for (int p = 0; p < nK; ++p) h_taken[order[p]] = tk[p];
+    if (n_matched) *n_matched = nm;
+    return SG_OK;
+}
+
+extern "C" int sg_feature_index(const float *h_x, const float *h_y, int n, int32_t *h_order) {
+    struct Node { float x, y; int idx; };
+    std::vector<Node> v(std::max(n, 0));
+    for (int i = 0; i < n; ++i) v[i] = Node{h_x[i], h_y[i], i};
+    std::sort(v.begin(), v.end(), [](const Node &a, const Node &b) { return a.y < b.y; });
+    for (int i = 0; i < n; ++i) h_order[i] = v[i].idx;
+    return SG_OK;
+}

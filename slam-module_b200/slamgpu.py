@@ -61,7 +61,7 @@ ABI_SYMBOLS = [
     "sg_angle_bin_order", "sg_angle_bin_order_depth", "sg_angle_bin", "sg_device_count", "sg_malloc", "sg_free",
     "sg_memcpy_h2d", "sg_memcpy_d2h", "sg_host_alloc_pinned", "sg_host_free_pinned", "sg_timer_start",
     "sg_timer_stop", "sg_flush_l2", "sg_microbench_popc", "sg_set_profiling", "sg_get_stage_ms",
-    "sg_set_pipeline_chunk",
+    "sg_set_pipeline_chunk", "sg_search_candidates", "sg_feature_index", "sg_medoid",
 ]
 
 _lib = None
@@ -127,6 +127,13 @@ def lib():
         L.sg_get_stage_ms.restype = C.c_int
         L.sg_synchronize.argtypes = [C.c_void_p]
         L.sg_set_pipeline_chunk.argtypes = [C.c_void_p, C.c_int]
+        L.sg_search_candidates.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p] + [C.c_void_p] * 5 + \
+            [C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sg_search_candidates.restype = C.c_int
+        L.sg_feature_index.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sg_feature_index.restype = C.c_int
+        L.sg_medoid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sg_medoid.restype = C.c_int
         L.sg_set_pipeline_chunk.restype = C.c_int
         L.sg_detect.argtypes = [C.c_void_p]
         L.sg_keypoint_capacity.argtypes = [C.c_void_p]
@@ -140,6 +147,14 @@ def lib():
 
 def device_count():
     return int(lib().sg_device_count())
+
+
+def feature_index(x, y):
+    """FeatureSearch's Y-sorted keypoint order (host code of the library, no GPU)."""
+    x = np.ascontiguousarray(x, np.float32); y = np.ascontiguousarray(y, np.float32)
+    order = np.empty(max(len(x), 1), np.int32)
+    lib().sg_feature_index(x.ctypes.data, y.ctypes.data, len(x), order.ctypes.data)
+    return order[:len(x)]
 
 
 def angle_bin_order(sizes, depth_limit=None):
@@ -421,6 +436,35 @@ class Context:
 
     def rescans(self):
         return int(lib().sg_match_rescans(self._h))
+
+    # ---- candidate-list matchers and descriptor medoid ------------------------------------
+    def search_candidates(self, kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=0, thr=50, taken=None, qlevel=None, order=None):
+        """Radius query + best (/ second best) Hamming per query; returns (n_matched, idx[nQ], dist[nQ]);
+        `taken` (uint8, mode 1) is updated in place."""
+        kx = np.ascontiguousarray(kx, np.float32); ky = np.ascontiguousarray(ky, np.float32)
+        koct = np.ascontiguousarray(koct, np.int32); kdesc = np.ascontiguousarray(kdesc, np.uint32).reshape(-1, 8)
+        qx = np.ascontiguousarray(qx, np.float32); qy = np.ascontiguousarray(qy, np.float32)
+        qr = np.ascontiguousarray(qr, np.float32); qdesc = np.ascontiguousarray(qdesc, np.uint32).reshape(-1, 8)
+        ql = None if qlevel is None else np.ascontiguousarray(qlevel, np.int32)
+        od = None if order is None else np.ascontiguousarray(order, np.int32)
+        if taken is not None:
+            assert taken.dtype == np.uint8 and taken.flags.c_contiguous and len(taken) == len(kx)
+        idx = np.empty(max(len(qx), 1), np.int32)
+        dist = np.empty(max(len(qx), 1), np.uint32)
+        n = C.c_uint32()
+        self._check(lib().sg_search_candidates(
+            self._h, kx.ctypes.data, ky.ctypes.data, koct.ctypes.data, kdesc.ctypes.data, len(kx),
+            None if od is None else od.ctypes.data, None if taken is None else taken.ctypes.data,
+            qx.ctypes.data, qy.ctypes.data, qr.ctypes.data, qdesc.ctypes.data, None if ql is None else ql.ctypes.data,
+            len(qx), int(mode), int(thr), idx.ctypes.data, dist.ctypes.data, C.byref(n)))
+        return int(n.value), idx[:len(qx)], dist[:len(qx)]
+
+    def medoid(self, desc, offsets):
+        desc = np.ascontiguousarray(desc, np.uint32).reshape(-1, 8)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        best = np.empty(max(len(offsets) - 1, 1), np.int32)
+        self._check(lib().sg_medoid(self._h, desc.ctypes.data, offsets.ctypes.data, len(offsets) - 1, best.ctypes.data))
+        return best[:len(offsets) - 1]
 
 
 class DescriptorDB:

@@ -1,0 +1,163 @@
+"""Candidate-list matchers and descriptor medoid: the oracle against plain-python restatements of
+the reference loops (CPU), and the CUDA library against the oracle (GPU, through the C ABI)."""
+import numpy as np
+import pytest
+
+
+def _popc(a, b):
+    return int(sum(bin(int(x) ^ int(y)).count("1") for x, y in zip(a, b)))
+
+
+def _scene(seed, nk=600, nq=300, w=640, h=480):
+    """Keypoints of one keyframe and projected map points: queries are noisy copies of keypoint descriptors
+    placed near their keypoint (so matches exist), some far away, some with duplicated y (sort ties)."""
+    rng = np.random.default_rng(seed)
+    kx = rng.uniform(0, w, nk).astype(np.float32)
+    ky = np.round(rng.uniform(0, h, nk) * 2) / 2            # half-pixel grid: many equal y values
+    ky = ky.astype(np.float32)
+    koct = rng.integers(0, 8, nk).astype(np.int32)
+    kdesc = rng.integers(0, 2 ** 32, (nk, 8), dtype=np.uint32)
+    src = rng.integers(0, nk, nq)
+    qdesc = kdesc[src].copy()
+    for q in range(nq):
+        for b in rng.integers(0, 256, int(rng.integers(0, 60))):
+            qdesc[q, b >> 5] ^= np.uint32(1 << (int(b) & 31))
+    qx = (kx[src] + rng.normal(0, 3, nq)).astype(np.float32)
+    qy = (ky[src] + rng.normal(0, 3, nq)).astype(np.float32)
+    far = rng.random(nq) < 0.1
+    qx[far] = rng.uniform(-50, w + 50, far.sum()).astype(np.float32)
+    qr = rng.uniform(2, 25, nq).astype(np.float32)
+    qlevel = np.clip(koct[src] + rng.integers(-1, 2, nq), 0, 7).astype(np.int32)
+    # near-duplicate keypoints: several candidates with the same distance inside one radius
+    kx[1::7] = kx[0::7][:len(kx[1::7])] + 0.5
+    ky[1::7] = ky[0::7][:len(ky[1::7])]
+    kdesc[1::7] = kdesc[0::7][:len(kdesc[1::7])]
+    return kx, ky, koct, kdesc, qx, qy, qr, qdesc, qlevel
+
+
+def test_oracle_feature_search_matches_python(oracle):
+    kx, ky, koct, kdesc, qx, qy, qr, qdesc, _ = _scene(1, nk=300, nq=40)
+    order = oracle.feature_index(kx, ky)
+    assert sorted(order.tolist()) == list(range(300))
+    assert (np.diff(ky[order]) >= 0).all()
+    for q in range(40):
+        got = oracle.features_around(kx, ky, qx[q], qy[q], qr[q])
+        want = [int(i) for i in order if ky[i] >= np.float32(qy[q] - qr[q]) and ky[i] <= np.float32(qy[q] + qr[q])
+                and np.float32(np.float32((qx[q] - kx[i]) * (qx[q] - kx[i])) + np.float32((qy[q] - ky[i]) * (qy[q] - ky[i])))
+                < np.float32(qr[q] * qr[q])]
+        assert got.tolist() == want
+
+
+def test_oracle_search_and_medoid_match_python(oracle):
+    kx, ky, koct, kdesc, qx, qy, qr, qdesc, qlevel = _scene(2, nk=200, nq=60)
+    # mode 1 (searchByProjection), plain python
+    taken = (np.arange(200) % 5 == 0).astype(np.uint8)
+    tk = taken.copy()
+    want_idx = []
+    for q in range(60):
+        cand = oracle.features_around(kx, ky, qx[q], qy[q], qr[q])
+        best, best2, lvl, lvl2, bi = 256, 256, -1, -1, -1
+        for i in cand:
+            if tk[i]:
+                continue
+            d = _popc(qdesc[q], kdesc[i])
+            if d < best:
+                best2, best, lvl2, lvl, bi = best, d, lvl, int(koct[i]), int(i)
+            elif d < best2:
+                lvl2, best2 = int(koct[i]), d
+        ok = bi != -1 and best <= 100 and not (lvl == lvl2 and best > 0.8 * best2)
+        want_idx.append(bi if ok else -1)
+        if ok:
+            tk[bi] = 1
+    t2 = taken.copy()
+    n, idx, dist = oracle.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=1, thr=100, taken=t2)
+    assert idx.tolist() == want_idx and n == sum(i >= 0 for i in want_idx) and np.array_equal(t2, tk)
+    assert n > 10
+    # medoid, plain python
+    rng = np.random.default_rng(3)
+    sizes = [1, 2, 3, 7, 12, 0, 5]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    desc = rng.integers(0, 2 ** 32, (offs[-1], 8), dtype=np.uint32)
+    want = []
+    for s, n_ in enumerate(sizes):
+        d = desc[offs[s]:offs[s + 1]]
+        best_m, best_i = 256, 0
+        for i in range(n_):
+            row = sorted(_popc(d[i], d[j]) for j in range(n_))
+            m = row[int(0.5 * (n_ - 1))]
+            if m < best_m:
+                best_m, best_i = m, i
+        want.append(best_i)
+    assert oracle.medoid(desc, offs).tolist() == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,nk,nq", [(11, 600, 300), (12, 2000, 1500), (13, 50, 400)])
+def test_gpu_search_candidates_bit_exact(slamgpu, oracle, seed, nk, nq):
+    kx, ky, koct, kdesc, qx, qy, qr, qdesc, qlevel = _scene(seed, nk, nq)
+    with slamgpu.Context(640, 480, max_frames=1) as ctx:
+        assert np.array_equal(slamgpu.feature_index(kx, ky), oracle.feature_index(kx, ky))
+        # replaceDuplication: best only, threshold 50
+        n, idx, dist = ctx.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=0, thr=50)
+        rn, ridx, rdist = oracle.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=0, thr=50)
+        assert n == rn and np.array_equal(idx, ridx) and np.array_equal(dist, rdist) and n > 0
+        # findMatchesTranformedMps: threshold 100 + octave window
+        n, idx, dist = ctx.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=0, thr=100, qlevel=qlevel)
+        rn, ridx, rdist = oracle.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=0, thr=100, qlevel=qlevel)
+        assert n == rn and np.array_equal(idx, ridx) and np.array_equal(dist, rdist)
+        # searchByProjection: consumed keypoints, level-aware ratio rule, queries in order
+        taken = (np.arange(nk) % 4 == 0).astype(np.uint8)
+        t1, t2 = taken.copy(), taken.copy()
+        n, idx, dist = ctx.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=1, thr=100, taken=t1)
+        rn, ridx, rdist = oracle.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=1, thr=100, taken=t2)
+        assert n == rn and np.array_equal(idx, ridx) and np.array_equal(dist, rdist) and np.array_equal(t1, t2)
+        assert n > 0
+
+
+@pytest.mark.gpu
+def test_gpu_search_consumption_forces_rescans(slamgpu, oracle):
+    """Many queries compete for few keypoints inside one radius: the truncated top-4 lists run dry and the exact
+    rescan path decides."""
+    rng = np.random.default_rng(5)
+    nk, nq = 40, 200
+    kx = rng.uniform(100, 110, nk).astype(np.float32)
+    ky = rng.uniform(100, 110, nk).astype(np.float32)
+    koct = (np.arange(nk) % 8).astype(np.int32)
+    base = rng.integers(0, 2 ** 32, 8, dtype=np.uint32)
+    kdesc = np.tile(base, (nk, 1))
+    for i in range(nk):                                   # distances 0 .. 19 from the common query descriptor
+        for b in rng.choice(256, i // 2, replace=False):
+            kdesc[i, b >> 5] ^= np.uint32(1 << (int(b) & 31))
+    qdesc = np.tile(base, (nq, 1))
+    qx = np.full(nq, 105, np.float32)
+    qy = np.full(nq, 105, np.float32)
+    qr = np.full(nq, 30, np.float32)
+    with slamgpu.Context(640, 480, max_frames=1) as ctx:
+        t1, t2 = np.zeros(nk, np.uint8), np.zeros(nk, np.uint8)
+        n, idx, dist = ctx.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=1, thr=100, taken=t1)
+        rn, ridx, rdist = oracle.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=1, thr=100, taken=t2)
+        assert n == rn and np.array_equal(idx, ridx) and np.array_equal(dist, rdist) and np.array_equal(t1, t2)
+        assert n > 8 and ctx.rescans() > 0
+        # empty inputs
+        n, idx, _ = ctx.search_candidates(kx[:0], ky[:0], koct[:0], kdesc[:0], qx, qy, qr, qdesc, mode=0, thr=50)
+        assert n == 0 and (idx == -1).all()
+
+
+@pytest.mark.gpu
+def test_gpu_medoid_bit_exact(slamgpu, oracle, synth):
+    rng = np.random.default_rng(21)
+    sizes = [1, 2, 3, 4, 5, 8, 13, 31, 32, 33, 64, 100, 0, 257, 1024] + rng.integers(1, 40, 200).tolist()
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    desc = rng.integers(0, 2 ** 32, (offs[-1], 8), dtype=np.uint32)
+    # observations of one map point are noisy copies of one descriptor (the realistic case: many equal medians)
+    for s in range(20, len(sizes)):
+        base = desc[offs[s]].copy()
+        for i in range(offs[s], offs[s + 1]):
+            desc[i] = base
+            for b in rng.integers(0, 256, int(rng.integers(0, 12))):
+                desc[i, b >> 5] ^= np.uint32(1 << (int(b) & 31))
+    with slamgpu.Context(640, 480, max_frames=1) as ctx:
+        got = ctx.medoid(desc, offs)
+        assert np.array_equal(got, oracle.medoid(desc, offs))
+        with pytest.raises(slamgpu.SlamGpuError):
+            ctx.medoid(rng.integers(0, 2 ** 32, (1025, 8), dtype=np.uint32), np.array([0, 1025], np.int64))
