@@ -58,7 +58,7 @@ if lf.exists():
     tot = sum(v for _, v in agg.values())
     with open(dst / ("launches_%s.md" % tag), "w") as f:
         f.write("# ncu launch list, %s\n\n`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` on "
-                "`python bench.py --steps 2 --warmup 3 --skip-cpu-baseline` (cold-cache, serialised: compare shares).\n\n"
+                "`python bench.py --steps 2 --warmup 3 --skip-cpu-baseline --skip-extra-configs --skip-e2e` (cold-cache, serialised: compare shares).\n\n"
                 "| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n" % tag)
         for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("| %s | %d | %.1f | %.1f | %.3f |\n" % (k, n, v / 1e3, v / 1e3 / n, v / tot))
