@@ -39,6 +39,7 @@ struct Level {
     // resize; for level 0: box over level 0 itself for the blur-only kernel).  map_fast: 80x70 box over
     // this level for the FAST cells.  Maps over level 0 are re-encoded when the input pointer changes.
     CUtensorMap map_src{}, map_fast{};
+    CUtensorMap map_mom{}, map_blur{};   // describe kernel: 48x31 box over this level's plane, 64x37 over its blurred plane
     int src_tile_w = 0, src_tile_h = 0;  // smem extent of the source tile of the resize kernel
     // detection geometry
     int area_w = 0, area_h = 0;     // working area (image minus 19-px border)

@@ -11,6 +11,7 @@
 // done in double like orb_extractor.cpp:286.
 #include <algorithm>
 #include "ctx.h"
+#include "tma.cuh"
 
 namespace sg {
 
@@ -90,7 +91,9 @@ struct DescOut {
 //      1.5*2^23 magic-number add (exact round-half-even for |v| < 2^22) instead of the quarter-rate F2I.
 constexpr int MOM_WORDS = 9;            // aligned words covering the 31 columns of the moment disc
 constexpr int BLUR_R = 18;              // max |rotated pattern coordinate| (pattern radius 18.38, |cos|,|sin| <= 1.001)
-constexpr int BLUR_ROWS = 2 * BLUR_R + 1, BLUR_WORDS = 10, BLUR_PITCH = 44;   // bytes per staged row (11 words: odd)
+constexpr int BLUR_ROWS = 2 * BLUR_R + 1, BLUR_PITCH = 64;   // TMA box of the blurred window: 64 x 37 (x origin 16-byte aligned)
+constexpr int MOM_ROWS = 2 * HALF_PATCH + 1, MOM_PITCH = 48;  // TMA box of the moment window: 48 x 31
+constexpr int PATCH_BYTES = 2432;                            // per buffer: >= 37 * 64 and >= 31 * 48, multiple of 128
 constexpr float ROUND_MAGIC = 12582912.f;        // 1.5 * 2^23
 constexpr int ROUND_MAGIC_BITS = 0x4B400000;
 
@@ -104,14 +107,16 @@ __device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
 }
 __device__ __forceinline__ int rint_magic_bits(float v) { return __float_as_int(__fadd_rn(v, ROUND_MAGIC)); }
 
+struct DescMaps { CUtensorMap mom[SG_MAX_LEVELS], blur[SG_MAX_LEVELS]; };   // 48 x 31 boxes over the pyramid planes, 64 x 37 over the blurred ones
+
 __global__ void __launch_bounds__(DESC_WARPS * 32)
-describe_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int level0_pitch,
-                unsigned long long level0_stride, const int *kp_xy, const int *kp_count,
+describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescMaps maps, const int *kp_xy, const int *kp_count,
                 const int *trk_xy, const float *trk_pt, const int *trk_id, const int *trk_count,
                 int track_level, int n_frames, DescOut o) {
     __shared__ uint32_t s_wu[4][16][MOM_WORDS];    // u weights (signed bytes) per (alignment, |v|, word)
     __shared__ uint32_t s_wm[4][16][MOM_WORDS];    // disc mask (0 / 1 bytes)
-    __shared__ __align__(16) uint8_t s_patch[DESC_WARPS][2 * BLUR_ROWS * BLUR_PITCH];   // two buffers per warp
+    __shared__ __align__(128) uint8_t s_patch[DESC_WARPS][2 * PATCH_BYTES];   // two TMA destinations per warp
+    __shared__ __align__(8) uint64_t s_bar[DESC_WARPS][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // ---- per-CTA tables --------------------------------------------------------------------------------
@@ -141,13 +146,15 @@ describe_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int le
             }
         }
     }
+    if (lane == 0) { mbar_init(&s_bar[warp][0], 1); mbar_init(&s_bar[warp][1], 1); }
     __syncthreads();
+    unsigned bar_phase = 0;    // bit b: parity the next wait on buffer b expects
 
     const int groups_per_frame = (g.out_cap + 31) >> 5;
     const int n_groups = groups_per_frame * n_frames;
     const int mrow = lane / MOM_WORDS, mword = lane - mrow * MOM_WORDS;        // lanes 0..26: 3 rows x 9 words
-    const int brow = lane / BLUR_WORDS, bword = lane - brow * BLUR_WORDS;      // lanes 0..29: 3 rows x 10 words
     uint8_t *patch = s_patch[warp];
+    uint64_t *bars = s_bar[warp];
 
     for (int grp = blockIdx.x * DESC_WARPS + warp; grp < n_groups; grp += gridDim.x * DESC_WARPS) {
         const int f = g.frame0 + grp / groups_per_frame;
@@ -205,45 +212,45 @@ describe_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int le
         }
 
         // ---- phase A: intensity-centroid moments (un-blurred level) ----------------------------------------
-        // software pipelined: the 11 words of keypoint j + 1 are in flight while keypoint j is summed
+        // double buffered: lane 0 issues the TMA box load (48 x 31, x origin aligned down to 16 bytes) of keypoint
+        // j + 1 while the warp sums keypoint j from shared memory
         int my_m10 = 0, my_m01 = 0;
         {
-            uint32_t pix[11], nxt[11];
-            int off = 0, off_n = 0;
-            auto issue = [&](int j, uint32_t (&dst)[11], int &o_) {
+            auto issue = [&](int j) {
                 const int ix = __shfl_sync(0xffffffffu, k.ix, j), iy = __shfl_sync(0xffffffffu, k.iy, j);
                 const int l = __shfl_sync(0xffffffffu, k.l, j);
-                const uint8_t *img = l == 0 ? level0 + (size_t)f * level0_stride : g.lv[l].pyr + (size_t)f * g.lv[l].frame_stride;
-                const int pitch = l == 0 ? level0_pitch : g.lv[l].pitch;
-                o_ = (ix - HALF_PATCH) & 3;
-                const uint8_t *c = img + (size_t)(iy - HALF_PATCH + mrow) * pitch + (ix - HALF_PATCH - o_) + 4 * mword;
-                if (lane < 3 * MOM_WORDS) {
-#pragma unroll
-                    for (int i = 0; i < 11; ++i)
-                        if (3 * i + mrow <= 2 * HALF_PATCH) dst[i] = __ldg(reinterpret_cast<const uint32_t *>(c + (size_t)(3 * i) * pitch));
+                if (lane == 0) {
+                    uint64_t *bar = bars + (j & 1);
+                    mbar_expect_tx(bar, MOM_ROWS * MOM_PITCH);
+                    tma_load_3d(patch + (j & 1) * PATCH_BYTES, &maps.mom[l], (ix - HALF_PATCH) & ~15, iy - HALF_PATCH, f, bar);
                 }
             };
-            issue(0, pix, off);
+            __syncwarp();   // every lane is done with both buffers (previous group)
+            issue(0);
             for (int j = 0; j < n_here; ++j) {
-                if (j + 1 < n_here) issue(j + 1, nxt, off_n);
+                const int b = j & 1;
+                if (j + 1 < n_here) issue(j + 1);     // buffer b ^ 1 was last read for keypoint j - 1 (syncwarp below)
+                const int ix = __shfl_sync(0xffffffffu, k.ix, j);
+                const int off16 = (ix - HALF_PATCH) & 15, off = off16 & 3;
+                mbar_wait(bars + b, (bar_phase >> b) & 1u);
+                bar_phase ^= 1u << b;
                 int m10 = 0, m01 = 0;
                 if (lane < 3 * MOM_WORDS) {
+                    const uint8_t *c = patch + b * PATCH_BYTES + mrow * MOM_PITCH + (off16 & ~3) + 4 * mword;
 #pragma unroll
                     for (int i = 0; i < 11; ++i) {
                         const int v = 3 * i + mrow - HALF_PATCH;
                         if (v <= HALF_PATCH) {
+                            const uint32_t pix = *reinterpret_cast<const uint32_t *>(c + 3 * i * MOM_PITCH);
                             const int av = abs(v);
-                            m10 = dp4a_us(pix[i], (int)s_wu[off][av][mword], m10);
-                            m01 += v * (int)__dp4a(pix[i], s_wm[off][av][mword], 0u);
+                            m10 = dp4a_us(pix, (int)s_wu[off][av][mword], m10);
+                            m01 += v * (int)__dp4a(pix, s_wm[off][av][mword], 0u);
                         }
                     }
                 }
-                m10 = __reduce_add_sync(0xffffffffu, m10);
+                m10 = __reduce_add_sync(0xffffffffu, m10);     // (also orders this keypoint's reads before the next issue)
                 m01 = __reduce_add_sync(0xffffffffu, m01);
                 if (lane == j) { my_m10 = m10; my_m01 = m01; }
-#pragma unroll
-                for (int i = 0; i < 11; ++i) pix[i] = nxt[i];
-                off = off_n;
             }
         }
 
@@ -259,41 +266,29 @@ describe_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int le
         }
 
         // ---- phase C: rBRIEF on the blurred level -----------------------------------------------------------
-        // software pipelined over two patch buffers: the 37 x 40-byte window of keypoint j + 1 is loaded into
-        // registers before keypoint j is sampled, and stored to the other buffer afterwards
-        uint32_t win[13];
-        auto fetch = [&](int j) {
+        // same double buffering with 64 x 37 boxes of the blurred plane
+        auto issue_blur = [&](int j) {
             const int ix = __shfl_sync(0xffffffffu, k.ix, j), iy = __shfl_sync(0xffffffffu, k.iy, j);
             const int l = __shfl_sync(0xffffffffu, k.l, j);
-            const int pitch = g.lv[l].pitch;
-            const int off = (ix - BLUR_R) & 3;
-            const uint8_t *src = g.lv[l].blur + (size_t)f * g.lv[l].frame_stride + (size_t)(iy - BLUR_R + brow) * pitch
-                                 + (ix - BLUR_R - off) + 4 * bword;
-            if (lane < 3 * BLUR_WORDS) {
-#pragma unroll
-                for (int i = 0; i < 13; ++i)
-                    if (3 * i + brow < BLUR_ROWS) win[i] = __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)(3 * i) * pitch));
+            if (lane == 0) {
+                uint64_t *bar = bars + (j & 1);
+                mbar_expect_tx(bar, BLUR_ROWS * BLUR_PITCH);
+                tma_load_3d(patch + (j & 1) * PATCH_BYTES, &maps.blur[l], (ix - BLUR_R) & ~15, iy - BLUR_R, f, bar);
             }
         };
-        auto stash = [&](uint8_t *dst) {
-            if (lane < 3 * BLUR_WORDS) {
-#pragma unroll
-                for (int i = 0; i < 13; ++i)
-                    if (3 * i + brow < BLUR_ROWS) *reinterpret_cast<uint32_t *>(dst + (3 * i + brow) * BLUR_PITCH + 4 * bword) = win[i];
-            }
-        };
-        fetch(0);
-        __syncwarp();       // the previous group's samples have been read
-        stash(patch);
+        __syncwarp();       // phase A's reads are complete
+        issue_blur(0);
         for (int j = 0; j < n_here; ++j) {
-            uint8_t *cur = patch + (j & 1) * (BLUR_ROWS * BLUR_PITCH);
-            if (j + 1 < n_here) fetch(j + 1);
-            __syncwarp();   // buffer j is complete
+            const int b = j & 1;
+            __syncwarp();   // keypoint j - 1 has been sampled by every lane: its buffer may be refilled
+            if (j + 1 < n_here) issue_blur(j + 1);
             const int ix = __shfl_sync(0xffffffffu, k.ix, j);
             const float c_ = __shfl_sync(0xffffffffu, cs, j), s_ = __shfl_sync(0xffffffffu, sn, j);
-            const int off = (ix - BLUR_R) & 3;
-            const uint8_t *patch_j = cur;
-            // sample index = (r + 18) * 44 + (c + 18 + off); r, c arrive as MAGIC_BITS + integer
+            const int off = (ix - BLUR_R) & 15;
+            const uint8_t *patch_j = patch + b * PATCH_BYTES;
+            mbar_wait(bars + b, (bar_phase >> b) & 1u);
+            bar_phase ^= 1u << b;
+            // sample index = (r + 18) * 64 + (c + 18 + off); r, c arrive as MAGIC_BITS + integer
             // (unsigned arithmetic: the magic offsets cancel modulo 2^32)
             const unsigned bias = (unsigned)(BLUR_R * BLUR_PITCH + BLUR_R + off) - (unsigned)ROUND_MAGIC_BITS * (unsigned)(BLUR_PITCH + 1);
             unsigned bits = 0;
@@ -313,8 +308,6 @@ describe_kernel(const __grid_constant__ GeomDev g, const uint8_t *level0, int le
             // 8 words per descriptor: lanes 0, 4, 8, ... hold words 0..7
             const unsigned wsel = __shfl_sync(0xffffffffu, word, (lane & 7) << 2);
             if (lane < 8) o.desc[8 * (oi0 + j) + lane] = wsel;
-            // the other buffer was last read for keypoint j - 1: every lane is past that (syncwarp above)
-            if (j + 1 < n_here) stash(patch + ((j + 1) & 1) * (BLUR_ROWS * BLUR_PITCH));
         }
     }
 }
@@ -332,8 +325,10 @@ int launch_describe(sg_ctx *ctx, int n_frames) {
         per_sm = std::max(per_sm, 1);
     }
     const int blocks = std::max(1, std::min((groups + DESC_WARPS - 1) / DESC_WARPS, ctx->sm_count * per_sm));
+    DescMaps maps;
+    for (int l = 0; l < g.levels; ++l) { maps.mom[l] = ctx->lv[l].map_mom; maps.blur[l] = ctx->lv[l].map_blur; }
     describe_kernel<<<blocks, DESC_WARPS * 32, 0, ctx->stream>>>(
-        g, ctx->level0, ctx->level0_pitch, ctx->level0_stride, ctx->d_kp_xy, ctx->d_kp_count,
+        g, maps, ctx->d_kp_xy, ctx->d_kp_count,
         trk ? ctx->d_trk_xy : nullptr, trk ? ctx->d_trk_pt : nullptr, trk ? ctx->d_trk_id : nullptr,
         trk ? ctx->d_trk_count : nullptr, ctx->p.track_level, n_frames, o);
     SG_LAUNCH_CHECK(ctx);
