@@ -119,11 +119,13 @@ static int build_context(sg_ctx *ctx) {
         D.cand_off = L.cand_off; D.kp_off = L.kp_off;
     }
     // TMA descriptors over the context's own planes (level-0 based ones follow the input: set_level0)
+    int mom_w, mom_h, blur_w, blur_h;
+    describe_box_dims(&mom_w, &mom_h, &blur_w, &blur_h);
     for (int l = 0; l < p.levels; ++l) {
         Level &L = ctx->lv[l];
-        if (int r = encode_plane_map(ctx, &L.map_blur, L.blur, L.w, L.h, L.pitch, L.frame_stride, p.max_frames, 64, 37)) return r;
+        if (int r = encode_plane_map(ctx, &L.map_blur, L.blur, L.w, L.h, L.pitch, L.frame_stride, p.max_frames, blur_w, blur_h)) return r;
         if (l > 0)
-            if (int r = encode_plane_map(ctx, &L.map_mom, L.pyr, L.w, L.h, L.pitch, L.frame_stride, p.max_frames, 48, 31)) return r;
+            if (int r = encode_plane_map(ctx, &L.map_mom, L.pyr, L.w, L.h, L.pitch, L.frame_stride, p.max_frames, mom_w, mom_h)) return r;
     }
     for (int l = 1; l < p.levels; ++l) {
         Level &L = ctx->lv[l];

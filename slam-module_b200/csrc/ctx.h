@@ -191,6 +191,7 @@ bool is_area2x(int sw, int sh, int dw, int dh);
 int launch_pyramid(sg_ctx *ctx, int n_frames);
 int launch_detect(sg_ctx *ctx, int n_frames);
 int launch_describe(sg_ctx *ctx, int n_frames);
+void describe_box_dims(int *mom_w, int *mom_h, int *blur_w, int *blur_h);
 int grow(sg_ctx *ctx, void **ptr, size_t *cap, size_t need, size_t elem);
 // TMA descriptor of an 8-bit plane stack {w, h, frames} with a fixed box (tma.cpp).
 int encode_plane_map(sg_ctx *ctx, CUtensorMap *out, const uint8_t *base, int w, int h, int pitch, size_t frame_stride,

@@ -91,8 +91,10 @@ struct DescOut {
 //      1.5*2^23 magic-number add (exact round-half-even for |v| < 2^22) instead of the quarter-rate F2I.
 constexpr int MOM_WORDS = 9;            // aligned words covering the 31 columns of the moment disc
 constexpr int BLUR_R = 18;              // max |rotated pattern coordinate| (pattern radius 18.38, |cos|,|sin| <= 1.001)
-constexpr int BLUR_ROWS = 2 * BLUR_R + 1, BLUR_PITCH = 64;   // TMA box of the blurred window: 64 x 37 (x origin 16-byte aligned)
-constexpr int MOM_ROWS = 2 * HALF_PATCH + 1, MOM_PITCH = 48;  // TMA box of the moment window: 48 x 31
+// TMA boxes 64 x 37 / 48 x 31 with the x origin aligned down to 16 bytes: a box origin at the exact window column
+// (48 x 37 / 32 x 31 boxes, 28% fewer bytes) raises "illegal instruction" on sm_100a / driver 580 -- measured twice.
+constexpr int XALIGN = 16, BLUR_PITCH = 64, MOM_PITCH = 48;
+constexpr int BLUR_ROWS = 2 * BLUR_R + 1, MOM_ROWS = 2 * HALF_PATCH + 1;
 constexpr int PATCH_BYTES = 2432;                            // per buffer: >= 37 * 64 and >= 31 * 48, multiple of 128
 constexpr float ROUND_MAGIC = 12582912.f;        // 1.5 * 2^23
 constexpr int ROUND_MAGIC_BITS = 0x4B400000;
@@ -222,7 +224,7 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
                 if (lane == 0) {
                     uint64_t *bar = bars + (j & 1);
                     mbar_expect_tx(bar, MOM_ROWS * MOM_PITCH);
-                    tma_load_3d(patch + (j & 1) * PATCH_BYTES, &maps.mom[l], (ix - HALF_PATCH) & ~15, iy - HALF_PATCH, f, bar);
+                    tma_load_3d(patch + (j & 1) * PATCH_BYTES, &maps.mom[l], (ix - HALF_PATCH) & ~(XALIGN - 1), iy - HALF_PATCH, f, bar);
                 }
             };
             __syncwarp();   // every lane is done with both buffers (previous group)
@@ -231,7 +233,7 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
                 const int b = j & 1;
                 if (j + 1 < n_here) issue(j + 1);     // buffer b ^ 1 was last read for keypoint j - 1 (syncwarp below)
                 const int ix = __shfl_sync(0xffffffffu, k.ix, j);
-                const int off16 = (ix - HALF_PATCH) & 15, off = off16 & 3;
+                const int off16 = (ix - HALF_PATCH) & (XALIGN - 1), off = off16 & 3;
                 mbar_wait(bars + b, (bar_phase >> b) & 1u);
                 bar_phase ^= 1u << b;
                 int m10 = 0, m01 = 0;
@@ -273,7 +275,7 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
             if (lane == 0) {
                 uint64_t *bar = bars + (j & 1);
                 mbar_expect_tx(bar, BLUR_ROWS * BLUR_PITCH);
-                tma_load_3d(patch + (j & 1) * PATCH_BYTES, &maps.blur[l], (ix - BLUR_R) & ~15, iy - BLUR_R, f, bar);
+                tma_load_3d(patch + (j & 1) * PATCH_BYTES, &maps.blur[l], (ix - BLUR_R) & ~(XALIGN - 1), iy - BLUR_R, f, bar);
             }
         };
         __syncwarp();       // phase A's reads are complete
@@ -284,7 +286,7 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
             if (j + 1 < n_here) issue_blur(j + 1);
             const int ix = __shfl_sync(0xffffffffu, k.ix, j);
             const float c_ = __shfl_sync(0xffffffffu, cs, j), s_ = __shfl_sync(0xffffffffu, sn, j);
-            const int off = (ix - BLUR_R) & 15;
+            const int off = (ix - BLUR_R) & (XALIGN - 1);
             const uint8_t *patch_j = patch + b * PATCH_BYTES;
             mbar_wait(bars + b, (bar_phase >> b) & 1u);
             bar_phase ^= 1u << b;
@@ -310,6 +312,11 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
             if (lane < 8) o.desc[8 * (oi0 + j) + lane] = wsel;
         }
     }
+}
+
+// TMA box extents of the describe kernel's windows (host, for the tensor maps)
+void describe_box_dims(int *mom_w, int *mom_h, int *blur_w, int *blur_h) {
+    *mom_w = MOM_PITCH; *mom_h = MOM_ROWS; *blur_w = BLUR_PITCH; *blur_h = BLUR_ROWS;
 }
 
 int launch_describe(sg_ctx *ctx, int n_frames) {

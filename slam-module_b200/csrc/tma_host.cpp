@@ -45,8 +45,10 @@ int encode_level0_maps(sg_ctx *ctx) {
                                  frames, 96, 70)) return r;   // window of the blur-only kernel: 64 + 32 x 64 + 6
     if (int r = encode_plane_map(ctx, &ctx->lv[0].map_fast, ctx->level0, L0.w, L0.h, ctx->level0_pitch, ctx->level0_stride,
                                  frames, 80, 70)) return r;
+    int mom_w, mom_h, blur_w, blur_h;
+    describe_box_dims(&mom_w, &mom_h, &blur_w, &blur_h);
     if (int r = encode_plane_map(ctx, &ctx->lv[0].map_mom, ctx->level0, L0.w, L0.h, ctx->level0_pitch, ctx->level0_stride,
-                                 frames, 48, 31)) return r;
+                                 frames, mom_w, mom_h)) return r;
     if (ctx->p.levels > 1 && ctx->lv[1].fast_resize)
         if (int r = encode_plane_map(ctx, &ctx->lv[1].map_src, ctx->level0, L0.w, L0.h, ctx->level0_pitch, ctx->level0_stride,
                                      frames, ctx->lv[1].tma_src_w, ctx->lv[1].tma_src_h)) return r;
