@@ -582,7 +582,36 @@ int sg_extract_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t fram
     if (int r = check_device_images(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
     if (int r = set_level0(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
     ctx->have_tracks = false;
-    return extract_launches(ctx, n_frames);
+    const int parts = std::min(ctx->overlap_parts, 4);
+    if (parts <= 1 || n_frames < 16 * parts || ctx->profiling) return extract_launches(ctx, n_frames);
+    // Independent slices of the batch on separate streams: the latency-bound quadtree kernel and the kernel tails
+    // of one slice run under the issue-bound pyramid / FAST kernels of another.  Joined back on the main stream.
+    while ((int)ctx->pipe_ev.size() < parts) {
+        cudaEvent_t e;
+        SG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pipe_ev.push_back(e);
+    }
+    SG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->main_stream));
+    int rc = SG_OK, f0 = 0;
+    for (int c = 0; c < parts && rc == SG_OK; ++c) {
+        const int n = (n_frames - f0) / (parts - c);
+        cudaStream_t cmp = ctx->s_cmp[c];
+        SG_CUDA(ctx, cudaStreamWaitEvent(cmp, ctx->ev_fork, 0));
+        ctx->stream = cmp; ctx->frame0 = f0; ctx->in_pipeline = true;
+        rc = extract_launches(ctx, n);
+        ctx->stream = ctx->main_stream; ctx->frame0 = 0; ctx->in_pipeline = false;
+        if (rc) break;
+        SG_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[c], cmp));
+        SG_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->pipe_ev[c], 0));
+        f0 += n;
+    }
+    return rc;
+}
+
+int sg_set_overlap(sg_ctx *ctx, int parts) {
+    if (parts < 1 || parts > 4) return fail(ctx, SG_ERR_INVALID, "parts must be 1..4");
+    ctx->overlap_parts = parts;
+    return SG_OK;
 }
 
 int sg_extract_device_views(sg_ctx *ctx, sg_keypoints_dev *out) {

@@ -93,6 +93,7 @@ struct sg_ctx {
     cudaStream_t stream = nullptr;      // stream the stage launchers use (swapped per chunk by the pipelined sg_extract)
     cudaStream_t main_stream = nullptr, s_in = nullptr, s_out = nullptr, s_cmp[4] = {nullptr, nullptr, nullptr, nullptr};
     int pipe_streams = 4;               // compute streams the chunks rotate over
+    int overlap_parts = 4;              // sg_extract_device: independent slices of the batch on separate streams
     std::vector<cudaEvent_t> pipe_ev;   // [2 * chunks]: H2D done, compute done
     int pipe_chunk = 32;                // frames per pipeline chunk of sg_extract
     int frame0 = 0;                     // first frame the stage launchers work on

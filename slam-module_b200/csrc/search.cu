@@ -24,6 +24,8 @@
 #include <vector>
 #include "ctx.h"
 
+extern "C" int sg_feature_index(const float *h_x, const float *h_y, int n, int32_t *h_order);
+
 namespace sg {
 
 constexpr int SK = 4;                       // keys kept per query
@@ -245,17 +247,24 @@ medoid_kernel(const uint32_t *desc, const long long *offsets, int *best_out) {
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
-template <class T>
-static int up(sg_ctx *ctx, T **d, const T *h, size_t n) {
-    SG_CUDA(ctx, cudaMalloc((void **)d, std::max<size_t>(n, 1) * sizeof(T)));
-    if (n) SG_CUDA(ctx, cudaMemcpyAsync(*d, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    return SG_OK;
-}
-
-struct DevBufs {
-    std::vector<void *> p;
-    ~DevBufs() { for (void *q : p) cudaFree(q); }
-    template <class T> T *keep(T *q) { p.push_back((void *)q); return q; }
+// Device scratch carved from the context's grow-only buffer (no cudaMalloc / cudaFree per call).
+struct Scratch {
+    sg_ctx *ctx;
+    size_t need = 0, at = 0;
+    explicit Scratch(sg_ctx *c) : ctx(c) {}
+    static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+    void want(size_t bytes) { need += pad(std::max<size_t>(bytes, 1)); }
+    int commit() { return grow(ctx, &ctx->d_tmp, &ctx->tmp_bytes, need, 1); }
+    template <class T> T *take(size_t n) {
+        T *p = reinterpret_cast<T *>(static_cast<uint8_t *>(ctx->d_tmp) + at);
+        at += pad(std::max<size_t>(n * sizeof(T), 1));
+        return p;
+    }
+    template <class T> int put(T **d, const T *h, size_t n) {
+        *d = take<T>(n);
+        if (n) SG_CUDA(ctx, cudaMemcpyAsync(*d, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        return SG_OK;
+    }
 };
 
 }  // namespace sg
@@ -270,17 +279,15 @@ extern "C" int sg_medoid(sg_ctx *ctx, const uint32_t *h_desc, const int64_t *h_o
         const long long n = h_offsets[s + 1] - h_offsets[s];
         if (n < 0 || n > MED_MAX) return fail(ctx, SG_ERR_INVALID, "segment %d has %lld descriptors (supported: 0..%d)", s, n, MED_MAX);
     }
-    DevBufs bufs;
-    uint32_t *d_desc = nullptr;
-    long long *d_off = nullptr;
-    int *d_best = nullptr;
     const size_t total = (size_t)h_offsets[n_seg];
-    if (int r = up(ctx, &d_desc, h_desc, 8 * total)) return r;
-    bufs.keep(d_desc);
-    if (int r = up(ctx, &d_off, (const long long *)h_offsets, (size_t)n_seg + 1)) return r;
-    bufs.keep(d_off);
-    SG_CUDA(ctx, cudaMalloc((void **)&d_best, sizeof(int) * (size_t)n_seg));
-    bufs.keep(d_best);
+    Scratch sc(ctx);
+    sc.want(32 * total); sc.want(8 * ((size_t)n_seg + 1)); sc.want(4 * (size_t)n_seg);
+    if (int r = sc.commit()) return r;
+    uint32_t *d_desc;
+    long long *d_off;
+    if (int r = sc.put(&d_desc, h_desc, 8 * total)) return r;
+    if (int r = sc.put(&d_off, (const long long *)h_offsets, (size_t)n_seg + 1)) return r;
+    int *d_best = sc.take<int>(n_seg);
     medoid_kernel<<<n_seg, MED_THREADS, 0, ctx->stream>>>(d_desc, d_off, d_best);
     SG_LAUNCH_CHECK(ctx);
     SG_CUDA(ctx, cudaMemcpyAsync(h_best, d_best, sizeof(int) * (size_t)n_seg, cudaMemcpyDeviceToHost, ctx->stream));
@@ -303,13 +310,7 @@ extern "C" int sg_search_candidates(sg_ctx *ctx, const float *h_kx, const float 
     // FeatureSearch index (feature_search.cpp:22-31): keypoints sorted by y with the very same std::sort call
     std::vector<int> order(nK);
     if (h_order) std::copy(h_order, h_order + nK, order.begin());
-    else {
-        struct Node { float x, y; int idx; };
-        std::vector<Node> v(nK);
-        for (int i = 0; i < nK; ++i) v[i] = Node{h_kx[i], h_ky[i], i};
-        std::sort(v.begin(), v.end(), [](const Node &a, const Node &b) { return a.y < b.y; });
-        for (int i = 0; i < nK; ++i) order[i] = v[i].idx;
-    }
+    else if (nK) sg_feature_index(h_kx, h_ky, nK, order.data());
     std::vector<float> sx(nK), sy(nK);
     std::vector<int> soct(nK);
     std::vector<uint32_t> sdesc(8 * (size_t)nK);
@@ -321,34 +322,33 @@ extern "C" int sg_search_candidates(sg_ctx *ctx, const float *h_kx, const float 
         std::copy(h_kdesc + 8 * (size_t)i, h_kdesc + 8 * (size_t)i + 8, sdesc.begin() + 8 * (size_t)p);
         if (mode == 1 && h_taken) tk[p] = h_taken[i] ? 1 : 0;
     }
-    DevBufs bufs;
+    const size_t K = (size_t)nK, Q = (size_t)nQ;
+    Scratch sc(ctx);
+    sc.want(4 * K); sc.want(4 * K); sc.want(4 * K); sc.want(4 * K); sc.want(32 * K); sc.want(tk.size());
+    sc.want(4 * Q); sc.want(4 * Q); sc.want(4 * Q); sc.want(32 * Q); sc.want(4 * Q);
+    sc.want(16 * Q); sc.want(4 * Q); sc.want(8 * Q); sc.want(4 * Q); sc.want(4 * Q); sc.want(4); sc.want(8);
+    if (int r = sc.commit()) return r;
     SearchArgs a{};
     float *d_sx, *d_sy, *d_qx, *d_qy, *d_qr;
     int *d_sidx, *d_soct, *d_ql = nullptr;
     uint32_t *d_sdesc, *d_qdesc;
     unsigned char *d_tk;
-    if (int r = up(ctx, &d_sx, sx.data(), (size_t)nK)) return r; bufs.keep(d_sx);
-    if (int r = up(ctx, &d_sy, sy.data(), (size_t)nK)) return r; bufs.keep(d_sy);
-    if (int r = up(ctx, &d_sidx, order.data(), (size_t)nK)) return r; bufs.keep(d_sidx);
-    if (int r = up(ctx, &d_soct, soct.data(), (size_t)nK)) return r; bufs.keep(d_soct);
-    if (int r = up(ctx, &d_sdesc, sdesc.data(), 8 * (size_t)nK)) return r; bufs.keep(d_sdesc);
-    if (int r = up(ctx, &d_tk, tk.data(), tk.size())) return r; bufs.keep(d_tk);
-    if (int r = up(ctx, &d_qx, h_qx, (size_t)nQ)) return r; bufs.keep(d_qx);
-    if (int r = up(ctx, &d_qy, h_qy, (size_t)nQ)) return r; bufs.keep(d_qy);
-    if (int r = up(ctx, &d_qr, h_qr, (size_t)nQ)) return r; bufs.keep(d_qr);
-    if (int r = up(ctx, &d_qdesc, h_qdesc, 8 * (size_t)nQ)) return r; bufs.keep(d_qdesc);
-    if (h_qlevel) { if (int r = up(ctx, &d_ql, (const int *)h_qlevel, (size_t)nQ)) return r; bufs.keep(d_ql); }
-    uint32_t *d_keys, *d_nseen, *d_dist, *d_nm;
-    int2 *d_range;
-    int *d_idx;
-    unsigned long long *d_resc;
-    SG_CUDA(ctx, cudaMalloc((void **)&d_keys, 16 * (size_t)nQ)); bufs.keep(d_keys);
-    SG_CUDA(ctx, cudaMalloc((void **)&d_nseen, 4 * (size_t)nQ)); bufs.keep(d_nseen);
-    SG_CUDA(ctx, cudaMalloc((void **)&d_range, 8 * (size_t)nQ)); bufs.keep(d_range);
-    SG_CUDA(ctx, cudaMalloc((void **)&d_idx, 4 * (size_t)nQ)); bufs.keep(d_idx);
-    SG_CUDA(ctx, cudaMalloc((void **)&d_dist, 4 * (size_t)nQ)); bufs.keep(d_dist);
-    SG_CUDA(ctx, cudaMalloc((void **)&d_nm, 4)); bufs.keep(d_nm);
-    SG_CUDA(ctx, cudaMalloc((void **)&d_resc, 8)); bufs.keep(d_resc);
+    if (int r = sc.put(&d_sx, sx.data(), K)) return r;
+    if (int r = sc.put(&d_sy, sy.data(), K)) return r;
+    if (int r = sc.put(&d_sidx, order.data(), K)) return r;
+    if (int r = sc.put(&d_soct, soct.data(), K)) return r;
+    if (int r = sc.put(&d_sdesc, sdesc.data(), 8 * K)) return r;
+    if (int r = sc.put(&d_tk, tk.data(), tk.size())) return r;
+    if (int r = sc.put(&d_qx, h_qx, Q)) return r;
+    if (int r = sc.put(&d_qy, h_qy, Q)) return r;
+    if (int r = sc.put(&d_qr, h_qr, Q)) return r;
+    if (int r = sc.put(&d_qdesc, h_qdesc, 8 * Q)) return r;
+    if (h_qlevel) { if (int r = sc.put(&d_ql, (const int *)h_qlevel, Q)) return r; } else sc.take<int>(Q);
+    uint32_t *d_keys = sc.take<uint32_t>(4 * Q), *d_nseen = sc.take<uint32_t>(Q);
+    int2 *d_range = sc.take<int2>(Q);
+    int *d_idx = sc.take<int>(Q);
+    uint32_t *d_dist = sc.take<uint32_t>(Q), *d_nm = sc.take<uint32_t>(1);
+    unsigned long long *d_resc = sc.take<unsigned long long>(1);
     SG_CUDA(ctx, cudaMemsetAsync(d_nm, 0, 4, ctx->stream));
     SG_CUDA(ctx, cudaMemsetAsync(d_resc, 0, 8, ctx->stream));
     a.sx = d_sx; a.sy = d_sy; a.sidx = d_sidx; a.soct = d_soct; a.sdesc = d_sdesc; a.elig0 = d_tk; a.nK = nK;
@@ -358,8 +358,8 @@ extern "C" int sg_search_candidates(sg_ctx *ctx, const float *h_kx, const float 
     if (mode == 0) search_resolve_independent_kernel<<<(nQ + 255) / 256, 256, 0, ctx->stream>>>(a, d_keys, d_idx, d_dist, d_nm);
     else search_resolve_sequential_kernel<<<1, 32, 0, ctx->stream>>>(a, d_keys, d_range, d_nseen, d_tk, d_idx, d_dist, d_nm, d_resc);
     SG_LAUNCH_CHECK(ctx);
-    SG_CUDA(ctx, cudaMemcpyAsync(h_idx, d_idx, 4 * (size_t)nQ, cudaMemcpyDeviceToHost, ctx->stream));
-    SG_CUDA(ctx, cudaMemcpyAsync(h_dist, d_dist, 4 * (size_t)nQ, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(h_idx, d_idx, 4 * Q, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(h_dist, d_dist, 4 * Q, cudaMemcpyDeviceToHost, ctx->stream));
     uint32_t nm = 0;
     SG_CUDA(ctx, cudaMemcpyAsync(&nm, d_nm, 4, cudaMemcpyDeviceToHost, ctx->stream));
     SG_CUDA(ctx, cudaMemcpyAsync(&ctx->rescans, d_resc, 8, cudaMemcpyDeviceToHost, ctx->stream));

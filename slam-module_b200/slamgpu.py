@@ -61,7 +61,7 @@ ABI_SYMBOLS = [
     "sg_angle_bin_order", "sg_angle_bin_order_depth", "sg_angle_bin", "sg_device_count", "sg_malloc", "sg_free",
     "sg_memcpy_h2d", "sg_memcpy_d2h", "sg_host_alloc_pinned", "sg_host_free_pinned", "sg_timer_start",
     "sg_timer_stop", "sg_flush_l2", "sg_microbench_popc", "sg_set_profiling", "sg_get_stage_ms",
-    "sg_set_pipeline_chunk", "sg_search_candidates", "sg_feature_index", "sg_medoid",
+    "sg_set_pipeline_chunk", "sg_search_candidates", "sg_feature_index", "sg_medoid", "sg_set_overlap",
 ]
 
 _lib = None
@@ -135,6 +135,8 @@ def lib():
         L.sg_medoid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.sg_medoid.restype = C.c_int
         L.sg_set_pipeline_chunk.restype = C.c_int
+        L.sg_set_overlap.argtypes = [C.c_void_p, C.c_int]
+        L.sg_set_overlap.restype = C.c_int
         L.sg_detect.argtypes = [C.c_void_p]
         L.sg_keypoint_capacity.argtypes = [C.c_void_p]
         L.sg_microbench_popc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -356,6 +358,9 @@ class Context:
             arrs = {k: np.empty(s, d) for k, (s, d) in spec.items()}
         ks = Keypoints(*[arrs[k].ctypes.data for k, _ in Keypoints._fields_])
         return arrs, ks
+
+    def set_overlap(self, parts):
+        self._check(lib().sg_set_overlap(self._h, int(parts)))
 
     def set_pipeline_chunk(self, frames):
         self._check(lib().sg_set_pipeline_chunk(self._h, int(frames)))
