@@ -36,7 +36,7 @@ constexpr int TILE_SHIFT = 3;          // the window origin 19 + 64*j is always 
 static_assert((EVAL_ORIGIN - FAST_BORDER) % 4 == TILE_SHIFT && CELL % 4 == 0, "tile alignment");
 constexpr int WP = TP / 2;             // pair-word pitch: 40 words per row
 constexpr int MAX_ENTRIES = CELL * CELL;   // 2048 pixel pairs, each at most twice (both polarities)
-constexpr int WARP_Q = MAX_ENTRIES / (FAST_THREADS / 32);   // per-warp queue: 8 rows x 32 pairs x 2
+constexpr int WARP_Q = MAX_ENTRIES / 2 / (FAST_THREADS / 32);   // per-warp queue: 8 rows x 32 pairs
 constexpr int MAX_SCORED = 1024;           // list of scored pixels (NMS candidates); beyond it the map is scanned
 
 // ---- FAST-9/16 in u16x2 lanes ---------------------------------------------------------------------------
@@ -72,7 +72,7 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(16) uint32_t We[TILE_ROWS * WP], Wo[TILE_ROWS * WP];
     __shared__ __align__(16) uint8_t resp[(CELL + 2) * RPW];
-    __shared__ unsigned short ent[MAX_ENTRIES];                // k | y << 5 | side_a << 11 | side_b << 13 | dup << 15
+    __shared__ unsigned short ent[MAX_ENTRIES / 2];            // per-warp queues of pairs that pass stage 1: k | y << 5
     __shared__ unsigned short keep[(CELL / 2) * (CELL / 2)];   // NMS winners (at most one per 2x2 block)
     __shared__ unsigned short scored[MAX_SCORED];              // y << 6 | x of the pixels with a score >= t
     __shared__ int s_nscored, s_nkeep, s_base;
@@ -120,75 +120,86 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
     for (int pass = 0; pass < 2; ++pass, t = g.min_thr) {
         const unsigned thi = (unsigned)(256 + t) * 0x00010001u, tlo = (unsigned)(256 - t) * 0x00010001u;
         // ---- stage 1: compass test, one warp per row, lane = pixel pair (2k, 2k + 1) ------------------------
-        // Passing pairs go to a queue PRIVATE to the warp (ballot + prefix popc, no atomics, no CTA barrier):
-        // a warp owns rows warp, warp + 8, ... and scores its own queue right after.
+        // Only "does either pixel of the pair pass" is decided here (the polarity flags are recomputed for the few
+        // pairs that reach stage 2).  Passing pairs go to a queue PRIVATE to the warp (ballot + prefix popc, no
+        // atomics, no CTA barrier): a warp owns rows warp, warp + 8, ... and scores its own queue right after.
         unsigned short *q = ent + warp * WARP_Q;
         int nq = 0;
         const unsigned lt = (1u << lane) - 1u;
-        const unsigned okmask = (2 * lane < cw ? 3u : 0u) | (2 * lane + 1 < cw ? 12u : 0u);   // pixels outside the cell never count
+        // pixels outside the cell never count
+        const unsigned okH = (2 * lane < cw ? 0x00008000u : 0u) | (2 * lane + 1 < cw ? 0x80000000u : 0u);
+        const unsigned thiH = thi | 0x80008000u;
         for (int y = warp; y < ch; y += FAST_THREADS / 32) {
             const uint32_t *we = We + (y + 3) * WP + lane + 3, *wo = Wo + (y + 3) * WP + lane;
             const unsigned vb = we[0] | 0x01000100u;
             const unsigned e0 = vb - we[3 * WP], e8 = vb - we[-3 * WP], e4 = vb - wo[4], e12 = vb - wo[1];
             const unsigned dk = __vminu2(__vmaxu2(e0, e8), __vmaxu2(e4, e12));
             const unsigned br = __vmaxu2(__vminu2(e0, e8), __vminu2(e4, e12));
-            // per-lane dk > thi -> bits 0 / 16, br < tlo -> bits 1 / 17
-            const unsigned tt = ((~((thi | 0x80008000u) - dk) & 0x80008000u) >> 15) | ((~((br | 0x80008000u) - tlo) & 0x80008000u) >> 14);
-            const unsigned nib = ((tt & 3u) | ((tt >> 14) & 12u)) & okmask;      // lane a dark / bright, lane b dark / bright
-            const unsigned m = __ballot_sync(0xffffffffu, nib != 0u);
-            if (m) {
-                const unsigned fa = nib & 3u, fbb = nib >> 2;
-                const unsigned pos = (unsigned)lane | ((unsigned)y << 5);
-                if (nib) {
-                    const unsigned sa = (fa & 1u) ? 1u : fa, sb = (fbb & 1u) ? 1u : fbb;      // dark first
-                    q[nq + __popc(m & lt)] = (unsigned short)(pos | (sa << 11) | (sb << 13));
-                }
-                nq += __popc(m);
-                const unsigned m2 = __ballot_sync(0xffffffffu, fa == 3u || fbb == 3u);        // both polarities: rare
-                if (m2) {
-                    if (fa == 3u || fbb == 3u)
-                        q[nq + __popc(m2 & lt)] = (unsigned short)(pos | ((fa == 3u ? 2u : 0u) << 11) | ((fbb == 3u ? 2u : 0u) << 13) | 0x8000u);
-                    nq += __popc(m2);
-                }
-            }
+            // lane bit 15 / 31 of (thiH - dk) is clear iff dk > thi; of ((br | H) - tlo) iff br < tlo
+            const unsigned pass = ~((thiH - dk) & ((br | 0x80008000u) - tlo)) & okH;
+            const unsigned m = __ballot_sync(0xffffffffu, pass != 0u);
+            if (pass) q[nq + __popc(m & lt)] = (unsigned short)(lane | (y << 5));
+            nq += __popc(m);
         }
         __syncwarp();
 
         // ---- stage 2: exact one-sided score of both lanes of every queued pair ----------------------------
-        for (int i = lane; i < nq; i += 32) {
-            const unsigned e = q[i];
+        for (int i0 = 0; i0 < nq; i0 += 32) {
+            const int i = i0 + lane;
+            const bool live = i < nq;
+            const unsigned e = live ? q[i] : 0u;
             const int k = e & 31, y = (e >> 5) & 63;
-            const unsigned sa = (e >> 11) & 3u, sb = (e >> 13) & 3u;
-            const unsigned cm = (sa == 2u ? 0x000000ffu : 0u) | (sb == 2u ? 0x00ff0000u : 0u);   // complement -> bright test
             const uint32_t *we = We + (y + 3) * WP + k + 3, *wo = Wo + (y + 3) * WP + k;
-            const unsigned vb = (we[0] ^ cm) | 0x01000100u;
             unsigned r[16];
+            const unsigned c = we[0];
             r[0] = we[3 * WP];      r[1] = wo[3 * WP + 3];  r[2] = we[2 * WP + 1];   r[3] = wo[WP + 4];
             r[4] = wo[4];           r[5] = wo[-WP + 4];     r[6] = we[-2 * WP + 1];  r[7] = wo[-3 * WP + 3];
             r[8] = we[-3 * WP];     r[9] = wo[-3 * WP + 2]; r[10] = we[-2 * WP - 1]; r[11] = wo[-WP + 1];
             r[12] = wo[1];          r[13] = wo[WP + 1];     r[14] = we[2 * WP - 1];  r[15] = wo[3 * WP + 2];
-            unsigned d[16], m2[16], m4[16];
+            // polarity each lane can still have (bit 0 dark, bit 1 bright), from the compass pixels
+            unsigned fa, fbb;
+            {
+                const unsigned vb = c | 0x01000100u;
+                const unsigned e0 = vb - r[0], e8 = vb - r[8], e4 = vb - r[4], e12 = vb - r[12];
+                const unsigned dk = __vminu2(__vmaxu2(e0, e8), __vmaxu2(e4, e12));
+                const unsigned br = __vmaxu2(__vminu2(e0, e8), __vminu2(e4, e12));
+                const unsigned fd = ~(thiH - dk) & 0x80008000u, fb = ~((br | 0x80008000u) - tlo) & 0x80008000u;
+                fa = ((fd >> 15) & 1u) | ((fb >> 14) & 2u);
+                fbb = (fd >> 31) | ((fb >> 30) & 2u);
+                if (!live || 2 * k >= cw) fa = 0;
+                if (!live || 2 * k + 1 >= cw) fbb = 0;
+            }
+            uint8_t *rp = resp + (y + 1) * RPW + 4 + 2 * k;
+            // dark first; a lane that can have both polarities (rare) is scored a second time as bright
+            unsigned sa = (fa & 1u) ? 1u : fa, sb = (fbb & 1u) ? 1u : fbb;
+            for (int round = 0; round < 2; ++round) {
+                const unsigned cm = (sa == 2u ? 0x000000ffu : 0u) | (sb == 2u ? 0x00ff0000u : 0u);   // complement -> bright test
+                const unsigned vb = (c ^ cm) | 0x01000100u;
+                unsigned d[16], m2[16], m4[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) d[j] = vb - (r[j] ^ cm);
-            // sliding min over windows of 9 of the circular sequence, by doubling: 2, 4, 8, then +1
+                for (int j = 0; j < 16; ++j) d[j] = vb - (r[j] ^ cm);
+                // sliding min over windows of 9 of the circular sequence, by doubling: 2, 4, 8, then +1
 #pragma unroll
-            for (int j = 0; j < 16; ++j) m2[j] = __vminu2(d[j], d[(j + 1) & 15]);
+                for (int j = 0; j < 16; ++j) m2[j] = __vminu2(d[j], d[(j + 1) & 15]);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) m4[j] = __vminu2(m2[j], m2[(j + 2) & 15]);
-            unsigned lo = 0u;
+                for (int j = 0; j < 16; ++j) m4[j] = __vminu2(m2[j], m2[(j + 2) & 15]);
+                unsigned lo = 0u;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) lo = __vmaxu2(lo, __vminu2(__vminu2(m4[j], m4[(j + 4) & 15]), d[(j + 8) & 15]));
-            const int s0 = (int)(lo & 0xffffu) - 257, s1 = (int)(lo >> 16) - 257;
-            const bool w0 = sa && s0 >= t, w1 = sb && s1 >= t;
-            if (w0 || w1) {
-                uint8_t *rp = resp + (y + 1) * RPW + 4 + 2 * k;
-                if (w0) rp[0] = (uint8_t)s0;
-                if (w1) rp[1] = (uint8_t)s1;
-                // pixels with a score are the only NMS candidates (a pixel scores in at most one of its entries)
-                int at = atomicAdd(&s_nscored, (w0 ? 1 : 0) + (w1 ? 1 : 0));
-                if (w0 && at < MAX_SCORED) scored[at] = (unsigned short)((y << 6) | (2 * k));
-                at += w0 ? 1 : 0;
-                if (w1 && at < MAX_SCORED) scored[at] = (unsigned short)((y << 6) | (2 * k + 1));
+                for (int j = 0; j < 16; ++j) lo = __vmaxu2(lo, __vminu2(__vminu2(m4[j], m4[(j + 4) & 15]), d[(j + 8) & 15]));
+                const int s0 = (int)(lo & 0xffffu) - 257, s1 = (int)(lo >> 16) - 257;
+                const bool w0 = sa && s0 >= t, w1 = sb && s1 >= t;
+                if (w0 || w1) {
+                    if (w0) rp[0] = (uint8_t)s0;
+                    if (w1) rp[1] = (uint8_t)s1;
+                    // pixels with a score are the only NMS candidates (a pixel scores in at most one polarity)
+                    int at = atomicAdd(&s_nscored, (w0 ? 1 : 0) + (w1 ? 1 : 0));
+                    if (w0 && at < MAX_SCORED) scored[at] = (unsigned short)((y << 6) | (2 * k));
+                    at += w0 ? 1 : 0;
+                    if (w1 && at < MAX_SCORED) scored[at] = (unsigned short)((y << 6) | (2 * k + 1));
+                }
+                sa = fa == 3u ? 2u : 0u;
+                sb = fbb == 3u ? 2u : 0u;
+                if (!__any_sync(0xffffffffu, (sa | sb) != 0u)) break;
             }
         }
         __syncthreads();
