@@ -269,9 +269,11 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
         uint32_t r_addr = smem_u32(R) + 2u * cp + (unsigned)(rg * ROWS_PER_G) * FW;
         const uint32_t yt_addr = smem_u32(yt) + (unsigned)(rg * ROWS_PER_G) * (unsigned)sizeof(YTap);
         mbar_wait(bar, 0);        // source tile landed
-        if (rg < ROWG) {
+        // partial tiles (right / bottom image edge): only the window columns / rows the blur of the tile reads
+        if (rg < ROWG && 2 * cp < tw + 8) {
 #pragma unroll
             for (int k = 0; k < ROWS_PER_G; ++k) {
+                if (rg * ROWS_PER_G + k >= th + 6) break;
                 const uint4 ty = lds128(yt_addr + k * (unsigned)sizeof(YTap));
                 const uint32_t a0 = s_col + ty.x, a1 = s_col + ty.y;
                 const uint32_t g0 = __byte_perm(lds32(a0), lds32(a0 + 4), sel), g1 = __byte_perm(lds32(a1), lds32(a1 + 4), sel);
@@ -350,7 +352,8 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
         constexpr uint32_t D1 = K0 | (K1 << 8) | (K2 << 16) | (K3 << 24);           // j = 3: w1
         constexpr uint32_t D2 = K2 | (K1 << 8) | (K0 << 16);                        //        w2 bytes 0..2
         const int g = tid & 15;
-        for (int rp = tid >> 4; rp < FRH / 2; rp += PYR_THREADS / 16) {
+        const int rp_end = min(FRH / 2, (th + 7) >> 1);     // partial tiles: rows / columns of the tile only
+        for (int rp = tid >> 4; rp < rp_end && 4 * g < tw; rp += PYR_THREADS / 16) {
             uint32_t o[2][4];
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
