@@ -136,6 +136,19 @@ def test_extract_bit_exact(slamgpu, oracle, synth, w, h, seed, maxkp):
         _assert_same_extraction(got, ref)
 
 
+@pytest.mark.parametrize("w,h,levels,factor,maxkp", [(752, 480, 8, 1.2, 1500), (641, 479, 5, 1.2, 800), (128, 96, 3, 1.2, 200),
+                                                     (320, 240, 1, 1.2, 300), (800, 600, 6, 1.3, 5000), (1920, 1080, 8, 1.2, 4000)])
+def test_extract_unusual_geometries(slamgpu, oracle, synth, w, h, levels, factor, maxkp):
+    """Image sizes that are not multiples of the tile / cell sizes, a single-level pyramid, another scale factor,
+    budgets above and below the usual 2000."""
+    img = synth.frame(w, h, 8000 + w)
+    with slamgpu.Context(w, h, levels=levels, scale_factor=factor, max_keypoints=maxkp, max_frames=1) as ctx:
+        got = ctx.detect_and_extract(img)[0]
+        ref = oracle.extract(oracle.make_params(w, h, levels=levels, scale_factor=factor, max_keypoints=maxkp), img)
+        _assert_same_extraction(got, ref)
+        assert got["n"] > 0
+
+
 def test_extract_batch_matches_single_frames(slamgpu, oracle, synth):
     imgs = synth.frames(640, 480, 6, 2100)
     with slamgpu.Context(640, 480, max_frames=6) as ctx:
