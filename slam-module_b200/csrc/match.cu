@@ -266,7 +266,7 @@ match_resolve_kernel(const MatchArgs a, int n_pairs, const uint32_t *topk, const
     hist[lane] = 0;
     __syncwarp();
 
-    unsigned count = 0, my_bin_count = 0, n_rescan = 0;
+    unsigned count = 0, n_rescan = 0;
     // the match row is also the record the angle filter re-reads, so it always exists: the caller's
     // buffer or the context's scratch (run_match)
     for (int base = 0; base < nA; base += 32) {
@@ -346,17 +346,19 @@ match_resolve_kernel(const MatchArgs a, int n_pairs, const uint32_t *topk, const
                     taken[best_idx >> 5] |= 1u << (best_idx & 31);
                     mrow[row] = (int)best_idx;
                 }
-                if (a.check_orientation) {
-                    const int bin = angle_bin(angA[row] - angB[best_idx]);
-                    if (lane == bin) ++my_bin_count;
-                }
                 __syncwarp();
             }
         }
     }
     // ---- angle histogram filter ------------------------------------------------------------------------
     if (a.check_orientation) {
-        hist[lane] = my_bin_count;
+        // delta-angle histogram of the accepted matches, after the sequential walk: the angle loads are global
+        // memory round trips that must not sit inside the row-by-row dependency chain
+        __syncwarp();
+        for (int i = lane; i < nA; i += 32) {
+            const int m = mrow[i];
+            if (m >= 0) atomicAdd(&hist[angle_bin(angA[i] - angB[m])], 1u);
+        }
         __syncwarp();
         unsigned valid = 0;
         if (lane == 0) {
