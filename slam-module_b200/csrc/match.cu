@@ -11,7 +11,7 @@
 //     streams all B descriptors from a shared-memory tile (broadcast 128-bit reads), 8 XOR + 8 POPC
 //     per pair, and keeps the K = 4 smallest (distance, index) keys with distance <= C, where C is
 //     the largest "second best" that can still change a ratio decision (host, match_cutoff).
-//   match_resolve_kernel: the order-dependent part.  One warp per keyframe pair walks the A rows
+//   match_resolve_kernel: the order-dependent part.  One warp per keyframe pair walks the A rows (32 at a time, optimistically: see the kernel)
 //     in order; best / second are the first two unconsumed entries of a row's list.  When the list
 //     cannot decide (entries consumed and the list was truncated) the warp rescans the whole row
 //     exactly.  Then the angle histogram filter, with libstdc++'s std::sort order of the 30 bins
@@ -26,6 +26,7 @@ constexpr int MT_THREADS = 256;
 constexpr int B_CHUNK = 1024;        // B descriptors per shared-memory tile (32 KB)
 constexpr unsigned EMPTY_KEY = 0xffffffffu;
 constexpr int RES_WARPS = 4;
+constexpr int CLAIM_SLOTS = 2048;    // claim table of the optimistic resolve (power of two)
 
 // ---- libstdc++ std::sort (introsort, _S_threshold 16) restated for 30 bin indices -----------------
 // comp(a, b) == sizes[a] > sizes[b]  (match_angle_checker.h:129-132).  Equal sizes make the result
@@ -251,8 +252,10 @@ match_resolve_kernel(const MatchArgs a, int n_pairs, const uint32_t *topk, const
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int p = blockIdx.x * RES_WARPS + warp;
     if (p >= n_pairs) return;
-    uint32_t *taken = rsm + warp * (taken_words + 32);
+    uint32_t *taken = rsm + warp * (taken_words + 32 + CLAIM_SLOTS);
     uint32_t *hist = taken + taken_words;   // 32 words, 30 used
+    uint32_t *claim = hist + 32;            // [CLAIM_SLOTS], slot = B index mod CLAIM_SLOTS: round tag << 8 | 31 - lane of the earliest
+                                            // claiming row (a slot shared by two indices can only make a row look unsafe: conservative)
 
     const int sa = a.pairs[2 * p], sb = a.pairs[2 * p + 1];
     const long long oa = a.offsets[sa], ob = a.offsets[sb];
@@ -262,11 +265,12 @@ match_resolve_kernel(const MatchArgs a, int n_pairs, const uint32_t *topk, const
     int *mrow = matches + (size_t)p * a.match_stride;
 
     for (int i = lane; i < taken_words; i += 32) taken[i] = 0;
+    for (int i = lane; i < CLAIM_SLOTS; i += 32) claim[i] = 0;
     for (int i = nA + lane; i < a.match_stride; i += 32) mrow[i] = -1;   // padding behind the A set
     hist[lane] = 0;
     __syncwarp();
 
-    unsigned count = 0, n_rescan = 0;
+    unsigned count = 0, n_rescan = 0, round_tag = 0;
     // the match row is also the record the angle filter re-reads, so it always exists: the caller's
     // buffer or the context's scratch (run_match)
     for (int base = 0; base < nA; base += 32) {
@@ -279,41 +283,60 @@ match_resolve_kernel(const MatchArgs a, int n_pairs, const uint32_t *topk, const
             if (ns) keys = reinterpret_cast<const uint4 *>(topk)[r];
             mrow[i] = -1;
         }
-        unsigned active = __ballot_sync(0xffffffffu, ns > 0);
-        while (active) {
-            const int src = __ffs(active) - 1;
-            active &= active - 1;
-            const unsigned k[4] = {__shfl_sync(0xffffffffu, keys.x, src), __shfl_sync(0xffffffffu, keys.y, src),
-                                   __shfl_sync(0xffffffffu, keys.z, src), __shfl_sync(0xffffffffu, keys.w, src)};
-            const unsigned rns = __shfl_sync(0xffffffffu, ns, src);
-            const int row = base + src;
-            unsigned u0 = EMPTY_KEY, u1 = EMPTY_KEY, last = EMPTY_KEY;
+        // Optimistic batch: every lane evaluates its own row against the current `taken` bits; accepted rows
+        // claim their B index; a row is SAFE when no earlier pending row of the batch claimed one of its keys.
+        // The safe prefix is committed at once (its tentative decisions are exactly the sequential ones), the
+        // first unsafe row is re-evaluated in the next round (it is then first and therefore safe) or, when its
+        // truncated list cannot decide, rescanned exactly by the whole warp.
+        unsigned pending = __ballot_sync(0xffffffffu, ns > 0);
+        const bool complete = ns <= TOPK;
+        const unsigned kk[TOPK] = {keys.x, keys.y, keys.z, keys.w};
+        while (pending) {
+            ++round_tag;
+            int decision = 0;   // 0 reject, 1 accept u0, 2 rescan
+            unsigned best_idx = 0;
+            const bool mine = (pending >> lane) & 1u;
+            if (mine) {
+                unsigned u0 = EMPTY_KEY, u1 = EMPTY_KEY, last = EMPTY_KEY;
 #pragma unroll
-            for (int e = 0; e < TOPK; ++e) {
-                if (k[e] == EMPTY_KEY) continue;
-                last = k[e];
-                const unsigned idx = k[e] & 0xffffu;
-                const bool tk = (taken[idx >> 5] >> (idx & 31)) & 1u;
-                if (!tk) {
-                    if (u0 == EMPTY_KEY) u0 = k[e];
-                    else if (u1 == EMPTY_KEY) u1 = k[e];
+                for (int e = 0; e < TOPK; ++e) {
+                    if (kk[e] == EMPTY_KEY) continue;
+                    last = kk[e];
+                    const unsigned idx = kk[e] & 0xffffu;
+                    if (!((taken[idx >> 5] >> (idx & 31)) & 1u)) {
+                        if (u0 == EMPTY_KEY) u0 = kk[e];
+                        else if (u1 == EMPTY_KEY) u1 = kk[e];
+                    }
+                }
+                const unsigned last_d = last >> 16;
+                if (u0 == EMPTY_KEY) {
+                    decision = (complete || last_d > a.thr) ? 0 : 2;
+                } else {
+                    const unsigned best = u0 >> 16;
+                    if (best > a.thr) decision = 0;
+                    else if (u1 != EMPTY_KEY) decision = ratio_rejects(a.ratio, u1 >> 16, best, a.ratio_is_double) ? 0 : 1;
+                    else if (complete) decision = ratio_rejects(a.ratio, 256u, best, a.ratio_is_double) ? 0 : 1;
+                    else decision = ratio_rejects(a.ratio, last_d, best, a.ratio_is_double) ? 2 : 1;
+                }
+                best_idx = u0 & 0xffffu;
+                if (decision == 1) atomicMax(&claim[best_idx & (CLAIM_SLOTS - 1)], (round_tag << 8) | (unsigned)(31 - lane));   // earliest row wins
+            }
+            __syncwarp();
+            bool unsafe = mine && decision == 2;
+            if (mine && !unsafe) {
+#pragma unroll
+                for (int e = 0; e < TOPK; ++e) {
+                    if (kk[e] == EMPTY_KEY) continue;
+                    const unsigned c = claim[kk[e] & (CLAIM_SLOTS - 1)];
+                    if ((c >> 8) == round_tag && 31 - (int)(c & 0xffu) < lane) unsafe = true;   // claimed by an earlier row
                 }
             }
-            const bool complete = rns <= TOPK;
-            const unsigned last_d = last >> 16;
-            int decision;   // 0 reject, 1 accept u0, 2 rescan
-            if (u0 == EMPTY_KEY) {
-                decision = (complete || last_d > a.thr) ? 0 : 2;
-            } else {
-                const unsigned best = u0 >> 16;
-                if (best > a.thr) decision = 0;
-                else if (u1 != EMPTY_KEY) decision = ratio_rejects(a.ratio, u1 >> 16, best, a.ratio_is_double) ? 0 : 1;
-                else if (complete) decision = ratio_rejects(a.ratio, 256u, best, a.ratio_is_double) ? 0 : 1;
-                else decision = ratio_rejects(a.ratio, last_d, best, a.ratio_is_double) ? 2 : 1;
-            }
-            unsigned best_idx = u0 & 0xffffu;
-            if (decision == 2) {
-                // exact full-row scan over the unconsumed B features
+            const unsigned bad = __ballot_sync(0xffffffffu, unsafe);
+            const int first_bad = bad ? __ffs(bad) - 1 : 32;
+            const int first = __ffs(pending) - 1;
+            if (first_bad == first) {
+                // the first pending row is unsafe only when it needs the exact full-row scan (nothing precedes it)
+                const int row = base + first;
                 ++n_rescan;
                 uint32_t ar[8];
 #pragma unroll
@@ -337,19 +360,28 @@ match_resolve_kernel(const MatchArgs a, int n_pairs, const uint32_t *topk, const
                     bkey = min(bkey, ob_);
                 }
                 const unsigned best = bkey >> 16;
-                best_idx = bkey & 0xffffu;
-                decision = (a.thr < best || ratio_rejects(a.ratio, sec, best, a.ratio_is_double)) ? 0 : 1;
-            }
-            if (decision == 1) {
-                ++count;
-                if (lane == 0) {
-                    taken[best_idx >> 5] |= 1u << (best_idx & 31);
-                    mrow[row] = (int)best_idx;
+                if (!(a.thr < best || ratio_rejects(a.ratio, sec, best, a.ratio_is_double))) {
+                    if (lane == 0) {
+                        ++count;
+                        taken[(bkey & 0xffffu) >> 5] |= 1u << (bkey & 31u);
+                        mrow[row] = (int)(bkey & 0xffffu);
+                    }
                 }
-                __syncwarp();
+                pending &= ~(1u << first);
+            } else {
+                // commit the safe prefix: pending rows before the first unsafe one
+                const unsigned commit = pending & ((first_bad < 32 ? (1u << first_bad) : 0u) - 1u);
+                if (((commit >> lane) & 1u) && decision == 1) {
+                    ++count;
+                    atomicOr(&taken[best_idx >> 5], 1u << (best_idx & 31));
+                    mrow[base + lane] = (int)best_idx;
+                }
+                pending &= ~commit;
             }
+            __syncwarp();
         }
     }
+    count = __reduce_add_sync(0xffffffffu, count);
     // ---- angle histogram filter ------------------------------------------------------------------------
     if (a.check_orientation) {
         // delta-angle histogram of the accepted matches, after the sequential walk: the angle loads are global
@@ -462,7 +494,9 @@ int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, con
     a.cutoff = match_cutoff(mp); a.thr = mp.thr; a.ratio = mp.ratio;
     a.ratio_is_double = mp.ratio_is_double; a.check_orientation = mp.check_orientation;
     const int taken_words = (db->max_set + 31) / 32;
-    const size_t rsmem = (size_t)RES_WARPS * (taken_words + 32) * 4;
+    const size_t rsmem = (size_t)RES_WARPS * (taken_words + 32 + CLAIM_SLOTS) * 4;
+    if (rsmem > 48 * 1024)
+        SG_CUDA(ctx, cudaFuncSetAttribute(match_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
     for (int p0 = 0; p0 < n_pairs; p0 += chunk) {
         const int np = std::min(chunk, n_pairs - p0);
         if (p0 == 0) mark(ctx, EV_MATCH0, true);
