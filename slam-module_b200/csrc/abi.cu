@@ -286,17 +286,15 @@ int sg_create(int device, const sg_params *params, sg_ctx **out) {
         return bail(SG_ERR_CUDA);
     }
     ctx->main_stream = ctx->stream;
-    if (const char *e = getenv("SG_PIPE_STREAMS")) ctx->pipe_streams = std::min(4, std::max(1, atoi(e)));   // tuning knob (default 4)
+    if (const char *e = getenv("SG_PIPE_STREAMS")) ctx->pipe_streams = std::min((int)sg_ctx::N_CMP, std::max(1, atoi(e)));   // tuning knob
     if (cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) != cudaSuccess
         || cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) != cudaSuccess
-        || cudaStreamCreateWithFlags(&ctx->s_cmp[0], cudaStreamNonBlocking) != cudaSuccess
-        || cudaStreamCreateWithFlags(&ctx->s_cmp[1], cudaStreamNonBlocking) != cudaSuccess
-        || cudaStreamCreateWithFlags(&ctx->s_cmp[2], cudaStreamNonBlocking) != cudaSuccess
-        || cudaStreamCreateWithFlags(&ctx->s_cmp[3], cudaStreamNonBlocking) != cudaSuccess
         || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
         ctx->err = "stream / event creation failed";
         return bail(SG_ERR_CUDA);
     }
+    for (auto &q : ctx->s_cmp)
+        if (cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream creation failed"; return bail(SG_ERR_CUDA); }
     for (auto &slot : ctx->ev_stage)
         for (auto &e : slot)
             if (cudaEventCreate(&e) != cudaSuccess) { ctx->err = "event creation failed"; return bail(SG_ERR_CUDA); }
@@ -323,7 +321,8 @@ void sg_destroy(sg_ctx *ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (auto &e : ctx->pipe_ev) cudaEventDestroy(e);
-    for (cudaStream_t q : {ctx->s_in, ctx->s_out, ctx->s_cmp[0], ctx->s_cmp[1], ctx->s_cmp[2], ctx->s_cmp[3]}) if (q) cudaStreamDestroy(q);
+    for (cudaStream_t q : {ctx->s_in, ctx->s_out}) if (q) cudaStreamDestroy(q);
+    for (cudaStream_t q : ctx->s_cmp) if (q) cudaStreamDestroy(q);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -509,7 +508,8 @@ static int extract_pipelined(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size
     if (int r = set_level0(ctx, L0.pyr, L0.pitch, L0.frame_stride, n_frames)) return r;
     // work queued earlier on the main stream (an un-synchronised sg_extract_device, ...) comes first
     SG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->main_stream));
-    for (cudaStream_t q : {ctx->s_in, ctx->s_out, ctx->s_cmp[0], ctx->s_cmp[1], ctx->s_cmp[2], ctx->s_cmp[3]}) SG_CUDA(ctx, cudaStreamWaitEvent(q, ctx->ev_fork, 0));
+    for (cudaStream_t q : {ctx->s_in, ctx->s_out}) SG_CUDA(ctx, cudaStreamWaitEvent(q, ctx->ev_fork, 0));
+    for (cudaStream_t q : ctx->s_cmp) SG_CUDA(ctx, cudaStreamWaitEvent(q, ctx->ev_fork, 0));
     const size_t cap = ctx->geom.out_cap;
     const int levels = ctx->p.levels;
     int rc = SG_OK;
@@ -550,8 +550,8 @@ static int extract_pipelined(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size
             break;
     }
     const auto t_submitted = std::chrono::steady_clock::now();
-    for (cudaStream_t q : {ctx->s_cmp[0], ctx->s_cmp[1], ctx->s_cmp[2], ctx->s_cmp[3], ctx->s_out}) {
-        const cudaError_t e = cudaStreamSynchronize(q);
+    for (int i = 0; i <= sg_ctx::N_CMP; ++i) {
+        const cudaError_t e = cudaStreamSynchronize(i < sg_ctx::N_CMP ? ctx->s_cmp[i] : ctx->s_out);
         if (e != cudaSuccess && rc == SG_OK) rc = fail(ctx, SG_ERR_CUDA, "pipeline synchronise failed: %s", cudaGetErrorString(e));
     }
     if (dbg) {

@@ -91,8 +91,9 @@ struct sg_ctx {
     int device = 0;
     sg_params p{};
     cudaStream_t stream = nullptr;      // stream the stage launchers use (swapped per chunk by the pipelined sg_extract)
-    cudaStream_t main_stream = nullptr, s_in = nullptr, s_out = nullptr, s_cmp[4] = {nullptr, nullptr, nullptr, nullptr};
-    int pipe_streams = 4;               // compute streams the chunks rotate over
+    static constexpr int N_CMP = 8;
+    cudaStream_t main_stream = nullptr, s_in = nullptr, s_out = nullptr, s_cmp[N_CMP] = {};
+    int pipe_streams = 4;               // compute streams the chunks rotate over (up to N_CMP; more than 4 measured no gain)
     int overlap_parts = 4;              // sg_extract_device: independent slices of the batch on separate streams
     std::vector<cudaEvent_t> pipe_ev;   // [2 * chunks]: H2D done, compute done
     int pipe_chunk = 32;                // frames per pipeline chunk of sg_extract
