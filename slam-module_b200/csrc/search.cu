@@ -140,65 +140,121 @@ __global__ void search_resolve_independent_kernel(const SearchArgs a, const uint
 }
 
 // searchByProjection semantics: queries in order, accepted keypoints are consumed (keyframe_matcher.cpp:356-386).
+// One warp, 32 queries at a time, optimistically (same scheme as match_resolve_kernel): every lane evaluates its
+// query against the current `taken` bits and claims the keypoint it would take; the prefix of queries none of
+// whose keys was claimed by an earlier query of the batch is committed at once -- its decisions are exactly the
+// sequential ones -- and the first unsafe query is re-evaluated in the next round, or rescanned exactly by the
+// whole warp when its truncated list cannot decide.
+constexpr int SEARCH_CLAIMS = 2048;
 __global__ void __launch_bounds__(32)
 search_resolve_sequential_kernel(const SearchArgs a, const uint32_t *keys, const int2 *range, const uint32_t *nseen,
                                  unsigned char *taken_pos, int *out_idx, unsigned *out_dist, unsigned *n_matched,
                                  unsigned long long *rescans) {
+    __shared__ uint32_t taken[2048];            // one bit per sorted position (nK <= 65535)
+    __shared__ uint32_t claim[SEARCH_CLAIMS];   // slot = position mod SEARCH_CLAIMS: round << 8 | 31 - lane of the earliest claimant
     const int lane = threadIdx.x;
-    unsigned count = 0, n_rescan = 0;
-    for (int q = 0; q < a.nQ; ++q) {
-        const uint4 kk = reinterpret_cast<const uint4 *>(keys)[q];
-        const unsigned k[SK] = {kk.x, kk.y, kk.z, kk.w};
-        const bool complete = nseen[q] <= SK;
-        unsigned u0 = NOKEY, u1 = NOKEY, last = NOKEY;
-#pragma unroll
-        for (int e = 0; e < SK; ++e) {
-            if (k[e] == NOKEY) continue;
-            last = k[e];
-            if (!taken_pos[k[e] & 0xffffu]) {
-                if (u0 == NOKEY) u0 = k[e];
-                else if (u1 == NOKEY) u1 = k[e];
-            }
-        }
-        bool need_scan = false;
-        if (u0 == NOKEY) need_scan = !complete && (last >> 16) <= a.thr;          // an unconsumed candidate <= thr may exist
-        else if ((u0 >> 16) <= a.thr && u1 == NOKEY && !complete) need_scan = true;   // the second best decides the ratio rule
-        if (need_scan) {
-            ++n_rescan;
-            uint32_t d[8];
-#pragma unroll
-            for (int w = 0; w < 8; ++w) d[w] = __ldg(a.qdesc + 8 * (size_t)q + w);
-            const float qx = a.qx[q], qy = a.qy[q], r = a.qr[q];
-            unsigned b0 = NOKEY, b1 = NOKEY;
-            for (int p = range[q].x + lane; p < range[q].y; p += 32) {
-                if (taken_pos[p] || !in_circle(qx, qy, r, a.sx[p], a.sy[p]) || !level_ok(a, q, a.soct[p])) continue;
-                const unsigned key = (hamming8(d, a.sdesc + 8 * (size_t)p) << 16) | (unsigned)p;
-                if (key < b0) { b1 = b0; b0 = key; } else if (key < b1) b1 = key;
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const unsigned o0 = __shfl_xor_sync(0xffffffffu, b0, o), o1 = __shfl_xor_sync(0xffffffffu, b1, o);
-                const unsigned lo = min(b0, o0), hi = max(b0, o0);
-                b1 = min(min(b1, o1), hi);
-                b0 = lo;
-            }
-            u0 = b0; u1 = b1;
-        }
-        int idx = -1;
-        unsigned dist = 256;
-        if (u0 != NOKEY && (u0 >> 16) <= a.thr) {
-            const int best = (int)(u0 >> 16), lvl = a.soct[u0 & 0xffffu];
-            const int best2 = u1 != NOKEY ? (int)(u1 >> 16) : 256, lvl2 = u1 != NOKEY ? a.soct[u1 & 0xffffu] : -1;
-            if (!(lvl == lvl2 && (double)best > 0.8 * (double)best2)) {          // keyframe_matcher.cpp:384-386
-                idx = a.sidx[u0 & 0xffffu];
-                dist = (unsigned)best;
-                if (lane == 0) taken_pos[u0 & 0xffffu] = 1;
-                ++count;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) { out_idx[q] = idx; out_dist[q] = dist; }
+    // bitmap of the initially taken positions: one ballot per 32 positions
+    for (int w0 = 0; w0 * 32 < a.nK; ++w0) {
+        const int pos = 32 * w0 + lane;
+        const unsigned bits = __ballot_sync(0xffffffffu, pos < a.nK && taken_pos[pos] != 0);
+        if (lane == 0) taken[w0] = bits;
     }
+    for (int i = lane; i < SEARCH_CLAIMS; i += 32) claim[i] = 0;
+    __syncwarp();
+    unsigned count = 0, n_rescan = 0, round_tag = 0;
+    for (int base = 0; base < a.nQ; base += 32) {
+        const int q = base + lane;
+        uint4 kq = make_uint4(NOKEY, NOKEY, NOKEY, NOKEY);
+        unsigned ns = 0;
+        if (q < a.nQ) { kq = reinterpret_cast<const uint4 *>(keys)[q]; ns = nseen[q]; out_idx[q] = -1; out_dist[q] = 256; }
+        const unsigned kk[SK] = {kq.x, kq.y, kq.z, kq.w};
+        const bool complete = ns <= SK;
+        unsigned pending = __ballot_sync(0xffffffffu, ns > 0);
+        while (pending) {
+            ++round_tag;
+            const bool mine = (pending >> lane) & 1u;
+            int decision = 0;   // 0 reject, 1 accept u0, 2 rescan
+            unsigned u0 = NOKEY, u1 = NOKEY, last = NOKEY;
+            if (mine) {
+#pragma unroll
+                for (int e = 0; e < SK; ++e) {
+                    if (kk[e] == NOKEY) continue;
+                    last = kk[e];
+                    const unsigned pos = kk[e] & 0xffffu;
+                    if (!((taken[pos >> 5] >> (pos & 31)) & 1u)) {
+                        if (u0 == NOKEY) u0 = kk[e];
+                        else if (u1 == NOKEY) u1 = kk[e];
+                    }
+                }
+                if (u0 == NOKEY) decision = (!complete && (last >> 16) <= a.thr) ? 2 : 0;       // an unconsumed candidate <= thr may exist
+                else if ((u0 >> 16) > a.thr) decision = 0;
+                else if (u1 == NOKEY && !complete) decision = 2;                                  // the second best decides the ratio rule
+                else {
+                    const int best = (int)(u0 >> 16), lvl = a.soct[u0 & 0xffffu];
+                    const int best2 = u1 != NOKEY ? (int)(u1 >> 16) : 256, lvl2 = u1 != NOKEY ? a.soct[u1 & 0xffffu] : -1;
+                    decision = (lvl == lvl2 && (double)best > 0.8 * (double)best2) ? 0 : 1;       // keyframe_matcher.cpp:384-386
+                }
+                if (decision == 1) atomicMax(&claim[u0 & (SEARCH_CLAIMS - 1)], (round_tag << 8) | (unsigned)(31 - lane));
+            }
+            __syncwarp();
+            bool unsafe = mine && decision == 2;
+            if (mine && !unsafe) {
+#pragma unroll
+                for (int e = 0; e < SK; ++e) {
+                    if (kk[e] == NOKEY) continue;
+                    const unsigned c = claim[kk[e] & (SEARCH_CLAIMS - 1)];
+                    if ((c >> 8) == round_tag && 31 - (int)(c & 0xffu) < lane) unsafe = true;
+                }
+            }
+            const unsigned bad = __ballot_sync(0xffffffffu, unsafe);
+            const int first_bad = bad ? __ffs(bad) - 1 : 32, first = __ffs(pending) - 1;
+            if (first_bad == first) {
+                // exact rescan of the first pending query (nothing precedes it, so it is unsafe only for this reason)
+                const int qq = base + first;
+                ++n_rescan;
+                uint32_t d[8];
+#pragma unroll
+                for (int w = 0; w < 8; ++w) d[w] = __ldg(a.qdesc + 8 * (size_t)qq + w);
+                const float qx = a.qx[qq], qy = a.qy[qq], r = a.qr[qq];
+                unsigned b0 = NOKEY, b1 = NOKEY;
+                for (int p = range[qq].x + lane; p < range[qq].y; p += 32) {
+                    if (((taken[p >> 5] >> (p & 31)) & 1u) || !in_circle(qx, qy, r, a.sx[p], a.sy[p]) || !level_ok(a, qq, a.soct[p])) continue;
+                    const unsigned key = (hamming8(d, a.sdesc + 8 * (size_t)p) << 16) | (unsigned)p;
+                    if (key < b0) { b1 = b0; b0 = key; } else if (key < b1) b1 = key;
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    const unsigned o0 = __shfl_xor_sync(0xffffffffu, b0, o), o1 = __shfl_xor_sync(0xffffffffu, b1, o);
+                    const unsigned lo = min(b0, o0), hi = max(b0, o0);
+                    b1 = min(min(b1, o1), hi);
+                    b0 = lo;
+                }
+                if (b0 != NOKEY && (b0 >> 16) <= a.thr) {
+                    const int best = (int)(b0 >> 16), lvl = a.soct[b0 & 0xffffu];
+                    const int best2 = b1 != NOKEY ? (int)(b1 >> 16) : 256, lvl2 = b1 != NOKEY ? a.soct[b1 & 0xffffu] : -1;
+                    if (!(lvl == lvl2 && (double)best > 0.8 * (double)best2) && lane == 0) {
+                        ++count;
+                        taken[(b0 & 0xffffu) >> 5] |= 1u << (b0 & 31u);
+                        out_idx[qq] = a.sidx[b0 & 0xffffu];
+                        out_dist[qq] = (unsigned)best;
+                    }
+                }
+                pending &= ~(1u << first);
+            } else {
+                const unsigned commit = pending & ((first_bad < 32 ? (1u << first_bad) : 0u) - 1u);
+                if (((commit >> lane) & 1u) && decision == 1) {
+                    ++count;
+                    atomicOr(&taken[(u0 & 0xffffu) >> 5], 1u << (u0 & 31u));
+                    out_idx[q] = a.sidx[u0 & 0xffffu];
+                    out_dist[q] = u0 >> 16;
+                }
+                pending &= ~commit;
+            }
+            __syncwarp();
+        }
+    }
+    count = __reduce_add_sync(0xffffffffu, count);
+    for (int pos = lane; pos < a.nK; pos += 32) taken_pos[pos] = (taken[pos >> 5] >> (pos & 31)) & 1u;
     if (lane == 0) { *n_matched = count; *rescans = n_rescan; }
 }
 
