@@ -132,7 +132,7 @@ int sg_set_pipeline_chunk(sg_ctx *ctx, int frames);
  * sg_extract_download.  This is the call the throughput bench times. */
 int sg_extract_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t frame_stride, int n_frames);
 int sg_extract_download(sg_ctx *ctx, int n_frames, sg_keypoints *h_out);
-/* sg_extract_device runs `parts` (1..4, default 4) independent slices of the batch on separate streams so that the
+/* sg_extract_device runs `parts` (1..8, default 4) independent slices of the batch on separate streams so that the
  * latency-bound stages of one slice overlap the issue-bound stages of another; 1 = one stream.  With per-stage
  * profiling switched on (sg_set_profiling) the stages run on one stream so that their event times are meaningful. */
 int sg_set_overlap(sg_ctx *ctx, int parts);

@@ -582,7 +582,7 @@ int sg_extract_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t fram
     if (int r = check_device_images(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
     if (int r = set_level0(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
     ctx->have_tracks = false;
-    const int parts = std::min(ctx->overlap_parts, 4);
+    const int parts = std::min(ctx->overlap_parts, (int)sg_ctx::N_CMP);
     if (parts <= 1 || n_frames < 16 * parts || ctx->profiling) return extract_launches(ctx, n_frames);
     // Independent slices of the batch on separate streams: the latency-bound quadtree kernel and the kernel tails
     // of one slice run under the issue-bound pyramid / FAST kernels of another.  Joined back on the main stream.
@@ -609,7 +609,7 @@ int sg_extract_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t fram
 }
 
 int sg_set_overlap(sg_ctx *ctx, int parts) {
-    if (parts < 1 || parts > 4) return fail(ctx, SG_ERR_INVALID, "parts must be 1..4");
+    if (parts < 1 || parts > sg_ctx::N_CMP) return fail(ctx, SG_ERR_INVALID, "parts must be 1..%d", (int)sg_ctx::N_CMP);
     ctx->overlap_parts = parts;
     return SG_OK;
 }

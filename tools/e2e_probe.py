@@ -38,7 +38,7 @@ for chunk in (8, 16, 32, 64, 128, 256):
 for n in (8, 16, 32, 64, 128, 256):
     dt = t(lambda: ctx.extract_device(dbuf.ptr, W, W * H, n), 20)
     print("device-resident extract of %3d frames: %.3f ms  (%.1f us/frame)" % (n, dt * 1e3, dt * 1e6 / n))
-for parts in (1, 2, 3, 4):
+for parts in (1, 2, 4, 6, 8):
     ctx.set_overlap(parts)
     dt = t(lambda: ctx.extract_device(dbuf.ptr, W, W * H, F), 20)
     print("overlap parts %d: device-resident extract %.3f ms (%.0f fps)" % (parts, dt * 1e3, F / dt))
