@@ -167,6 +167,15 @@ int sg_match_bruteforce(sg_ctx *ctx, const uint32_t *h_descA, const float *h_ang
                         const uint32_t *h_descB, const float *h_angB, int nB,
                         const sg_match_params *mp, int32_t *h_matches, uint32_t *n_matches);
 
+/* matchForLoopClosures with the reference's DBoW2 node buckets (keyframe_matcher.cpp:65-146): only features under
+ * the same vocabulary node are compared.  h_node*[i] = node id of feature i as in the keyframe's bowFeatureVec
+ * (features of a node in index order; < 0: in no node), h_elig* = the map-point filters of :79-84 / :93-96
+ * evaluated by the caller (NULL: all eligible).  Every shared node runs as one pair of the batched brute-force
+ * matcher; the angle histogram spans all nodes.  Outputs as sg_match_bruteforce. */
+int sg_match_bow(sg_ctx *ctx, const uint32_t *h_descA, const float *h_angA, const int32_t *h_nodeA, const uint8_t *h_eligA,
+                 int nA, const uint32_t *h_descB, const float *h_angB, const int32_t *h_nodeB, const uint8_t *h_eligB,
+                 int nB, const sg_match_params *mp, int32_t *h_matches, uint32_t *n_matches);
+
 /* Device-resident descriptor database: n_sets keyframes, set s owns features
  * [offsets[s], offsets[s+1]) of desc (8 words each) / angle. */
 typedef struct sg_db sg_db;

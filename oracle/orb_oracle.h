@@ -123,6 +123,12 @@ void orc_bin_order_heap(const unsigned *sizes30, unsigned *order30);
 
 /* Threaded drivers for the CPU baseline (frames / keyframe pairs sharded over host threads; the
  * reference itself is single-threaded).  Return wall seconds. */
+/* matchForLoopClosures with the DBoW2 node buckets of the reference (keyframe_matcher.cpp:50-158): features are
+ * compared only under the same vocabulary node; node[i] < 0 = in no node; elig = the caller's map-point filters. */
+unsigned orc_match_bow(const uint32_t *descA, const float *angA, const int *nodeA, const unsigned char *eligA, int nA,
+                       const uint32_t *descB, const float *angB, const int *nodeB, const unsigned char *eligB, int nB,
+                       float ratio, unsigned thr, int check_orientation, int ratio_is_double, int *matches);
+
 /* ---- "next" rows ---------------------------------------------------------------- */
 /* MapPoint::updateDescriptor (map_point.cpp:75-116): medoid index of every descriptor segment. */
 void orc_medoid(const uint32_t *desc, const long long *offsets, int n_seg, int *best);

@@ -238,6 +238,21 @@ def match_bruteforce(dA, aA, dB, aB, ratio=0.8, thr=50, check_orientation=True, 
     return int(n), m
 
 
+def match_bow(dA, aA, nodeA, dB, aB, nodeB, eligA=None, eligB=None, ratio=0.8, thr=50, check_orientation=True, ratio_is_double=False):
+    dA = np.ascontiguousarray(dA, np.uint32); dB = np.ascontiguousarray(dB, np.uint32)
+    aA = np.ascontiguousarray(aA, np.float32); aB = np.ascontiguousarray(aB, np.float32)
+    nodeA = np.ascontiguousarray(nodeA, np.int32); nodeB = np.ascontiguousarray(nodeB, np.int32)
+    eA = None if eligA is None else np.ascontiguousarray(eligA, np.uint8)
+    eB = None if eligB is None else np.ascontiguousarray(eligB, np.uint8)
+    m = np.empty(max(len(dA), 1), np.int32)
+    L = lib()
+    L.orc_match_bow.restype = C.c_uint
+    vp = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+    n = L.orc_match_bow(vp(dA), vp(aA), vp(nodeA), vp(eA), len(dA), vp(dB), vp(aB), vp(nodeB), vp(eB), len(dB),
+                        C.c_float(ratio), C.c_uint(thr), int(check_orientation), int(ratio_is_double), vp(m))
+    return int(n), m[:len(dA)]
+
+
 def angle_invalid(deltas, ids):
     deltas = np.ascontiguousarray(deltas, np.float32)
     ids = np.ascontiguousarray(ids, np.int32)

@@ -3,6 +3,7 @@
 // Follows openvslam/match_base.h:18-39, keyframe_matcher.cpp:50-158, and
 // openvslam/match_angle_checker.h:61-134.
 #include "common.h"
+#include <map>
 #include <numeric>
 
 namespace orc {
@@ -76,6 +77,55 @@ unsigned match_bruteforce(const uint32_t *dA, const float *aA, int nA, const uin
     return num;
 }
 
+// matchForLoopClosures as the reference runs it (keyframe_matcher.cpp:50-158): the DBoW2 feature vectors
+// (std::map<NodeId, std::vector<unsigned>>, indices in insertion order) restrict the comparison to features
+// under the same vocabulary node; the two maps are walked in node order with lower_bound skips (:70-146).
+// nodeA / nodeB give the node of every feature (-1: in no node); eligA / eligB are the map-point filters of
+// :79-84 and :93-96 evaluated by the caller (nullptr: every feature passes).
+unsigned match_bow(const uint32_t *dA, const float *aA, const int *nodeA, const unsigned char *eligA, int nA,
+                   const uint32_t *dB, const float *aB, const int *nodeB, const unsigned char *eligB, int nB,
+                   float ratio, unsigned thr, bool check_orientation, bool ratio_is_double, int *matches) {
+    constexpr unsigned MAX_DIST = 256;
+    std::map<int, std::vector<unsigned>> fv1, fv2;
+    for (int i = 0; i < nA; ++i) if (nodeA[i] >= 0) fv1[nodeA[i]].push_back(i);
+    for (int i = 0; i < nB; ++i) if (nodeB[i] >= 0) fv2[nodeB[i]].push_back(i);
+    unsigned num = 0;
+    AngleChecker checker;
+    for (int i = 0; i < nA; ++i) matches[i] = -1;
+    std::vector<bool> taken(nB, false);
+    auto it1 = fv1.begin();
+    auto it2 = fv2.begin();
+    while (it1 != fv1.end() && it2 != fv2.end()) {
+        if (it1->first == it2->first) {
+            for (const auto i1 : it1->second) {
+                if (eligA && !eligA[i1]) continue;
+                unsigned best = MAX_DIST, second = MAX_DIST;
+                int best_idx = -1;
+                for (const auto i2 : it2->second) {
+                    if (eligB && !eligB[i2]) continue;
+                    if (taken[i2]) continue;
+                    const unsigned d = hamming(dA + 8 * i1, dB + 8 * i2);
+                    if (d < best) { second = best; best = d; best_idx = (int)i2; }
+                    else if (d < second) second = d;
+                }
+                if (thr < best) continue;
+                if (ratio_is_double ? ((double)ratio * second < (double)static_cast<float>(best))
+                                    : (ratio * second < static_cast<float>(best))) continue;
+                matches[i1] = best_idx;
+                taken[best_idx] = true;
+                ++num;
+                if (check_orientation) checker.append(aA[i1] - aB[best_idx], (int)i1);
+            }
+            ++it1;
+            ++it2;
+        } else if (it1->first < it2->first) it1 = fv1.lower_bound(it2->first);
+        else it2 = fv2.lower_bound(it1->first);
+    }
+    if (check_orientation)
+        for (int idx : checker.invalid()) { matches[idx] = -1; --num; }
+    return num;
+}
+
 }  // namespace orc
 
 using namespace orc;
@@ -87,6 +137,12 @@ extern "C" unsigned orc_match_bruteforce(const uint32_t *descA, const float *ang
                                          int *matches) {
     return match_bruteforce(descA, angA, nA, descB, angB, nB, ratio, thr, check_orientation != 0,
                             ratio_is_double != 0, matches);
+}
+extern "C" unsigned orc_match_bow(const uint32_t *descA, const float *angA, const int *nodeA, const unsigned char *eligA, int nA,
+                                  const uint32_t *descB, const float *angB, const int *nodeB, const unsigned char *eligB, int nB,
+                                  float ratio, unsigned thr, int check_orientation, int ratio_is_double, int *matches) {
+    return match_bow(descA, angA, nodeA, eligA, nA, descB, angB, nodeB, eligB, nB, ratio, thr, check_orientation != 0,
+                     ratio_is_double != 0, matches);
 }
 extern "C" int orc_angle_bin(float delta) { return AngleChecker::bin_of(delta, 1.0f / 30); }
 extern "C" int orc_angle_invalid(const float *deltas, const int *ids, int n, int *invalid_out) {

@@ -748,6 +748,93 @@ int sg_match_bruteforce(sg_ctx *ctx, const uint32_t *h_descA, const float *h_ang
     return r;
 }
 
+// matchForLoopClosures with the reference's DBoW2 node buckets (keyframe_matcher.cpp:50-158).  Keypoints of
+// different nodes never meet, so the sequential "already matched in kf2" state is per node: every node shared by
+// the two keyframes becomes one small (A-part, B-part) pair of the batched brute-force matcher, and the angle
+// histogram -- the one step that spans the nodes -- runs over the gathered matches on the host with the library's
+// restated std::sort order (sg_angle_bin_order).
+int sg_match_bow(sg_ctx *ctx, const uint32_t *h_descA, const float *h_angA, const int32_t *h_nodeA, const uint8_t *h_eligA,
+                 int nA, const uint32_t *h_descB, const float *h_angB, const int32_t *h_nodeB, const uint8_t *h_eligB,
+                 int nB, const sg_match_params *mp, int32_t *h_matches, uint32_t *n_matches) {
+    cudaSetDevice(ctx->device);
+    if (nA < 0 || nB < 0 || !mp || !n_matches || (nA && (!h_descA || !h_angA || !h_nodeA || !h_matches))
+        || (nB && (!h_descB || !h_angB || !h_nodeB)))
+        return fail(ctx, SG_ERR_INVALID, "bad argument");
+    *n_matches = 0;
+    for (int i = 0; i < nA; ++i) h_matches[i] = -1;
+    if (nA == 0 || nB == 0) return SG_OK;
+    // DBoW2::FeatureVector order: nodes ascending, features of a node in index order
+    std::vector<std::pair<int, int>> fa, fb;   // (node, feature)
+    for (int i = 0; i < nA; ++i) if (h_nodeA[i] >= 0 && (!h_eligA || h_eligA[i])) fa.emplace_back(h_nodeA[i], i);
+    for (int i = 0; i < nB; ++i) if (h_nodeB[i] >= 0 && (!h_eligB || h_eligB[i])) fb.emplace_back(h_nodeB[i], i);
+    std::stable_sort(fa.begin(), fa.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
+    std::stable_sort(fb.begin(), fb.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
+    std::vector<uint32_t> desc;
+    std::vector<float> ang;
+    std::vector<int64_t> offs{0};
+    std::vector<int32_t> pairs, idxA, idxB;     // feature index of every database row
+    std::vector<int> startA, startB;            // first row of every shared node inside idxA / idxB
+    size_t ia = 0, ib = 0;
+    while (ia < fa.size() && ib < fb.size()) {
+        if (fa[ia].first < fb[ib].first) { ++ia; continue; }
+        if (fb[ib].first < fa[ia].first) { ++ib; continue; }
+        const int node = fa[ia].first;
+        const int set = (int)offs.size() - 1;
+        startA.push_back((int)idxA.size());
+        for (; ia < fa.size() && fa[ia].first == node; ++ia) {
+            const int i = fa[ia].second;
+            desc.insert(desc.end(), h_descA + 8 * (size_t)i, h_descA + 8 * (size_t)i + 8);
+            ang.push_back(h_angA[i]);
+            idxA.push_back(i);
+        }
+        offs.push_back((int64_t)ang.size());
+        startB.push_back((int)idxB.size());
+        for (; ib < fb.size() && fb[ib].first == node; ++ib) {
+            const int i = fb[ib].second;
+            desc.insert(desc.end(), h_descB + 8 * (size_t)i, h_descB + 8 * (size_t)i + 8);
+            ang.push_back(h_angB[i]);
+            idxB.push_back(i);
+        }
+        offs.push_back((int64_t)ang.size());
+        pairs.push_back(set);
+        pairs.push_back(set + 1);
+    }
+    const int n_nodes = (int)pairs.size() / 2;
+    if (n_nodes == 0) return SG_OK;
+    sg_db *db = nullptr;
+    if (int r = sg_db_create(ctx, desc.data(), ang.data(), offs.data(), (int)offs.size() - 1, &db)) return r;
+    sg_match_params q = *mp;
+    q.check_orientation = 0;                    // the histogram spans all nodes: applied below
+    const int stride = std::max(db->max_set, 1);
+    std::vector<int32_t> rows((size_t)n_nodes * stride);
+    std::vector<uint32_t> counts(n_nodes);
+    const int r = sg_match_pairs(ctx, db, pairs.data(), n_nodes, &q, rows.data(), stride, counts.data());
+    sg_db_destroy(db);
+    if (r) return r;
+    uint32_t num = 0;
+    for (int k = 0; k < n_nodes; ++k) {
+        const int na = (int)(offs[2 * k + 1] - offs[2 * k]);
+        for (int j = 0; j < na; ++j) {
+            const int m = rows[(size_t)k * stride + j];
+            if (m >= 0) { h_matches[idxA[startA[k] + j]] = idxB[startB[k] + m]; ++num; }
+        }
+    }
+    if (mp->check_orientation) {                // match_angle_checker.h:72-134
+        uint32_t sizes[30] = {0}, order[30];
+        std::vector<int> bin(nA, -1);
+        for (int i = 0; i < nA; ++i)
+            if (h_matches[i] >= 0) { bin[i] = sg_angle_bin(h_angA[i] - h_angB[h_matches[i]]); ++sizes[bin[i]]; }
+        sg_angle_bin_order(sizes, order);
+        for (int i = 0; i < nA; ++i)
+            if (bin[i] >= 0 && (uint32_t)bin[i] != order[0] && (uint32_t)bin[i] != order[1] && (uint32_t)bin[i] != order[2]) {
+                h_matches[i] = -1;
+                --num;
+            }
+    }
+    *n_matches = num;
+    return SG_OK;
+}
+
 unsigned long long sg_match_rescans(const sg_ctx *ctx) { return ctx->rescans; }
 
 // ---- helpers --------------------------------------------------------------------------------------------

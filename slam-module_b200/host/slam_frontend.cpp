@@ -355,19 +355,49 @@ unsigned int matchForLoopClosures(const Keyframe &kf1, const Keyframe &kf2, cons
                                   sg_ctx *ctx) {
     const auto &kps1 = kf1.shared->keyPoints, &kps2 = kf2.shared->keyPoints;
     matchedMapPoints.resize(kps1.size(), -1);                       // keyframe_matcher.cpp:61
-    std::vector<int> idx1, idx2;
-    for (size_t i = 0; i < kps1.size(); ++i) {                      // :79-84
+    // the map-point filters of :79-84 (kf1) and :93-96 (kf2)
+    std::vector<std::uint8_t> elig1(kps1.size(), 0), elig2(kps2.size(), 0);
+    for (size_t i = 0; i < kps1.size(); ++i) {
         const MpId id = kf1.mapPoints.at(i);
         if (id.v == -1) continue;
         if (parameters.requireTringulationForLoopClosures && mapDB1.mapPoints.at(id.v).status != MapPointStatus::TRIANGULATED) continue;
-        idx1.push_back((int)i);
+        elig1[i] = 1;
     }
-    for (size_t i = 0; i < kps2.size(); ++i) {                      // :93-96
+    for (size_t i = 0; i < kps2.size(); ++i) {
         const MpId id = kf2.mapPoints.at(i);
         if (id.v == -1 || mapDB2.mapPoints.at(id.v).status != MapPointStatus::TRIANGULATED) continue;
-        idx2.push_back((int)i);
+        elig2[i] = 1;
     }
-    return matchSubset(kps1, idx1, kps2, idx2, matchedMapPoints, parameters.loopClosureFeatureMatchLoweRatio, true, ctx);
+    const auto &fv1 = kf1.shared->bowFeatureVec, &fv2 = kf2.shared->bowFeatureVec;
+    if (fv1.empty() && fv2.empty()) {                               // no vocabulary: one node holds everything
+        std::vector<int> idx1, idx2;
+        for (size_t i = 0; i < kps1.size(); ++i) if (elig1[i]) idx1.push_back((int)i);
+        for (size_t i = 0; i < kps2.size(); ++i) if (elig2[i]) idx2.push_back((int)i);
+        return matchSubset(kps1, idx1, kps2, idx2, matchedMapPoints, parameters.loopClosureFeatureMatchLoweRatio, true, ctx);
+    }
+    // node of every feature; DBoW2 lists the features of a node in index order (bow_index.cpp:59-93), which is
+    // the order the library assumes inside a node
+    auto nodes = [](const std::map<unsigned, std::vector<unsigned>> &fv, size_t n) {
+        std::vector<std::int32_t> node(n, -1);
+        for (const auto &kv : fv) {
+            assert(std::is_sorted(kv.second.begin(), kv.second.end()));
+            for (unsigned i : kv.second) node.at(i) = (std::int32_t)kv.first;
+        }
+        return node;
+    };
+    const auto node1 = nodes(fv1, kps1.size()), node2 = nodes(fv2, kps2.size());
+    std::vector<std::uint32_t> d1(8 * kps1.size()), d2(8 * kps2.size());
+    std::vector<float> a1(kps1.size()), a2(kps2.size());
+    for (size_t i = 0; i < kps1.size(); ++i) { std::memcpy(&d1[8 * i], kps1[i].descriptor.data(), 32); a1[i] = kps1[i].angle; }
+    for (size_t i = 0; i < kps2.size(); ++i) { std::memcpy(&d2[8 * i], kps2[i].descriptor.data(), 32); a2[i] = kps2[i].angle; }
+    sg_match_params mp{};
+    mp.ratio = parameters.loopClosureFeatureMatchLoweRatio; mp.thr = HAMMING_DIST_THR_LOW; mp.check_orientation = 1;
+    std::vector<std::int32_t> m(std::max<size_t>(kps1.size(), 1));
+    std::uint32_t n = 0;
+    SG_CHECK(ctx, sg_match_bow(ctx, d1.data(), a1.data(), node1.data(), elig1.data(), (int)kps1.size(), d2.data(), a2.data(),
+                               node2.data(), elig2.data(), (int)kps2.size(), &mp, m.data(), &n));
+    for (size_t i = 0; i < kps1.size(); ++i) matchedMapPoints[i] = m[i];
+    return n;
 }
 
 unsigned int bruteForceMatch(const KeyPointVector &kps1, const KeyPointVector &kps2, std::vector<int> &matches,

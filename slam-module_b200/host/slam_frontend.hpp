@@ -7,6 +7,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <map>
 #include <memory>
 #include <utility>
 #include <vector>
@@ -106,13 +107,16 @@ enum class MapPointStatus { NOT_TRIANGULATED, TRIANGULATED, BAD };
 struct MpId { int v = -1; };
 struct MapPoint { MapPointStatus status = MapPointStatus::NOT_TRIANGULATED; };
 struct MapDB { std::vector<MapPoint> mapPoints; };   // indexed by MpId::v
-struct KeyframeShared { KeyPointVector keyPoints; };
+// bowFeatureVec: DBoW2::FeatureVector = std::map<NodeId, std::vector<unsigned>> (keyframe.hpp, bow_index.cpp:59-93)
+struct KeyframeShared { KeyPointVector keyPoints; std::map<unsigned, std::vector<unsigned>> bowFeatureVec; };
 struct Keyframe {
     std::shared_ptr<KeyframeShared> shared;
     std::vector<MpId> mapPoints;   // per keypoint, v == -1: none
 };
 
-/** keyframe_matcher.hpp:33-40 with every feature in ONE BoW node (brute force, BASELINE.json north star):
+/** keyframe_matcher.hpp:33-40.  With bowFeatureVec filled in on both keyframes: the reference's node-bucketed
+ *  comparison (keyframe_matcher.cpp:65-146); with empty feature vectors every feature is in ONE node (brute force,
+ *  BASELINE.json north star).
  *  `matchedMapPoints[i]` = keypoint index of kf2 matched to keypoint i of kf1, or -1.  @return match count */
 unsigned int matchForLoopClosures(const Keyframe &kf1, const Keyframe &kf2, const MapDB &mapDB1, const MapDB &mapDB2,
                                   std::vector<int> &matchedMapPoints, const odometry::ParametersSlam &parameters,

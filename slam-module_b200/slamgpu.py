@@ -61,7 +61,7 @@ ABI_SYMBOLS = [
     "sg_angle_bin_order", "sg_angle_bin_order_depth", "sg_angle_bin", "sg_device_count", "sg_malloc", "sg_free",
     "sg_memcpy_h2d", "sg_memcpy_d2h", "sg_host_alloc_pinned", "sg_host_free_pinned", "sg_timer_start",
     "sg_timer_stop", "sg_flush_l2", "sg_microbench_popc", "sg_set_profiling", "sg_get_stage_ms",
-    "sg_set_pipeline_chunk", "sg_search_candidates", "sg_feature_index", "sg_medoid", "sg_set_overlap",
+    "sg_set_pipeline_chunk", "sg_search_candidates", "sg_feature_index", "sg_medoid", "sg_set_overlap", "sg_match_bow",
 ]
 
 _lib = None
@@ -137,6 +137,8 @@ def lib():
         L.sg_set_pipeline_chunk.restype = C.c_int
         L.sg_set_overlap.argtypes = [C.c_void_p, C.c_int]
         L.sg_set_overlap.restype = C.c_int
+        L.sg_match_bow.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3
+        L.sg_match_bow.restype = C.c_int
         L.sg_detect.argtypes = [C.c_void_p]
         L.sg_keypoint_capacity.argtypes = [C.c_void_p]
         L.sg_microbench_popc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -437,6 +439,22 @@ class Context:
         n = C.c_uint32()
         self._check(lib().sg_match_bruteforce(self._h, dA.ctypes.data, aA.ctypes.data, len(dA), dB.ctypes.data,
                                               aB.ctypes.data, len(dB), C.byref(mp), m.ctypes.data, C.byref(n)))
+        return int(n.value), m[:len(dA)]
+
+    def match_bow(self, dA, aA, nodeA, dB, aB, nodeB, eligA=None, eligB=None, ratio=0.8, thr=50, check_orientation=True,
+                  ratio_is_double=False):
+        """matchForLoopClosures with DBoW2 node buckets: returns (num_matches, matches[nA])."""
+        dA = np.ascontiguousarray(dA, np.uint32).reshape(-1, 8); dB = np.ascontiguousarray(dB, np.uint32).reshape(-1, 8)
+        aA = np.ascontiguousarray(aA, np.float32); aB = np.ascontiguousarray(aB, np.float32)
+        nodeA = np.ascontiguousarray(nodeA, np.int32); nodeB = np.ascontiguousarray(nodeB, np.int32)
+        eA = None if eligA is None else np.ascontiguousarray(eligA, np.uint8)
+        eB = None if eligB is None else np.ascontiguousarray(eligB, np.uint8)
+        mp = MatchParams(ratio, thr, int(check_orientation), int(ratio_is_double))
+        m = np.empty(max(len(dA), 1), np.int32)
+        n = C.c_uint32()
+        p = lambda a: None if a is None else a.ctypes.data
+        self._check(lib().sg_match_bow(self._h, p(dA), p(aA), p(nodeA), p(eA), len(dA), p(dB), p(aB), p(nodeB), p(eB), len(dB),
+                                       C.byref(mp), m.ctypes.data, C.byref(n)))
         return int(n.value), m[:len(dA)]
 
     def rescans(self):

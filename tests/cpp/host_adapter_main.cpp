@@ -134,6 +134,17 @@ int main(int argc, char **argv) {
     m.push_back((int)n);
     dump(out + "/loop_matches.i32", m);
 
+    // the same keyframes with DBoW2-style feature vectors: node = a few descriptor bits (vocabulary stand-in)
+    for (size_t i = 0; i < kf1.shared->keyPoints.size(); ++i)
+        kf1.shared->bowFeatureVec[(kf1.shared->keyPoints[i].descriptor[0] ^ kf1.shared->keyPoints[i].descriptor[3]) % 7u].push_back((unsigned)i);
+    for (size_t i = 0; i < kf2.shared->keyPoints.size(); ++i)
+        kf2.shared->bowFeatureVec[(kf2.shared->keyPoints[i].descriptor[0] ^ kf2.shared->keyPoints[i].descriptor[3]) % 7u].push_back((unsigned)i);
+    std::vector<int> matchedBow;
+    const unsigned nbow = matchForLoopClosures(kf1, kf2, db1, db2, matchedBow, params.slam, cudaContext(fe));
+    std::vector<std::int32_t> mw(matchedBow.begin(), matchedBow.end());
+    mw.push_back((int)nbow);
+    dump(out + "/loop_matches_bow.i32", mw);
+
     std::vector<int> bf;
     const unsigned nb = bruteForceMatch(batch[1], kpsB, bf, 0.8f, true, cudaContext(fe));
     std::vector<std::int32_t> mb(bf.begin(), bf.end());

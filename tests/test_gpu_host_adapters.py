@@ -98,6 +98,16 @@ def test_host_adapters_match_oracle(tmp_path, oracle, synth):
     assert lm[-1] == n and np.array_equal(lm[:-1], want)
     assert n > 0
 
+    # ... and with bowFeatureVec: the reference's node-bucketed comparison
+    nodeA = ((refA["desc"][:, 0] ^ refA["desc"][:, 3]) % np.uint32(7)).astype(np.int32)
+    nodeB = ((refB["desc"][:, 0] ^ refB["desc"][:, 3]) % np.uint32(7)).astype(np.int32)
+    eA = np.zeros(n1, np.uint8); eA[i1] = 1
+    eB = np.zeros(n2, np.uint8); eB[i2] = 1
+    nw, mw = oracle.match_bow(refA["desc"], refA["angle"], nodeA, refB["desc"], refB["angle"], nodeB, eA, eB)
+    lw = np.fromfile(tmp_path / "loop_matches_bow.i32", np.int32)
+    assert lw[-1] == nw and np.array_equal(lw[:-1], mw)
+    assert nw > 0
+
     nb, mb = oracle.match_bruteforce(refA["desc"], refA["angle"], refB["desc"], refB["angle"])
     bf = np.fromfile(tmp_path / "bf_matches.i32", np.int32)
     assert bf[-1] == nb and np.array_equal(bf[:-1], mb)

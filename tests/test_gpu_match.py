@@ -129,3 +129,30 @@ def test_match_properties_full_size(ctx, slamgpu, synth):
     n2, _ = db.match_pairs(pairs, want_matches=False)
     assert np.array_equal(n, n2)
     db.close()
+
+
+@pytest.mark.parametrize("seed,n_nodes", [(41, 1), (42, 12), (43, 97)])
+def test_match_bow_node_buckets(ctx, oracle, synth, seed, n_nodes):
+    """matchForLoopClosures as the reference runs it: DBoW2 node buckets (keyframe_matcher.cpp:65-146), map-point
+    eligibility filters, one angle histogram over all nodes."""
+    rng = np.random.default_rng(seed)
+    dA, aA, dB, aB = synth.correlated_descriptors(900, seed)
+    # a vocabulary stand-in: node = a few descriptor bits (noisy copies mostly land in the same node), some features in no node
+    bits = lambda d: ((d[:, 0] ^ d[:, 3]) % np.uint32(n_nodes)).astype(np.int32) * 3 + 5
+    nodeA, nodeB = bits(dA), bits(dB)
+    nodeA[rng.random(900) < 0.05] = -1
+    nodeB[rng.random(900) < 0.05] = -1
+    eligA = (rng.random(900) < 0.9).astype(np.uint8)
+    eligB = (rng.random(900) < 0.9).astype(np.uint8)
+    for eA, eB in ((None, None), (eligA, eligB)):
+        n, m = ctx.match_bow(dA, aA, nodeA, dB, aB, nodeB, eA, eB)
+        rn, rm = oracle.match_bow(dA, aA, nodeA, dB, aB, nodeB, eA, eB)
+        assert n == rn and np.array_equal(m, rm), (n, rn)
+    if n_nodes == 1:
+        keep = nodeA >= 0
+        assert n > 50
+    # disjoint node sets and empty inputs
+    n, m = ctx.match_bow(dA, aA, np.zeros(900, np.int32), dB, aB, np.ones(900, np.int32))
+    assert n == 0 and (m == -1).all()
+    n, m = ctx.match_bow(dA[:0], aA[:0], nodeA[:0], dB, aB, nodeB)
+    assert n == 0 and len(m) == 0
