@@ -334,13 +334,25 @@ def extra_configs(slamgpu, sm, sh, rank, world, local, barrier_max_, td):
                                                                     taken=np.zeros(nk, np.uint8)))
         t_dup, (n_dup, _, _) = timed(lambda: c6.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=0, thr=50))
         t_med, _ = timed(lambda: c6.medoid(mdesc, offs))
+        vocab = sm.synth.random_vocabulary(10, 4, 3)                     # 11 111 nodes, 10 000 words
+        voc = slamgpu.Vocabulary(c6, vocab)
+        t_bow, (bw, _, bn) = timed(lambda: voc.transform(kdesc, 2))
+        nodes_k = bn
+        nodes_q = voc.transform(qdesc, 2)[2]
+        ang_k = rng.uniform(0, 360, nk).astype(np.float32); ang_q = rng.uniform(0, 360, nq).astype(np.float32)
+        t_mbow, (n_mbow, _) = timed(lambda: c6.match_bow(qdesc, ang_q, nodes_q, kdesc, ang_k, nodes_k, check_orientation=False))
+        voc.close()
         out["next_rows"] = {
             "search_by_projection": {"workload": "%d projected map points against %d keypoints, radius 20 px (keyframe_matcher.cpp:295-414 inner loop)" % (nq, nk),
                                      "ms_per_call_host_buffers": t_proj * 1e3, "matches": n_proj},
             "replace_duplication": {"workload": "same queries, best only, thr 50 (keyframe_matcher.cpp:482-499)",
                                     "ms_per_call_host_buffers": t_dup * 1e3, "matches": n_dup},
             "map_point_medoid": {"workload": "%d map points, 2..29 observations each (map_point.cpp:75-116)" % len(sizes),
-                                 "ms_per_call_host_buffers": t_med * 1e3, "map_points_per_s": len(sizes) / t_med}}
+                                 "ms_per_call_host_buffers": t_med * 1e3, "map_points_per_s": len(sizes) / t_med},
+            "bow_transform": {"workload": "%d descriptors through a synthetic 10-ary, 4-level vocabulary tree (bow_index.cpp:59-93)" % nk,
+                              "ms_per_call_host_buffers": t_bow * 1e3, "distinct_words": int(len(np.unique(bw)))},
+            "match_for_loop_closures_bow": {"workload": "%d x %d features in DBoW2 node buckets (keyframe_matcher.cpp:65-146)" % (nq, nk),
+                                            "ms_per_call_host_buffers": t_mbow * 1e3, "matches": n_mbow}}
     return out
 
 

@@ -221,6 +221,23 @@ int sg_feature_index(const float *h_x, const float *h_y, int n, int32_t *h_order
  * median Hamming distance to the segment is smallest (first wins; 0 for an empty segment). */
 int sg_medoid(sg_ctx *ctx, const uint32_t *h_desc, const int64_t *h_offsets, int n_seg, int32_t *h_best);
 
+/* ---- BoW transform: BowIndex::transform (bow_index.cpp:59-93) = DBoW2 TemplatedVocabulary<ORB>::
+ *      transform(features, bowVector, featureVector, levelsUp).  DBoW2 is not part of the reference tree; the tree
+ *      descent is restated from its published algorithm (nearest child by Hamming distance at every level, first child
+ *      wins ties).  Vocabulary: node 0 is the root, the children of node i are h_child_ids[h_child_off[i] ..
+ *      h_child_off[i+1]) (larger ids than i), a leaf has none and carries word id and weight; `levels` = DBoW2's L.
+ *      Per feature: word id, word weight and the feature-vector node (the node reached at level L - levels_up; the
+ *      root when that is <= 0).  Summing the weights per word and the L1 normalisation of the BowVector are the
+ *      caller's few host lines (std::map order, double arithmetic, as DBoW2 does). */
+typedef struct sg_vocab sg_vocab;
+int sg_vocab_create(sg_ctx *ctx, const int32_t *h_child_off, const int32_t *h_child_ids, const uint32_t *h_node_desc,
+                    const float *h_node_weight, const int32_t *h_node_word, int n_nodes, int levels, sg_vocab **out);
+void sg_vocab_destroy(sg_vocab *vocab);
+int sg_bow_transform(sg_ctx *ctx, const sg_vocab *vocab, const uint32_t *h_desc, int n, int levels_up, int32_t *h_word,
+                     float *h_weight, int32_t *h_node);
+int sg_bow_transform_device(sg_ctx *ctx, const sg_vocab *vocab, const uint32_t *d_desc, int n, int levels_up,
+                            int32_t *d_word, float *d_weight, int32_t *d_node);
+
 /* ---- angle histogram: angle_checker<int> (openvslam/match_angle_checker.h:72-134) -----------
  * Test hook for the restated libstdc++ std::sort order of the 30 bins (host code, no GPU). */
 void sg_angle_bin_order(const uint32_t *sizes30, uint32_t *order30);

@@ -142,6 +142,12 @@ int orc_search_candidates(const float *kx, const float *ky, const int *koct, con
                           const uint32_t *qdesc, const int *q_pred_level, int nQ, int mode, unsigned thr,
                           int *out_idx, unsigned *out_dist);
 
+/* DBoW2 vocabulary-tree descent behind BowIndex::transform (bow_index.cpp:59-93); DBoW2 itself is absent: restated
+ * from its published algorithm, parity unpinned.  See oracle/src/search.cpp. */
+void orc_bow_transform(const int *child_off, const int *child_ids, const uint32_t *node_desc, const float *node_weight,
+                       const int *node_word, int n_nodes, int levels, const uint32_t *desc, int n, int levels_up,
+                       int *out_word, float *out_weight, int *out_node);
+
 double orc_bench_extract(const orc_params *p, const uint8_t *imgs, int n_frames, int threads, long *total_kp);
 double orc_bench_match(const uint32_t *desc, const float *ang, int n_sets, int n_per_set,
                        const int *pairs, int n_pairs, float ratio, unsigned thr, int threads, long *total_matches);

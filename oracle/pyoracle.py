@@ -321,6 +321,18 @@ def search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=0, thr=50, ta
     return int(n), idx[:len(qx)], dist[:len(qx)]
 
 
+def bow_transform(vocab, desc, levels_up=4):
+    """vocab: dict(child_off, child_ids, node_desc, node_weight, node_word, levels) (see synth.random_vocabulary)."""
+    desc = np.ascontiguousarray(desc, np.uint32).reshape(-1, 8)
+    n = len(desc)
+    word = np.zeros(max(n, 1), np.int32); weight = np.zeros(max(n, 1), np.float32); node = np.zeros(max(n, 1), np.int32)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    lib().orc_bow_transform(vp(vocab["child_off"]), vp(vocab["child_ids"]), vp(vocab["node_desc"]), vp(vocab["node_weight"]),
+                            vp(vocab["node_word"]), len(vocab["node_word"]), int(vocab["levels"]), vp(desc), n, int(levels_up),
+                            vp(word), vp(weight), vp(node))
+    return word[:n], weight[:n], node[:n]
+
+
 def bench_extract(p, imgs, threads):
     imgs = np.ascontiguousarray(imgs, np.uint8)
     total = C.c_long(0)

@@ -61,7 +61,8 @@ ABI_SYMBOLS = [
     "sg_angle_bin_order", "sg_angle_bin_order_depth", "sg_angle_bin", "sg_device_count", "sg_malloc", "sg_free",
     "sg_memcpy_h2d", "sg_memcpy_d2h", "sg_host_alloc_pinned", "sg_host_free_pinned", "sg_timer_start",
     "sg_timer_stop", "sg_flush_l2", "sg_microbench_popc", "sg_set_profiling", "sg_get_stage_ms",
-    "sg_set_pipeline_chunk", "sg_search_candidates", "sg_feature_index", "sg_medoid", "sg_set_overlap", "sg_match_bow",
+    "sg_set_pipeline_chunk", "sg_search_candidates", "sg_feature_index", "sg_medoid", "sg_set_overlap", "sg_match_bow", "sg_vocab_create", "sg_vocab_destroy",
+    "sg_bow_transform", "sg_bow_transform_device",
 ]
 
 _lib = None
@@ -139,6 +140,14 @@ def lib():
         L.sg_set_overlap.restype = C.c_int
         L.sg_match_bow.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3
         L.sg_match_bow.restype = C.c_int
+        L.sg_vocab_create.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p]
+        L.sg_vocab_create.restype = C.c_int
+        L.sg_vocab_destroy.argtypes = [C.c_void_p]
+        L.sg_vocab_destroy.restype = None
+        L.sg_bow_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sg_bow_transform.restype = C.c_int
+        L.sg_bow_transform_device.argtypes = L.sg_bow_transform.argtypes
+        L.sg_bow_transform_device.restype = C.c_int
         L.sg_detect.argtypes = [C.c_void_p]
         L.sg_keypoint_capacity.argtypes = [C.c_void_p]
         L.sg_microbench_popc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -530,6 +539,33 @@ class DescriptorDB:
     def close(self):
         if self._h:
             lib().sg_db_destroy(self._h)
+            self._h = None
+
+
+class Vocabulary:
+    """Device-resident DBoW2-shaped vocabulary tree (see synth.random_vocabulary for the array layout)."""
+
+    def __init__(self, ctx, vocab):
+        self.ctx = ctx
+        a = {k: np.ascontiguousarray(vocab[k], t) for k, t in (("child_off", np.int32), ("child_ids", np.int32),
+             ("node_desc", np.uint32), ("node_weight", np.float32), ("node_word", np.int32))}
+        h = C.c_void_p()
+        ctx._check(lib().sg_vocab_create(ctx._h, a["child_off"].ctypes.data, a["child_ids"].ctypes.data, a["node_desc"].ctypes.data,
+                                         a["node_weight"].ctypes.data, a["node_word"].ctypes.data, len(a["node_word"]),
+                                         int(vocab["levels"]), C.byref(h)))
+        self._h = h
+
+    def transform(self, desc, levels_up=4):
+        desc = np.ascontiguousarray(desc, np.uint32).reshape(-1, 8)
+        n = len(desc)
+        word = np.empty(max(n, 1), np.int32); weight = np.empty(max(n, 1), np.float32); node = np.empty(max(n, 1), np.int32)
+        self.ctx._check(lib().sg_bow_transform(self.ctx._h, self._h, desc.ctypes.data, n, int(levels_up), word.ctypes.data,
+                                               weight.ctypes.data, node.ctypes.data))
+        return word[:n], weight[:n], node[:n]
+
+    def close(self):
+        if self._h:
+            lib().sg_vocab_destroy(self._h)
             self._h = None
 
 

@@ -89,3 +89,37 @@ def correlated_descriptors(n_per_set, seed, flip_bits=20, keep=0.6, angle_jitter
             dB[j] = d
             aB[j] = np.float32((aA[i] - rot + rng.normal(0, angle_jitter)) % 360.0)
     return dA, aA, dB, aB
+
+
+def random_vocabulary(branching, levels, seed, ragged=False):
+    """A DBoW2-shaped vocabulary tree for tests and benches (there is no vocabulary file offline): node 0 is the
+    root, every inner node has `branching` children (2..branching when ragged) whose descriptors are noisy copies of
+    the parent's, leaves at depth `levels` carry a word id and a weight.  Children are stored breadth first, so the
+    ids of a node's children are contiguous, but the arrays use DBoW2's general form (a child-id list per node)."""
+    rng = np.random.default_rng(seed)
+    desc = [rng.integers(0, 2 ** 32, 8, dtype=np.uint32)]
+    depth = [0]
+    child_off, child_ids = [0], []
+    i = 0
+    while i < len(desc):
+        if depth[i] < levels:
+            k = int(rng.integers(2, branching + 1)) if ragged else branching
+            for _ in range(k):
+                d = desc[i].copy()
+                for b in rng.integers(0, 256, max(2, 48 >> depth[i])):
+                    d[b >> 5] ^= np.uint32(1 << (int(b) & 31))
+                if rng.random() < 0.05 and child_ids and len(child_ids) > child_off[-1]:
+                    d = desc[child_ids[-1]].copy()          # a twin of the previous sibling: distance ties
+                child_ids.append(len(desc))
+                desc.append(d)
+                depth.append(depth[i] + 1)
+        child_off.append(len(child_ids))
+        i += 1
+    n = len(desc)
+    child_off = np.asarray(child_off, np.int32)
+    is_leaf = np.diff(child_off) == 0
+    word = np.full(n, -1, np.int32)
+    word[is_leaf] = np.arange(int(is_leaf.sum()), dtype=np.int32)
+    weight = np.where(is_leaf, rng.uniform(0.1, 5.0, n), 0.0).astype(np.float32)
+    return dict(child_off=child_off, child_ids=np.asarray(child_ids, np.int32), node_desc=np.stack(desc).astype(np.uint32),
+                node_weight=weight, node_word=word, levels=levels)

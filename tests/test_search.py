@@ -161,3 +161,54 @@ def test_gpu_medoid_bit_exact(slamgpu, oracle, synth):
         assert np.array_equal(got, oracle.medoid(desc, offs))
         with pytest.raises(slamgpu.SlamGpuError):
             ctx.medoid(rng.integers(0, 2 ** 32, (1025, 8), dtype=np.uint32), np.array([0, 1025], np.int64))
+
+
+def test_oracle_bow_transform_matches_python(oracle, synth):
+    v = synth.random_vocabulary(4, 3, 7, ragged=True)
+    rng = np.random.default_rng(8)
+    desc = np.concatenate([v["node_desc"][rng.integers(0, len(v["node_word"]), 40)], rng.integers(0, 2 ** 32, (20, 8), dtype=np.uint32)])
+    for levels_up in (0, 1, 2, 5):
+        word, weight, node = oracle.bow_transform(v, desc, levels_up)
+        for f in range(len(desc)):
+            cur, level, nid = 0, 0, 0
+            while v["child_off"][cur + 1] > v["child_off"][cur]:
+                level += 1
+                ch = v["child_ids"][v["child_off"][cur]:v["child_off"][cur + 1]]
+                dists = [_popc(desc[f], v["node_desc"][c]) for c in ch]
+                cur = int(ch[int(np.argmin(dists))])          # argmin: first minimum, like DBoW2's strict '<'
+                if level == v["levels"] - levels_up:
+                    nid = cur
+            assert word[f] == v["node_word"][cur] and node[f] == (0 if v["levels"] - levels_up <= 0 else nid)
+            assert weight[f] == v["node_weight"][cur]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("branching,levels,ragged,seed", [(10, 4, False, 31), (7, 3, True, 32), (40, 2, False, 33), (2, 9, True, 34)])
+def test_gpu_bow_transform_bit_exact(slamgpu, oracle, synth, branching, levels, ragged, seed):
+    v = synth.random_vocabulary(branching, levels, seed, ragged=ragged)
+    rng = np.random.default_rng(seed)
+    n_nodes = len(v["node_word"])
+    desc = np.concatenate([v["node_desc"][rng.integers(0, n_nodes, 1500)], rng.integers(0, 2 ** 32, (500, 8), dtype=np.uint32)])
+    for i in range(1500):                                   # noisy copies of vocabulary nodes + unrelated descriptors
+        for b in rng.integers(0, 256, int(rng.integers(0, 10))):
+            desc[i, b >> 5] ^= np.uint32(1 << (int(b) & 31))
+    with slamgpu.Context(640, 480, max_frames=1) as ctx:
+        voc = slamgpu.Vocabulary(ctx, v)
+        for levels_up in (0, 1, 4):
+            word, weight, node = voc.transform(desc, levels_up)
+            rw, rwt, rn = oracle.bow_transform(v, desc, levels_up)
+            assert np.array_equal(word, rw) and np.array_equal(weight, rwt) and np.array_equal(node, rn), levels_up
+        assert len(np.unique(word)) > 10
+        # the nodes feed the node-bucketed matcher (matchForLoopClosures as the reference runs it)
+        dA, dB = desc[:1000], desc[500:1500]
+        aA = rng.uniform(0, 360, 1000).astype(np.float32); aB = aA[::-1].copy()
+        nA, nB = voc.transform(dA, 1)[2], voc.transform(dB, 1)[2]
+        n, m = ctx.match_bow(dA, aA, nA, dB, aB, nB, check_orientation=False)
+        rn_, rm_ = oracle.match_bow(dA, aA, nA, dB, aB, nB, check_orientation=False)
+        assert n == rn_ and np.array_equal(m, rm_) and n > 100
+        voc.close()
+        bad = dict(v)
+        bad["child_ids"] = v["child_ids"].copy()
+        bad["child_ids"][0] = 0                              # a child that points back at the root
+        with pytest.raises(slamgpu.SlamGpuError):
+            slamgpu.Vocabulary(ctx, bad)
