@@ -176,6 +176,24 @@ int sg_match_bow(sg_ctx *ctx, const uint32_t *h_descA, const float *h_angA, cons
                  int nA, const uint32_t *h_descB, const float *h_angB, const int32_t *h_nodeB, const uint8_t *h_eligB,
                  int nB, const sg_match_params *mp, int32_t *h_matches, uint32_t *n_matches);
 
+/* matchForTriangulationDBoW (keyframe_matcher.hpp:54, keyframe_matcher.cpp:160-293): features WITHOUT a map point
+ * (h_elig* = 1) in the same DBoW2 node; per kf1 feature the last kf2 feature with distance <= thr and <= the best so far
+ * that passes check_epipolar_constraint (:23-44) and is not matched yet; angle histogram over all nodes.  The Hamming
+ * candidate lists come from the GPU; the epipolar test (fp64, acos) and the uniqueness walk run on the host over those
+ * short lists.  E = create_E_21(kf2.R, kf2.t, kf1.R, kf1.t) row-major; bearings are 3 doubles per keypoint. */
+typedef struct sg_triangulation_params {
+    double E[9];
+    const float *scale_factors;   /* StaticSettings::scaleFactors, n_levels entries */
+    int n_levels;
+    float residual_deg_thr;       /* slam.epipolarCheckThresholdDegrees */
+    uint32_t thr;                 /* HAMMING_DIST_THR_LOW = 50 */
+    int check_orientation;
+} sg_triangulation_params;
+int sg_match_triangulation(sg_ctx *ctx, const uint32_t *h_descA, const float *h_angA, const int32_t *h_octA, const double *h_bearA,
+                           const int32_t *h_nodeA, const uint8_t *h_eligA, int nA, const uint32_t *h_descB, const float *h_angB,
+                           const double *h_bearB, const int32_t *h_nodeB, const uint8_t *h_eligB, int nB,
+                           const sg_triangulation_params *tp, int32_t *h_matches, uint32_t *n_matches);
+
 /* Device-resident descriptor database: n_sets keyframes, set s owns features
  * [offsets[s], offsets[s+1]) of desc (8 words each) / angle. */
 typedef struct sg_db sg_db;

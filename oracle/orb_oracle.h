@@ -129,6 +129,14 @@ unsigned orc_match_bow(const uint32_t *descA, const float *angA, const int *node
                        const uint32_t *descB, const float *angB, const int *nodeB, const unsigned char *eligB, int nB,
                        float ratio, unsigned thr, int check_orientation, int ratio_is_double, int *matches);
 
+/* matchForTriangulationDBoW (keyframe_matcher.cpp:160-293) and its epipolar test (:23-44, E row-major). */
+unsigned orc_match_triangulation(const uint32_t *dA, const float *aA, const int *octA, const double *bearA, const int *nodeA,
+                                 const unsigned char *eligA, int nA, const uint32_t *dB, const float *aB, const double *bearB,
+                                 const int *nodeB, const unsigned char *eligB, int nB, const double *E,
+                                 const float *scale_factors, float residual_deg_thr, unsigned thr, int check_orientation,
+                                 int *matches);
+int orc_check_epipolar(const double *b1, const double *b2, const double *E, float scale, float residual_deg_thr);
+
 /* ---- "next" rows ---------------------------------------------------------------- */
 /* MapPoint::updateDescriptor (map_point.cpp:75-116): medoid index of every descriptor segment. */
 void orc_medoid(const uint32_t *desc, const long long *offsets, int n_seg, int *best);

@@ -253,6 +253,26 @@ def match_bow(dA, aA, nodeA, dB, aB, nodeB, eligA=None, eligB=None, ratio=0.8, t
     return int(n), m[:len(dA)]
 
 
+def match_triangulation(dA, aA, octA, bearA, nodeA, dB, aB, bearB, nodeB, E, scale_factors, eligA=None, eligB=None,
+                        residual_deg_thr=0.2, thr=50, check_orientation=True):
+    dA = np.ascontiguousarray(dA, np.uint32); dB = np.ascontiguousarray(dB, np.uint32)
+    aA = np.ascontiguousarray(aA, np.float32); aB = np.ascontiguousarray(aB, np.float32)
+    octA = np.ascontiguousarray(octA, np.int32)
+    bearA = np.ascontiguousarray(bearA, np.float64); bearB = np.ascontiguousarray(bearB, np.float64)
+    nodeA = np.ascontiguousarray(nodeA, np.int32); nodeB = np.ascontiguousarray(nodeB, np.int32)
+    E = np.ascontiguousarray(E, np.float64).reshape(9); sf = np.ascontiguousarray(scale_factors, np.float32)
+    eA = None if eligA is None else np.ascontiguousarray(eligA, np.uint8)
+    eB = None if eligB is None else np.ascontiguousarray(eligB, np.uint8)
+    m = np.empty(max(len(dA), 1), np.int32)
+    L = lib()
+    L.orc_match_triangulation.restype = C.c_uint
+    vp = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+    n = L.orc_match_triangulation(vp(dA), vp(aA), vp(octA), vp(bearA), vp(nodeA), vp(eA), len(dA), vp(dB), vp(aB), vp(bearB),
+                                  vp(nodeB), vp(eB), len(dB), vp(E), vp(sf), C.c_float(residual_deg_thr), C.c_uint(thr),
+                                  int(check_orientation), vp(m))
+    return int(n), m[:len(dA)]
+
+
 def angle_invalid(deltas, ids):
     deltas = np.ascontiguousarray(deltas, np.float32)
     ids = np.ascontiguousarray(ids, np.int32)

@@ -3,6 +3,7 @@
 // Follows openvslam/match_base.h:18-39, keyframe_matcher.cpp:50-158, and
 // openvslam/match_angle_checker.h:61-134.
 #include "common.h"
+#include <cmath>
 #include <map>
 #include <numeric>
 
@@ -126,6 +127,66 @@ unsigned match_bow(const uint32_t *dA, const float *aA, const int *nodeA, const 
     return num;
 }
 
+// check_epipolar_constraint (keyframe_matcher.cpp:23-44) on plain doubles.  E is row-major.  Eigen evaluates a fixed
+// size-3 sum as p0 + (p1 + p2) (redux_novec_unroller halves the range) [recall: Eigen is not in the reference tree].
+static inline double sum3(double p0, double p1, double p2) { return p0 + (p1 + p2); }
+bool check_epipolar(const double *b1, const double *b2, const double *E, float scale, float residual_deg_thr) {
+    const double e[3] = {sum3(E[0] * b2[0], E[1] * b2[1], E[2] * b2[2]), sum3(E[3] * b2[0], E[4] * b2[1], E[5] * b2[2]),
+                         sum3(E[6] * b2[0], E[7] * b2[1], E[8] * b2[2])};
+    const double cos_residual = sum3(e[0] * b1[0], e[1] * b1[1], e[2] * b1[2]) / std::sqrt(sum3(e[0] * e[0], e[1] * e[1], e[2] * e[2]));
+    const double residual_rad = M_PI / 2.0 - std::abs(std::acos(cos_residual));
+    const double residual_rad_thr = residual_deg_thr * M_PI / 180.0;
+    return residual_rad < residual_rad_thr * scale;
+}
+
+// matchForTriangulationDBoW (keyframe_matcher.cpp:160-293): features WITHOUT a map point (elig = 1), node buckets as in
+// match_bow, per kf1 feature the last kf2 feature with distance <= thr and <= the best so far that passes the epipolar
+// test, uniqueness in kf2, angle histogram over all nodes.
+unsigned match_triangulation(const uint32_t *dA, const float *aA, const int *octA, const double *bearA, const int *nodeA,
+                             const unsigned char *eligA, int nA, const uint32_t *dB, const float *aB, const double *bearB,
+                             const int *nodeB, const unsigned char *eligB, int nB, const double *E, const float *scale_factors,
+                             float residual_deg_thr, unsigned thr, bool check_orientation, int *matches) {
+    std::map<int, std::vector<unsigned>> fv1, fv2;
+    for (int i = 0; i < nA; ++i) if (nodeA[i] >= 0) fv1[nodeA[i]].push_back(i);
+    for (int i = 0; i < nB; ++i) if (nodeB[i] >= 0) fv2[nodeB[i]].push_back(i);
+    unsigned num = 0;
+    AngleChecker checker;
+    for (int i = 0; i < nA; ++i) matches[i] = -1;
+    std::vector<bool> taken(nB, false);
+    auto it1 = fv1.begin();
+    auto it2 = fv2.begin();
+    while (it1 != fv1.end() && it2 != fv2.end()) {
+        if (it1->first == it2->first) {
+            for (const auto i1 : it1->second) {
+                if (eligA && !eligA[i1]) continue;
+                unsigned best = thr;
+                int best_idx = -1;
+                for (const auto i2 : it2->second) {
+                    if (eligB && !eligB[i2]) continue;
+                    if (taken[i2]) continue;
+                    const unsigned d = hamming(dA + 8 * i1, dB + 8 * i2);
+                    if (d > thr || d > best) continue;
+                    if (check_epipolar(bearA + 3 * i1, bearB + 3 * i2, E, scale_factors[octA[i1]], residual_deg_thr)) {
+                        best_idx = (int)i2;
+                        best = d;
+                    }
+                }
+                if (best_idx < 0) continue;
+                taken[best_idx] = true;
+                matches[i1] = best_idx;
+                ++num;
+                if (check_orientation) checker.append(aA[i1] - aB[best_idx], (int)i1);
+            }
+            ++it1;
+            ++it2;
+        } else if (it1->first < it2->first) it1 = fv1.lower_bound(it2->first);
+        else it2 = fv2.lower_bound(it1->first);
+    }
+    if (check_orientation)
+        for (int idx : checker.invalid()) { matches[idx] = -1; --num; }
+    return num;
+}
+
 }  // namespace orc
 
 using namespace orc;
@@ -143,6 +204,17 @@ extern "C" unsigned orc_match_bow(const uint32_t *descA, const float *angA, cons
                                   float ratio, unsigned thr, int check_orientation, int ratio_is_double, int *matches) {
     return match_bow(descA, angA, nodeA, eligA, nA, descB, angB, nodeB, eligB, nB, ratio, thr, check_orientation != 0,
                      ratio_is_double != 0, matches);
+}
+extern "C" unsigned orc_match_triangulation(const uint32_t *dA, const float *aA, const int *octA, const double *bearA, const int *nodeA,
+                                            const unsigned char *eligA, int nA, const uint32_t *dB, const float *aB,
+                                            const double *bearB, const int *nodeB, const unsigned char *eligB, int nB,
+                                            const double *E, const float *scale_factors, float residual_deg_thr, unsigned thr,
+                                            int check_orientation, int *matches) {
+    return match_triangulation(dA, aA, octA, bearA, nodeA, eligA, nA, dB, aB, bearB, nodeB, eligB, nB, E, scale_factors,
+                               residual_deg_thr, thr, check_orientation != 0, matches);
+}
+extern "C" int orc_check_epipolar(const double *b1, const double *b2, const double *E, float scale, float residual_deg_thr) {
+    return check_epipolar(b1, b2, E, scale, residual_deg_thr) ? 1 : 0;
 }
 extern "C" int orc_angle_bin(float delta) { return AngleChecker::bin_of(delta, 1.0f / 30); }
 extern "C" int orc_angle_invalid(const float *deltas, const int *ids, int n, int *invalid_out) {

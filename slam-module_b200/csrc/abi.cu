@@ -37,6 +37,10 @@ int pyramid_fast_source_rows(const std::vector<ResizeTap> &yt, int h);
 int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, const sg_match_params &mp,
               int *d_matches, int match_stride, uint32_t *d_n_matches);
 int match_chunk_pairs(const sg_db *db, bool own_matches);
+int run_topk_lists(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, unsigned thr, uint32_t **d_topk,
+                   uint32_t **d_nseen, int *row_stride);
+int run_row_scan(sg_ctx *ctx, const sg_db *db, const int *d_rows, int n_rows, unsigned thr, int out_stride, uint32_t *d_out,
+                 uint32_t *d_count);
 int run_hamming(sg_ctx *ctx, const uint32_t *d_a, const uint32_t *d_b, int n, uint32_t *d_out);
 int run_popc_bench(sg_ctx *ctx, double *popc_per_s, float *ms_out);
 size_t distribute_smem_bytes(int node_cap_max);
@@ -820,6 +824,156 @@ int sg_match_bow(sg_ctx *ctx, const uint32_t *h_descA, const float *h_angA, cons
         }
     }
     if (mp->check_orientation) {                // match_angle_checker.h:72-134
+        uint32_t sizes[30] = {0}, order[30];
+        std::vector<int> bin(nA, -1);
+        for (int i = 0; i < nA; ++i)
+            if (h_matches[i] >= 0) { bin[i] = sg_angle_bin(h_angA[i] - h_angB[h_matches[i]]); ++sizes[bin[i]]; }
+        sg_angle_bin_order(sizes, order);
+        for (int i = 0; i < nA; ++i)
+            if (bin[i] >= 0 && (uint32_t)bin[i] != order[0] && (uint32_t)bin[i] != order[1] && (uint32_t)bin[i] != order[2]) {
+                h_matches[i] = -1;
+                --num;
+            }
+    }
+    *n_matches = num;
+    return SG_OK;
+}
+
+// matchForTriangulationDBoW (keyframe_matcher.cpp:160-293).  The O(nA * nB) Hamming work runs on the GPU (per node and
+// kf1 feature the candidate kf2 features within thr, ascending distance, ties by descending index); the acceptance walks
+// those short lists on the host: uniqueness in kf2 and the fp64 epipolar test (:23-44: acos / sqrt from the host libm, as
+// the reference evaluates it).  A list that is truncated and exhausted is completed exactly by a second GPU pass.
+namespace {
+inline double sum3(double p0, double p1, double p2) { return p0 + (p1 + p2); }   // Eigen's fixed-size redux order
+bool epipolar_ok(const double *b1, const double *b2, const double *E, float scale, float residual_deg_thr) {
+    const double e[3] = {sum3(E[0] * b2[0], E[1] * b2[1], E[2] * b2[2]), sum3(E[3] * b2[0], E[4] * b2[1], E[5] * b2[2]),
+                         sum3(E[6] * b2[0], E[7] * b2[1], E[8] * b2[2])};
+    const double cos_residual = sum3(e[0] * b1[0], e[1] * b1[1], e[2] * b1[2]) / std::sqrt(sum3(e[0] * e[0], e[1] * e[1], e[2] * e[2]));
+    const double residual_rad = M_PI / 2.0 - std::abs(std::acos(cos_residual));
+    const double residual_rad_thr = residual_deg_thr * M_PI / 180.0;
+    return residual_rad < residual_rad_thr * scale;
+}
+}  // namespace
+
+int sg_match_triangulation(sg_ctx *ctx, const uint32_t *h_descA, const float *h_angA, const int32_t *h_octA, const double *h_bearA,
+                           const int32_t *h_nodeA, const uint8_t *h_eligA, int nA, const uint32_t *h_descB, const float *h_angB,
+                           const double *h_bearB, const int32_t *h_nodeB, const uint8_t *h_eligB, int nB,
+                           const sg_triangulation_params *tp, int32_t *h_matches, uint32_t *n_matches) {
+    cudaSetDevice(ctx->device);
+    if (nA < 0 || nB < 0 || !tp || !n_matches || !tp->scale_factors
+        || (nA && (!h_descA || !h_angA || !h_octA || !h_bearA || !h_nodeA || !h_matches))
+        || (nB && (!h_descB || !h_angB || !h_bearB || !h_nodeB)))
+        return fail(ctx, SG_ERR_INVALID, "bad argument");
+    if (tp->thr > 256) return fail(ctx, SG_ERR_INVALID, "thr must be <= 256");
+    *n_matches = 0;
+    for (int i = 0; i < nA; ++i) {
+        h_matches[i] = -1;
+        if (h_octA[i] < 0 || h_octA[i] >= tp->n_levels) return fail(ctx, SG_ERR_INVALID, "octave of feature %d outside the scale factors", i);
+    }
+    if (nA == 0 || nB == 0) return SG_OK;
+    std::vector<std::pair<int, int>> fa, fb;   // (node, feature), DBoW2::FeatureVector order
+    for (int i = 0; i < nA; ++i) if (h_nodeA[i] >= 0 && (!h_eligA || h_eligA[i])) fa.emplace_back(h_nodeA[i], i);
+    for (int i = 0; i < nB; ++i) if (h_nodeB[i] >= 0 && (!h_eligB || h_eligB[i])) fb.emplace_back(h_nodeB[i], i);
+    std::stable_sort(fa.begin(), fa.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
+    std::stable_sort(fb.begin(), fb.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
+    std::vector<uint32_t> desc;
+    std::vector<float> ang;
+    std::vector<int64_t> offs{0};
+    std::vector<int32_t> pairs, idxA, idxB;
+    std::vector<int> startA, startB;
+    size_t ia = 0, ib = 0;
+    while (ia < fa.size() && ib < fb.size()) {
+        if (fa[ia].first < fb[ib].first) { ++ia; continue; }
+        if (fb[ib].first < fa[ia].first) { ++ib; continue; }
+        const int node = fa[ia].first, set = (int)offs.size() - 1;
+        startA.push_back((int)idxA.size());
+        for (; ia < fa.size() && fa[ia].first == node; ++ia) {
+            const int i = fa[ia].second;
+            desc.insert(desc.end(), h_descA + 8 * (size_t)i, h_descA + 8 * (size_t)i + 8);
+            ang.push_back(h_angA[i]);
+            idxA.push_back(i);
+        }
+        offs.push_back((int64_t)ang.size());
+        startB.push_back((int)idxB.size());
+        for (; ib < fb.size() && fb[ib].first == node; ++ib) {
+            const int i = fb[ib].second;
+            desc.insert(desc.end(), h_descB + 8 * (size_t)i, h_descB + 8 * (size_t)i + 8);
+            ang.push_back(h_angB[i]);
+            idxB.push_back(i);
+        }
+        offs.push_back((int64_t)ang.size());
+        pairs.push_back(set);
+        pairs.push_back(set + 1);
+    }
+    const int n_nodes = (int)pairs.size() / 2;
+    if (n_nodes == 0) return SG_OK;
+    sg_db *db = nullptr;
+    if (int r = sg_db_create(ctx, desc.data(), ang.data(), offs.data(), (int)offs.size() - 1, &db)) return r;
+    struct DbGuard { sg_db *d; ~DbGuard() { sg_db_destroy(d); } } guard{db};
+    if (int r = grow(ctx, (void **)&ctx->d_pairs, &ctx->pairs_cap, pairs.size(), sizeof(int))) return r;
+    SG_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t *d_topk = nullptr, *d_nseen = nullptr;
+    int stride = 0;
+    if (int r = run_topk_lists(ctx, db, ctx->d_pairs, n_nodes, tp->thr, &d_topk, &d_nseen, &stride)) return r;
+    std::vector<uint32_t> topk((size_t)n_nodes * stride * 4), nseen((size_t)n_nodes * stride);
+    SG_CUDA(ctx, cudaMemcpyAsync(topk.data(), d_topk, topk.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(nseen.data(), d_nseen, nseen.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+    std::vector<char> taken(nB, 0);
+    uint32_t num = 0;
+    unsigned long long rescans = 0;
+    std::vector<uint32_t> full;     // complete candidate list of a row whose top-4 list ran dry
+    for (int k = 0; k < n_nodes; ++k) {
+        const int na = (int)(offs[2 * k + 1] - offs[2 * k]), nb = (int)(offs[2 * k + 2] - offs[2 * k + 1]);
+        for (int j = 0; j < na; ++j) {
+            const int i1 = idxA[startA[k] + j];
+            const size_t r = (size_t)k * stride + j;
+            const uint32_t ns = nseen[r];
+            if (ns == 0) continue;
+            const float scale = tp->scale_factors[h_octA[i1]];
+            int best = -1;
+            // the reference keeps the LAST candidate with d <= best-so-far that passes: the smallest distance wins,
+            // among equal distances the largest index -- exactly the order of the keys
+            auto try_key = [&](uint32_t key) {
+                const int m = (int)(0xffffu - (key & 0xffffu));
+                const int i2 = idxB[startB[k] + m];
+                if (taken[i2]) return false;
+                if (!epipolar_ok(h_bearA + 3 * (size_t)i1, h_bearB + 3 * (size_t)i2, tp->E, scale, tp->residual_deg_thr)) return false;
+                best = i2;
+                return true;
+            };
+            bool done = false;
+            for (int e = 0; e < 4 && !done; ++e) {
+                const uint32_t key = topk[4 * r + e];
+                if (key == 0xffffffffu) break;
+                done = try_key(key);
+            }
+            if (!done && ns > 4) {
+                // truncated and exhausted: exact rescan of this row on the GPU (all candidates within thr)
+                ++rescans;
+                const int row[2] = {(int)(offs[2 * k] + j), 2 * k + 1};
+                if (int rr = grow(ctx, &ctx->d_tmp, &ctx->tmp_bytes, 8 + 4 * ((size_t)nb + 1), 1)) return rr;
+                int *d_row = (int *)ctx->d_tmp;
+                uint32_t *d_out = (uint32_t *)((uint8_t *)ctx->d_tmp + 8), *d_cnt = d_out + nb;
+                SG_CUDA(ctx, cudaMemcpyAsync(d_row, row, 8, cudaMemcpyHostToDevice, ctx->stream));
+                if (int rr = run_row_scan(ctx, db, d_row, 1, tp->thr, nb, d_out, d_cnt)) return rr;
+                full.resize((size_t)nb + 1);
+                SG_CUDA(ctx, cudaMemcpyAsync(full.data(), d_out, 4 * ((size_t)nb + 1), cudaMemcpyDeviceToHost, ctx->stream));
+                SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                const uint32_t cnt = full[nb];
+                for (uint32_t c = 0; c < cnt; ++c) full[c] = (full[c] & 0xffff0000u) | (0xffffu - (full[c] & 0xffffu));
+                std::sort(full.begin(), full.begin() + cnt);
+                for (uint32_t c = 0; c < cnt && !done; ++c) done = try_key(full[c]);
+            }
+            if (best < 0) continue;
+            taken[best] = 1;
+            h_matches[i1] = best;
+            ++num;
+        }
+    }
+    ctx->rescans = rescans;
+    if (tp->check_orientation) {                // match_angle_checker.h:72-134
         uint32_t sizes[30] = {0}, order[30];
         std::vector<int> bin(nA, -1);
         for (int i = 0; i < nA; ++i)

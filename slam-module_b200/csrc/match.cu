@@ -163,6 +163,7 @@ struct MatchArgs {
     float ratio;
     int ratio_is_double;
     int check_orientation;
+    int last_wins;             // ties between equal distances resolve to the LARGER B index (matchForTriangulationDBoW :231)
 };
 
 __device__ __forceinline__ void topk_insert(unsigned (&t)[TOPK], unsigned key) {
@@ -225,7 +226,7 @@ hamming_topk_kernel(const MatchArgs a, uint32_t *topk, uint32_t *nseen_out) {
                 const unsigned d = hamming256_csa(a0, a1, b0, b1);
                 if (d <= C) {
                     ++nseen;
-                    const unsigned key = (d << 16) | (unsigned)(j0 + j);
+                    const unsigned key = (d << 16) | (a.last_wins ? 0xffffu - (unsigned)(j0 + j) : (unsigned)(j0 + j));
                     if (key < t[TOPK - 1]) topk_insert(t, key);
                 }
             }
@@ -513,6 +514,68 @@ int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, con
         SG_LAUNCH_CHECK(ctx);
         if (p0 == 0) mark(ctx, EV_RESOLVE1);
     }
+    return SG_OK;
+}
+
+// ---- candidate lists for matchForTriangulationDBoW (keyframe_matcher.cpp:160-293) ----------------------------------
+// That matcher keeps, per kf1 feature, the LAST kf2 feature (in node order) whose distance is <= 50 and <= the best so
+// far AND that passes the fp64 epipolar test (:231-242).  The Hamming part runs here: per row the 4 smallest keys
+// (distance << 16 | 0xffff - index), i.e. ascending distance, ties by descending index -- the order in which the host
+// has to try the epipolar test.  A row whose list is truncated and exhausted is rescanned exactly by row_scan_kernel.
+int run_topk_lists(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, unsigned thr, uint32_t **d_topk,
+                   uint32_t **d_nseen, int *row_stride) {
+    if (db->max_set > 65535) return fail(ctx, SG_ERR_INVALID, "descriptor sets larger than 65535 features are not supported");
+    const int stride = std::max(db->max_set, 1);
+    const size_t need = (size_t)n_pairs * stride;
+    if (need > ctx->topk_rows) {
+        if (ctx->d_topk) cudaFree(ctx->d_topk);
+        if (ctx->d_nseen) cudaFree(ctx->d_nseen);
+        ctx->d_topk = nullptr; ctx->d_nseen = nullptr; ctx->topk_rows = 0;
+        SG_CUDA(ctx, cudaMalloc(&ctx->d_topk, need * TOPK * 4));
+        SG_CUDA(ctx, cudaMalloc(&ctx->d_nseen, need * 4));
+        ctx->topk_rows = need;
+    }
+    MatchArgs a{};
+    a.desc = db->d_desc; a.angle = db->d_angle; a.offsets = db->d_offsets; a.pairs = d_pairs;
+    a.cutoff = thr; a.thr = thr; a.row_stride = stride; a.last_wins = 1;
+    hamming_topk_kernel<<<dim3((stride + MT_THREADS - 1) / MT_THREADS, n_pairs), MT_THREADS, 0, ctx->stream>>>(a, ctx->d_topk, ctx->d_nseen);
+    SG_LAUNCH_CHECK(ctx);
+    *d_topk = ctx->d_topk; *d_nseen = ctx->d_nseen; *row_stride = stride;
+    return SG_OK;
+}
+
+// All B indices of a set within `thr` of one A descriptor: rows[r] = {setA row (absolute), setB}; out[r][..] unsorted.
+__global__ void __launch_bounds__(128)
+row_scan_kernel(const uint32_t *desc, const long long *offsets, const int *rows, int n_rows, unsigned thr, int out_stride,
+                uint32_t *out, uint32_t *out_count) {
+    const int lane = threadIdx.x & 31, r = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const long long rowA = rows[2 * r];
+    const int sb = rows[2 * r + 1];
+    const long long ob = offsets[sb];
+    const int nB = (int)(offsets[sb + 1] - ob);
+    const uint4 a0 = __ldg(reinterpret_cast<const uint4 *>(desc + 8 * rowA)), a1 = __ldg(reinterpret_cast<const uint4 *>(desc + 8 * rowA) + 1);
+    unsigned n = 0;
+    for (int j0 = 0; j0 < nB; j0 += 32) {
+        const int j = j0 + lane;
+        unsigned d = 0xffffffffu;
+        if (j < nB) {
+            const uint4 *pb = reinterpret_cast<const uint4 *>(desc + 8 * (ob + j));
+            d = hamming256_csa(a0, a1, __ldg(pb), __ldg(pb + 1));
+        }
+        const bool hit = d <= thr;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) out[(size_t)r * out_stride + n + __popc(m & ((1u << lane) - 1u))] = (d << 16) | (unsigned)j;
+        n += __popc(m);
+    }
+    if (lane == 0) out_count[r] = n;
+}
+
+int run_row_scan(sg_ctx *ctx, const sg_db *db, const int *d_rows, int n_rows, unsigned thr, int out_stride, uint32_t *d_out,
+                 uint32_t *d_count) {
+    if (n_rows <= 0) return SG_OK;
+    row_scan_kernel<<<(n_rows + 3) / 4, 128, 0, ctx->stream>>>(db->d_desc, db->d_offsets, d_rows, n_rows, thr, out_stride, d_out, d_count);
+    SG_LAUNCH_CHECK(ctx);
     return SG_OK;
 }
 

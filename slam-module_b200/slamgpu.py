@@ -45,6 +45,11 @@ class Keypoints(C.Structure):
                 ("count", C.c_void_p), ("level_count", C.c_void_p)]
 
 
+class TriangulationParams(C.Structure):
+    _fields_ = [("E", C.c_double * 9), ("scale_factors", C.c_void_p), ("n_levels", C.c_int), ("residual_deg_thr", C.c_float),
+                ("thr", C.c_uint32), ("check_orientation", C.c_int)]
+
+
 class KeypointsDev(C.Structure):
     _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("angle", C.c_void_p), ("octave", C.c_void_p),
                 ("desc", C.c_void_p), ("count", C.c_void_p), ("cap", C.c_int)]
@@ -62,7 +67,7 @@ ABI_SYMBOLS = [
     "sg_memcpy_h2d", "sg_memcpy_d2h", "sg_host_alloc_pinned", "sg_host_free_pinned", "sg_timer_start",
     "sg_timer_stop", "sg_flush_l2", "sg_microbench_popc", "sg_set_profiling", "sg_get_stage_ms",
     "sg_set_pipeline_chunk", "sg_search_candidates", "sg_feature_index", "sg_medoid", "sg_set_overlap", "sg_match_bow", "sg_vocab_create", "sg_vocab_destroy",
-    "sg_bow_transform", "sg_bow_transform_device",
+    "sg_bow_transform", "sg_bow_transform_device", "sg_match_triangulation",
 ]
 
 _lib = None
@@ -140,6 +145,8 @@ def lib():
         L.sg_set_overlap.restype = C.c_int
         L.sg_match_bow.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3
         L.sg_match_bow.restype = C.c_int
+        L.sg_match_triangulation.argtypes = [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 3
+        L.sg_match_triangulation.restype = C.c_int
         L.sg_vocab_create.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p]
         L.sg_vocab_create.restype = C.c_int
         L.sg_vocab_destroy.argtypes = [C.c_void_p]
@@ -464,6 +471,29 @@ class Context:
         p = lambda a: None if a is None else a.ctypes.data
         self._check(lib().sg_match_bow(self._h, p(dA), p(aA), p(nodeA), p(eA), len(dA), p(dB), p(aB), p(nodeB), p(eB), len(dB),
                                        C.byref(mp), m.ctypes.data, C.byref(n)))
+        return int(n.value), m[:len(dA)]
+
+    def match_triangulation(self, dA, aA, octA, bearA, nodeA, dB, aB, bearB, nodeB, E, scale_factors, eligA=None, eligB=None,
+                            residual_deg_thr=0.2, thr=50, check_orientation=True):
+        """matchForTriangulationDBoW: returns (num_matches, matches[nA])."""
+        dA = np.ascontiguousarray(dA, np.uint32).reshape(-1, 8); dB = np.ascontiguousarray(dB, np.uint32).reshape(-1, 8)
+        aA = np.ascontiguousarray(aA, np.float32); aB = np.ascontiguousarray(aB, np.float32)
+        octA = np.ascontiguousarray(octA, np.int32)
+        bearA = np.ascontiguousarray(bearA, np.float64); bearB = np.ascontiguousarray(bearB, np.float64)
+        nodeA = np.ascontiguousarray(nodeA, np.int32); nodeB = np.ascontiguousarray(nodeB, np.int32)
+        eA = None if eligA is None else np.ascontiguousarray(eligA, np.uint8)
+        eB = None if eligB is None else np.ascontiguousarray(eligB, np.uint8)
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        tp = TriangulationParams()
+        for i, x in enumerate(np.asarray(E, np.float64).reshape(9)):
+            tp.E[i] = float(x)
+        tp.scale_factors = sf.ctypes.data; tp.n_levels = len(sf); tp.residual_deg_thr = residual_deg_thr
+        tp.thr = thr; tp.check_orientation = int(check_orientation)
+        m = np.empty(max(len(dA), 1), np.int32)
+        n = C.c_uint32()
+        p = lambda a: None if a is None else a.ctypes.data
+        self._check(lib().sg_match_triangulation(self._h, p(dA), p(aA), p(octA), p(bearA), p(nodeA), p(eA), len(dA), p(dB), p(aB),
+                                                 p(bearB), p(nodeB), p(eB), len(dB), C.byref(tp), m.ctypes.data, C.byref(n)))
         return int(n.value), m[:len(dA)]
 
     def rescans(self):

@@ -156,3 +156,81 @@ def test_match_bow_node_buckets(ctx, oracle, synth, seed, n_nodes):
     assert n == 0 and (m == -1).all()
     n, m = ctx.match_bow(dA[:0], aA[:0], nodeA[:0], dB, aB, nodeB)
     assert n == 0 and len(m) == 0
+
+
+def _two_view_scene(seed, n=700, n_nodes=9):
+    """Two keyframes looking at random 3-D points: bearings, the essential matrix the reference builds
+    (create_E_21(kf2.R, kf2.t, kf1.R, kf1.t), openvslam/essential_solver.cc:157-162), noisy descriptor copies."""
+    rng = np.random.default_rng(seed)
+    def rot(ax, ang):
+        ax = ax / np.linalg.norm(ax)
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+    R1, t1 = np.eye(3), np.zeros(3)
+    R2, t2 = rot(rng.normal(size=3), 0.1), np.array([0.5, 0.05, -0.02])
+    X = rng.uniform(-3, 3, (n, 3)) + np.array([0, 0, 8.0])
+    b1 = (R1 @ X.T).T + t1; b1 /= np.linalg.norm(b1, axis=1, keepdims=True)
+    b2 = (R2 @ X.T).T + t2; b2 /= np.linalg.norm(b2, axis=1, keepdims=True)
+    # E = create_E_21(rot_1w = R2, trans_1w = t2, rot_2w = R1, trans_2w = t1)
+    R21 = R1 @ R2.T
+    t21 = -R21 @ t2 + t1
+    E = np.array([[0, -t21[2], t21[1]], [t21[2], 0, -t21[0]], [-t21[1], t21[0], 0]]) @ R21
+    dA = rng.integers(0, 2 ** 32, (n, 8), dtype=np.uint32)
+    dB = dA.copy()
+    for i in range(n):
+        for b in rng.integers(0, 256, int(rng.integers(0, 40))):
+            dB[i, b >> 5] ^= np.uint32(1 << (int(b) & 31))
+    # duplicates: several kf2 features with the same descriptor (ties: the last one wins), some off the epipolar plane
+    dB[1::9] = dB[0::9][:len(dB[1::9])]
+    wrong = rng.random(n) < 0.25
+    b2[wrong] = rng.normal(size=(int(wrong.sum()), 3)); b2[wrong] /= np.linalg.norm(b2[wrong], axis=1, keepdims=True)
+    perm = rng.permutation(n)
+    dB, b2 = dB[perm], b2[perm]
+    aA = rng.uniform(0, 360, n).astype(np.float32)
+    aB = ((aA + rng.normal(0, 4, n)) % 360).astype(np.float32)[perm]
+    octA = rng.integers(0, 8, n).astype(np.int32)
+    node = lambda d: ((d[:, 1] >> 7) % np.uint32(n_nodes)).astype(np.int32)
+    # nodes from bits the noise rarely touches would be ideal; a vocabulary stand-in: share the node of the source feature mostly
+    nodeA = rng.integers(0, n_nodes, n).astype(np.int32)
+    nodeB = nodeA.copy()
+    nodeB[rng.random(n) < 0.1] = rng.integers(0, n_nodes)
+    nodeB = nodeB[perm]
+    return dA, aA, octA, b1, nodeA, dB, aB, b2, nodeB, E
+
+
+@pytest.mark.parametrize("seed,n,n_nodes", [(61, 700, 9), (62, 1500, 1), (63, 300, 40)])
+def test_match_triangulation_bit_exact(ctx, oracle, seed, n, n_nodes):
+    """matchForTriangulationDBoW (keyframe_matcher.cpp:160-293): node buckets, last-wins ties, epipolar test, uniqueness."""
+    dA, aA, octA, b1, nodeA, dB, aB, b2, nodeB, E = _two_view_scene(seed, n, n_nodes)
+    sf = (1.2 ** np.arange(8)).astype(np.float32)
+    rng = np.random.default_rng(seed)
+    eligA = (rng.random(n) < 0.8).astype(np.uint8)
+    eligB = (rng.random(n) < 0.8).astype(np.uint8)
+    for thr_deg in (0.2, 2.0):
+        for eA, eB in ((None, None), (eligA, eligB)):
+            got = ctx.match_triangulation(dA, aA, octA, b1, nodeA, dB, aB, b2, nodeB, E, sf, eA, eB, residual_deg_thr=thr_deg)
+            ref = oracle.match_triangulation(dA, aA, octA, b1, nodeA, dB, aB, b2, nodeB, E, sf, eA, eB, residual_deg_thr=thr_deg)
+            assert got[0] == ref[0] and np.array_equal(got[1], ref[1]), (thr_deg, got[0], ref[0])
+    assert ref[0] > n // 20
+
+
+def test_match_triangulation_exhausted_lists_are_rescanned(ctx, oracle):
+    """Many identical kf2 descriptors that fail the epipolar test in front of the one that passes: the top-4 list runs dry
+    and the exact row scan decides."""
+    rng = np.random.default_rng(9)
+    n = 64
+    base = rng.integers(0, 2 ** 32, 8, dtype=np.uint32)
+    dA = np.tile(base, (n, 1)); dB = np.tile(base, (n, 1))
+    b1 = np.tile(np.array([0.0, 0.0, 1.0]), (n, 1))
+    E = np.array([[0, 0, 0], [0, 0, -1.0], [0, 1.0, 0]])      # pure x translation: epipolar plane normal = (0, -b2z, b2y)
+    b2 = np.tile(np.array([0.0, 0.6, 0.8]), (n, 1))            # off the plane of b1
+    ok = rng.permutation(n)[:20]
+    b2[ok] = [0.3, 0.0, 0.954]                                  # on it
+    b2 /= np.linalg.norm(b2, axis=1, keepdims=True)
+    aA = np.zeros(n, np.float32); aB = np.zeros(n, np.float32)
+    octA = np.zeros(n, np.int32); node = np.zeros(n, np.int32)
+    sf = np.ones(8, np.float32)
+    got = ctx.match_triangulation(dA, aA, octA, b1, node, dB, aB, b2, node, E, sf)
+    ref = oracle.match_triangulation(dA, aA, octA, b1, node, dB, aB, b2, node, E, sf)
+    assert got[0] == ref[0] == 20 and np.array_equal(got[1], ref[1])
+    assert ctx.rescans() > 0
