@@ -110,6 +110,7 @@ struct sg_ctx {
     unsigned char stage_mark[PROF_SLOTS][8] = {};
     long prof_call = -1;                             // index of the current call since profiling was switched on
     int sm_count = 148;
+    int describe_ctas_per_sm = 0;      // occupancy of the persistent describe kernel (queried on first use)
 
     std::vector<sg::Level> lv;
     sg::GeomDev geom{};

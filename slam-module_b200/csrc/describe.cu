@@ -326,12 +326,12 @@ int launch_describe(sg_ctx *ctx, int n_frames) {
               ctx->d_desc, ctx->d_count};
     const bool trk = ctx->have_tracks;
     const int groups = ((g.out_cap + 31) / 32) * n_frames;
-    static int per_sm = 0;   // resident CTAs per SM of this (persistent) kernel
-    if (!per_sm) {
+    if (!ctx->describe_ctas_per_sm) {   // resident CTAs per SM of this (persistent) kernel, asked once per context
+        int per_sm = 0;
         SG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, describe_kernel, DESC_WARPS * 32, 0));
-        per_sm = std::max(per_sm, 1);
+        ctx->describe_ctas_per_sm = std::max(per_sm, 1);
     }
-    const int blocks = std::max(1, std::min((groups + DESC_WARPS - 1) / DESC_WARPS, ctx->sm_count * per_sm));
+    const int blocks = std::max(1, std::min((groups + DESC_WARPS - 1) / DESC_WARPS, ctx->sm_count * ctx->describe_ctas_per_sm));
     DescMaps maps;
     for (int l = 0; l < g.levels; ++l) { maps.mom[l] = ctx->lv[l].map_mom; maps.blur[l] = ctx->lv[l].map_blur; }
     describe_kernel<<<blocks, DESC_WARPS * 32, 0, ctx->stream>>>(
