@@ -316,7 +316,7 @@ void sg_destroy(sg_ctx *ctx) {
                     ctx->d_err, ctx->d_trk_xy, ctx->d_trk_pt, ctx->d_trk_id, ctx->d_trk_count, ctx->d_x, ctx->d_y,
                     ctx->d_angle, ctx->d_octave, ctx->d_track_id, ctx->d_lvl_x, ctx->d_lvl_y, ctx->d_desc, ctx->d_count,
                     ctx->d_flush, ctx->d_topk, ctx->d_nseen, ctx->d_pairs, ctx->d_matches, ctx->d_nmatch,
-                    ctx->d_rescans, ctx->d_tmp};
+                    ctx->d_rescans, ctx->d_tmp, ctx->d_dbtmp};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (auto &slot : ctx->ev_stage)
@@ -676,6 +676,31 @@ static int db_create(sg_ctx *ctx, const uint32_t *desc, const float *angle, cons
     return SG_OK;
 }
 
+// A transient database for the single-call matchers (sg_match_bruteforce / _bow / _triangulation): descriptors, angles
+// and offsets live in a grow-only buffer of the context, so a call costs no cudaMalloc / cudaFree.
+static int scratch_db(sg_ctx *ctx, sg_db *db, const uint32_t *h_desc, const float *h_angle, const int64_t *h_offsets, int n_sets) {
+    db->ctx = ctx;
+    db->n_sets = n_sets;
+    db->offsets.assign(h_offsets, h_offsets + n_sets + 1);
+    db->max_set = 0;
+    for (int s = 0; s < n_sets; ++s) db->max_set = std::max<long long>(db->max_set, h_offsets[s + 1] - h_offsets[s]);
+    const size_t total = (size_t)h_offsets[n_sets];
+    const size_t b_desc = (total * 32 + 32 + 255) & ~(size_t)255, b_ang = (total * 4 + 4 + 255) & ~(size_t)255;
+    const size_t b_off = (sizeof(long long) * ((size_t)n_sets + 1) + 255) & ~(size_t)255;
+    if (int r = grow(ctx, &ctx->d_dbtmp, &ctx->dbtmp_bytes, b_desc + b_ang + b_off, 1)) return r;
+    uint8_t *base = (uint8_t *)ctx->d_dbtmp;
+    db->d_desc = (uint32_t *)base;
+    db->d_angle = (float *)(base + b_desc);
+    db->d_offsets = (long long *)(base + b_desc + b_ang);
+    if (total) {
+        SG_CUDA(ctx, cudaMemcpyAsync(db->d_desc, h_desc, total * 32, cudaMemcpyHostToDevice, ctx->stream));
+        SG_CUDA(ctx, cudaMemcpyAsync(db->d_angle, h_angle, total * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    SG_CUDA(ctx, cudaMemcpyAsync(db->d_offsets, db->offsets.data(), sizeof(long long) * ((size_t)n_sets + 1), cudaMemcpyHostToDevice, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the host vectors behind h_desc / h_angle may die with the caller's scope
+    return SG_OK;
+}
+
 int sg_db_create(sg_ctx *ctx, const uint32_t *h_desc, const float *h_angle, const int64_t *h_offsets, int n_sets, sg_db **out) {
     return db_create(ctx, h_desc, h_angle, h_offsets, n_sets, out, cudaMemcpyHostToDevice);
 }
@@ -742,13 +767,12 @@ int sg_match_bruteforce(sg_ctx *ctx, const uint32_t *h_descA, const float *h_ang
     memcpy(ang.data(), h_angA, 4 * (size_t)nA);
     memcpy(ang.data() + nA, h_angB, 4 * (size_t)nB);
     const int64_t offs[3] = {0, nA, (int64_t)nA + nB};
-    sg_db *db = nullptr;
-    if (int r = sg_db_create(ctx, desc.data(), ang.data(), offs, 2, &db)) return r;
+    sg_db tmp, *db = &tmp;
+    if (int r = scratch_db(ctx, db, desc.data(), ang.data(), offs, 2)) return r;
     const int32_t pair[2] = {0, 1};
     std::vector<int32_t> m(db->max_set);
     const int r = sg_match_pairs(ctx, db, pair, 1, mp, m.data(), db->max_set, n_matches);
     if (!r) memcpy(h_matches, m.data(), 4 * (size_t)nA);
-    sg_db_destroy(db);
     return r;
 }
 
@@ -805,16 +829,14 @@ int sg_match_bow(sg_ctx *ctx, const uint32_t *h_descA, const float *h_angA, cons
     }
     const int n_nodes = (int)pairs.size() / 2;
     if (n_nodes == 0) return SG_OK;
-    sg_db *db = nullptr;
-    if (int r = sg_db_create(ctx, desc.data(), ang.data(), offs.data(), (int)offs.size() - 1, &db)) return r;
+    sg_db tmp, *db = &tmp;
+    if (int r = scratch_db(ctx, db, desc.data(), ang.data(), offs.data(), (int)offs.size() - 1)) return r;
     sg_match_params q = *mp;
     q.check_orientation = 0;                    // the histogram spans all nodes: applied below
     const int stride = std::max(db->max_set, 1);
     std::vector<int32_t> rows((size_t)n_nodes * stride);
     std::vector<uint32_t> counts(n_nodes);
-    const int r = sg_match_pairs(ctx, db, pairs.data(), n_nodes, &q, rows.data(), stride, counts.data());
-    sg_db_destroy(db);
-    if (r) return r;
+    if (int r = sg_match_pairs(ctx, db, pairs.data(), n_nodes, &q, rows.data(), stride, counts.data())) return r;
     uint32_t num = 0;
     for (int k = 0; k < n_nodes; ++k) {
         const int na = (int)(offs[2 * k + 1] - offs[2 * k]);
@@ -907,9 +929,8 @@ int sg_match_triangulation(sg_ctx *ctx, const uint32_t *h_descA, const float *h_
     }
     const int n_nodes = (int)pairs.size() / 2;
     if (n_nodes == 0) return SG_OK;
-    sg_db *db = nullptr;
-    if (int r = sg_db_create(ctx, desc.data(), ang.data(), offs.data(), (int)offs.size() - 1, &db)) return r;
-    struct DbGuard { sg_db *d; ~DbGuard() { sg_db_destroy(d); } } guard{db};
+    sg_db tmp, *db = &tmp;
+    if (int r = scratch_db(ctx, db, desc.data(), ang.data(), offs.data(), (int)offs.size() - 1)) return r;
     if (int r = grow(ctx, (void **)&ctx->d_pairs, &ctx->pairs_cap, pairs.size(), sizeof(int))) return r;
     SG_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     uint32_t *d_topk = nullptr, *d_nseen = nullptr;

@@ -163,6 +163,8 @@ struct sg_ctx {
     unsigned long long rescans = 0;
     void *d_tmp = nullptr;                 // small uploads for the single-pair entry points
     size_t tmp_bytes = 0;
+    void *d_dbtmp = nullptr;               // transient descriptor database of the single-call matchers
+    size_t dbtmp_bytes = 0;
 };
 
 namespace sg {

@@ -42,3 +42,9 @@ for parts in (1, 2, 4, 6, 8):
     ctx.set_overlap(parts)
     dt = t(lambda: ctx.extract_device(dbuf.ptr, W, W * H, F), 20)
     print("overlap parts %d: device-resident extract %.3f ms (%.0f fps)" % (parts, dt * 1e3, F / dt))
+dA, aA, dB, aB = sm.synth.correlated_descriptors(2000, 7)
+ctx.match_bruteforce(dA, aA, dB, aB)
+t0 = time.perf_counter()
+for _ in range(20):
+    n, m = ctx.match_bruteforce(dA, aA, dB, aB)
+print("sg_match_bruteforce 2000 x 2000, host buffers: %.3f ms per call (%d matches)" % ((time.perf_counter() - t0) / 20 * 1e3, n))
