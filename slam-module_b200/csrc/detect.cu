@@ -50,8 +50,9 @@ constexpr int MAX_SCORED = 1024;           // list of scored pixels (NMS candida
 //   dark score                    ==   max over arcs of min9(e) - 257        (cv::cornerScore convention)
 // The bright polarity is the dark polarity of the complemented image (p -> 255 - p), so a lane that needs the
 // bright test XORs its pixels with 0xff and runs the same code.
-// Stage 1 (every pair): an arc of 9 contains one pixel of each antipodal pair, so for the compass pairs
-//   (e0 or e8 dark) and (e4 or e12 dark)  <=>  min(max(e0, e8), max(e4, e12)) > 256 + t   is necessary.
+// Stage 1 (every pair): an arc of 9 contains one pixel of each antipodal pair, so for the compass and the diagonal pairs
+//   (e0 or e8 dark) and (e4 or e12 dark) and (e2 or e10 dark) and (e6 or e14 dark)
+//   <=>  min(max(e0, e8), max(e4, e12), max(e2, e10), max(e6, e14)) > 256 + t   is necessary.
 // Stage 2 (pairs that pass, compacted): exact one-sided score of both lanes for the polarity stage 1 left
 // possible (a pixel can be a corner of one polarity only; a lane that passes both is queued twice).
 // NOTE: the scalar formulation `max(min9, -max9)` on int is miscompiled by ptxas 12.9 (-O1 and above,
@@ -133,8 +134,10 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
             const uint32_t *we = We + (y + 3) * WP + lane + 3, *wo = Wo + (y + 3) * WP + lane;
             const unsigned vb = we[0] | 0x01000100u;
             const unsigned e0 = vb - we[3 * WP], e8 = vb - we[-3 * WP], e4 = vb - wo[4], e12 = vb - wo[1];
-            const unsigned dk = __vminu2(__vmaxu2(e0, e8), __vmaxu2(e4, e12));
-            const unsigned br = __vmaxu2(__vminu2(e0, e8), __vminu2(e4, e12));
+            // the two diagonal antipodal pairs (2, 2) / (-2, -2) and (2, -2) / (-2, 2) halve what reaches stage 2
+            const unsigned e2 = vb - we[2 * WP + 1], e10 = vb - we[-2 * WP - 1], e6 = vb - we[-2 * WP + 1], e14 = vb - we[2 * WP - 1];
+            const unsigned dk = __vminu2(__vminu2(__vmaxu2(e0, e8), __vmaxu2(e4, e12)), __vminu2(__vmaxu2(e2, e10), __vmaxu2(e6, e14)));
+            const unsigned br = __vmaxu2(__vmaxu2(__vminu2(e0, e8), __vminu2(e4, e12)), __vmaxu2(__vminu2(e2, e10), __vminu2(e6, e14)));
             // lane bit 15 / 31 of (thiH - dk) is clear iff dk > thi; of ((br | H) - tlo) iff br < tlo
             const unsigned pass = ~((thiH - dk) & ((br | 0x80008000u) - tlo)) & okH;
             const unsigned m = __ballot_sync(0xffffffffu, pass != 0u);
