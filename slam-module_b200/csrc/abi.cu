@@ -44,6 +44,7 @@ int run_row_scan(sg_ctx *ctx, const sg_db *db, const int *d_rows, int n_rows, un
 int run_hamming(sg_ctx *ctx, const uint32_t *d_a, const uint32_t *d_b, int n, uint32_t *d_out);
 int run_popc_bench(sg_ctx *ctx, double *popc_per_s, float *ms_out);
 size_t distribute_smem_bytes(int node_cap_max);
+void fast_cell_table(const GeomDev &g, std::vector<int4> &cells);
 
 template <class T>
 static int dev_alloc(sg_ctx *ctx, T **p, size_t n) {
@@ -144,6 +145,12 @@ static int build_context(sg_ctx *ctx) {
     g.det_cap = kp_off;
     g.out_cap = kp_off + p.max_tracks;
 
+    {
+        std::vector<int4> cells;
+        fast_cell_table(g, cells);
+        if (int r = dev_alloc(ctx, &ctx->d_cell_table, cells.size())) return r;
+        if (!cells.empty()) SG_CUDA(ctx, cudaMemcpy(ctx->d_cell_table, cells.data(), cells.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    }
     if (int r = dev_alloc(ctx, &ctx->d_cand, F * cand_off)) return r;
     if (int r = dev_alloc(ctx, &ctx->d_cand_node, F * cand_off)) return r;
     if (int r = dev_alloc(ctx, &ctx->d_cand_count, F * p.levels)) return r;
@@ -316,7 +323,7 @@ void sg_destroy(sg_ctx *ctx) {
                     ctx->d_err, ctx->d_trk_xy, ctx->d_trk_pt, ctx->d_trk_id, ctx->d_trk_count, ctx->d_x, ctx->d_y,
                     ctx->d_angle, ctx->d_octave, ctx->d_track_id, ctx->d_lvl_x, ctx->d_lvl_y, ctx->d_desc, ctx->d_count,
                     ctx->d_flush, ctx->d_topk, ctx->d_nseen, ctx->d_pairs, ctx->d_matches, ctx->d_nmatch,
-                    ctx->d_rescans, ctx->d_tmp, ctx->d_dbtmp};
+                    ctx->d_rescans, ctx->d_tmp, ctx->d_dbtmp, ctx->d_cell_table};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (auto &slot : ctx->ev_stage)

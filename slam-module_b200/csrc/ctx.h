@@ -129,6 +129,7 @@ struct sg_ctx {
     int *d_kp_resp = nullptr;
     int *d_kp_count = nullptr;             // [max_frames][levels]
     int *d_err = nullptr;                  // device-side overflow flag
+    int4 *d_cell_table = nullptr;          // FAST cells: level, cell row / column, origin, extent (fast_cell_table)
 
     // tracker points (host-filtered, orb_extractor.cpp:89-104)
     int *d_trk_xy = nullptr;               // [max_frames][max_tracks]  x | y<<16 at track_level

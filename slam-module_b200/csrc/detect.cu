@@ -67,7 +67,7 @@ __device__ __forceinline__ unsigned gt16x2(unsigned a, unsigned b) {
 struct FastMaps { CUtensorMap m[SG_MAX_LEVELS]; };   // 80 x 70 box over every pyramid level
 
 __global__ void __launch_bounds__(FAST_THREADS, 4)
-fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ FastMaps maps, int total_cells,
+fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ FastMaps maps, const int4 *cells,
                   unsigned long long *cand, int *cand_count, int *err) {
     __shared__ __align__(128) uint8_t tile[TILE_ROWS * TP + 16];
     __shared__ __align__(8) uint64_t s_bar;
@@ -79,18 +79,12 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
     __shared__ int s_nscored, s_nkeep, s_base;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, f = blockIdx.y + g.frame0;
-    // which level / cell
-    int cell = blockIdx.x, l = 0;
-    for (; l < g.levels; ++l) {
-        const int n = g.lv[l].cells_x * g.lv[l].cells_y;
-        if (cell < n) break;
-        cell -= n;
-    }
-    if (l >= g.levels) return;
+    // which level / cell: one broadcast load of the table built at sg_create (fast_cell_table)
+    const int4 ce = __ldg(cells + blockIdx.x);
+    const int l = ce.x & 0xff, ci = (ce.x >> 8) & 0xfff, cj = ce.x >> 20;
     const LevelDev &L = g.lv[l];
-    const int ci = cell / L.cells_x, cj = cell - ci * L.cells_x;
-    const int ex0 = EVAL_ORIGIN + CELL * cj, ey0 = EVAL_ORIGIN + CELL * ci;   // first evaluated pixel
-    const int cw = min(CELL, L.w - EVAL_ORIGIN - ex0), ch = min(CELL, L.h - EVAL_ORIGIN - ey0);
+    const int ex0 = ce.y, ey0 = ce.z;                      // first evaluated pixel
+    const int cw = ce.w & 0xffff, ch = ce.w >> 16;
     const int ax0 = ex0 - 3 - TILE_SHIFT, wy0 = ey0 - 3;   // word-aligned window origin
 
     // ---- stage the 80 x 70 window with one TMA box load (zero outside the plane) -------------------------
@@ -513,6 +507,20 @@ distribute_kernel(const __grid_constant__ GeomDev g, int node_cap_max, const uns
     if (tid == 0) kp_count[f * g.levels + l] = n;
 }
 
+// {level | cell row << 8 | cell column << 20, first evaluated x, y, width | height << 16} of every FAST cell (host, sg_create)
+void fast_cell_table(const GeomDev &g, std::vector<int4> &cells) {
+    cells.clear();
+    for (int l = 0; l < g.levels; ++l) {
+        const LevelDev &L = g.lv[l];
+        for (int ci = 0; ci < L.cells_y; ++ci)
+            for (int cj = 0; cj < L.cells_x; ++cj) {
+                const int ex0 = EVAL_ORIGIN + CELL * cj, ey0 = EVAL_ORIGIN + CELL * ci;
+                const int cw = std::min(CELL, L.w - EVAL_ORIGIN - ex0), ch = std::min(CELL, L.h - EVAL_ORIGIN - ey0);
+                cells.push_back(make_int4(l | (ci << 8) | (cj << 20), ex0, ey0, cw | (ch << 16)));
+            }
+    }
+}
+
 size_t distribute_smem_bytes(int node_cap_max) {
     const size_t NC = node_cap_max;
     return NC * (8 + 2 * sizeof(NodeBox) + 2 * 4 + 4 * 4 + 4 * 4 + 4 + 4 + 4 + 4) + 16;
@@ -531,7 +539,7 @@ int launch_detect(sg_ctx *ctx, int n_frames) {
         FastMaps maps;
         for (int l = 0; l < g.levels; ++l) maps.m[l] = ctx->lv[l].map_fast;
         fast_cells_kernel<<<dim3(total_cells, n_frames), FAST_THREADS, 0, ctx->stream>>>(
-            g, maps, total_cells, ctx->d_cand, ctx->d_cand_count, ctx->d_err);
+            g, maps, ctx->d_cell_table, ctx->d_cand, ctx->d_cand_count, ctx->d_err);
         SG_LAUNCH_CHECK(ctx);
     }
     mark(ctx, EV_FAST1);
