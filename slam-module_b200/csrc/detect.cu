@@ -119,6 +119,7 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
         // pairs that reach stage 2).  Passing pairs go to a queue PRIVATE to the warp (ballot + prefix popc, no
         // atomics, no CTA barrier): a warp owns rows warp, warp + 8, ... and scores its own queue right after.
         unsigned short *q = ent + warp * WARP_Q;
+        const uint32_t q_addr = smem_u32(q);
         int nq = 0;
         const unsigned lt = (1u << lane) - 1u;
         // pixels outside the cell never count
@@ -135,7 +136,7 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
             // lane bit 15 / 31 of (thiH - dk) is clear iff dk > thi; of ((br | H) - tlo) iff br < tlo
             const unsigned pass = ~((thiH - dk) & ((br | 0x80008000u) - tlo)) & okH;
             const unsigned m = __ballot_sync(0xffffffffu, pass != 0u);
-            if (pass) q[nq + __popc(m & lt)] = (unsigned short)(lane | (y << 5));
+            if (pass) sts16(q_addr + 2u * (unsigned)(nq + __popc(m & lt)), (unsigned)(lane | (y << 5)));   // shared-space store: no generic address math per row
             nq += __popc(m);
         }
         __syncwarp();
