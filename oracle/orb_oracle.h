@@ -18,6 +18,11 @@
  *   - matchForLoopClosures brute-force degenerate case: restated from keyframe_matcher.cpp:50-158;
  *     the reference ships no test vectors for it (parity pinned only through the verbatim
  *     leaf headers it is built from).
+ *   - candidate-list matchers, matchForTriangulationDBoW, MapPoint::updateDescriptor, FeatureSearch: restated from
+ *     keyframe_matcher.cpp / feature_search.cpp / map_point.cpp; the reference has no vectors for them, so they are
+ *     checked against plain-python restatements in tests/test_search.py only -- PARITY UNPINNED.  The epipolar test uses
+ *     Eigen's summation order from memory (Eigen is not in the tree).
+ *   - BoW transform: DBoW2 is an absent dependency; its published tree descent is restated -- PARITY UNPINNED.
  */
 #ifndef ORB_ORACLE_H
 #define ORB_ORACLE_H
