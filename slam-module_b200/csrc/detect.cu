@@ -34,6 +34,7 @@ constexpr int TILE_ROWS = CELL + 6;    // 70
 constexpr int RPW = CELL + 8;          // response map pitch: 4-byte left pad (word-aligned rows) + 64 + right pad
 constexpr int TILE_SHIFT = 3;          // the window origin 19 + 64*j is always 3 past a word boundary
 static_assert((EVAL_ORIGIN - FAST_BORDER) % 4 == TILE_SHIFT && CELL % 4 == 0, "tile alignment");
+static_assert(((CELL + 2) * (CELL + 8)) % 16 == 0 && (CELL + 6) * 80 % 8 == 0, "vector widths of the zeroing / pair-word loops");
 constexpr int WP = TP / 2;             // pair-word pitch: 40 words per row
 constexpr int MAX_ENTRIES = CELL * CELL;   // 2048 pixel pairs, each at most twice (both polarities)
 constexpr int WARP_Q = MAX_ENTRIES / 2 / (FAST_THREADS / 32);   // per-warp queue: 8 rows x 32 pairs
@@ -94,16 +95,23 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
         tma_load_3d(tile, &maps.m[l], ax0, wy0, f, &s_bar);
         s_nscored = 0; s_nkeep = 0;
     }
-    for (int i = tid; i < (CELL + 2) * RPW / 4; i += FAST_THREADS) reinterpret_cast<uint32_t *>(resp)[i] = 0;
+    for (int i = tid; i < (CELL + 2) * RPW / 16; i += FAST_THREADS) reinterpret_cast<uint4 *>(resp)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     mbar_wait(&s_bar, 0);
 
     // ---- pair words: 4 per aligned tile word ----------------------------------------------------------------
-    for (int i = tid; i < TILE_ROWS * (TP / 4); i += FAST_THREADS) {
-        const uint32_t w = reinterpret_cast<const uint32_t *>(tile)[i], nx = reinterpret_cast<const uint32_t *>(tile)[i + 1];
-        // row r, word j of the row: i = r * 20 + j; pair index 2j, 2j + 1 of the row: 2 * i overall
-        *reinterpret_cast<uint2 *>(We + 2 * i) = make_uint2(__byte_perm(w, 0u, 0x4140), __byte_perm(w, 0u, 0x4342));
-        *reinterpret_cast<uint2 *>(Wo + 2 * i) = make_uint2(__byte_perm(w, 0u, 0x4241), __byte_perm(w, nx, 0x0403) & 0x00ff00ffu);
+    // two tile words (8 pixels) per item: 64-bit load, 128-bit stores, shared-space addresses
+    {
+        const uint32_t t_addr = smem_u32(tile), we_addr = smem_u32(We), wo_addr = smem_u32(Wo);
+        for (int i = tid; i < TILE_ROWS * (TP / 8); i += FAST_THREADS) {
+            // words 2i, 2i + 1 of the tile and the word behind them; pair indices 4i .. 4i + 3 of both tiles
+            const uint2 w = lds64(t_addr + 8u * i);
+            const uint32_t nx = lds32(t_addr + 8u * i + 8u);
+            sts128(we_addr + 16u * i, make_uint4(__byte_perm(w.x, 0u, 0x4140), __byte_perm(w.x, 0u, 0x4342),
+                                                 __byte_perm(w.y, 0u, 0x4140), __byte_perm(w.y, 0u, 0x4342)));
+            sts128(wo_addr + 16u * i, make_uint4(__byte_perm(w.x, 0u, 0x4241), __byte_perm(w.x, w.y, 0x0403) & 0x00ff00ffu,
+                                                 __byte_perm(w.y, 0u, 0x4241), __byte_perm(w.y, nx, 0x0403) & 0x00ff00ffu));
+        }
     }
     __syncthreads();
 
