@@ -341,7 +341,16 @@ def extra_configs(slamgpu, sm, sh, rank, world, local, barrier_max_, td):
         nodes_q = voc.transform(qdesc, 2)[2]
         ang_k = rng.uniform(0, 360, nk).astype(np.float32); ang_q = rng.uniform(0, 360, nq).astype(np.float32)
         t_mbow, (n_mbow, _) = timed(lambda: c6.match_bow(qdesc, ang_q, nodes_q, kdesc, ang_k, nodes_k, check_orientation=False))
+        bword, bweight, _ = voc.transform(kdesc, 2)
+        t_bvec, (vw, vv) = timed(lambda: voc.bow_vector(bword, bweight))
         voc.close()
+        NKF = 10000
+        vecs = sm.synth.random_bow_vectors(NKF, 100000, 1500, 9, n_topics=40)
+        bdb = slamgpu.BowDatabase(c6, NKF, 2048)
+        for i, (w_, v_) in enumerate(vecs):
+            bdb.add(0, i, w_, v_)
+        t_sim, (_, sim_kf, _) = timed(lambda: bdb.similar(*vecs[17], self_key=(0, 17)))
+        bdb.close()
         out["next_rows"] = {
             "search_by_projection": {"workload": "%d projected map points against %d keypoints, radius 20 px (keyframe_matcher.cpp:295-414 inner loop)" % (nq, nk),
                                      "ms_per_call_host_buffers": t_proj * 1e3, "matches": n_proj},
@@ -351,6 +360,10 @@ def extra_configs(slamgpu, sm, sh, rank, world, local, barrier_max_, td):
                                  "ms_per_call_host_buffers": t_med * 1e3, "map_points_per_s": len(sizes) / t_med},
             "bow_transform": {"workload": "%d descriptors through a synthetic 10-ary, 4-level vocabulary tree (bow_index.cpp:59-93)" % nk,
                               "ms_per_call_host_buffers": t_bow * 1e3, "distinct_words": int(len(np.unique(bw)))},
+            "bow_vector": {"workload": "BowVector of %d features: per-word sums in feature order + L1 norm, doubles (DBoW2 transform / normalize)" % nk,
+                           "ms_per_call_host_buffers": t_bvec * 1e3, "words": int(len(vw))},
+            "bow_similar": {"workload": "getBowSimilar (bow_index.cpp:95-176): one query against %d stored keyframes of 750..1700 words" % NKF,
+                            "ms_per_call_host_buffers": t_sim * 1e3, "keyframes_scored_per_s": NKF / t_sim, "candidates": int(len(sim_kf))},
             "match_for_loop_closures_bow": {"workload": "%d x %d features in DBoW2 node buckets (keyframe_matcher.cpp:65-146)" % (nq, nk),
                                             "ms_per_call_host_buffers": t_mbow * 1e3, "matches": n_mbow}}
     return out

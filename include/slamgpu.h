@@ -239,22 +239,44 @@ int sg_feature_index(const float *h_x, const float *h_y, int n, int32_t *h_order
  * median Hamming distance to the segment is smallest (first wins; 0 for an empty segment). */
 int sg_medoid(sg_ctx *ctx, const uint32_t *h_desc, const int64_t *h_offsets, int n_seg, int32_t *h_best);
 
-/* ---- BoW transform: BowIndex::transform (bow_index.cpp:59-93) = DBoW2 TemplatedVocabulary<ORB>::
- *      transform(features, bowVector, featureVector, levelsUp).  DBoW2 is not part of the reference tree; the tree
- *      descent is restated from its published algorithm (nearest child by Hamming distance at every level, first child
- *      wins ties).  Vocabulary: node 0 is the root, the children of node i are h_child_ids[h_child_off[i] ..
- *      h_child_off[i+1]) (larger ids than i), a leaf has none and carries word id and weight; `levels` = DBoW2's L.
- *      Per feature: word id, word weight and the feature-vector node (the node reached at level L - levels_up; the
- *      root when that is <= 0).  Summing the weights per word and the L1 normalisation of the BowVector are the
- *      caller's few host lines (std::map order, double arithmetic, as DBoW2 does). */
+/* ---- bag of words: BowIndex::transform (bow_index.cpp:59-93), add / remove (:44-57) and
+ *      getBowSimilar (:95-176) over a DBoW2 vocabulary tree.  DBoW2 is an external dependency of the reference;
+ *      its published arithmetic is restated: WordValue = double, TF-IDF weighting, L1 norm, L1 scoring.
+ *   vocabulary : nodes in breadth-first order, node 0 = root; children of node i are
+ *                h_child_ids[h_child_off[i] .. h_child_off[i+1]) (ids larger than i); per node a 256-bit
+ *                descriptor, a weight and (leaves) a word id.
+ *   transform  : per feature the word id, the word weight and the feature-vector node (the node reached at level
+ *                L - levels_up; the root when that is <= 0).
+ *   vector     : the keyframe's BowVector from those per-feature arrays: features with weight > 0 only, the value
+ *                of a word = its features' weights added in feature order, then divided by the sum of |value| taken
+ *                in ascending word order.  Output words ascending (std::map order); n <= 4096. */
 typedef struct sg_vocab sg_vocab;
 int sg_vocab_create(sg_ctx *ctx, const int32_t *h_child_off, const int32_t *h_child_ids, const uint32_t *h_node_desc,
-                    const float *h_node_weight, const int32_t *h_node_word, int n_nodes, int levels, sg_vocab **out);
+                    const double *h_node_weight, const int32_t *h_node_word, int n_nodes, int levels, sg_vocab **out);
 void sg_vocab_destroy(sg_vocab *vocab);
 int sg_bow_transform(sg_ctx *ctx, const sg_vocab *vocab, const uint32_t *h_desc, int n, int levels_up, int32_t *h_word,
-                     float *h_weight, int32_t *h_node);
+                     double *h_weight, int32_t *h_node);
 int sg_bow_transform_device(sg_ctx *ctx, const sg_vocab *vocab, const uint32_t *d_desc, int n, int levels_up,
-                            int32_t *d_word, float *d_weight, int32_t *d_node);
+                            int32_t *d_word, double *d_weight, int32_t *d_node);
+int sg_bow_vector(sg_ctx *ctx, const int32_t *h_word, const double *h_weight, int n, uint32_t *h_vec_word,
+                  double *h_vec_value, int *n_words);
+/* Device-resident BowVectors of up to max_keyframes keyframes (max_words_per_keyframe each), keyed by
+ * (map id, keyframe id) like the reference's MapKf.  add = BowIndex::add, remove = BowIndex::remove (unknown
+ * keyframe: no-op).  sg_bow_similar = getBowSimilar: every stored keyframe except (self_map, self_kf) that shares a
+ * word with the query is counted; those with more than (unsigned)(min_in_common_ratio * max count) common words are
+ * scored (DBoW2 L1 score of (query, stored), narrowed to float), sorted by descending score with std::sort from the
+ * (map id, keyframe id) order, and cut at the first score < best * score_ratio.  *n_out = number of results; the
+ * first min(*n_out, capacity) are written. */
+typedef struct sg_bowdb sg_bowdb;
+int sg_bowdb_create(sg_ctx *ctx, int max_keyframes, int max_words_per_keyframe, sg_bowdb **out);
+void sg_bowdb_destroy(sg_bowdb *db);
+int sg_bowdb_size(const sg_bowdb *db);
+int sg_bowdb_add(sg_ctx *ctx, sg_bowdb *db, int map_id, int kf_id, const uint32_t *h_vec_word, const double *h_vec_value,
+                 int n_words);
+int sg_bowdb_remove(sg_ctx *ctx, sg_bowdb *db, int map_id, int kf_id);
+int sg_bow_similar(sg_ctx *ctx, sg_bowdb *db, const uint32_t *h_q_word, const double *h_q_value, int nq, int self_map,
+                   int self_kf, float min_in_common_ratio, float score_ratio, int32_t *h_map, int32_t *h_kf, float *h_score,
+                   int capacity, int *n_out);
 
 /* ---- angle histogram: angle_checker<int> (openvslam/match_angle_checker.h:72-134) -----------
  * Test hook for the restated libstdc++ std::sort order of the 30 bins (host code, no GPU). */

@@ -22,7 +22,8 @@
  *     keyframe_matcher.cpp / feature_search.cpp / map_point.cpp; the reference has no vectors for them, so they are
  *     checked against plain-python restatements in tests/test_search.py only -- PARITY UNPINNED.  The epipolar test uses
  *     Eigen's summation order from memory (Eigen is not in the tree).
- *   - BoW transform: DBoW2 is an absent dependency; its published tree descent is restated -- PARITY UNPINNED.
+ *   - BoW transform / BowVector / L1 score / getBowSimilar: DBoW2 is an absent dependency; its published tree descent,
+ *     addWeight / normalize and L1Scoring::score are restated -- PARITY UNPINNED.
  */
 #ifndef ORB_ORACLE_H
 #define ORB_ORACLE_H
@@ -155,11 +156,19 @@ int orc_search_candidates(const float *kx, const float *ky, const int *koct, con
                           const uint32_t *qdesc, const int *q_pred_level, int nQ, int mode, unsigned thr,
                           int *out_idx, unsigned *out_dist);
 
-/* DBoW2 vocabulary-tree descent behind BowIndex::transform (bow_index.cpp:59-93); DBoW2 itself is absent: restated
- * from its published algorithm, parity unpinned.  See oracle/src/search.cpp. */
-void orc_bow_transform(const int *child_off, const int *child_ids, const uint32_t *node_desc, const float *node_weight,
+/* Bag of words behind BowIndex (bow_index.cpp:44-176); DBoW2 itself is absent: restated from its published
+ * algorithm, PARITY UNPINNED.  See oracle/src/bow.cpp. */
+void orc_bow_transform(const int *child_off, const int *child_ids, const uint32_t *node_desc, const double *node_weight,
                        const int *node_word, int n_nodes, int levels, const uint32_t *desc, int n, int levels_up,
-                       int *out_word, float *out_weight, int *out_node);
+                       int *out_word, double *out_weight, int *out_node);
+int orc_bow_vector(const int *word, const double *weight, int n, unsigned *out_word, double *out_value);
+void *orc_bowindex_create(int vocabulary_size);
+void orc_bowindex_destroy(void *index);
+void orc_bowindex_add(void *index, int map_id, int kf_id, const unsigned *word, const double *value, int n);
+void orc_bowindex_remove(void *index, int map_id, int kf_id);
+int orc_bowindex_similar(void *index, const unsigned *q_word, const double *q_value, int nq, int self_map, int self_kf,
+                         float bowMinInCommonRatio, float bowScoreRatio, int *out_map, int *out_kf, float *out_score,
+                         int capacity);
 
 double orc_bench_extract(const orc_params *p, const uint8_t *imgs, int n_frames, int threads, long *total_kp);
 double orc_bench_match(const uint32_t *desc, const float *ang, int n_sets, int n_per_set,

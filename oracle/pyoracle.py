@@ -345,12 +345,58 @@ def bow_transform(vocab, desc, levels_up=4):
     """vocab: dict(child_off, child_ids, node_desc, node_weight, node_word, levels) (see synth.random_vocabulary)."""
     desc = np.ascontiguousarray(desc, np.uint32).reshape(-1, 8)
     n = len(desc)
-    word = np.zeros(max(n, 1), np.int32); weight = np.zeros(max(n, 1), np.float32); node = np.zeros(max(n, 1), np.int32)
+    word = np.zeros(max(n, 1), np.int32); weight = np.zeros(max(n, 1), np.float64); node = np.zeros(max(n, 1), np.int32)
     vp = lambda a: C.c_void_p(a.ctypes.data)
-    lib().orc_bow_transform(vp(vocab["child_off"]), vp(vocab["child_ids"]), vp(vocab["node_desc"]), vp(vocab["node_weight"]),
+    nw = np.ascontiguousarray(vocab["node_weight"], np.float64)
+    lib().orc_bow_transform(vp(vocab["child_off"]), vp(vocab["child_ids"]), vp(vocab["node_desc"]), vp(nw),
                             vp(vocab["node_word"]), len(vocab["node_word"]), int(vocab["levels"]), vp(desc), n, int(levels_up),
                             vp(word), vp(weight), vp(node))
     return word[:n], weight[:n], node[:n]
+
+def bow_vector(word, weight):
+    """DBoW2 BowVector of one keyframe (addWeight in feature order, L1 normalise) -> (words ascending, values)."""
+    word = np.ascontiguousarray(word, np.int32); weight = np.ascontiguousarray(weight, np.float64)
+    n = len(word)
+    vw = np.zeros(max(n, 1), np.uint32); vv = np.zeros(max(n, 1), np.float64)
+    L = lib()
+    L.orc_bow_vector.restype = C.c_int
+    k = L.orc_bow_vector(C.c_void_p(word.ctypes.data), C.c_void_p(weight.ctypes.data), n, C.c_void_p(vw.ctypes.data),
+                         C.c_void_p(vv.ctypes.data))
+    return vw[:k].copy(), vv[:k].copy()
+
+
+class BowIndex:
+    """Restatement of BowIndex (bow_index.cpp:31-57, 95-176): inverted lists + getBowSimilar."""
+
+    def __init__(self, vocabulary_size):
+        L = lib()
+        L.orc_bowindex_create.restype = C.c_void_p
+        L.orc_bowindex_similar.restype = C.c_int
+        self._h = C.c_void_p(L.orc_bowindex_create(int(vocabulary_size)))
+        self.n = 0
+
+    def add(self, map_id, kf_id, vec_word, vec_value):
+        vw = np.ascontiguousarray(vec_word, np.uint32); vv = np.ascontiguousarray(vec_value, np.float64)
+        lib().orc_bowindex_add(self._h, int(map_id), int(kf_id), C.c_void_p(vw.ctypes.data), C.c_void_p(vv.ctypes.data), len(vw))
+        self.n += 1
+
+    def remove(self, map_id, kf_id):
+        lib().orc_bowindex_remove(self._h, int(map_id), int(kf_id))
+
+    def similar(self, vec_word, vec_value, self_key=(-1, -1), min_in_common_ratio=0.8, score_ratio=0.75):
+        vw = np.ascontiguousarray(vec_word, np.uint32); vv = np.ascontiguousarray(vec_value, np.float64)
+        cap = max(self.n, 1)
+        om = np.zeros(cap, np.int32); ok = np.zeros(cap, np.int32); osc = np.zeros(cap, np.float32)
+        k = lib().orc_bowindex_similar(self._h, C.c_void_p(vw.ctypes.data), C.c_void_p(vv.ctypes.data), len(vw), int(self_key[0]),
+                                       int(self_key[1]), C.c_float(min_in_common_ratio), C.c_float(score_ratio),
+                                       C.c_void_p(om.ctypes.data), C.c_void_p(ok.ctypes.data), C.c_void_p(osc.ctypes.data), cap)
+        k = min(k, cap)
+        return om[:k].copy(), ok[:k].copy(), osc[:k].copy()
+
+    def close(self):
+        if self._h:
+            lib().orc_bowindex_destroy(self._h)
+            self._h = None
 
 
 def bench_extract(p, imgs, threads):

@@ -121,35 +121,3 @@ extern "C" int orc_search_candidates(const float *kx, const float *ky, const int
     }
     return count;
 }
-
-// ---- BoW transform ---------------------------------------------------------------------------
-// bow_index.cpp:59-93 calls DBoW2's TemplatedVocabulary<ORB>::transform(features, bowVector, featureVector, levelsUp = 4).
-// DBoW2 is an un-vendored dependency of the reference (absent from /root/reference, version unpinned): this restates
-// its published per-feature descent -- PARITY UNPINNED.  From the root, at every level take the child with the
-// smallest Hamming distance (strict '<': the first child wins ties) until a leaf; the word is the leaf's word id and
-// weight; the feature-vector node is the node reached at level L - levelsUp (the root when that is <= 0).
-// Tree: children of node i are child_ids[child_off[i] .. child_off[i+1]); a leaf has none.
-extern "C" void orc_bow_transform(const int *child_off, const int *child_ids, const uint32_t *node_desc, const float *node_weight,
-                                  const int *node_word, int n_nodes, int levels, const uint32_t *desc, int n, int levels_up,
-                                  int *out_word, float *out_weight, int *out_node) {
-    (void)n_nodes;
-    const int nid_level = levels - levels_up;
-    for (int f = 0; f < n; ++f) {
-        int cur = 0, level = 0, nid = 0;
-        while (child_off[cur + 1] > child_off[cur]) {
-            ++level;
-            const int b = child_off[cur], e = child_off[cur + 1];
-            int best = child_ids[b];
-            unsigned best_d = orc_hamming(desc + 8 * f, node_desc + 8 * (size_t)best);
-            for (int c = b + 1; c < e; ++c) {
-                const unsigned d = orc_hamming(desc + 8 * f, node_desc + 8 * (size_t)child_ids[c]);
-                if (d < best_d) { best_d = d; best = child_ids[c]; }
-            }
-            cur = best;
-            if (level == nid_level) nid = cur;
-        }
-        out_word[f] = node_word[cur];
-        out_weight[f] = node_weight[cur];
-        out_node[f] = nid_level <= 0 ? 0 : nid;
-    }
-}

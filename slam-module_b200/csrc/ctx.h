@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <algorithm>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -199,6 +200,25 @@ int launch_detect(sg_ctx *ctx, int n_frames);
 int launch_describe(sg_ctx *ctx, int n_frames);
 void describe_box_dims(int *mom_w, int *mom_h, int *blur_w, int *blur_h);
 int grow(sg_ctx *ctx, void **ptr, size_t *cap, size_t need, size_t elem);
+// Device scratch carved from the context's grow-only buffer (no cudaMalloc / cudaFree per call).
+struct Scratch {
+    sg_ctx *ctx;
+    size_t need = 0, at = 0;
+    explicit Scratch(sg_ctx *c) : ctx(c) {}
+    static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+    void want(size_t bytes) { need += pad(std::max<size_t>(bytes, 1)); }
+    int commit() { return grow(ctx, &ctx->d_tmp, &ctx->tmp_bytes, need, 1); }
+    template <class T> T *take(size_t n) {
+        T *p = reinterpret_cast<T *>(static_cast<uint8_t *>(ctx->d_tmp) + at);
+        at += pad(std::max<size_t>(n * sizeof(T), 1));
+        return p;
+    }
+    template <class T> int put(T **d, const T *h, size_t n) {
+        *d = take<T>(n);
+        if (n) SG_CUDA(ctx, cudaMemcpyAsync(*d, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        return SG_OK;
+    }
+};
 // TMA descriptor of an 8-bit plane stack {w, h, frames} with a fixed box (tma.cpp).
 int encode_plane_map(sg_ctx *ctx, CUtensorMap *out, const uint8_t *base, int w, int h, int pitch, size_t frame_stride,
                      int frames, int box_w, int box_h);

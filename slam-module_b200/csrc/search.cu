@@ -302,69 +302,6 @@ medoid_kernel(const uint32_t *desc, const long long *offsets, int *best_out) {
     }
 }
 
-// ---- BoW transform: DBoW2 vocabulary-tree descent (bow_index.cpp:59-93 -> TemplatedVocabulary::transform) ---------
-// One warp per feature: at every level the lanes take the children of the current node (32 at a time), each computes
-// one Hamming distance, the warp minimum of (distance << 16 | child position) picks the nearest child with DBoW2's
-// tie rule (strict '<': the first child wins).  The word is the leaf's; the feature-vector node is the one reached at
-// level L - levelsUp.
-struct VocabDev {
-    const int *child_off, *child_ids, *node_word;
-    const uint32_t *node_desc;
-    const float *node_weight;
-    int levels;
-};
-
-__global__ void __launch_bounds__(SEARCH_WARPS * 32)
-bow_transform_kernel(const VocabDev v, const uint32_t *desc, int n, int levels_up, int *out_word, float *out_weight, int *out_node) {
-    const int lane = threadIdx.x & 31, f = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5);
-    if (f >= n) return;
-    uint32_t d[8];
-#pragma unroll
-    for (int w = 0; w < 8; ++w) d[w] = __ldg(desc + 8 * (size_t)f + w);
-    const int nid_level = v.levels - levels_up;
-    int cur = 0, level = 0, nid = 0;
-    while (true) {
-        const int b = __ldg(v.child_off + cur), e = __ldg(v.child_off + cur + 1);
-        if (e <= b) break;
-        ++level;
-        unsigned best = 0xffffffffu;
-        for (int c0 = b; c0 < e; c0 += 32) {          // position inside the child list orders the ties
-            const int c = c0 + lane;
-            unsigned key = 0xffffffffu;
-            if (c < e) key = (hamming8(d, v.node_desc + 8 * (size_t)__ldg(v.child_ids + c)) << 16) | (unsigned)min(c - b, 0xffff);
-            best = min(best, __reduce_min_sync(0xffffffffu, key));
-        }
-        cur = __ldg(v.child_ids + b + (int)(best & 0xffffu));
-        if (level == nid_level) nid = cur;
-    }
-    if (lane == 0) {
-        out_word[f] = v.node_word[cur];
-        out_weight[f] = v.node_weight[cur];
-        out_node[f] = nid_level <= 0 ? 0 : nid;
-    }
-}
-
-// ---- host side ----------------------------------------------------------------------------------------------
-// Device scratch carved from the context's grow-only buffer (no cudaMalloc / cudaFree per call).
-struct Scratch {
-    sg_ctx *ctx;
-    size_t need = 0, at = 0;
-    explicit Scratch(sg_ctx *c) : ctx(c) {}
-    static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
-    void want(size_t bytes) { need += pad(std::max<size_t>(bytes, 1)); }
-    int commit() { return grow(ctx, &ctx->d_tmp, &ctx->tmp_bytes, need, 1); }
-    template <class T> T *take(size_t n) {
-        T *p = reinterpret_cast<T *>(static_cast<uint8_t *>(ctx->d_tmp) + at);
-        at += pad(std::max<size_t>(n * sizeof(T), 1));
-        return p;
-    }
-    template <class T> int put(T **d, const T *h, size_t n) {
-        *d = take<T>(n);
-        if (n) SG_CUDA(ctx, cudaMemcpyAsync(*d, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-        return SG_OK;
-    }
-};
-
 }  // namespace sg
 
 using namespace sg;
@@ -476,88 +413,4 @@ extern "C" int sg_feature_index(const float *h_x, const float *h_y, int n, int32
     std::sort(v.begin(), v.end(), [](const Node &a, const Node &b) { return a.y < b.y; });
     for (int i = 0; i < n; ++i) h_order[i] = v[i].idx;
     return SG_OK;
-}
-
-struct sg_vocab {
-    sg_ctx *ctx = nullptr;
-    int *child_off = nullptr, *child_ids = nullptr, *node_word = nullptr;
-    uint32_t *node_desc = nullptr;
-    float *node_weight = nullptr;
-    int n_nodes = 0, levels = 0;
-};
-
-extern "C" void sg_vocab_destroy(sg_vocab *v) {
-    if (!v) return;
-    if (v->ctx) cudaSetDevice(v->ctx->device);
-    cudaFree(v->child_off); cudaFree(v->child_ids); cudaFree(v->node_word); cudaFree(v->node_desc); cudaFree(v->node_weight);
-    delete v;
-}
-
-extern "C" int sg_vocab_create(sg_ctx *ctx, const int32_t *h_child_off, const int32_t *h_child_ids, const uint32_t *h_node_desc,
-                               const float *h_node_weight, const int32_t *h_node_word, int n_nodes, int levels, sg_vocab **out) {
-    cudaSetDevice(ctx->device);
-    if (!h_child_off || !h_node_desc || !h_node_weight || !h_node_word || n_nodes < 1 || levels < 0 || !out)
-        return fail(ctx, SG_ERR_INVALID, "null / empty vocabulary");
-    const int n_children = h_child_off[n_nodes];
-    if (h_child_off[0] != 0 || n_children < 0 || (n_children && !h_child_ids)) return fail(ctx, SG_ERR_INVALID, "bad child offsets");
-    for (int i = 0; i < n_nodes; ++i) {
-        if (h_child_off[i + 1] < h_child_off[i]) return fail(ctx, SG_ERR_INVALID, "child offsets must be non-decreasing");
-        if (h_child_off[i + 1] - h_child_off[i] > 65535) return fail(ctx, SG_ERR_INVALID, "more than 65535 children under one node");
-    }
-    for (int c = 0; c < n_children; ++c)   // a child id must be a later node: the descent then terminates on any input
-        if (h_child_ids[c] <= 0 || h_child_ids[c] >= n_nodes) return fail(ctx, SG_ERR_INVALID, "child id %d outside the tree", h_child_ids[c]);
-    for (int i = 0; i < n_nodes; ++i)
-        for (int c = h_child_off[i]; c < h_child_off[i + 1]; ++c)
-            if (h_child_ids[c] <= i) return fail(ctx, SG_ERR_INVALID, "node %d lists child %d: children must have larger ids than their parent", i, h_child_ids[c]);
-    sg_vocab *v = new sg_vocab();
-    v->ctx = ctx; v->n_nodes = n_nodes; v->levels = levels;
-    auto put = [&](auto **d, const auto *h, size_t n) -> bool {
-        if (cudaMalloc((void **)d, std::max<size_t>(n, 1) * sizeof(**d)) != cudaSuccess) return false;
-        return n == 0 || cudaMemcpy(*d, h, n * sizeof(**d), cudaMemcpyHostToDevice) == cudaSuccess;
-    };
-    if (!put(&v->child_off, h_child_off, (size_t)n_nodes + 1) || !put(&v->child_ids, h_child_ids, (size_t)n_children)
-        || !put(&v->node_desc, h_node_desc, 8 * (size_t)n_nodes) || !put(&v->node_weight, h_node_weight, (size_t)n_nodes)
-        || !put(&v->node_word, h_node_word, (size_t)n_nodes)) {
-        sg_vocab_destroy(v);
-        return fail(ctx, SG_ERR_CUDA, "vocabulary upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-    }
-    *out = v;
-    return SG_OK;
-}
-
-static int bow_launch(sg_ctx *ctx, const sg_vocab *v, const uint32_t *d_desc, int n, int levels_up, int *d_word, float *d_weight, int *d_node) {
-    VocabDev dv{v->child_off, v->child_ids, v->node_word, v->node_desc, v->node_weight, v->levels};
-    bow_transform_kernel<<<(n + SEARCH_WARPS - 1) / SEARCH_WARPS, SEARCH_WARPS * 32, 0, ctx->stream>>>(dv, d_desc, n, levels_up, d_word, d_weight, d_node);
-    SG_LAUNCH_CHECK(ctx);
-    return SG_OK;
-}
-
-extern "C" int sg_bow_transform(sg_ctx *ctx, const sg_vocab *vocab, const uint32_t *h_desc, int n, int levels_up, int32_t *h_word,
-                                float *h_weight, int32_t *h_node) {
-    cudaSetDevice(ctx->device);
-    if (n <= 0) return SG_OK;
-    if (!vocab || !h_desc || !h_word || !h_weight || !h_node) return fail(ctx, SG_ERR_INVALID, "null argument");
-    Scratch sc(ctx);
-    sc.want(32 * (size_t)n); sc.want(4 * (size_t)n); sc.want(4 * (size_t)n); sc.want(4 * (size_t)n);
-    if (int r = sc.commit()) return r;
-    uint32_t *d_desc;
-    if (int r = sc.put(&d_desc, h_desc, 8 * (size_t)n)) return r;
-    int *d_word = sc.take<int>(n);
-    float *d_weight = sc.take<float>(n);
-    int *d_node = sc.take<int>(n);
-    if (int r = bow_launch(ctx, vocab, d_desc, n, levels_up, d_word, d_weight, d_node)) return r;
-    SG_CUDA(ctx, cudaMemcpyAsync(h_word, d_word, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    SG_CUDA(ctx, cudaMemcpyAsync(h_weight, d_weight, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    SG_CUDA(ctx, cudaMemcpyAsync(h_node, d_node, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return SG_OK;
-}
-
-// Device-resident form: descriptors already on the device (e.g. sg_extract_device_views), results stay there.
-extern "C" int sg_bow_transform_device(sg_ctx *ctx, const sg_vocab *vocab, const uint32_t *d_desc, int n, int levels_up,
-                                       int32_t *d_word, float *d_weight, int32_t *d_node) {
-    cudaSetDevice(ctx->device);
-    if (n <= 0) return SG_OK;
-    if (!vocab || !d_desc || !d_word || !d_weight || !d_node) return fail(ctx, SG_ERR_INVALID, "null argument");
-    return bow_launch(ctx, vocab, d_desc, n, levels_up, d_word, d_weight, d_node);
 }

@@ -64,6 +64,8 @@ struct ParametersSlam {
     std::string slamFeatureDetector = "FAST"; // feature_detector.cpp:38-41
     float loopClosureFeatureMatchLoweRatio = 0.8f;     // keyframe_matcher.cpp:120
     bool requireTringulationForLoopClosures = true;    // keyframe_matcher.cpp:82 (sic)
+    float bowMinInCommonRatio = 0.8f;         // bow_index.cpp:144
+    float bowScoreRatio = 0.75f;              // bow_index.cpp:170
     // upstream OpenVSLAM FAST thresholds of the detector the north star names
     int orbIniFastThreshold = 20, orbMinFastThreshold = 7;
     // batch geometry of the CUDA context (not in the reference: it handles one frame per call)

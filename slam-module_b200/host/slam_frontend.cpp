@@ -409,6 +409,76 @@ unsigned int bruteForceMatch(const KeyPointVector &kps1, const KeyPointVector &k
     return matchSubset(kps1, idx1, kps2, idx2, matches, loweRatio, checkOrientation, ctx);
 }
 
+// ---- BowIndex (bow_index.cpp:31-188) ----------------------------------------------------------------------
+bool operator==(const MapKf &lhs, const MapKf &rhs) { return lhs.mapId.v == rhs.mapId.v && lhs.kfId.v == rhs.kfId.v; }
+bool operator<(const MapKf &lhs, const MapKf &rhs) {
+    if (lhs.mapId.v == rhs.mapId.v) return lhs.kfId.v < rhs.kfId.v;
+    return lhs.mapId.v < rhs.mapId.v;
+}
+
+BowIndex::BowIndex(const odometry::ParametersSlam &p, const BowVocabulary &v, sg_ctx *c, int maxKeyframes)
+    : parameters(p), ctx(c), capacity(maxKeyframes) {
+    assert(!v.nodeWord.empty() && v.childOff.size() == v.nodeWord.size() + 1);
+    SG_CHECK(ctx, sg_vocab_create(ctx, v.childOff.data(), v.childIds.data(), v.nodeDescriptor.data(), v.nodeWeight.data(),
+                                  v.nodeWord.data(), (int)v.nodeWord.size(), v.levels, &vocab));
+    SG_CHECK(ctx, sg_bowdb_create(ctx, maxKeyframes, 4096, &db));
+}
+
+BowIndex::~BowIndex() {
+    sg_bowdb_destroy(db);
+    sg_vocab_destroy(vocab);
+}
+
+namespace {
+void flatten(const DBoW2::BowVector &v, std::vector<std::uint32_t> &words, std::vector<double> &values) {
+    words.clear(); values.clear();
+    for (const auto &e : v) { words.push_back(e.first); values.push_back(e.second); }
+}
+}  // namespace
+
+void BowIndex::add(const Keyframe &keyframe, MapId mapId) {
+    std::vector<std::uint32_t> words;
+    std::vector<double> values;
+    flatten(keyframe.shared->bowVec, words, values);
+    SG_CHECK(ctx, sg_bowdb_add(ctx, db, mapId.v, keyframe.id.v, words.data(), values.data(), (int)words.size()));
+}
+
+void BowIndex::remove(MapKf mapKf) { SG_CHECK(ctx, sg_bowdb_remove(ctx, db, mapKf.mapId.v, mapKf.kfId.v)); }
+
+void BowIndex::transform(const KeyPointVector &keypoints, DBoW2::BowVector &bowVector, DBoW2::FeatureVector &bowFeatureVector) {
+    bowVector.clear();
+    bowFeatureVector.clear();
+    const int n = (int)keypoints.size();
+    if (n == 0) return;
+    std::vector<std::uint32_t> desc(8 * (size_t)n), vecWord(n);
+    std::vector<std::int32_t> word(n), node(n);
+    std::vector<double> weight(n), vecValue(n);
+    for (int i = 0; i < n; ++i) std::memcpy(&desc[8 * (size_t)i], keypoints[i].descriptor.data(), 32);
+    const int levelsUp = 4;                                                         // bow_index.cpp:85
+    SG_CHECK(ctx, sg_bow_transform(ctx, vocab, desc.data(), n, levelsUp, word.data(), weight.data(), node.data()));
+    int nWords = 0;
+    SG_CHECK(ctx, sg_bow_vector(ctx, word.data(), weight.data(), n, vecWord.data(), vecValue.data(), &nWords));
+    for (int i = 0; i < nWords; ++i) bowVector.emplace_hint(bowVector.end(), vecWord[i], vecValue[i]);
+    for (int i = 0; i < n; ++i)                                                      // fv.addFeature(nid, i_feature), w > 0 only
+        if (weight[i] > 0) bowFeatureVector[(unsigned)node[i]].push_back((unsigned)i);
+}
+
+std::vector<BowSimilar> BowIndex::getBowSimilar(const MapDB &, const Atlas &, const Keyframe &kf) {
+    std::vector<std::uint32_t> words;
+    std::vector<double> values;
+    flatten(kf.shared->bowVec, words, values);
+    const int cap = std::max(sg_bowdb_size(db), 1);
+    std::vector<std::int32_t> maps(cap), kfs(cap);
+    std::vector<float> scores(cap);
+    int n = 0;
+    SG_CHECK(ctx, sg_bow_similar(ctx, db, words.data(), values.data(), (int)words.size(), CURRENT_MAP_ID, kf.id.v,
+                                 parameters.bowMinInCommonRatio, parameters.bowScoreRatio, maps.data(), kfs.data(), scores.data(),
+                                 cap, &n));
+    std::vector<BowSimilar> similar((size_t)n);
+    for (int i = 0; i < n; ++i) { similar[i].mapKf.mapId.v = maps[i]; similar[i].mapKf.kfId.v = kfs[i]; similar[i].score = scores[i]; }
+    return similar;
+}
+
 namespace match {
 void compute_descriptor_distance_32(const std::uint32_t *desc_1, const std::uint32_t *desc_2, int n, unsigned int *out,
                                     sg_ctx *ctx) {

@@ -15,6 +15,8 @@
 #include "compat.hpp"
 
 struct sg_ctx;
+struct sg_vocab;
+struct sg_bowdb;
 
 namespace slam {
 
@@ -105,11 +107,19 @@ constexpr unsigned int MAX_HAMMING_DIST = 256;
 // keypoints with descriptors and angles, the map point id of every keypoint and its status.
 enum class MapPointStatus { NOT_TRIANGULATED, TRIANGULATED, BAD };
 struct MpId { int v = -1; };
+struct KfId { int v = -1; };    // id.hpp:48-51
+struct MapId { int v = -1; };
 struct MapPoint { MapPointStatus status = MapPointStatus::NOT_TRIANGULATED; };
 struct MapDB { std::vector<MapPoint> mapPoints; };   // indexed by MpId::v
 // bowFeatureVec: DBoW2::FeatureVector = std::map<NodeId, std::vector<unsigned>> (keyframe.hpp, bow_index.cpp:59-93)
-struct KeyframeShared { KeyPointVector keyPoints; std::map<unsigned, std::vector<unsigned>> bowFeatureVec; };
+// bowVec: DBoW2::BowVector = std::map<WordId, WordValue (double)>
+struct KeyframeShared {
+    KeyPointVector keyPoints;
+    std::map<unsigned, double> bowVec;
+    std::map<unsigned, std::vector<unsigned>> bowFeatureVec;
+};
 struct Keyframe {
+    KfId id;
     std::shared_ptr<KeyframeShared> shared;
     std::vector<MpId> mapPoints;   // per keypoint, v == -1: none
 };
@@ -125,6 +135,51 @@ unsigned int matchForLoopClosures(const Keyframe &kf1, const Keyframe &kf2, cons
 /** The same loop on bare keypoint vectors (every feature eligible). */
 unsigned int bruteForceMatch(const KeyPointVector &kps1, const KeyPointVector &kps2, std::vector<int> &matches,
                              float loweRatio, bool checkOrientation, sg_ctx *ctx);
+
+// ---- bag of words (bow_index.hpp:21-65) ---------------------------------------------------------------
+namespace DBoW2 {
+using BowVector = std::map<unsigned, double>;                       // WordId -> WordValue
+using FeatureVector = std::map<unsigned, std::vector<unsigned>>;    // NodeId -> feature indices
+}  // namespace DBoW2
+using Atlas = std::vector<MapDB>;
+struct MapKf { MapId mapId; KfId kfId; };
+bool operator==(const MapKf &lhs, const MapKf &rhs);
+bool operator<(const MapKf &lhs, const MapKf &rhs);
+struct BowSimilar { MapKf mapKf; float score; };
+
+/** The loaded DBoW2 vocabulary tree, flattened: node 0 = root, the children of node i are
+ *  childIds[childOff[i] .. childOff[i+1]) (breadth first, larger ids than i). */
+struct BowVocabulary {
+    std::vector<std::int32_t> childOff, childIds, nodeWord;
+    std::vector<std::uint32_t> nodeDescriptor;   // 8 words per node
+    std::vector<double> nodeWeight;
+    int levels = 0;
+};
+
+/** bow_index.hpp:36-63 on the GPU: the vocabulary and every added keyframe's BowVector live on the device. */
+class BowIndex {
+public:
+    BowIndex(const odometry::ParametersSlam &parameters, const BowVocabulary &vocabulary, sg_ctx *ctx, int maxKeyframes = 16384);
+    ~BowIndex();
+    BowIndex(const BowIndex &) = delete;
+    BowIndex &operator=(const BowIndex &) = delete;
+
+    void add(const Keyframe &keyframe, MapId mapId);
+    void remove(MapKf mapKf);
+    void transform(const KeyPointVector &keypoints, DBoW2::BowVector &bowVector, DBoW2::FeatureVector &bowFeatureVector);
+    /** Keyframes similar to `kf` (its shared->bowVec), best first; `kf` itself is taken as MapKf{CURRENT_MAP_ID, kf.id}.
+     *  mapDB / atlas are not read: the stored BowVectors are the device copies made by add(). */
+    std::vector<BowSimilar> getBowSimilar(const MapDB &mapDB, const Atlas &atlas, const Keyframe &kf);
+
+    static constexpr int CURRENT_MAP_ID = 0;
+
+private:
+    const odometry::ParametersSlam &parameters;
+    sg_ctx *ctx;
+    ::sg_vocab *vocab = nullptr;
+    ::sg_bowdb *db = nullptr;
+    int capacity;
+};
 
 namespace match {
 /** openvslam/match_base.h:18-39, evaluated on the GPU for n descriptor pairs. */

@@ -67,7 +67,8 @@ ABI_SYMBOLS = [
     "sg_memcpy_h2d", "sg_memcpy_d2h", "sg_host_alloc_pinned", "sg_host_free_pinned", "sg_timer_start",
     "sg_timer_stop", "sg_flush_l2", "sg_microbench_popc", "sg_set_profiling", "sg_get_stage_ms",
     "sg_set_pipeline_chunk", "sg_search_candidates", "sg_feature_index", "sg_medoid", "sg_set_overlap", "sg_match_bow", "sg_vocab_create", "sg_vocab_destroy",
-    "sg_bow_transform", "sg_bow_transform_device", "sg_match_triangulation",
+    "sg_bow_transform", "sg_bow_transform_device", "sg_match_triangulation", "sg_bow_vector", "sg_bowdb_create",
+    "sg_bowdb_destroy", "sg_bowdb_size", "sg_bowdb_add", "sg_bowdb_remove", "sg_bow_similar",
 ]
 
 _lib = None
@@ -155,6 +156,21 @@ def lib():
         L.sg_bow_transform.restype = C.c_int
         L.sg_bow_transform_device.argtypes = L.sg_bow_transform.argtypes
         L.sg_bow_transform_device.restype = C.c_int
+        L.sg_bow_vector.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sg_bow_vector.restype = C.c_int
+        L.sg_bowdb_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.sg_bowdb_create.restype = C.c_int
+        L.sg_bowdb_destroy.argtypes = [C.c_void_p]
+        L.sg_bowdb_destroy.restype = None
+        L.sg_bowdb_size.argtypes = [C.c_void_p]
+        L.sg_bowdb_size.restype = C.c_int
+        L.sg_bowdb_add.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.sg_bowdb_add.restype = C.c_int
+        L.sg_bowdb_remove.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.sg_bowdb_remove.restype = C.c_int
+        L.sg_bow_similar.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sg_bow_similar.restype = C.c_int
         L.sg_detect.argtypes = [C.c_void_p]
         L.sg_keypoint_capacity.argtypes = [C.c_void_p]
         L.sg_microbench_popc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -578,7 +594,7 @@ class Vocabulary:
     def __init__(self, ctx, vocab):
         self.ctx = ctx
         a = {k: np.ascontiguousarray(vocab[k], t) for k, t in (("child_off", np.int32), ("child_ids", np.int32),
-             ("node_desc", np.uint32), ("node_weight", np.float32), ("node_word", np.int32))}
+             ("node_desc", np.uint32), ("node_weight", np.float64), ("node_word", np.int32))}
         h = C.c_void_p()
         ctx._check(lib().sg_vocab_create(ctx._h, a["child_off"].ctypes.data, a["child_ids"].ctypes.data, a["node_desc"].ctypes.data,
                                          a["node_weight"].ctypes.data, a["node_word"].ctypes.data, len(a["node_word"]),
@@ -588,14 +604,59 @@ class Vocabulary:
     def transform(self, desc, levels_up=4):
         desc = np.ascontiguousarray(desc, np.uint32).reshape(-1, 8)
         n = len(desc)
-        word = np.empty(max(n, 1), np.int32); weight = np.empty(max(n, 1), np.float32); node = np.empty(max(n, 1), np.int32)
+        word = np.empty(max(n, 1), np.int32); weight = np.empty(max(n, 1), np.float64); node = np.empty(max(n, 1), np.int32)
         self.ctx._check(lib().sg_bow_transform(self.ctx._h, self._h, desc.ctypes.data, n, int(levels_up), word.ctypes.data,
                                                weight.ctypes.data, node.ctypes.data))
         return word[:n], weight[:n], node[:n]
 
+    def bow_vector(self, word, weight):
+        """BowVector (ascending words, L1-normalised double values) from the per-feature output of transform()."""
+        word = np.ascontiguousarray(word, np.int32); weight = np.ascontiguousarray(weight, np.float64)
+        n = len(word)
+        vw = np.empty(max(n, 1), np.uint32); vv = np.empty(max(n, 1), np.float64); k = C.c_int(0)
+        self.ctx._check(lib().sg_bow_vector(self.ctx._h, word.ctypes.data, weight.ctypes.data, n, vw.ctypes.data, vv.ctypes.data,
+                                            C.byref(k)))
+        return vw[:k.value].copy(), vv[:k.value].copy()
+
     def close(self):
         if self._h:
             lib().sg_vocab_destroy(self._h)
+            self._h = None
+
+
+class BowDatabase:
+    """Device-resident BowVectors of the keyframes (BowIndex::add / remove / getBowSimilar, bow_index.cpp:44-176)."""
+
+    def __init__(self, ctx, max_keyframes, max_words_per_keyframe=2048):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._check(lib().sg_bowdb_create(ctx._h, int(max_keyframes), int(max_words_per_keyframe), C.byref(h)))
+        self._h = h
+
+    def __len__(self):
+        return int(lib().sg_bowdb_size(self._h))
+
+    def add(self, map_id, kf_id, vec_word, vec_value):
+        vw = np.ascontiguousarray(vec_word, np.uint32); vv = np.ascontiguousarray(vec_value, np.float64)
+        self.ctx._check(lib().sg_bowdb_add(self.ctx._h, self._h, int(map_id), int(kf_id), vw.ctypes.data, vv.ctypes.data, len(vw)))
+
+    def remove(self, map_id, kf_id):
+        self.ctx._check(lib().sg_bowdb_remove(self.ctx._h, self._h, int(map_id), int(kf_id)))
+
+    def similar(self, vec_word, vec_value, self_key=(-1, -1), min_in_common_ratio=0.8, score_ratio=0.75, capacity=None):
+        """-> (map ids, keyframe ids, scores), best first."""
+        vw = np.ascontiguousarray(vec_word, np.uint32); vv = np.ascontiguousarray(vec_value, np.float64)
+        cap = max(len(self), 1) if capacity is None else int(capacity)
+        om = np.empty(cap, np.int32); ok = np.empty(cap, np.int32); osc = np.empty(cap, np.float32); n = C.c_int(0)
+        self.ctx._check(lib().sg_bow_similar(self.ctx._h, self._h, vw.ctypes.data, vv.ctypes.data, len(vw), int(self_key[0]),
+                                             int(self_key[1]), C.c_float(min_in_common_ratio), C.c_float(score_ratio),
+                                             om.ctypes.data, ok.ctypes.data, osc.ctypes.data, cap, C.byref(n)))
+        k = min(n.value, cap)
+        return om[:k].copy(), ok[:k].copy(), osc[:k].copy()
+
+    def close(self):
+        if self._h:
+            lib().sg_bowdb_destroy(self._h)
             self._h = None
 
 

@@ -120,6 +120,24 @@ def random_vocabulary(branching, levels, seed, ragged=False):
     is_leaf = np.diff(child_off) == 0
     word = np.full(n, -1, np.int32)
     word[is_leaf] = np.arange(int(is_leaf.sum()), dtype=np.int32)
-    weight = np.where(is_leaf, rng.uniform(0.1, 5.0, n), 0.0).astype(np.float32)
+    weight = np.where(is_leaf, rng.uniform(0.1, 5.0, n), 0.0).astype(np.float64)
+    weight[is_leaf & (rng.random(n) < 0.03)] = 0.0         # "stopped" words: DBoW2 skips features with weight 0
     return dict(child_off=child_off, child_ids=np.asarray(child_ids, np.int32), node_desc=np.stack(desc).astype(np.uint32),
                 node_weight=weight, node_word=word, levels=levels)
+
+
+def random_bow_vectors(n_keyframes, vocabulary_size, words_per_keyframe, seed, n_topics=12):
+    """Sparse L1-normalised BowVectors for database tests / benches: every keyframe draws most of its words from one
+    of `n_topics` overlapping word pools (so that keyframes of a topic share many words) plus uniform noise words.
+    -> list of (words ascending uint32, values float64)."""
+    rng = np.random.default_rng(seed)
+    pools = [rng.choice(vocabulary_size, min(vocabulary_size, 3 * words_per_keyframe), replace=False) for _ in range(n_topics)]
+    out = []
+    for _ in range(n_keyframes):
+        pool = pools[int(rng.integers(0, n_topics))]
+        k = int(rng.integers(max(1, words_per_keyframe // 2), words_per_keyframe + 1))
+        w = np.unique(np.concatenate([rng.choice(pool, min(len(pool), k), replace=False),
+                                      rng.integers(0, vocabulary_size, max(1, k // 8))])).astype(np.uint32)
+        v = rng.uniform(0.1, 5.0, len(w)) * rng.integers(1, 4, len(w))
+        out.append((w, (v / np.abs(v).sum()).astype(np.float64)))
+    return out

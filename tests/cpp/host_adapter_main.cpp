@@ -21,6 +21,16 @@ static std::vector<std::uint8_t> readRaw(const char *path, size_t n) {
     return v;
 }
 template <class T>
+static std::vector<T> readAll(const std::string &path) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) return {};
+    const std::streamsize bytes = f.tellg();
+    f.seekg(0);
+    std::vector<T> v((size_t)bytes / sizeof(T));
+    f.read(reinterpret_cast<char *>(v.data()), bytes);
+    return v;
+}
+template <class T>
 static void dump(const std::string &path, const std::vector<T> &v) {
     std::ofstream f(path, std::ios::binary);
     f.write(reinterpret_cast<const char *>(v.data()), (std::streamsize)(v.size() * sizeof(T)));
@@ -159,6 +169,53 @@ int main(int argc, char **argv) {
     }
     match::compute_descriptor_distance_32(da.data(), dbv.data(), (int)dist.size(), dist.data(), cudaContext(fe));
     dump(out + "/hamming.u32", std::vector<std::uint32_t>(dist.begin(), dist.end()));
+    // ---- BowIndex: transform / add / remove / getBowSimilar with the vocabulary the test wrote (bow_index.hpp) ----
+    BowVocabulary voc;
+    voc.childOff = readAll<std::int32_t>(out + "/voc_child_off.i32");
+    if (!voc.childOff.empty()) {
+        voc.childIds = readAll<std::int32_t>(out + "/voc_child_ids.i32");
+        voc.nodeWord = readAll<std::int32_t>(out + "/voc_node_word.i32");
+        voc.nodeDescriptor = readAll<std::uint32_t>(out + "/voc_node_desc.u32");
+        voc.nodeWeight = readAll<double>(out + "/voc_node_weight.f64");
+        voc.levels = readAll<std::int32_t>(out + "/voc_levels.i32").at(0);
+        BowIndex bow(params.slam, voc, cudaContext(fe), 64);
+        // keyframes 1..8: A, B, B again (a twin), and slices of both
+        std::vector<Keyframe> kfs;
+        auto slice = [](const KeyPointVector &v, size_t lo, size_t hi) { return KeyPointVector(v.begin() + (long)lo, v.begin() + (long)hi); };
+        const std::vector<KeyPointVector> sets = {batch[1], kpsB, batch[0], slice(batch[1], 0, batch[1].size() / 2),
+                                                  slice(kpsB, kpsB.size() / 3, kpsB.size()), slice(batch[1], batch[1].size() / 4, batch[1].size()),
+                                                  slice(kpsB, 0, 50), KeyPointVector()};
+        for (size_t i = 0; i < sets.size(); ++i) {
+            Keyframe kf;
+            kf.id.v = (int)i + 1;
+            kf.shared = std::make_shared<KeyframeShared>();
+            kf.shared->keyPoints = sets[i];
+            bow.transform(kf.shared->keyPoints, kf.shared->bowVec, kf.shared->bowFeatureVec);
+            MapId mapId; mapId.v = (int)(i % 2);
+            bow.add(kf, mapId);
+            kfs.push_back(kf);
+        }
+        std::vector<std::uint32_t> vw, fvNode, fvFeat;
+        std::vector<double> vv;
+        for (const auto &e : kfs[0].shared->bowVec) { vw.push_back(e.first); vv.push_back(e.second); }
+        for (const auto &e : kfs[0].shared->bowFeatureVec)
+            for (unsigned f : e.second) { fvNode.push_back(e.first); fvFeat.push_back(f); }
+        dump(out + "/bow_vec_word.u32", vw);
+        dump(out + "/bow_vec_value.f64", vv);
+        dump(out + "/bow_fv_node.u32", fvNode);
+        dump(out + "/bow_fv_feature.u32", fvFeat);
+        MapKf gone; gone.mapId.v = 1; gone.kfId.v = 6;
+        bow.remove(gone);
+        std::vector<std::int32_t> simIds;     // per query: count, then (map, kf) pairs
+        std::vector<float> simScores;
+        for (int q : {0, 1, 4}) {
+            const auto similar = bow.getBowSimilar(db1, Atlas(), kfs[(size_t)q]);
+            simIds.push_back((int)similar.size());
+            for (const auto &sim : similar) { simIds.push_back(sim.mapKf.mapId.v); simIds.push_back(sim.mapKf.kfId.v); simScores.push_back(sim.score); }
+        }
+        dump(out + "/bow_similar_ids.i32", simIds);
+        dump(out + "/bow_similar_scores.f32", simScores);
+    }
     std::printf("ok %zu %zu %u %u\n", kpsA.size(), kpsB.size(), n, nb);
     return 0;
 }

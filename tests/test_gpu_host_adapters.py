@@ -22,7 +22,7 @@ def test_host_adapter_library_builds_and_exports():
     _build()
     syms = subprocess.check_output(["nm", "-DC", str(HOST / "libslam_frontend.so")], text=True)
     for s in ("slam::ImagePyramid::build(", "slam::FeatureDetector::build(", "slam::OrbExtractor::build(",
-              "slam::matchForLoopClosures(", "slam::StaticSettings::maxNumberOfKeypointsPerLevel()",
+              "slam::matchForLoopClosures(", "slam::BowIndex::transform(", "slam::BowIndex::getBowSimilar(", "slam::StaticSettings::maxNumberOfKeypointsPerLevel()",
               "slam::match::compute_descriptor_distance_32("):
         assert s in syms, s
 
@@ -47,6 +47,12 @@ def test_host_adapters_match_oracle(tmp_path, oracle, synth):
     a, b = synth.frame(w, h, 7100), synth.frame(w, h, 7101)
     a.tofile(tmp_path / "a.raw")
     b.tofile(tmp_path / "b.raw")
+    voc = synth.random_vocabulary(4, 5, 21)                     # levelsUp = 4 of 5 levels: feature-vector nodes at level 1
+    for name, key, t in (("child_off.i32", "child_off", np.int32), ("child_ids.i32", "child_ids", np.int32),
+                         ("node_word.i32", "node_word", np.int32), ("node_desc.u32", "node_desc", np.uint32),
+                         ("node_weight.f64", "node_weight", np.float64)):
+        np.ascontiguousarray(voc[key], t).tofile(tmp_path / ("voc_" + name))
+    np.array([voc["levels"]], np.int32).tofile(tmp_path / "voc_levels.i32")
     r = subprocess.run([str(exe), str(w), str(h), str(tmp_path / "a.raw"), str(tmp_path / "b.raw"), str(tmp_path), str(maxkp)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
@@ -115,3 +121,34 @@ def test_host_adapters_match_oracle(tmp_path, oracle, synth):
     k = min(len(got["x"]), n2)
     hd = np.fromfile(tmp_path / "hamming.u32", np.uint32)
     assert hd.tolist() == [oracle.hamming(got["desc"][i], refB["desc"][i]) for i in range(k)]
+
+    # BowIndex adapter: transform -> BowVector / FeatureVector, add / remove, getBowSimilar (bow_index.cpp:44-176)
+    dA, dB = refA["desc"], refB["desc"]
+    sets = [dA, dB, dB, dA[:n1 // 2], dB[n2 // 3:], dA[n1 // 4:], dB[:50], dA[:0]]
+    idx = oracle.BowIndex(int(voc["node_word"].max()) + 1)
+    vecs = []
+    for i, d in enumerate(sets):
+        word, weight, node = oracle.bow_transform(voc, d, 4)
+        vecs.append(oracle.bow_vector(word, weight))
+        if i != 5:                                              # keyframe 6 is removed again by the driver
+            idx.add(i % 2, i + 1, *vecs[-1])
+        if i == 0:
+            assert np.array_equal(np.fromfile(tmp_path / "bow_vec_word.u32", np.uint32), vecs[0][0])
+            assert np.array_equal(np.fromfile(tmp_path / "bow_vec_value.f64", np.float64), vecs[0][1])
+            keep = weight > 0
+            order = np.lexsort((np.arange(len(d))[keep], node[keep]))     # std::map node order, features ascending
+            assert np.array_equal(np.fromfile(tmp_path / "bow_fv_node.u32", np.uint32), node[keep][order].astype(np.uint32))
+            assert np.array_equal(np.fromfile(tmp_path / "bow_fv_feature.u32", np.uint32), np.arange(len(d))[keep][order].astype(np.uint32))
+            assert len(vecs[0][0]) > 50
+    ids = np.fromfile(tmp_path / "bow_similar_ids.i32", np.int32).tolist()
+    scores = np.fromfile(tmp_path / "bow_similar_scores.f32", np.float32).tolist()
+    for q in (0, 1, 4):
+        m, k, sc = idx.similar(*vecs[q], self_key=(0, q + 1), min_in_common_ratio=0.8, score_ratio=0.75)
+        cnt = ids.pop(0)
+        assert cnt == len(m)
+        for j in range(cnt):
+            assert (ids.pop(0), ids.pop(0)) == (int(m[j]), int(k[j]))
+            assert scores.pop(0) == float(sc[j])
+    assert not ids and not scores
+    idx.close()
+

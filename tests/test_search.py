@@ -212,3 +212,170 @@ def test_gpu_bow_transform_bit_exact(slamgpu, oracle, synth, branching, levels, 
         bad["child_ids"][0] = 0                              # a child that points back at the root
         with pytest.raises(slamgpu.SlamGpuError):
             slamgpu.Vocabulary(ctx, bad)
+
+
+# ---- BowVector, BowIndex::add / remove / getBowSimilar (bow_index.cpp:44-176) -------------------------------------
+def _py_bow_vector(word, weight):
+    v = {}
+    for w, x in zip(word.tolist(), weight.tolist()):
+        if x > 0:
+            v[w] = v[w] + x if w in v else x
+    keys = sorted(v)
+    norm = 0.0
+    for k in keys:
+        norm += abs(v[k])
+    return np.array(keys, np.uint32), np.array([v[k] / norm if norm > 0 else v[k] for k in keys], np.float64)
+
+
+def _py_score(qw, qv, dw, dv):
+    q = dict(zip(qw.tolist(), qv.tolist()))
+    s, common = 0.0, 0
+    for w, x in zip(dw.tolist(), dv.tolist()):          # ascending word order
+        if w in q:
+            s += abs(q[w] - x) - abs(q[w]) - abs(x)
+            common += 1
+    return common, np.float32(-s / 2.0)
+
+
+def _py_similar(db, qw, qv, self_key, min_ratio, score_ratio):
+    """db: {(map, kf): (words, values)}; python restatement of bow_index.cpp:95-176 (no score ties assumed)."""
+    rows = []
+    for key in sorted(db):
+        if key == self_key:
+            continue
+        c, sc = _py_score(qw, qv, *db[key])
+        if c:
+            rows.append((key, c, sc))
+    if not rows:
+        return []
+    min_common = int(np.float32(min_ratio) * np.float32(max(r[1] for r in rows)))
+    sim = sorted([(r[0], r[2]) for r in rows if r[1] > min_common], key=lambda t: -t[1])
+    if not sim:
+        return []
+    min_score = np.float32(sim[0][1] * np.float32(score_ratio))
+    return [t for t in sim if not t[1] < min_score]
+
+
+def test_oracle_bow_vector_kat(oracle):
+    w, v = oracle.bow_vector(np.array([5, 3, 5, 7, 3], np.int32), np.array([1.0, 2.0, 3.0, 0.0, 0.5]))
+    assert w.tolist() == [3, 5] and v.tolist() == [2.5 / 6.5, 4.0 / 6.5]        # weight 0 = stopped word, dropped
+    w, v = oracle.bow_vector(np.zeros(0, np.int32), np.zeros(0))
+    assert len(w) == 0
+    rng = np.random.default_rng(12)
+    word = rng.integers(0, 300, 2000).astype(np.int32)
+    weight = np.where(rng.random(2000) < 0.1, 0.0, rng.uniform(0.01, 9.0, 2000))
+    w, v = oracle.bow_vector(word, weight)
+    pw, pv = _py_bow_vector(word, weight)
+    assert np.array_equal(w, pw) and np.array_equal(v, pv)
+    assert abs(v.sum() - 1.0) < 1e-12
+
+
+def test_oracle_bow_similar_kat_and_python(oracle, synth):
+    idx = oracle.BowIndex(10)
+    a = (np.array([1, 4, 7], np.uint32), np.array([0.5, 0.25, 0.25]))
+    b = (np.array([1, 4, 8], np.uint32), np.array([0.5, 0.25, 0.25]))
+    c = (np.array([2, 9], np.uint32), np.array([0.5, 0.5]))
+    idx.add(0, 10, *a); idx.add(0, 11, *b); idx.add(1, 3, *c)
+    m, k, s = idx.similar(*a, self_key=(0, 99), min_in_common_ratio=0.0, score_ratio=0.0)
+    assert list(zip(m.tolist(), k.tolist())) == [(0, 10), (0, 11)] and s.tolist() == [1.0, 0.75]   # identical -> 1
+    m, k, s = idx.similar(*a, self_key=(0, 10), min_in_common_ratio=0.0, score_ratio=0.0)
+    assert list(zip(m.tolist(), k.tolist())) == [(0, 11)]                                          # self excluded
+    m, k, s = idx.similar(*a, self_key=(0, 99), min_in_common_ratio=0.8, score_ratio=0.0)
+    assert k.tolist() == [10]                                   # 3 common > (unsigned)(0.8 * 3) = 2; 2 common is not
+    m, k, s = idx.similar(*a, self_key=(0, 99), min_in_common_ratio=0.0, score_ratio=0.8)
+    assert k.tolist() == [10]                                   # 0.75 < 0.8 * 1.0
+    idx.remove(0, 10)
+    m, k, s = idx.similar(*a, self_key=(0, 99), min_in_common_ratio=0.0, score_ratio=0.0)
+    assert k.tolist() == [11]
+    assert len(idx.similar(np.array([0, 3], np.uint32), np.array([0.5, 0.5]))[0]) == 0           # no shared word
+    idx.close()
+
+    vecs = synth.random_bow_vectors(80, 600, 60, 77)
+    db = {}
+    idx = oracle.BowIndex(600)
+    for i, (w, v) in enumerate(vecs):
+        key = (i % 3, 100 - i)
+        db[key] = (w, v)
+        idx.add(key[0], key[1], w, v)
+    for key in [(0, 100), (1, 99), (2, 98)]:
+        idx.remove(*key); del db[key]
+    for qi in (5, 17, 40, 63):
+        key = (qi % 3, 100 - qi)
+        for mr, sr in ((0.8, 0.75), (0.3, 0.2), (0.0, 0.0)):
+            m, k, s = idx.similar(*db[key], self_key=key, min_in_common_ratio=mr, score_ratio=sr)
+            want = _py_similar(db, *db[key], key, mr, sr)
+            assert s.tolist() == [float(t[1]) for t in want]
+            # equal scores: std::sort's order of ties is libstdc++'s, python's sort is stable -> compare per score
+            assert sorted(zip(s.tolist(), m.tolist(), k.tolist())) == sorted((float(t[1]), t[0][0], t[0][1]) for t in want)
+            assert len(want) > 0
+    idx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_bow_vector_bit_exact(slamgpu, oracle, synth):
+    rng = np.random.default_rng(41)
+    v = synth.random_vocabulary(10, 3, 5)
+    with slamgpu.Context(640, 480, max_frames=1) as ctx:
+        voc = slamgpu.Vocabulary(ctx, v)
+        for n, n_words in ((0, 10), (1, 10), (5, 2), (777, 50), (2000, 1000), (4096, 100000), (4096, 3)):
+            word = rng.integers(0, n_words, n).astype(np.int32)
+            weight = np.where(rng.random(n) < 0.1, 0.0, rng.uniform(1e-3, 9.0, n))
+            w, x = voc.bow_vector(word, weight)
+            rw, rx = oracle.bow_vector(word, weight)
+            assert np.array_equal(w, rw) and np.array_equal(x, rx), (n, n_words)
+        w, x = voc.bow_vector(np.arange(50, dtype=np.int32), np.zeros(50))            # every word stopped
+        assert len(w) == 0
+        # the real chain: descriptors -> transform -> BowVector
+        desc = v["node_desc"][rng.integers(0, len(v["node_word"]), 2000)]
+        word, weight, _ = voc.transform(desc, 2)
+        w, x = voc.bow_vector(word, weight)
+        rw, rx = oracle.bow_vector(*oracle.bow_transform(v, desc, 2)[:2])
+        assert np.array_equal(w, rw) and np.array_equal(x, rx) and len(w) > 100
+        with pytest.raises(slamgpu.SlamGpuError):
+            voc.bow_vector(np.zeros(4097, np.int32), np.ones(4097))
+        voc.close()
+
+
+@pytest.mark.gpu
+def test_gpu_bow_similar_bit_exact(slamgpu, oracle, synth):
+    vocab_size = 5000
+    vecs = synth.random_bow_vectors(400, vocab_size, 300, 55)
+    with slamgpu.Context(640, 480, max_frames=1) as ctx:
+        db = slamgpu.BowDatabase(ctx, 420, 400)
+        idx = oracle.BowIndex(vocab_size)
+        assert len(db.similar(*vecs[0])[0]) == 0                              # empty database
+        keys = []
+        for i, (w, v) in enumerate(vecs):
+            key = (i % 2, 1000 - i)
+            keys.append(key)
+            db.add(key[0], key[1], w, v); idx.add(key[0], key[1], w, v)
+        # twins (equal scores: the std::sort order of ties must agree), removals, slot reuse
+        for j, i in enumerate((3, 3, 50, 51)):
+            db.add(7, j, *vecs[i]); idx.add(7, j, *vecs[i]); keys.append((7, j))
+        for key in (keys[10], keys[11], keys[200]):
+            db.remove(*key); idx.remove(*key)
+        db.remove(9, 9)                                                       # unknown keyframe: no-op
+        for j, i in enumerate((10, 200)):
+            db.add(8, j, *vecs[i][:2]); idx.add(8, j, *vecs[i][:2])
+        assert len(db) == 403
+        n_results = []
+        for qi in (0, 3, 50, 123, 399):
+            for self_key in (keys[qi], (-1, -1)):
+                for mr, sr in ((0.8, 0.75), (0.5, 0.3), (0.0, 0.0)):
+                    got = db.similar(*vecs[qi], self_key=self_key, min_in_common_ratio=mr, score_ratio=sr)
+                    ref = idx.similar(*vecs[qi], self_key=self_key, min_in_common_ratio=mr, score_ratio=sr)
+                    for g, r in zip(got, ref):
+                        assert np.array_equal(g, r), (qi, self_key, mr, sr)
+                    n_results.append(len(got[0]))
+        assert max(n_results) > 100 and min(n_results) >= 1
+        full = db.similar(*vecs[3], min_in_common_ratio=0.0, score_ratio=0.0)
+        part = db.similar(*vecs[3], min_in_common_ratio=0.0, score_ratio=0.0, capacity=5)
+        assert len(part[0]) == 5 and np.array_equal(part[1], full[1][:5])
+        lonely = (np.array([vocab_size + 5], np.uint32), np.array([1.0]))
+        assert len(db.similar(*lonely)[0]) == 0                               # shares no word with anybody
+        with pytest.raises(slamgpu.SlamGpuError):
+            db.add(0, 5000, np.array([4, 3], np.uint32), np.array([0.5, 0.5]))   # words must ascend
+        with pytest.raises(slamgpu.SlamGpuError):
+            db.add(keys[0][0], keys[0][1], *vecs[0])                          # already present
+        db.close(); idx.close()
+
