@@ -128,6 +128,16 @@ int sg_extract(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_strid
  * c+1 and the device->host copy of chunk c-1 run under the kernels of chunk c.  Pass pinned host memory
  * (sg_host_alloc_pinned) for the copies to be asynchronous. */
 int sg_set_pipeline_chunk(sg_ctx *ctx, int frames);
+/* Streaming form of sg_extract (no tracker points) for a sequence of batches: submit queues the copies and the
+ * kernels of the batch on the context's pipeline streams and returns; the host arrays of h_out (pinned) are complete
+ * after sg_extract_wait(ctx, ticket).  The batch occupies the context's frame slots [base_frame, base_frame +
+ * n_frames) -- a context created with max_frames = 2 x batch keeps two batches in flight on disjoint halves, so the
+ * host->device copy of batch i+1 runs under the kernels and the device->host copy of batch i.  A slot range may be
+ * reused once the batch that used it has been waited for; at most 8 tickets are outstanding.  h_imgs and the arrays
+ * of h_out must stay valid until the wait returns. */
+int sg_extract_submit(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames, int base_frame,
+                      const sg_keypoints *h_out, int *ticket);
+int sg_extract_wait(sg_ctx *ctx, int ticket);
 /* Device-resident variant: images in device memory, results stay on the device; fetch them with
  * sg_extract_download.  This is the call the throughput bench times. */
 int sg_extract_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t frame_stride, int n_frames);

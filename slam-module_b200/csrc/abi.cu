@@ -332,6 +332,7 @@ void sg_destroy(sg_ctx *ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (auto &e : ctx->pipe_ev) cudaEventDestroy(e);
+    for (auto &e : ctx->ticket_ev) if (e) cudaEventDestroy(e);
     for (cudaStream_t q : {ctx->s_in, ctx->s_out}) if (q) cudaStreamDestroy(q);
     for (cudaStream_t q : ctx->s_cmp) if (q) cudaStreamDestroy(q);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -489,19 +490,23 @@ int sg_extract_download(sg_ctx *ctx, int n_frames, sg_keypoints *o) {
 // small-level kernels overlaps the head of the next) and the D2H of chunk c-1 (second copy engine, s_out).
 // Frames are independent, every per-frame buffer is indexed by the absolute frame number, so the chunks
 // never touch the same memory.
-static int extract_pipelined(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames,
-                             sg_keypoints *o) {
+// Queues the whole batch (H2D, kernels, D2H) on the pipeline streams; frames occupy the context's frame slots
+// [base, base + n_frames), host arrays are indexed from 0.  Nothing is synchronised here.
+static int pipeline_submit(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames, int base,
+                           const sg_keypoints *o, bool streaming = false) {
     const Level &L0 = ctx->lv[0];
     if (!h_imgs || pitch < L0.w) return fail(ctx, SG_ERR_INVALID, "bad image pointer / pitch");
-    if (n_frames < 1 || n_frames > ctx->p.max_frames) return fail(ctx, SG_ERR_INVALID, "n_frames %d outside [1, %d]", n_frames, ctx->p.max_frames);
+    if (n_frames < 1 || base < 0 || base + n_frames > ctx->p.max_frames)
+        return fail(ctx, SG_ERR_INVALID, "frames [%d, %d) outside the context's [0, %d)", base, base + n_frames, ctx->p.max_frames);
     if (!o) return fail(ctx, SG_ERR_INVALID, "null output");
     // chunk schedule: small chunks at both ends (short pipeline fill and drain: the first kernels start after a
     // short copy, the last copy-out is short), full chunks in between (efficient grids)
     std::vector<int> sched;
     {
-        const int C = std::max(1, ctx->pipe_chunk), q = std::max(1, C / 4), h = std::max(1, C / 2);
+        // (a stream of batches keeps the pipeline full by itself: uniform, larger chunks)
+        const int C = std::max(1, streaming ? ctx->stream_chunk : ctx->pipe_chunk), q = std::max(1, C / 4), h = std::max(1, C / 2);
         int rest = n_frames;
-        if (n_frames >= 2 * (q + h) + C) {
+        if (!streaming && n_frames >= 2 * (q + h) + C) {
             sched.push_back(q); sched.push_back(h);
             rest -= 2 * (q + h);
             while (rest > 0) { const int n = std::min(C, rest); sched.push_back(n); rest -= n; }
@@ -516,7 +521,7 @@ static int extract_pipelined(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size
         SG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->pipe_ev.push_back(e);
     }
-    if (int r = set_level0(ctx, L0.pyr, L0.pitch, L0.frame_stride, n_frames)) return r;
+    if (int r = set_level0(ctx, L0.pyr, L0.pitch, L0.frame_stride, base + n_frames)) return r;
     // work queued earlier on the main stream (an un-synchronised sg_extract_device, ...) comes first
     SG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->main_stream));
     for (cudaStream_t q : {ctx->s_in, ctx->s_out}) SG_CUDA(ctx, cudaStreamWaitEvent(q, ctx->ev_fork, 0));
@@ -528,18 +533,18 @@ static int extract_pipelined(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size
     static const bool dbg = getenv("SG_DEBUG_TIMING") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     for (int c = 0; c < chunks && rc == SG_OK; ++c) {
-        const int f0 = f_next, n = sched[c];
+        const int fl = f_next, f0 = base + f_next, n = sched[c];     // fl: index in the host arrays, f0: frame slot
         f_next += n;
         if (pitch == L0.pitch && (n == 1 || frame_stride == L0.frame_stride)) {
-            SG_CUDA(ctx, cudaMemcpyAsync(L0.pyr + (size_t)f0 * L0.frame_stride, h_imgs + (size_t)f0 * frame_stride,
+            SG_CUDA(ctx, cudaMemcpyAsync(L0.pyr + (size_t)f0 * L0.frame_stride, h_imgs + (size_t)fl * frame_stride,
                                          (size_t)n * L0.frame_stride, cudaMemcpyHostToDevice, ctx->s_in));
         } else {
-            for (int f = f0; f < f0 + n; ++f)
-                SG_CUDA(ctx, cudaMemcpy2DAsync(L0.pyr + (size_t)f * L0.frame_stride, L0.pitch, h_imgs + (size_t)f * frame_stride,
+            for (int f = 0; f < n; ++f)
+                SG_CUDA(ctx, cudaMemcpy2DAsync(L0.pyr + (size_t)(f0 + f) * L0.frame_stride, L0.pitch, h_imgs + (size_t)(fl + f) * frame_stride,
                                                pitch, L0.w, L0.h, cudaMemcpyHostToDevice, ctx->s_in));
         }
         SG_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[2 * c], ctx->s_in));
-        cudaStream_t cmp = ctx->s_cmp[c % ctx->pipe_streams];
+        cudaStream_t cmp = ctx->s_cmp[ctx->pipe_rr++ % (unsigned)ctx->pipe_streams];   // rotates across calls too (batches in flight)
         SG_CUDA(ctx, cudaStreamWaitEvent(cmp, ctx->pipe_ev[2 * c], 0));
         ctx->stream = cmp; ctx->frame0 = f0; ctx->in_pipeline = true;
         rc = extract_launches(ctx, n);
@@ -549,7 +554,7 @@ static int extract_pipelined(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size
         SG_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[2 * c + 1], 0));
         auto out = [&](auto *h, const auto *d, size_t per_frame) -> int {
             if (!h) return SG_OK;
-            SG_CUDA(ctx, cudaMemcpyAsync(h + (size_t)f0 * per_frame, d + (size_t)f0 * per_frame,
+            SG_CUDA(ctx, cudaMemcpyAsync(h + (size_t)fl * per_frame, d + (size_t)f0 * per_frame,
                                          (size_t)n * per_frame * sizeof(*h), cudaMemcpyDeviceToHost, ctx->s_out));
             return SG_OK;
         };
@@ -560,16 +565,16 @@ static int extract_pipelined(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size
             || (rc = out(o->level_count, ctx->d_kp_count, (size_t)levels)))
             break;
     }
-    const auto t_submitted = std::chrono::steady_clock::now();
+    if (dbg)
+        fprintf(stderr, "sg_extract: %d chunks, submit %.3f ms\n", chunks,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    return rc;
+}
+
+static int pipeline_wait_all(sg_ctx *ctx, int rc) {
     for (int i = 0; i <= sg_ctx::N_CMP; ++i) {
         const cudaError_t e = cudaStreamSynchronize(i < sg_ctx::N_CMP ? ctx->s_cmp[i] : ctx->s_out);
         if (e != cudaSuccess && rc == SG_OK) rc = fail(ctx, SG_ERR_CUDA, "pipeline synchronise failed: %s", cudaGetErrorString(e));
-    }
-    if (dbg) {
-        const auto t_done = std::chrono::steady_clock::now();
-        fprintf(stderr, "sg_extract: %d chunks, submit %.3f ms, wait %.3f ms\n", chunks,
-                std::chrono::duration<double, std::milli>(t_submitted - t_begin).count(),
-                std::chrono::duration<double, std::milli>(t_done - t_submitted).count());
     }
     if (rc) return rc;
     return check_device_error(ctx);
@@ -579,12 +584,37 @@ int sg_extract(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_strid
                const float *h_track_xy, const int32_t *h_track_ids, const int32_t *n_tracks, sg_keypoints *h_out) {
     cudaSetDevice(ctx->device);
     if (int r = upload_tracks(ctx, h_track_xy, h_track_ids, n_tracks, n_frames)) return r;
-    return extract_pipelined(ctx, h_imgs, pitch, frame_stride, n_frames, h_out);
+    return pipeline_wait_all(ctx, pipeline_submit(ctx, h_imgs, pitch, frame_stride, n_frames, 0, h_out));
+}
+
+// Streaming form: several batches in flight on disjoint frame slots of the context (see slamgpu.h).
+int sg_extract_submit(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames, int base_frame,
+                      const sg_keypoints *h_out, int *ticket) {
+    cudaSetDevice(ctx->device);
+    if (!ticket) return fail(ctx, SG_ERR_INVALID, "null ticket");
+    ctx->have_tracks = false;
+    if (int r = pipeline_submit(ctx, h_imgs, pitch, frame_stride, n_frames, base_frame, h_out, true)) {
+        pipeline_wait_all(ctx, r);
+        return r;
+    }
+    const int t = ctx->next_ticket++ % sg_ctx::N_TICKETS;
+    if (!ctx->ticket_ev[t]) SG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ticket_ev[t], cudaEventDisableTiming));
+    SG_CUDA(ctx, cudaEventRecord(ctx->ticket_ev[t], ctx->s_out));      // every D2H of the batch is on s_out, after its kernels
+    *ticket = t;
+    return SG_OK;
+}
+
+int sg_extract_wait(sg_ctx *ctx, int ticket) {
+    cudaSetDevice(ctx->device);
+    if (ticket < 0 || ticket >= sg_ctx::N_TICKETS || !ctx->ticket_ev[ticket]) return fail(ctx, SG_ERR_INVALID, "unknown ticket %d", ticket);
+    SG_CUDA(ctx, cudaEventSynchronize(ctx->ticket_ev[ticket]));
+    return check_device_error(ctx);
 }
 
 int sg_set_pipeline_chunk(sg_ctx *ctx, int frames) {
     if (frames < 1) return fail(ctx, SG_ERR_INVALID, "chunk must be >= 1 frame");
     ctx->pipe_chunk = frames;
+    ctx->stream_chunk = frames;
     return SG_OK;
 }
 

@@ -97,6 +97,11 @@ struct sg_ctx {
     int pipe_streams = 4;               // compute streams the chunks rotate over (up to N_CMP; more than 4 measured no gain)
     int overlap_parts = 4;              // sg_extract_device: independent slices of the batch on separate streams
     std::vector<cudaEvent_t> pipe_ev;   // [2 * chunks]: H2D done, compute done
+    static constexpr int N_TICKETS = 8;  // sg_extract_submit: completion events of the batches in flight
+    cudaEvent_t ticket_ev[N_TICKETS] = {};
+    int next_ticket = 0;
+    int stream_chunk = 128;              // chunk of sg_extract_submit (no fill / drain ramp)
+    unsigned pipe_rr = 0;                // round-robin position over the compute streams
     int pipe_chunk = 32;                // frames per pipeline chunk of sg_extract
     int frame0 = 0;                     // first frame the stage launchers work on
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr;

@@ -68,7 +68,8 @@ ABI_SYMBOLS = [
     "sg_timer_stop", "sg_flush_l2", "sg_microbench_popc", "sg_set_profiling", "sg_get_stage_ms",
     "sg_set_pipeline_chunk", "sg_search_candidates", "sg_feature_index", "sg_medoid", "sg_set_overlap", "sg_match_bow", "sg_vocab_create", "sg_vocab_destroy",
     "sg_bow_transform", "sg_bow_transform_device", "sg_match_triangulation", "sg_bow_vector", "sg_bowdb_create",
-    "sg_bowdb_destroy", "sg_bowdb_size", "sg_bowdb_add", "sg_bowdb_remove", "sg_bow_similar",
+    "sg_bowdb_destroy", "sg_bowdb_size", "sg_bowdb_add", "sg_bowdb_remove", "sg_bow_similar", "sg_extract_submit",
+    "sg_extract_wait",
 ]
 
 _lib = None
@@ -111,6 +112,10 @@ def lib():
         L.sg_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]
         L.sg_extract_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int]
+        L.sg_extract_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.sg_extract_submit.restype = C.c_int
+        L.sg_extract_wait.argtypes = [C.c_void_p, C.c_int]
+        L.sg_extract_wait.restype = C.c_int
         L.sg_extract_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.sg_hamming.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.sg_match_bruteforce.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
@@ -387,7 +392,7 @@ class Context:
         if pinned:   # page-locked host memory: the D2H copies of sg_extract run asynchronously
             pins = {k: PinnedArray(s, d) for k, (s, d) in spec.items()}
             arrs = {k: v.array for k, v in pins.items()}
-            self._pins = pins   # keeps the allocations alive as long as the context
+            self.__dict__.setdefault("_pins", []).append(pins)   # keeps the allocations alive as long as the context
         else:
             arrs = {k: np.empty(s, d) for k, (s, d) in spec.items()}
         ks = Keypoints(*[arrs[k].ctypes.data for k, _ in Keypoints._fields_])
@@ -432,6 +437,20 @@ class Context:
                                      None if tn is None else tn.ctypes.data, C.byref(ks)))
         self._n = nf
         return self._split(arrs, nf)
+
+    def alloc_outputs(self, n_frames, pinned=True):
+        """Host output arrays of a batch (dict of numpy arrays) and the sg_keypoints struct that points at them."""
+        return self._alloc_out(n_frames, pinned)
+
+    def extract_submit(self, imgs, base_frame, out_struct):
+        """Streaming sg_extract: queue the batch on frame slots [base_frame, base_frame + len(imgs)) -> ticket."""
+        t = C.c_int(-1)
+        self._check(lib().sg_extract_submit(self._h, imgs.ctypes.data, imgs.strides[1], imgs.strides[0], imgs.shape[0],
+                                            int(base_frame), C.byref(out_struct), C.byref(t)))
+        return t.value
+
+    def extract_wait(self, ticket):
+        self._check(lib().sg_extract_wait(self._h, int(ticket)))
 
     def extract_device(self, dptr, pitch, frame_stride, n_frames):
         self._check(lib().sg_extract_device(self._h, dptr, pitch, frame_stride, n_frames))
