@@ -580,9 +580,19 @@ static int pipeline_wait_all(sg_ctx *ctx, int rc) {
     return check_device_error(ctx);
 }
 
+// A batch still in flight (sg_extract_submit without its sg_extract_wait) owns its frame slots.
+static int slots_free(sg_ctx *ctx, int base, int n) {
+    for (const auto &o : ctx->ticket)
+        if (o.busy && base < o.base + o.n && o.base < base + n)
+            return fail(ctx, SG_ERR_INVALID, "frame slots [%d, %d) are still used by a batch in flight ([%d, %d)): wait for it first",
+                        base, base + n, o.base, o.base + o.n);
+    return SG_OK;
+}
+
 int sg_extract(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames,
                const float *h_track_xy, const int32_t *h_track_ids, const int32_t *n_tracks, sg_keypoints *h_out) {
     cudaSetDevice(ctx->device);
+    if (int r = slots_free(ctx, 0, n_frames)) return r;
     if (int r = upload_tracks(ctx, h_track_xy, h_track_ids, n_tracks, n_frames)) return r;
     return pipeline_wait_all(ctx, pipeline_submit(ctx, h_imgs, pitch, frame_stride, n_frames, 0, h_out));
 }
@@ -592,12 +602,16 @@ int sg_extract_submit(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t fram
                       const sg_keypoints *h_out, int *ticket) {
     cudaSetDevice(ctx->device);
     if (!ticket) return fail(ctx, SG_ERR_INVALID, "null ticket");
+    const int t = ctx->next_ticket % sg_ctx::N_TICKETS;
+    if (ctx->ticket[t].busy) return fail(ctx, SG_ERR_INVALID, "%d batches are in flight: wait for one first", (int)sg_ctx::N_TICKETS);
+    if (int r = slots_free(ctx, base_frame, n_frames)) return r;
     ctx->have_tracks = false;
     if (int r = pipeline_submit(ctx, h_imgs, pitch, frame_stride, n_frames, base_frame, h_out, true)) {
         pipeline_wait_all(ctx, r);
         return r;
     }
-    const int t = ctx->next_ticket++ % sg_ctx::N_TICKETS;
+    ++ctx->next_ticket;
+    ctx->ticket[t].busy = true; ctx->ticket[t].base = base_frame; ctx->ticket[t].n = n_frames;
     if (!ctx->ticket_ev[t]) SG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ticket_ev[t], cudaEventDisableTiming));
     SG_CUDA(ctx, cudaEventRecord(ctx->ticket_ev[t], ctx->s_out));      // every D2H of the batch is on s_out, after its kernels
     *ticket = t;
@@ -606,8 +620,9 @@ int sg_extract_submit(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t fram
 
 int sg_extract_wait(sg_ctx *ctx, int ticket) {
     cudaSetDevice(ctx->device);
-    if (ticket < 0 || ticket >= sg_ctx::N_TICKETS || !ctx->ticket_ev[ticket]) return fail(ctx, SG_ERR_INVALID, "unknown ticket %d", ticket);
+    if (ticket < 0 || ticket >= sg_ctx::N_TICKETS || !ctx->ticket[ticket].busy) return fail(ctx, SG_ERR_INVALID, "ticket %d is not in flight", ticket);
     SG_CUDA(ctx, cudaEventSynchronize(ctx->ticket_ev[ticket]));
+    ctx->ticket[ticket].busy = false;
     return check_device_error(ctx);
 }
 

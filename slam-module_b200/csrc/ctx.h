@@ -99,6 +99,7 @@ struct sg_ctx {
     std::vector<cudaEvent_t> pipe_ev;   // [2 * chunks]: H2D done, compute done
     static constexpr int N_TICKETS = 8;  // sg_extract_submit: completion events of the batches in flight
     cudaEvent_t ticket_ev[N_TICKETS] = {};
+    struct Ticket { bool busy = false; int base = 0, n = 0; } ticket[N_TICKETS];
     int next_ticket = 0;
     int stream_chunk = 128;              // chunk of sg_extract_submit (no fill / drain ramp)
     unsigned pipe_rr = 0;                // round-robin position over the compute streams

@@ -137,7 +137,8 @@ def test_extract_bit_exact(slamgpu, oracle, synth, w, h, seed, maxkp):
 
 
 @pytest.mark.parametrize("w,h,levels,factor,maxkp", [(752, 480, 8, 1.2, 1500), (641, 479, 5, 1.2, 800), (128, 96, 3, 1.2, 200),
-                                                     (320, 240, 1, 1.2, 300), (800, 600, 6, 1.3, 5000), (1920, 1080, 8, 1.2, 4000)])
+                                                     (320, 240, 1, 1.2, 300), (800, 600, 6, 1.3, 5000), (1920, 1080, 8, 1.2, 4000),
+                                                     (96, 64, 8, 1.2, 100), (64, 64, 4, 1.2, 50)])
 def test_extract_unusual_geometries(slamgpu, oracle, synth, w, h, levels, factor, maxkp):
     """Image sizes that are not multiples of the tile / cell sizes, a single-level pyramid, another scale factor,
     budgets above and below the usual 2000."""
@@ -210,6 +211,15 @@ def test_extract_streaming_batches_in_flight(slamgpu, oracle, synth):
             ctx.extract_submit(pins[0].array, 2 * B, outs[0][1])        # slots [10, 15) exceed the 11 of the context
         with pytest.raises(slamgpu.SlamGpuError):
             ctx.extract_wait(7)                                          # never issued
+        t = ctx.extract_submit(pins[0].array, 0, outs[0][1])
+        with pytest.raises(slamgpu.SlamGpuError):
+            ctx.extract_submit(pins[1].array, 3, outs[1][1])            # slots [3, 8) overlap the batch in flight
+        with pytest.raises(slamgpu.SlamGpuError):
+            ctx.detect_and_extract(imgs[0])                              # the synchronous call uses slot 0 too
+        ctx.extract_wait(t)
+        with pytest.raises(slamgpu.SlamGpuError):
+            ctx.extract_wait(t)                                          # already waited for
+        _assert_same_extraction(ctx._split(outs[0][0], B)[2], ref[22])      # pins[0] still holds batch 4 = frames 20..24
 
 
 def test_extract_with_tracker_features(slamgpu, oracle, synth):
