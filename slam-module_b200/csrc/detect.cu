@@ -132,17 +132,21 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
         const unsigned lt = (1u << lane) - 1u;
         // pixels outside the cell never count
         const unsigned okH = (2 * lane < cw ? 0x00008000u : 0u) | (2 * lane + 1 < cw ? 0x80000000u : 0u);
-        const unsigned thiH = thi | 0x80008000u;
+        const unsigned thiH = thi | 0x80008000u, Hmtlo = 0x80008000u - tlo;
         for (int y = warp; y < ch; y += FAST_THREADS / 32) {
             const uint32_t *we = We + (y + 3) * WP + lane + 3, *wo = Wo + (y + 3) * WP + lane;
             const unsigned vb = we[0] | 0x01000100u;
-            const unsigned e0 = vb - we[3 * WP], e8 = vb - we[-3 * WP], e4 = vb - wo[4], e12 = vb - wo[1];
+            // e_i = vb - w_i (biased differences 256 + v - p_i, one per 16-bit lane).  Because vb is common,
+            //   dk = min_i max(e_i, e_i+8) = vb - max_i min(w_i, w_i+8),  br = max_i min(e_i, e_i+8) = vb - min_i max(w_i, w_i+8):
+            // the min / max lattice runs on the raw pair words and only two subtractions remain.
+            const unsigned w0 = we[3 * WP], w8 = we[-3 * WP], w4 = wo[4], w12 = wo[1];
             // the two diagonal antipodal pairs (2, 2) / (-2, -2) and (2, -2) / (-2, 2) halve what reaches stage 2
-            const unsigned e2 = vb - we[2 * WP + 1], e10 = vb - we[-2 * WP - 1], e6 = vb - we[-2 * WP + 1], e14 = vb - we[2 * WP - 1];
-            const unsigned dk = __vminu2(__vminu2(__vmaxu2(e0, e8), __vmaxu2(e4, e12)), __vminu2(__vmaxu2(e2, e10), __vmaxu2(e6, e14)));
-            const unsigned br = __vmaxu2(__vmaxu2(__vminu2(e0, e8), __vminu2(e4, e12)), __vmaxu2(__vminu2(e2, e10), __vminu2(e6, e14)));
-            // lane bit 15 / 31 of (thiH - dk) is clear iff dk > thi; of ((br | H) - tlo) iff br < tlo
-            const unsigned pass = ~((thiH - dk) & ((br | 0x80008000u) - tlo)) & okH;
+            const unsigned w2 = we[2 * WP + 1], w10 = we[-2 * WP - 1], w6 = we[-2 * WP + 1], w14 = we[2 * WP - 1];
+            const unsigned A = __vmaxu2(__vmaxu2(__vminu2(w0, w8), __vminu2(w4, w12)), __vmaxu2(__vminu2(w2, w10), __vminu2(w6, w14)));
+            const unsigned B = __vminu2(__vminu2(__vmaxu2(w0, w8), __vmaxu2(w4, w12)), __vminu2(__vmaxu2(w2, w10), __vmaxu2(w6, w14)));
+            // lane bit 15 / 31 of (thiH - dk) = thiH - vb + A is clear iff dk > thi; of (br + H) - tlo = vb - B + (H - tlo)
+            // iff br < tlo.  Every 16-bit lane of both sums stays inside [0x7f00, 0x8200]: no carry between the lanes.
+            const unsigned pass = ~((thiH - vb + A) & (vb - B + Hmtlo)) & okH;
             const unsigned m = __ballot_sync(0xffffffffu, pass != 0u);
             if (pass) sts16(q_addr + 2u * (unsigned)(nq + __popc(m & lt)), (unsigned)(lane | (y << 5)));   // shared-space store: no generic address math per row
             nq += __popc(m);
@@ -166,10 +170,9 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
             unsigned fa, fbb;
             {
                 const unsigned vb = c | 0x01000100u;
-                const unsigned e0 = vb - r[0], e8 = vb - r[8], e4 = vb - r[4], e12 = vb - r[12];
-                const unsigned dk = __vminu2(__vmaxu2(e0, e8), __vmaxu2(e4, e12));
-                const unsigned br = __vmaxu2(__vminu2(e0, e8), __vminu2(e4, e12));
-                const unsigned fd = ~(thiH - dk) & 0x80008000u, fb = ~((br | 0x80008000u) - tlo) & 0x80008000u;
+                const unsigned A = __vmaxu2(__vminu2(r[0], r[8]), __vminu2(r[4], r[12]));
+                const unsigned B = __vminu2(__vmaxu2(r[0], r[8]), __vmaxu2(r[4], r[12]));
+                const unsigned fd = ~(thiH - vb + A) & 0x80008000u, fb = ~(vb - B + Hmtlo) & 0x80008000u;
                 fa = ((fd >> 15) & 1u) | ((fb >> 14) & 2u);
                 fbb = (fd >> 31) | ((fb >> 30) & 2u);
                 if (!live || 2 * k >= cw) fa = 0;
@@ -181,17 +184,20 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
             for (int round = 0; round < 2; ++round) {
                 const unsigned cm = (sa == 2u ? 0x000000ffu : 0u) | (sb == 2u ? 0x00ff0000u : 0u);   // complement -> bright test
                 const unsigned vb = (c ^ cm) | 0x01000100u;
+                // score = max over the 16 arcs of min over the arc's 9 ring pixels of e_j = vb - r'_j
+                //       = vb - min over arcs of max over the arc of r'_j   (r' = ring pixels, complemented for bright).
+                // Sliding max over windows of 9 of the circular sequence, by doubling: 2, 4, 8, then +1.
                 unsigned d[16], m2[16], m4[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) d[j] = vb - (r[j] ^ cm);
-                // sliding min over windows of 9 of the circular sequence, by doubling: 2, 4, 8, then +1
+                for (int j = 0; j < 16; ++j) d[j] = r[j] ^ cm;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) m2[j] = __vminu2(d[j], d[(j + 1) & 15]);
+                for (int j = 0; j < 16; ++j) m2[j] = __vmaxu2(d[j], d[(j + 1) & 15]);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) m4[j] = __vminu2(m2[j], m2[(j + 2) & 15]);
-                unsigned lo = 0u;
+                for (int j = 0; j < 16; ++j) m4[j] = __vmaxu2(m2[j], m2[(j + 2) & 15]);
+                unsigned hi = 0xffffffffu;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) lo = __vmaxu2(lo, __vminu2(__vminu2(m4[j], m4[(j + 4) & 15]), d[(j + 8) & 15]));
+                for (int j = 0; j < 16; ++j) hi = __vminu2(hi, __vmaxu2(__vmaxu2(m4[j], m4[(j + 4) & 15]), d[(j + 8) & 15]));
+                const unsigned lo = vb - hi;
                 const int s0 = (int)(lo & 0xffffu) - 257, s1 = (int)(lo >> 16) - 257;
                 const bool w0 = sa && s0 >= t, w1 = sb && s1 >= t;
                 if (w0 || w1) {
