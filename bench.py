@@ -33,6 +33,7 @@ sys.path.insert(0, str(ROOT))
 
 W, H, LEVELS, FACTOR, MAXKP = 640, 480, 8, 1.2, 2000
 FRAMES = 256                      # frames per step per GPU
+WORKLOAD = "ORB extraction, %d synthetic 640x480 frames per GPU per step, 8 levels x1.2, 2000 keypoints (BASELINE configs[1])" % FRAMES
 IN_FLIGHT = 3                     # batches in flight in the streaming end-to-end pass (frame slots of the context)
 N_BATCHES = 4                     # rotating input batches: 4 x 78.6 MB > 126 MB of L2
 ALGO_BYTES_PYRAMID = 2208264      # A0 + 2*sum(A_l) per 640x480 frame
@@ -193,8 +194,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "ORB extraction, 640x480 synthetic frames, 8 levels x1.2, 2000 keypoints (configs[1])",
-                   "frames_per_step": sample, "levels": LEVELS, "scale_factor": FACTOR, "max_keypoints": MAXKP},
+        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": sample, "levels": LEVELS, "scale_factor": FACTOR,
+                   "max_keypoints": MAXKP},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "matching": {"value": len(pairs) * MATCH_N * MATCH_N / msec, "unit": "descriptor-pair distances/s",
@@ -584,8 +585,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "ORB extraction, %d synthetic 640x480 frames per GPU per step, 8 levels x1.2, 2000 keypoints "
-                                   "(BASELINE configs[1])" % FRAMES,
+            "config": {"workload": WORKLOAD,
                        "frames_per_step_per_gpu": FRAMES, "levels": LEVELS, "scale_factor": FACTOR, "max_keypoints": MAXKP,
                        "keypoints_per_frame": kp_per_frame, "sharding": "frames by rank, no collective", "extra_untimed_warmup_steps": extra_warm,
                        "l2": "inputs larger than L2: %d rotating batches x %.1f MB" % (N_BATCHES, FRAMES * frame_bytes / 1e6)},

@@ -180,6 +180,15 @@ static int build_context(sg_ctx *ctx) {
     return SG_OK;
 }
 
+// A batch still in flight (sg_extract_submit without its sg_extract_wait) owns its frame slots.
+static int slots_free(sg_ctx *ctx, int base, int n) {
+    for (const auto &o : ctx->ticket)
+        if (o.busy && base < o.base + o.n && o.base < base + n)
+            return fail(ctx, SG_ERR_INVALID, "frame slots [%d, %d) are still used by a batch in flight ([%d, %d)): wait for it first",
+                        base, base + n, o.base, o.base + o.n);
+    return SG_OK;
+}
+
 static int set_level0(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t stride, int n_frames) {
     const bool changed = ctx->level0 != d_imgs || ctx->level0_pitch != pitch || ctx->level0_stride != stride
                          || ctx->level0_frames < n_frames;
@@ -362,6 +371,7 @@ int sg_keypoint_capacity(const sg_ctx *ctx) { return ctx->geom.out_cap; }
 // ---- pyramid ------------------------------------------------------------------------------------------
 int sg_pyramid_update(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames) {
     cudaSetDevice(ctx->device);
+    if (int r = slots_free(ctx, 0, n_frames)) return r;
     if (int r = upload_frames(ctx, h_imgs, pitch, frame_stride, n_frames)) return r;
     if (int r = launch_pyramid(ctx, n_frames)) return r;
     SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -370,6 +380,7 @@ int sg_pyramid_update(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t fram
 
 int sg_pyramid_update_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t frame_stride, int n_frames) {
     cudaSetDevice(ctx->device);
+    if (int r = slots_free(ctx, 0, n_frames)) return r;
     if (int r = check_device_images(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
     if (int r = set_level0(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
     return launch_pyramid(ctx, n_frames);
@@ -580,15 +591,6 @@ static int pipeline_wait_all(sg_ctx *ctx, int rc) {
     return check_device_error(ctx);
 }
 
-// A batch still in flight (sg_extract_submit without its sg_extract_wait) owns its frame slots.
-static int slots_free(sg_ctx *ctx, int base, int n) {
-    for (const auto &o : ctx->ticket)
-        if (o.busy && base < o.base + o.n && o.base < base + n)
-            return fail(ctx, SG_ERR_INVALID, "frame slots [%d, %d) are still used by a batch in flight ([%d, %d)): wait for it first",
-                        base, base + n, o.base, o.base + o.n);
-    return SG_OK;
-}
-
 int sg_extract(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames,
                const float *h_track_xy, const int32_t *h_track_ids, const int32_t *n_tracks, sg_keypoints *h_out) {
     cudaSetDevice(ctx->device);
@@ -635,6 +637,7 @@ int sg_set_pipeline_chunk(sg_ctx *ctx, int frames) {
 
 int sg_extract_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t frame_stride, int n_frames) {
     cudaSetDevice(ctx->device);
+    if (int r = slots_free(ctx, 0, n_frames)) return r;
     if (int r = check_device_images(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
     if (int r = set_level0(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
     ctx->have_tracks = false;
