@@ -555,7 +555,35 @@ def main():
             v, secs = v2, secs2
         n_cpu_pairs = 16 * max(8, cores)
         msec, _ = po.bench_match(np.stack(sets_d[:8]), np.stack(sets_a[:8]), pairs[:n_cpu_pairs] % 8, cores)
-        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+        # parity of this very run against the oracle (checker role): keypoint sets, angles, descriptors, match indices
+        N_CHECK = 8
+        pp = po.make_params(W, H, levels=LEVELS, scale_factor=FACTOR, max_keypoints=MAXKP)
+        got = ctx.detect_and_extract(host_batches[0].array[:N_CHECK])
+        kp_equal, max_dang, desc_bad, n_kp = True, 0.0, 0, 0
+        feats = []
+        for f in range(N_CHECK):
+            ref = po.extract(pp, host_batches[0].array[f])
+            gf = got[f]
+            same = gf["n"] == ref["n"] and all(np.array_equal(gf[k], ref[k]) for k in ("x", "y", "octave"))
+            kp_equal = kp_equal and same
+            if same:
+                n_kp += ref["n"]
+                if ref["n"]:
+                    da = np.abs(gf["angle"].astype(np.float64) - ref["angle"].astype(np.float64))
+                    max_dang = max(max_dang, float(np.deg2rad(np.minimum(da, 360.0 - da)).max()))
+                desc_bad += int((gf["desc"] != ref["desc"]).any(axis=1).sum())
+            feats.append(ref)
+        match_bad = 0
+        for f in range(0, N_CHECK, 2):
+            a_, b_ = feats[f], feats[f + 1]
+            ng, mg = ctx.match_bruteforce(a_["desc"], a_["angle"], b_["desc"], b_["angle"])
+            nr, mr = po.match_bruteforce(a_["desc"], a_["angle"], b_["desc"], b_["angle"])
+            match_bad += int((mg != mr).sum()) + int(ng != nr)
+        parity = {"frames_checked": N_CHECK, "keypoints_checked": int(n_kp), "keypoint_sets_equal": bool(kp_equal),
+                  "max_angle_diff_rad": max_dang, "descriptor_mismatches": int(desc_bad),
+                  "keyframe_pairs_checked": N_CHECK // 2, "match_index_mismatches": int(match_bad),
+                  "checker": "oracle port (oracle/), same frames as the timed batch"}
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "parity": parity,
                "sample": "oracle port of the reference CPU path on the %d frames of one step, sharded over %d host "
                          "threads (%.1f s per pass, best of 2)" % (sample, cores, secs),
                "matching_value": n_cpu_pairs * MATCH_N * MATCH_N / msec, "matching_unit": "descriptor-pair distances/s",

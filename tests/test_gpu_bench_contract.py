@@ -35,6 +35,9 @@ def test_bench_line_contract():
     assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     c = d["cpu_baseline"]
     assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    par = c["parity"]                                       # the north star asks for the mismatch counts to be reported
+    assert par["keypoint_sets_equal"] and par["descriptor_mismatches"] == 0 and par["match_index_mismatches"] == 0
+    assert par["max_angle_diff_rad"] <= 1e-4 and par["keypoints_checked"] > 1000
     assert d["clocks"]["sm_mhz"] > 0 and isinstance(d["clocks"]["reasons"], list)
     m = d["matching"]
     assert m["roofline"]["unit"] == "POPC.b32/s" and m["value"] > 1e10
