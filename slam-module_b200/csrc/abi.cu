@@ -35,7 +35,7 @@ void pyramid_source_extent(const std::vector<ResizeTap> &xt, const std::vector<R
                            bool area2x, int sw, int sh, int *tile_w, int *tile_h);
 int pyramid_fast_source_rows(const std::vector<ResizeTap> &yt, int h);
 int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, const sg_match_params &mp,
-              int *d_matches, int match_stride, uint32_t *d_n_matches);
+              int *d_matches, int match_stride, uint32_t *d_n_matches, bool reset_rescans = true);
 int match_chunk_pairs(const sg_db *db, bool own_matches);
 int run_topk_lists(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, unsigned thr, uint32_t **d_topk,
                    uint32_t **d_nseen, int *row_stride);
@@ -787,19 +787,50 @@ int sg_match_pairs(sg_ctx *ctx, const sg_db *db, const int32_t *h_pairs, int n_p
     if (int r = grow(ctx, (void **)&ctx->d_pairs, &ctx->pairs_cap, 2 * (size_t)n_pairs, sizeof(int))) return r;
     if (int r = grow(ctx, (void **)&ctx->d_nmatch, &ctx->nmatch_cap, (size_t)n_pairs, sizeof(uint32_t))) return r;
     SG_CUDA(ctx, cudaMemcpyAsync(ctx->d_pairs, h_pairs, 2 * (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
-    // with a host match buffer the pairs are processed in slabs so the device copy stays bounded
-    const int slab = h_matches ? std::min(n_pairs, match_chunk_pairs(db, true)) : n_pairs;
-    for (int p0 = 0; p0 < n_pairs; p0 += slab) {
-        const int np = std::min(slab, n_pairs - p0);
-        if (int r = run_match(ctx, db, ctx->d_pairs + 2 * (size_t)p0, np, *mp, nullptr, 0, ctx->d_nmatch + p0)) return r;
-        if (h_matches) {
-            // run_match left the rows in ctx->d_matches with stride max_set
-            SG_CUDA(ctx, cudaMemcpy2DAsync(h_matches + (size_t)p0 * match_stride, (size_t)match_stride * 4, ctx->d_matches,
-                                           (size_t)db->max_set * 4, (size_t)db->max_set * 4, np, cudaMemcpyDeviceToHost, ctx->stream));
-            SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            for (int p = p0; p < p0 + np; ++p)   // -1 padding behind the largest set
-                for (int i = db->max_set; i < match_stride; ++i) h_matches[(size_t)p * match_stride + i] = -1;
+    if (!h_matches) {
+        if (int r = run_match(ctx, db, ctx->d_pairs, n_pairs, *mp, nullptr, 0, ctx->d_nmatch)) return r;
+    } else {
+        // Slabs of pairs through two device row buffers: the kernels of slab i+1 are queued before the copy-out of
+        // slab i is issued on the second copy stream, so the copies (also the blocking ones into pageable memory) run
+        // under the next slab's kernels.
+        const int slab = std::min(n_pairs, std::min(256, match_chunk_pairs(db, false)));
+        const size_t slab_rows = (size_t)slab * db->max_set;
+        {
+            size_t cap = ctx->matches_cap;
+            const int r = grow(ctx, (void **)&ctx->d_matches, &cap, 2 * slab_rows, sizeof(int));
+            ctx->matches_cap = cap;
+            if (r) return r;
         }
+        while ((int)ctx->pipe_ev.size() < 4) {
+            cudaEvent_t e;
+            SG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->pipe_ev.push_back(e);
+        }
+        if (match_stride > db->max_set)                  // -1 padding behind the largest set (the copies never touch it)
+            for (int p = 0; p < n_pairs; ++p)
+                for (int i = db->max_set; i < match_stride; ++i) h_matches[(size_t)p * match_stride + i] = -1;
+        auto copy_out = [&](int k) -> int {              // slab k: rows of pairs [k * slab, ...)
+            const int p0 = k * slab, np = std::min(slab, n_pairs - p0);
+            SG_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[k & 1], 0));
+            SG_CUDA(ctx, cudaMemcpy2DAsync(h_matches + (size_t)p0 * match_stride, (size_t)match_stride * 4,
+                                           ctx->d_matches + (k & 1) * slab_rows, (size_t)db->max_set * 4, (size_t)db->max_set * 4,
+                                           np, cudaMemcpyDeviceToHost, ctx->s_out));
+            SG_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[2 + (k & 1)], ctx->s_out));
+            return SG_OK;
+        };
+        const int n_slabs = (n_pairs + slab - 1) / slab;
+        for (int k = 0; k < n_slabs; ++k) {
+            const int p0 = k * slab, np = std::min(slab, n_pairs - p0);
+            if (k >= 2) SG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 + (k & 1)], 0));   // buffer free again
+            if (int r = run_match(ctx, db, ctx->d_pairs + 2 * (size_t)p0, np, *mp, ctx->d_matches + (k & 1) * slab_rows, db->max_set,
+                                  ctx->d_nmatch + p0, k == 0))
+                return r;
+            SG_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[k & 1], ctx->stream));
+            if (k >= 1)
+                if (int r = copy_out(k - 1)) return r;
+        }
+        if (int r = copy_out(n_slabs - 1)) return r;
+        SG_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     }
     SG_CUDA(ctx, cudaMemcpyAsync(h_n_matches, ctx->d_nmatch, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
     SG_CUDA(ctx, cudaMemcpyAsync(&ctx->rescans, ctx->d_rescans, 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -465,7 +465,7 @@ int match_chunk_pairs(const sg_db *db, bool own_matches) {
 }
 
 int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, const sg_match_params &mp,
-              int *d_matches, int match_stride, uint32_t *d_n_matches) {
+              int *d_matches, int match_stride, uint32_t *d_n_matches, bool reset_rescans) {
     if (n_pairs <= 0) return SG_OK;
     if (db->max_set > 65535) return fail(ctx, SG_ERR_INVALID, "descriptor sets larger than 65535 features are not supported");
     if (mp.thr > 256) return fail(ctx, SG_ERR_INVALID, "thr must be <= 256");
@@ -489,7 +489,7 @@ int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, con
             if (r) return r;
         }
     }
-    SG_CUDA(ctx, cudaMemsetAsync(ctx->d_rescans, 0, sizeof(unsigned long long), ctx->stream));
+    if (reset_rescans) SG_CUDA(ctx, cudaMemsetAsync(ctx->d_rescans, 0, sizeof(unsigned long long), ctx->stream));
     MatchArgs a{};
     a.desc = db->d_desc; a.angle = db->d_angle; a.offsets = db->d_offsets;
     a.cutoff = match_cutoff(mp); a.thr = mp.thr; a.ratio = mp.ratio;

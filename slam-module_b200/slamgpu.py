@@ -587,11 +587,17 @@ class DescriptorDB:
         self.offsets = offsets
         self.max_set = int(np.max(np.diff(offsets))) if len(offsets) > 1 else 0
 
-    def match_pairs(self, pairs, ratio=0.8, thr=50, check_orientation=True, ratio_is_double=False, want_matches=True):
+    def match_pairs(self, pairs, ratio=0.8, thr=50, check_orientation=True, ratio_is_double=False, want_matches=True, out=None):
+        """out: optional preallocated (counts uint32[n_pairs], rows int32[n_pairs, max_set]) -- e.g. PinnedArray.array."""
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         mp = MatchParams(ratio, thr, int(check_orientation), int(ratio_is_double))
-        n = np.zeros(len(pairs), np.uint32)
-        m = np.empty((len(pairs), max(self.max_set, 1)), np.int32) if want_matches else None
+        if out is not None:
+            n, m = out
+            assert n.dtype == np.uint32 and len(n) >= len(pairs) and m.dtype == np.int32 and m.shape[0] >= len(pairs)
+            assert m.shape[1] == max(self.max_set, 1) and m.flags.c_contiguous
+        else:
+            n = np.zeros(len(pairs), np.uint32)
+            m = np.empty((len(pairs), max(self.max_set, 1)), np.int32) if want_matches else None
         self.ctx._check(lib().sg_match_pairs(self.ctx._h, self._h, pairs.ctypes.data, len(pairs), C.byref(mp),
                                              None if m is None else m.ctypes.data, max(self.max_set, 1), n.ctypes.data))
         return n, m

@@ -101,6 +101,29 @@ def test_match_pairs_batched(ctx, slamgpu, oracle, synth):
         assert (m[k, sizes[i]:] == -1).all()
 
 
+def test_match_pairs_many_slabs(ctx, slamgpu, oracle, synth):
+    """More pairs than one 256-pair slab: the host-buffer call double-buffers the match rows (copy-out of slab i under
+    the kernels of slab i+1); rows, counts and the -1 padding must come out as from single calls."""
+    dA, aA, dB, aB = synth.correlated_descriptors(300, 91)
+    dC, aC, dD, aD = synth.correlated_descriptors(300, 92)
+    sets_d, sets_a = [dA, dB, dC[:190], dD], [aA, aB, aC[:190], aD]
+    offs = np.concatenate([[0], np.cumsum([len(d) for d in sets_d])]).astype(np.int64)
+    db = slamgpu.DescriptorDB(ctx, np.concatenate(sets_d), np.concatenate(sets_a).astype(np.float32), offs)
+    rng = np.random.default_rng(5)
+    pairs = rng.integers(0, 4, (700, 2)).astype(np.int32)
+    n, m = db.match_pairs(pairs)
+    n2, _ = db.match_pairs(pairs, want_matches=False)
+    assert np.array_equal(n, n2)
+    cache = {}
+    for k, (i, j) in enumerate(pairs.tolist()):
+        if (i, j) not in cache:
+            cache[(i, j)] = oracle.match_bruteforce(sets_d[i], sets_a[i], sets_d[j], sets_a[j])
+        rn, rm = cache[(i, j)]
+        assert n[k] == rn and np.array_equal(m[k, :len(rm)], rm) and (m[k, len(rm):] == -1).all(), k
+    assert int(n.max()) > 100
+    db.close()
+
+
 def test_match_extracted_frames(slamgpu, oracle, synth):
     """End to end on real descriptors: frame vs shifted/rotated frame (BASELINE config 3 inputs (i))."""
     img = synth.frame(640, 480, 1000)
