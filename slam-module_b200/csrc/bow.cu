@@ -413,10 +413,9 @@ extern "C" int sg_bow_similar(sg_ctx *ctx, sg_bowdb *db, const uint32_t *h_q_wor
     if (int r = sc.put(&d_qw, h_q_word, (size_t)nq)) return r;
     if (int r = sc.put(&d_qv, h_q_value, (size_t)nq)) return r;
     const size_t smem = 12 * (size_t)nq;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->bow_attr_set) {       // per device, so per context
         SG_CUDA(ctx, cudaFuncSetAttribute(bow_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * BOWV_MAX));
-        attr_set = true;
+        ctx->bow_attr_set = true;
     }
     bow_score_kernel<<<(db->n_slots + BOW_WARPS - 1) / BOW_WARPS, BOW_WARPS * 32, smem, ctx->stream>>>(
         db->d_word, db->d_value, db->d_len, db->stride, db->n_slots, d_qw, d_qv, nq, db->d_common, db->d_score);
