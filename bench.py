@@ -257,7 +257,7 @@ def extra_configs(slamgpu, sm, sh, rank, world, local, barrier_max_, td):
             offs[1::2] = np.arange(2 * PAIRS) * cap + counts
             offs[2::2] = (np.arange(2 * PAIRS) + 1) * cap
             v = c4.device_views()
-            db = slamgpu.DescriptorDB(c4, None, None, offsets=offs, device_ptrs=(v.desc, v.angle))
+            db = slamgpu.DescriptorDB(c4, None, None, offsets=offs, device_ptrs=(v.desc, v.angle), view=True)   # no copy
             db.match_pairs_device(d_pairs.ptr, PAIRS, d_counts.ptr)
             c4.synchronize()
             db.close()

@@ -212,6 +212,11 @@ int sg_db_create(sg_ctx *ctx, const uint32_t *h_desc, const float *h_angle, cons
 /* Same from device arrays (e.g. the views of sg_extract_device); data is copied. */
 int sg_db_create_device(sg_ctx *ctx, const uint32_t *d_desc, const float *d_angle, const int64_t *h_offsets,
                         int n_sets, sg_db **out);
+/* A view instead of a copy: the database reads d_desc / d_angle in place (they must stay valid and unchanged while
+ * the view is used, and d_desc needs 32 readable bytes behind the last descriptor -- the arrays of
+ * sg_extract_device_views qualify).  The extract -> match flow of one GPU then moves no descriptor at all. */
+int sg_db_wrap_device(sg_ctx *ctx, const uint32_t *d_desc, const float *d_angle, const int64_t *h_offsets,
+                      int n_sets, sg_db **out);
 void sg_db_destroy(sg_db *db);
 /* Batched matching of keyframe pairs (h_pairs: n_pairs x {setA, setB}).  h_matches may be NULL;
  * otherwise row p holds `match_stride` ints (>= size of the largest A set), -1 padded.

@@ -173,7 +173,7 @@ static int build_context(sg_ctx *ctx) {
     if (int r = dev_alloc(ctx, &ctx->d_track_id, O)) return r;
     if (int r = dev_alloc(ctx, &ctx->d_lvl_x, O)) return r;
     if (int r = dev_alloc(ctx, &ctx->d_lvl_y, O)) return r;
-    if (int r = dev_alloc(ctx, &ctx->d_desc, O * 8)) return r;
+    if (int r = dev_alloc(ctx, &ctx->d_desc, O * 8 + 8)) return r;   // + one descriptor of slack: a database view may end here
     if (int r = dev_alloc(ctx, &ctx->d_count, F)) return r;
     if (int r = dev_alloc(ctx, &ctx->d_rescans, 1)) return r;
     SG_CUDA(ctx, cudaMemset(ctx->d_rescans, 0, sizeof(unsigned long long)));
@@ -762,10 +762,24 @@ int sg_db_create(sg_ctx *ctx, const uint32_t *h_desc, const float *h_angle, cons
 int sg_db_create_device(sg_ctx *ctx, const uint32_t *d_desc, const float *d_angle, const int64_t *h_offsets, int n_sets, sg_db **out) {
     return db_create(ctx, d_desc, d_angle, h_offsets, n_sets, out, cudaMemcpyDeviceToDevice);
 }
+// A view: the descriptors stay where they are (e.g. the output of sg_extract_device); only the offsets are uploaded.
+int sg_db_wrap_device(sg_ctx *ctx, const uint32_t *d_desc, const float *d_angle, const int64_t *h_offsets, int n_sets, sg_db **out) {
+    cudaSetDevice(ctx->device);
+    if (!d_desc || !d_angle || !h_offsets || n_sets < 1 || !out) return fail(ctx, SG_ERR_INVALID, "null / empty database");
+    if (h_offsets[0] != 0) return fail(ctx, SG_ERR_INVALID, "offsets[0] must be 0");
+    sg_db *db = new sg_db();
+    db->owns_data = false;
+    if (int r = db_finish(ctx, db, h_offsets, n_sets)) { sg_db_destroy(db); return r; }
+    db->d_desc = const_cast<uint32_t *>(d_desc);
+    db->d_angle = const_cast<float *>(d_angle);
+    *out = db;
+    return SG_OK;
+}
 void sg_db_destroy(sg_db *db) {
     if (!db) return;
     if (db->ctx) cudaSetDevice(db->ctx->device);
-    cudaFree(db->d_desc); cudaFree(db->d_angle); cudaFree(db->d_offsets);
+    if (db->owns_data) { cudaFree(db->d_desc); cudaFree(db->d_angle); }
+    cudaFree(db->d_offsets);
     delete db;
 }
 

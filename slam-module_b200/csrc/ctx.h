@@ -86,6 +86,7 @@ struct sg_db {
     std::vector<long long> offsets;
     int n_sets = 0;
     int max_set = 0;
+    bool owns_data = true;   // false: d_desc / d_angle belong to the caller (sg_db_wrap_device)
 };
 
 struct sg_ctx {

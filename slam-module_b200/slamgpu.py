@@ -69,7 +69,7 @@ ABI_SYMBOLS = [
     "sg_set_pipeline_chunk", "sg_search_candidates", "sg_feature_index", "sg_medoid", "sg_set_overlap", "sg_match_bow", "sg_vocab_create", "sg_vocab_destroy",
     "sg_bow_transform", "sg_bow_transform_device", "sg_match_triangulation", "sg_bow_vector", "sg_bowdb_create",
     "sg_bowdb_destroy", "sg_bowdb_size", "sg_bowdb_add", "sg_bowdb_remove", "sg_bow_similar", "sg_extract_submit",
-    "sg_extract_wait",
+    "sg_extract_wait", "sg_db_wrap_device",
 ]
 
 _lib = None
@@ -122,6 +122,8 @@ def lib():
                                           C.c_void_p, C.c_void_p, C.c_void_p]
         L.sg_db_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.sg_db_create_device.argtypes = L.sg_db_create.argtypes
+        L.sg_db_wrap_device.argtypes = L.sg_db_create.argtypes
+        L.sg_db_wrap_device.restype = C.c_int
         L.sg_match_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.sg_match_pairs_device.argtypes = L.sg_match_pairs.argtypes
         L.sg_malloc.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
@@ -567,13 +569,15 @@ class Context:
 class DescriptorDB:
     """Device-resident descriptor sets (one per keyframe) for batched pair matching."""
 
-    def __init__(self, ctx, desc, angle, offsets=None, device_ptrs=None):
+    def __init__(self, ctx, desc, angle, offsets=None, device_ptrs=None, view=False):
+        """device_ptrs=(d_desc, d_angle): build from device arrays; view=True reads them in place instead of copying."""
         self.ctx = ctx
         h = C.c_void_p()
         if device_ptrs is not None:
             d_desc, d_angle = device_ptrs
             offsets = np.ascontiguousarray(offsets, np.int64)
-            ctx._check(lib().sg_db_create_device(ctx._h, d_desc, d_angle, offsets.ctypes.data, len(offsets) - 1, C.byref(h)))
+            fn = lib().sg_db_wrap_device if view else lib().sg_db_create_device
+            ctx._check(fn(ctx._h, d_desc, d_angle, offsets.ctypes.data, len(offsets) - 1, C.byref(h)))
         else:
             desc = np.ascontiguousarray(desc, np.uint32)
             angle = np.ascontiguousarray(angle, np.float32)

@@ -124,6 +124,33 @@ def test_match_pairs_many_slabs(ctx, slamgpu, oracle, synth):
     db.close()
 
 
+@pytest.mark.parametrize("view", [False, True])
+def test_match_from_device_views(slamgpu, oracle, synth, view):
+    """The one-GPU extract -> match flow of the stereo config: descriptors never leave the device.  The database is a
+    copy (sg_db_create_device) or a view (sg_db_wrap_device) of the extractor's output arrays; set 2f = keypoints of
+    frame f, set 2f+1 = the unused tail of its slot."""
+    a, b = synth.frame(640, 480, 1200), synth.frame(640, 480, 1201)
+    imgs = np.stack([a, synth.shifted_rotated(a), b, np.roll(b, -5, axis=1)])
+    with slamgpu.Context(640, 480, max_frames=4) as c:
+        buf = c.device_buffer(imgs.nbytes).upload(imgs)
+        c.extract_device(buf.ptr, 640, 640 * 480, 4)
+        kps = c.extract_download(4)
+        counts = np.array([k["n"] for k in kps])
+        offs = np.zeros(9, np.int64)
+        offs[1::2] = np.arange(4) * c.cap + counts
+        offs[2::2] = (np.arange(4) + 1) * c.cap
+        v = c.device_views()
+        db = slamgpu.DescriptorDB(c, None, None, offsets=offs, device_ptrs=(v.desc, v.angle), view=view)
+        pairs = np.array([(0, 2), (4, 6), (6, 4), (2, 2)], np.int32)
+        n, m = db.match_pairs(pairs)
+        db.close()
+        buf.free()
+    for k, (i, j) in enumerate(pairs // 2):
+        rn, rm = oracle.match_bruteforce(kps[i]["desc"], kps[i]["angle"], kps[j]["desc"], kps[j]["angle"])
+        assert n[k] == rn and np.array_equal(m[k, :len(rm)], rm), (k, view)
+    assert n[0] > 20 and n[3] == counts[1]
+
+
 def test_match_extracted_frames(slamgpu, oracle, synth):
     """End to end on real descriptors: frame vs shifted/rotated frame (BASELINE config 3 inputs (i))."""
     img = synth.frame(640, 480, 1000)
