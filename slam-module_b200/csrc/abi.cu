@@ -306,6 +306,13 @@ int sg_create(int device, const sg_params *params, sg_ctx **out) {
         return bail(SG_ERR_CUDA);
     }
     ctx->main_stream = ctx->stream;
+    {   // keep what the stream-ordered allocator (database offsets) has freed: no trimming at synchronisation points
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (const char *e = getenv("SG_PIPE_STREAMS")) ctx->pipe_streams = std::min((int)sg_ctx::N_CMP, std::max(1, atoi(e)));   // tuning knob
     if (cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) != cudaSuccess
         || cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) != cudaSuccess
@@ -705,8 +712,11 @@ static int db_finish(sg_ctx *ctx, sg_db *db, const int64_t *h_offsets, int n_set
         if (h_offsets[s + 1] < h_offsets[s]) return fail(ctx, SG_ERR_INVALID, "offsets must be non-decreasing");
         db->max_set = std::max<long long>(db->max_set, h_offsets[s + 1] - h_offsets[s]);
     }
-    SG_CUDA(ctx, cudaMalloc(&db->d_offsets, sizeof(long long) * (n_sets + 1)));
-    SG_CUDA(ctx, cudaMemcpy(db->d_offsets, db->offsets.data(), sizeof(long long) * (n_sets + 1), cudaMemcpyHostToDevice));
+    // stream-ordered allocation from the device's memory pool: creating / destroying a database (per step in the
+    // extract -> match flow) must not pay a device-wide cudaMalloc / cudaFree
+    SG_CUDA(ctx, cudaMallocAsync((void **)&db->d_offsets, sizeof(long long) * (n_sets + 1), ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(db->d_offsets, db->offsets.data(), sizeof(long long) * (n_sets + 1), cudaMemcpyHostToDevice, ctx->stream));
+    SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // db->offsets is pageable host memory that outlives the call, but keep the create synchronous
     return SG_OK;
 }
 
@@ -718,8 +728,8 @@ static int db_create(sg_ctx *ctx, const uint32_t *desc, const float *angle, cons
     sg_db *db = new sg_db();
     const size_t total = (size_t)h_offsets[n_sets];
     int r = db_finish(ctx, db, h_offsets, n_sets);
-    if (!r && cudaMalloc(&db->d_desc, std::max<size_t>(total, 1) * 32 + 32) != cudaSuccess) r = fail(ctx, SG_ERR_CUDA, "cudaMalloc failed");
-    if (!r && cudaMalloc(&db->d_angle, std::max<size_t>(total, 1) * 4) != cudaSuccess) r = fail(ctx, SG_ERR_CUDA, "cudaMalloc failed");
+    if (!r && cudaMallocAsync((void **)&db->d_desc, std::max<size_t>(total, 1) * 32 + 32, ctx->stream) != cudaSuccess) r = fail(ctx, SG_ERR_CUDA, "cudaMallocAsync failed");
+    if (!r && cudaMallocAsync((void **)&db->d_angle, std::max<size_t>(total, 1) * 4, ctx->stream) != cudaSuccess) r = fail(ctx, SG_ERR_CUDA, "cudaMallocAsync failed");
     if (!r && total) {
         if (cudaMemcpyAsync(db->d_desc, desc, total * 32, kind, ctx->stream) != cudaSuccess
             || cudaMemcpyAsync(db->d_angle, angle, total * 4, kind, ctx->stream) != cudaSuccess
@@ -778,8 +788,13 @@ int sg_db_wrap_device(sg_ctx *ctx, const uint32_t *d_desc, const float *d_angle,
 void sg_db_destroy(sg_db *db) {
     if (!db) return;
     if (db->ctx) cudaSetDevice(db->ctx->device);
-    if (db->owns_data) { cudaFree(db->d_desc); cudaFree(db->d_angle); }
-    cudaFree(db->d_offsets);
+    auto release = [&](void *p) {      // stream-ordered, after everything queued on the context's stream so far
+        if (!p) return;
+        if (db->ctx) cudaFreeAsync(p, db->ctx->main_stream);
+        else cudaFree(p);
+    };
+    if (db->owns_data) { release(db->d_desc); release(db->d_angle); }
+    release(db->d_offsets);
     delete db;
 }
 

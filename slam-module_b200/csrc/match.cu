@@ -164,6 +164,8 @@ struct MatchArgs {
     int ratio_is_double;
     int check_orientation;
     int last_wins;             // ties between equal distances resolve to the LARGER B index (matchForTriangulationDBoW :231)
+    int splits;                // the B set is cut into `splits` ranges (grid z); > 1 only when there are few pairs
+    long long split_rows;      // scratch rows per split (pairs in the launch x row_stride)
 };
 
 __device__ __forceinline__ void topk_insert(unsigned (&t)[TOPK], unsigned key) {
@@ -213,9 +215,13 @@ hamming_topk_kernel(const MatchArgs a, uint32_t *topk, uint32_t *nseen_out) {
     unsigned nseen = 0;
     const unsigned C = a.cutoff;
     const uint4 *pb = reinterpret_cast<const uint4 *>(a.desc + 8 * ob);
+    // few pairs in the launch: the B rows are shared out over grid z so that the chip is filled; the partial lists
+    // are merged by topk_merge_kernel
+    const int per_split = (nB + a.splits - 1) / a.splits;
+    const int jb = min(nB, (int)blockIdx.z * per_split), je = min(nB, jb + per_split);
 
-    for (int j0 = 0; j0 < nB; j0 += B_CHUNK) {
-        const int cn = min(B_CHUNK, nB - j0);
+    for (int j0 = jb; j0 < je; j0 += B_CHUNK) {
+        const int cn = min(B_CHUNK, je - j0);
         __syncthreads();
         for (int i = tid; i < 2 * cn; i += MT_THREADS) Bs[i] = __ldg(pb + 2 * (size_t)j0 + i);
         __syncthreads();
@@ -233,10 +239,49 @@ hamming_topk_kernel(const MatchArgs a, uint32_t *topk, uint32_t *nseen_out) {
         }
     }
     if (live) {
-        const size_t r = (size_t)p * a.row_stride + row;
+        const size_t r = (size_t)blockIdx.z * a.split_rows + (size_t)p * a.row_stride + row;
         reinterpret_cast<uint4 *>(topk)[r] = make_uint4(t[0], t[1], t[2], t[3]);
         nseen_out[r] = nseen;
     }
+}
+
+// Merge of the per-split lists into split 0: the 4 smallest keys (keys are unique: they carry the B index) and the
+// sum of the counts.  Rows no split wrote (row >= nA) hold stale keys that the resolve kernel never reads.
+__global__ void topk_merge_kernel(uint32_t *topk, uint32_t *nseen, int splits, long long split_rows) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= split_rows) return;
+    uint4 v = reinterpret_cast<uint4 *>(topk)[i];
+    unsigned t[TOPK] = {v.x, v.y, v.z, v.w};
+    unsigned n = nseen[i];
+    for (int sp = 1; sp < splits; ++sp) {
+        v = reinterpret_cast<const uint4 *>(topk)[sp * split_rows + i];
+        if (v.x < t[TOPK - 1]) topk_insert(t, v.x);
+        if (v.y < t[TOPK - 1]) topk_insert(t, v.y);
+        if (v.z < t[TOPK - 1]) topk_insert(t, v.z);
+        if (v.w < t[TOPK - 1]) topk_insert(t, v.w);
+        n += nseen[sp * split_rows + i];
+    }
+    reinterpret_cast<uint4 *>(topk)[i] = make_uint4(t[0], t[1], t[2], t[3]);
+    nseen[i] = n;
+}
+
+// How many B ranges a launch of `ctas` CTAs (row tiles x pairs) should use: 1 when the grid already fills the chip.
+static int pick_splits(int ctas, int max_set) {
+    if (ctas >= 2 * 148) return 1;
+    const int want = (4 * 148 + ctas - 1) / std::max(ctas, 1);
+    return std::max(1, std::min(std::min(want, 8), max_set / 128));
+}
+
+static int launch_topk(sg_ctx *ctx, MatchArgs &a, int tiles, int np, int splits, uint32_t *d_topk, uint32_t *d_nseen) {
+    a.splits = splits;
+    a.split_rows = (long long)np * a.row_stride;
+    hamming_topk_kernel<<<dim3(tiles, np, splits), MT_THREADS, 0, ctx->stream>>>(a, d_topk, d_nseen);
+    SG_LAUNCH_CHECK(ctx);
+    if (splits > 1) {
+        topk_merge_kernel<<<(unsigned)((a.split_rows + 255) / 256), 256, 0, ctx->stream>>>(d_topk, d_nseen, splits, a.split_rows);
+        SG_LAUNCH_CHECK(ctx);
+    }
+    return SG_OK;
 }
 
 // ---- sequential resolve + angle filter -------------------------------------------------------------
@@ -343,15 +388,30 @@ match_resolve_kernel(const MatchArgs a, int n_pairs, const uint32_t *topk, const
 #pragma unroll
                 for (int w = 0; w < 8; ++w) ar[w] = __ldg(dA + 8 * (size_t)row + w);
                 unsigned bkey = (256u << 16) | 0xffffu, sec = 256u;
-                for (int j = lane; j < nB; j += 32) {
-                    if ((taken[j >> 5] >> (j & 31)) & 1u) continue;
-                    const uint4 b0 = __ldg(reinterpret_cast<const uint4 *>(dB + 8 * (size_t)j));
-                    const uint4 b1 = __ldg(reinterpret_cast<const uint4 *>(dB + 8 * (size_t)j) + 1);
-                    const unsigned d = __popc(ar[0] ^ b0.x) + __popc(ar[1] ^ b0.y) + __popc(ar[2] ^ b0.z) + __popc(ar[3] ^ b0.w)
-                                       + __popc(ar[4] ^ b1.x) + __popc(ar[5] ^ b1.y) + __popc(ar[6] ^ b1.z) + __popc(ar[7] ^ b1.w);
-                    const unsigned key = (d << 16) | (unsigned)j;
-                    if (key < bkey) { sec = bkey >> 16; bkey = key; }
-                    else if (d < sec) sec = d;
+                // four independent 32-row groups per iteration: the loads of all four are in flight together (the scan is
+                // a chain of global-memory round trips otherwise); best / second do not depend on the visiting order
+                constexpr int RU = 4;
+                for (int j0 = lane; j0 < nB; j0 += 32 * RU) {
+                    uint4 b0[RU], b1[RU];
+                    bool ok[RU];
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) {
+                        const int j = j0 + 32 * u;
+                        ok[u] = j < nB && !((taken[j >> 5] >> (j & 31)) & 1u);
+                        if (ok[u]) {
+                            b0[u] = __ldg(reinterpret_cast<const uint4 *>(dB + 8 * (size_t)j));
+                            b1[u] = __ldg(reinterpret_cast<const uint4 *>(dB + 8 * (size_t)j) + 1);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) {
+                        if (!ok[u]) continue;
+                        const unsigned d = __popc(ar[0] ^ b0[u].x) + __popc(ar[1] ^ b0[u].y) + __popc(ar[2] ^ b0[u].z) + __popc(ar[3] ^ b0[u].w)
+                                           + __popc(ar[4] ^ b1[u].x) + __popc(ar[5] ^ b1[u].y) + __popc(ar[6] ^ b1[u].z) + __popc(ar[7] ^ b1[u].w);
+                        const unsigned key = (d << 16) | (unsigned)(j0 + 32 * u);
+                        if (key < bkey) { sec = bkey >> 16; bkey = key; }
+                        else if (d < sec) sec = d;
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o; o >>= 1) {
@@ -472,15 +532,19 @@ int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, con
     const int stride = db->max_set;
     if (d_matches && match_stride < stride) return fail(ctx, SG_ERR_INVALID, "match_stride smaller than the largest set");
     const int chunk = std::min(n_pairs, match_chunk_pairs(db, d_matches == nullptr));
+    const int tiles = (stride + MT_THREADS - 1) / MT_THREADS;
+    const int splits = pick_splits(tiles * chunk, db->max_set);
     {
         size_t need = (size_t)chunk * stride;
-        if (need > ctx->topk_rows) {
+        if (need * splits > ctx->topk_rows) {
+            need *= splits;
             if (ctx->d_topk) cudaFree(ctx->d_topk);
             if (ctx->d_nseen) cudaFree(ctx->d_nseen);
             ctx->d_topk = nullptr; ctx->d_nseen = nullptr; ctx->topk_rows = 0;
             SG_CUDA(ctx, cudaMalloc(&ctx->d_topk, need * TOPK * 4));
             SG_CUDA(ctx, cudaMalloc(&ctx->d_nseen, need * 4));
             ctx->topk_rows = need;
+            need /= splits;
         }
         if (!d_matches) {
             size_t cap = ctx->matches_cap;
@@ -503,9 +567,9 @@ int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, con
         if (p0 == 0) mark(ctx, EV_MATCH0, true);
         a.pairs = d_pairs + 2 * (size_t)p0;
         a.row_stride = stride;
-        dim3 grid((stride + MT_THREADS - 1) / MT_THREADS, np);
-        hamming_topk_kernel<<<grid, MT_THREADS, 0, ctx->stream>>>(a, ctx->d_topk, ctx->d_nseen);
-        SG_LAUNCH_CHECK(ctx);
+        int sp = np == chunk ? splits : pick_splits(tiles * np, db->max_set);
+        sp = (int)std::max<size_t>(1, std::min<size_t>(sp, ctx->topk_rows / ((size_t)np * stride)));   // never beyond the scratch
+        if (int r = launch_topk(ctx, a, tiles, np, sp, ctx->d_topk, ctx->d_nseen)) return r;
         if (p0 == 0) mark(ctx, EV_TOPK1);
         a.match_stride = d_matches ? match_stride : stride;
         int *mout = d_matches ? d_matches + (size_t)p0 * match_stride : ctx->d_matches;
@@ -526,7 +590,9 @@ int run_topk_lists(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs
                    uint32_t **d_nseen, int *row_stride) {
     if (db->max_set > 65535) return fail(ctx, SG_ERR_INVALID, "descriptor sets larger than 65535 features are not supported");
     const int stride = std::max(db->max_set, 1);
-    const size_t need = (size_t)n_pairs * stride;
+    const int tiles = (stride + MT_THREADS - 1) / MT_THREADS;
+    const int splits = pick_splits(tiles * n_pairs, db->max_set);
+    const size_t need = (size_t)n_pairs * stride * splits;
     if (need > ctx->topk_rows) {
         if (ctx->d_topk) cudaFree(ctx->d_topk);
         if (ctx->d_nseen) cudaFree(ctx->d_nseen);
@@ -538,8 +604,7 @@ int run_topk_lists(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs
     MatchArgs a{};
     a.desc = db->d_desc; a.angle = db->d_angle; a.offsets = db->d_offsets; a.pairs = d_pairs;
     a.cutoff = thr; a.thr = thr; a.row_stride = stride; a.last_wins = 1;
-    hamming_topk_kernel<<<dim3((stride + MT_THREADS - 1) / MT_THREADS, n_pairs), MT_THREADS, 0, ctx->stream>>>(a, ctx->d_topk, ctx->d_nseen);
-    SG_LAUNCH_CHECK(ctx);
+    if (int r = launch_topk(ctx, a, tiles, n_pairs, splits, ctx->d_topk, ctx->d_nseen)) return r;
     *d_topk = ctx->d_topk; *d_nseen = ctx->d_nseen; *row_stride = stride;
     return SG_OK;
 }

@@ -28,3 +28,12 @@ for it in range(8):
     db.match_pairs_device(d_pairs.ptr, PAIRS, d_counts.ptr); c4.synchronize(); t.append(time.perf_counter())
     db.close(); t.append(time.perf_counter())
     print("iter %d: extract %.2f  counts %.2f  db_create %.2f  match %.2f  db_close %.2f ms" % ((it,) + tuple(1e3 * (b - a) for a, b in zip(t, t[1:]))))
+c4.set_profiling(True)
+for it in range(3):
+    db = slamgpu.DescriptorDB(c4, None, None, offsets=offs, device_ptrs=(v.desc, v.angle), view=True)
+    db.match_pairs_device(d_pairs.ptr, PAIRS, d_counts.ptr); c4.synchronize()
+    db.close()
+print("stage ms", c4.stage_ms(), "rescans", c4.rescans(), "matches", d_counts.download(np.uint32, PAIRS)[:4])
+db = slamgpu.DescriptorDB(c4, None, None, offsets=offs, device_ptrs=(v.desc, v.angle), view=True)
+t0 = time.perf_counter(); n, m = db.match_pairs(pairs); t1 = time.perf_counter()
+print("host-variant call %.2f ms, rescans over %d pairs: %d" % (1e3 * (t1 - t0), PAIRS, c4.rescans()))
