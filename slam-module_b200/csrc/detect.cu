@@ -270,7 +270,7 @@ struct NodeBox { short bx, by, ex, ey; };
 
 // Exclusive scan of data[0..n) in place (block-wide); returns the total.  tmp: 33 ints of smem.
 __device__ int block_exclusive_scan(int *data, int n, int *tmp) {
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = DIST_THREADS;   // every caller runs DIST_THREADS threads: a shift, not a division
     const int per = (n + nt - 1) / nt;
     const int b = min(tid * per, n), e = min(b + per, n);
     int sum = 0;
@@ -412,15 +412,29 @@ distribute_kernel(const __grid_constant__ GeomDev g, int node_cap_max, const uns
             P = block_exclusive_scan(ord, n, tmp);
         } else {
             // most populated first; equal counts: the node nearer the list front (the newer one) first
-            for (int j = tid; j < n; j += DIST_THREADS) {
-                const int cj = cnt[j];
-                int r = 0;
-                if (cj > 1)
-                    for (int k = 0; k < n; ++k) {
-                        const int ck = cnt[k];
-                        r += (ck > 1 && (ck > cj || (ck == cj && k < j))) ? 1 : 0;
-                    }
-                ord[j] = r;
+            if (n <= 4096 && ncand < (1 << 19)) {
+                // rank = number of splittable nodes with a larger (count, -position) key: one compare per node pair
+                for (int j = tid; j < n; j += DIST_THREADS) kpos[j] = cnt[j] > 1 ? (cnt[j] << 12) | (4095 - j) : 0;
+                __syncthreads();
+                for (int j = tid; j < n; j += DIST_THREADS) {
+                    const int kj = kpos[j];
+                    int r = 0;
+                    if (kj)
+                        for (int k = 0; k < n; ++k) r += kpos[k] > kj ? 1 : 0;
+                    ord[j] = r;
+                }
+                __syncthreads();
+            } else {                                            // keys would not fit 31 bits
+                for (int j = tid; j < n; j += DIST_THREADS) {
+                    const int cj = cnt[j];
+                    int r = 0;
+                    if (cj > 1)
+                        for (int k = 0; k < n; ++k) {
+                            const int ck = cnt[k];
+                            r += (ck > 1 && (ck > cj || (ck == cj && k < j))) ? 1 : 0;
+                        }
+                    ord[j] = r;
+                }
             }
             for (int j = tid; j < n; j += DIST_THREADS) kpos[j] = cnt[j] > 1 ? 1 : 0;
             __syncthreads();
