@@ -271,9 +271,8 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
         mbar_wait(bar, 0);        // source tile landed
         // partial tiles (right / bottom image edge): only the window columns / rows the blur of the tile reads
         if (rg < ROWG && 2 * cp < tw + 8) {
-#pragma unroll
-            for (int k = 0; k < ROWS_PER_G; ++k) {
-                if (rg * ROWS_PER_G + k >= th + 6) break;
+            const int rows = min(ROWS_PER_G, th + 6 - rg * ROWS_PER_G);   // full tiles: ROWS_PER_G, no per-row test
+            auto resize_row = [&](int k) {
                 const uint4 ty = lds128(yt_addr + k * (unsigned)sizeof(YTap));
                 const uint32_t a0 = s_col + ty.x, a1 = s_col + ty.y;
                 const uint32_t g0 = __byte_perm(lds32(a0), lds32(a0 + 4), sel), g1 = __byte_perm(lds32(a1), lds32(a1 + 4), sel);
@@ -283,6 +282,12 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
                 const unsigned va = (__umulhi(ty.w, ha1 & ~15u) + __umulhi(ty.z, ha0 & ~15u) + 2u) >> 2;
                 const unsigned vb = (__umulhi(ty.w, hb1 & ~15u) + __umulhi(ty.z, hb0 & ~15u) + 2u) >> 2;
                 sts16(r_addr + k * FW, va | (vb << 8));
+            };
+            if (rows == ROWS_PER_G) {
+#pragma unroll
+                for (int k = 0; k < ROWS_PER_G; ++k) resize_row(k);
+            } else {
+                for (int k = 0; k < rows; ++k) resize_row(k);
             }
         }
     } else {
