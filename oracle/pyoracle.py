@@ -204,7 +204,7 @@ def extract(p, img, tracks=None, track_ids=None, track_level=0):
     """OrbExtractor::detectAndExtract for one frame; returns a dict of SoA arrays."""
     img = np.ascontiguousarray(img, np.uint8)
     nt = 0 if tracks is None else len(tracks)
-    cap = p.max_keypoints + nt + 64
+    cap = 2 * p.max_keypoints + nt + 1024     # extreme aspect ratios: more initial quadtree nodes than budget
     x = np.empty(cap, np.float32)
     y = np.empty(cap, np.float32)
     a = np.empty(cap, np.float32)
