@@ -24,9 +24,11 @@ int fail(sg_ctx *ctx, int code, const char *fmt, ...) {
 
 int grow(sg_ctx *ctx, void **ptr, size_t *cap, size_t need, size_t elem) {
     if (need <= *cap) return SG_OK;
-    if (*ptr) cudaFree(*ptr);
+    // stream-ordered pool allocation (the pool keeps what is freed): a growing scratch buffer must not cost a
+    // device-wide cudaFree / cudaMalloc, which takes milliseconds to seconds on virtualised hosts
+    if (*ptr) cudaFreeAsync(*ptr, ctx->main_stream);
     *ptr = nullptr; *cap = 0;
-    SG_CUDA(ctx, cudaMalloc(ptr, need * elem));
+    SG_CUDA(ctx, cudaMallocAsync(ptr, need * elem, ctx->main_stream));
     *cap = need;
     return SG_OK;
 }

@@ -538,11 +538,11 @@ int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, con
         size_t need = (size_t)chunk * stride;
         if (need * splits > ctx->topk_rows) {
             need *= splits;
-            if (ctx->d_topk) cudaFree(ctx->d_topk);
-            if (ctx->d_nseen) cudaFree(ctx->d_nseen);
+            if (ctx->d_topk) cudaFreeAsync(ctx->d_topk, ctx->main_stream);
+            if (ctx->d_nseen) cudaFreeAsync(ctx->d_nseen, ctx->main_stream);
             ctx->d_topk = nullptr; ctx->d_nseen = nullptr; ctx->topk_rows = 0;
-            SG_CUDA(ctx, cudaMalloc(&ctx->d_topk, need * TOPK * 4));
-            SG_CUDA(ctx, cudaMalloc(&ctx->d_nseen, need * 4));
+            SG_CUDA(ctx, cudaMallocAsync((void **)&ctx->d_topk, need * TOPK * 4, ctx->main_stream));
+            SG_CUDA(ctx, cudaMallocAsync((void **)&ctx->d_nseen, need * 4, ctx->main_stream));
             ctx->topk_rows = need;
             need /= splits;
         }
@@ -594,11 +594,11 @@ int run_topk_lists(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs
     const int splits = pick_splits(tiles * n_pairs, db->max_set);
     const size_t need = (size_t)n_pairs * stride * splits;
     if (need > ctx->topk_rows) {
-        if (ctx->d_topk) cudaFree(ctx->d_topk);
-        if (ctx->d_nseen) cudaFree(ctx->d_nseen);
+        if (ctx->d_topk) cudaFreeAsync(ctx->d_topk, ctx->main_stream);
+        if (ctx->d_nseen) cudaFreeAsync(ctx->d_nseen, ctx->main_stream);
         ctx->d_topk = nullptr; ctx->d_nseen = nullptr; ctx->topk_rows = 0;
-        SG_CUDA(ctx, cudaMalloc(&ctx->d_topk, need * TOPK * 4));
-        SG_CUDA(ctx, cudaMalloc(&ctx->d_nseen, need * 4));
+        SG_CUDA(ctx, cudaMallocAsync((void **)&ctx->d_topk, need * TOPK * 4, ctx->main_stream));
+        SG_CUDA(ctx, cudaMallocAsync((void **)&ctx->d_nseen, need * 4, ctx->main_stream));
         ctx->topk_rows = need;
     }
     MatchArgs a{};

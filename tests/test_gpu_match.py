@@ -151,6 +151,29 @@ def test_match_from_device_views(slamgpu, oracle, synth, view):
     assert n[0] > 20 and n[3] == counts[1]
 
 
+@pytest.mark.parametrize("nA,nB", [(8000, 6000), (65535, 300), (300, 65535)])
+def test_match_large_sets(ctx, slamgpu, oracle, nA, nB):
+    """Sets far beyond the usual 2000 features, up to the 65535 the 16-bit index fields allow; with nA > nB many A rows
+    compete for the same B feature (uniqueness pressure on the sequential walk)."""
+    rng = np.random.default_rng(nA + nB)
+    dB = rng.integers(0, 2 ** 32, (nB, 8), dtype=np.uint32)
+    aB = rng.uniform(0, 360, nB).astype(np.float32)
+    src = rng.integers(0, nB, nA)
+    dA = dB[src].copy()
+    bits = rng.integers(0, 256, (nA, 40))
+    keep = rng.integers(0, 40, nA)
+    for i in range(nA):
+        for b in bits[i, :keep[i]]:
+            dA[i, b >> 5] ^= np.uint32(1 << (int(b) & 31))
+    aA = ((aB[src] + rng.normal(0, 4, nA)) % 360).astype(np.float32)
+    n, m = ctx.match_bruteforce(dA, aA, dB, aB)
+    rn, rm = oracle.match_bruteforce(dA, aA, dB, aB)
+    assert n == rn and np.array_equal(m, rm) and n >= min(nA, nB) // 2
+    if nB == 65535:
+        with pytest.raises(slamgpu.SlamGpuError):
+            ctx.match_bruteforce(dA, aA, np.concatenate([dB, dB[:1]]), np.concatenate([aB, aB[:1]]))   # 65536 features
+
+
 def test_match_extracted_frames(slamgpu, oracle, synth):
     """End to end on real descriptors: frame vs shifted/rotated frame (BASELINE config 3 inputs (i))."""
     img = synth.frame(640, 480, 1000)
