@@ -604,7 +604,7 @@ def main():
         roof_stage = dom if dom in stage_bytes else "pyramid"
         roofline = {"kernel": {"pyramid": "pyr_fast_kernel (8 launches: blur of level 0 + 7 fused resize+blur levels; traffic: the level-1 launch)",
                                "fast": "fast_cells_kernel (1 launch per step)"}[roof_stage],
-                    "note": "integer-issue bound, not HBM bound: ALU pipe ~69% busy, issue slots ~67% (profiles/ncu_full_r1g.md)",
+                    "note": "integer-issue bound, not HBM bound: ALU pipe ~69% busy, issue slots ~67% (profiles/ncu_full_r1h.md)",
                     "bound": "hbm", "achieved": stages[roof_stage]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": stages[roof_stage]["frac_of_hbm"], "traffic": traffic_of(roof_stage), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch_group": stage_bytes[roof_stage], "dominant_stage_by_time": dom}
