@@ -397,11 +397,10 @@ match_resolve_kernel(const MatchArgs a, int n_pairs, const uint32_t *topk, const
 #pragma unroll
                     for (int u = 0; u < RU; ++u) {
                         const int j = j0 + 32 * u;
-                        ok[u] = j < nB && !((taken[j >> 5] >> (j & 31)) & 1u);
-                        if (ok[u]) {
-                            b0[u] = __ldg(reinterpret_cast<const uint4 *>(dB + 8 * (size_t)j));
-                            b1[u] = __ldg(reinterpret_cast<const uint4 *>(dB + 8 * (size_t)j) + 1);
-                        }
+                        const int jc = min(j, nB - 1);               // unconditional (clamped) loads: no branch between them
+                        ok[u] = j < nB && !((taken[jc >> 5] >> (jc & 31)) & 1u);
+                        b0[u] = __ldg(reinterpret_cast<const uint4 *>(dB + 8 * (size_t)jc));
+                        b1[u] = __ldg(reinterpret_cast<const uint4 *>(dB + 8 * (size_t)jc) + 1);
                     }
 #pragma unroll
                     for (int u = 0; u < RU; ++u) {
