@@ -79,3 +79,19 @@ def test_synthetic_inputs_are_deterministic(synth):
     b = synth.frame(640, 480, 1000)
     assert np.array_equal(a, b) and a.dtype == np.uint8 and a.shape == (480, 640)
     assert not np.array_equal(a, synth.frame(640, 480, 1001))
+
+
+def test_integration_doc_covers_every_entry_point(slamgpu):
+    """INTEGRATION.md names, for every exported entry point, the reference interface it replaces (or says it is a
+    harness helper); `sg_x[_device]` shorthands are expanded."""
+    import re
+    text = (ROOT / "INTEGRATION.md").read_text()
+    named = set(re.findall(r"sg_[a-z0-9_]+", text))
+    for m in re.finditer(r"(sg_[a-z0-9_]+)\[(_[a-z_]+)\]", text):
+        named.add(m.group(1) + m.group(2))
+    for m in re.finditer(r"(sg_[a-z0-9_]+)\[(_[a-z]+)\[(_[a-z]+)\]\]", text):
+        named.add(m.group(1) + m.group(2))
+        named.add(m.group(1) + m.group(2) + m.group(3))
+    missing = [s for s in slamgpu.ABI_SYMBOLS if s not in named]
+    assert not missing, missing
+
