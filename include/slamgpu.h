@@ -128,7 +128,8 @@ int sg_extract(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_strid
  * c+1 and the device->host copy of chunk c-1 run under the kernels of chunk c.  Pass pinned host memory
  * (sg_host_alloc_pinned) for the copies to be asynchronous. */
 int sg_set_pipeline_chunk(sg_ctx *ctx, int frames);
-/* Streaming form of sg_extract (no tracker points) for a sequence of batches: submit queues the copies and the
+/* Streaming form of sg_extract (OrbExtractor::detectAndExtract, orb_extractor.hpp:16-20, without tracker points) for a
+ * sequence of batches: submit queues the copies and the
  * kernels of the batch on the context's pipeline streams and returns; the host arrays of h_out (pinned) are complete
  * after sg_extract_wait(ctx, ticket).  The batch occupies the context's frame slots [base_frame, base_frame +
  * n_frames) -- a context created with max_frames = 2 x batch keeps two batches in flight on disjoint halves, so the
@@ -212,7 +213,8 @@ int sg_db_create(sg_ctx *ctx, const uint32_t *h_desc, const float *h_angle, cons
 /* Same from device arrays (e.g. the views of sg_extract_device); data is copied. */
 int sg_db_create_device(sg_ctx *ctx, const uint32_t *d_desc, const float *d_angle, const int64_t *h_offsets,
                         int n_sets, sg_db **out);
-/* A view instead of a copy: the database reads d_desc / d_angle in place (they must stay valid and unchanged while
+/* The descriptor sets matchForLoopClosures reads (keyframe_matcher.cpp:61-63) as a view instead of a copy: the database
+ * reads d_desc / d_angle in place (they must stay valid and unchanged while
  * the view is used, and d_desc needs 32 readable bytes behind the last descriptor -- the arrays of
  * sg_extract_device_views qualify).  The extract -> match flow of one GPU then moves no descriptor at all. */
 int sg_db_wrap_device(sg_ctx *ctx, const uint32_t *d_desc, const float *d_angle, const int64_t *h_offsets,
