@@ -335,7 +335,9 @@ int sg_create(int device, const sg_params *params, sg_ctx **out) {
 void sg_destroy(sg_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    // batches may still be in flight on the pipeline streams (sg_extract_submit without its wait)
+    for (cudaStream_t q : {ctx->main_stream, ctx->s_in, ctx->s_out}) if (q) cudaStreamSynchronize(q);
+    for (cudaStream_t q : ctx->s_cmp) if (q) cudaStreamSynchronize(q);
     for (auto &L : ctx->lv) { cudaFree(L.pyr); cudaFree(L.blur); cudaFree(L.xtab); cudaFree(L.ytab); }
     void *ptrs[] = {ctx->d_cand, ctx->d_cand_node, ctx->d_cand_count, ctx->d_kp_xy, ctx->d_kp_resp, ctx->d_kp_count,
                     ctx->d_err, ctx->d_trk_xy, ctx->d_trk_pt, ctx->d_trk_id, ctx->d_trk_count, ctx->d_x, ctx->d_y,
@@ -353,7 +355,7 @@ void sg_destroy(sg_ctx *ctx) {
     for (auto &e : ctx->ticket_ev) if (e) cudaEventDestroy(e);
     for (cudaStream_t q : {ctx->s_in, ctx->s_out}) if (q) cudaStreamDestroy(q);
     for (cudaStream_t q : ctx->s_cmp) if (q) cudaStreamDestroy(q);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (cudaStream_t m = ctx->main_stream ? ctx->main_stream : ctx->stream) cudaStreamDestroy(m);
     delete ctx;
 }
 
