@@ -162,7 +162,7 @@ struct sg_ctx {
     // matcher scratch (grown on demand)
     uint32_t *d_topk = nullptr;            // [rows][4] keys
     uint32_t *d_nseen = nullptr;           // [rows]
-    size_t topk_rows = 0;
+    size_t topk_rows = 0, topk_words = 0;   // capacity in rows (counts) and in 4-byte keys
     int *d_pairs = nullptr;
     size_t pairs_cap = 0;
     int *d_matches = nullptr;

@@ -21,7 +21,8 @@
 
 namespace sg {
 
-constexpr int TOPK = 4;
+constexpr int TOPK = 4;           // list length of the throughput path (and of run_topk_lists)
+constexpr int TOPK_WIDE = 16;     // launches with few pairs: longer lists, (almost) no exact rescans on clustered descriptors
 constexpr int MT_THREADS = 256;
 constexpr int B_CHUNK = 1024;        // B descriptors per shared-memory tile (32 KB)
 constexpr unsigned EMPTY_KEY = 0xffffffffu;
@@ -168,9 +169,10 @@ struct MatchArgs {
     long long split_rows;      // scratch rows per split (pairs in the launch x row_stride)
 };
 
-__device__ __forceinline__ void topk_insert(unsigned (&t)[TOPK], unsigned key) {
+template <int K>
+__device__ __forceinline__ void topk_insert(unsigned (&t)[K], unsigned key) {
 #pragma unroll
-    for (int i = 0; i < TOPK; ++i) {
+    for (int i = 0; i < K; ++i) {
         const unsigned lo = min(t[i], key);
         key = max(t[i], key);
         t[i] = lo;
@@ -193,6 +195,7 @@ __device__ __forceinline__ unsigned hamming256_csa(const uint4 &a0, const uint4 
     return __popc(s3) + __popc(a1.w ^ b1.w) + 2u * __popc(s4) + 4u * __popc(c4);
 }
 
+template <int K>
 __global__ void __launch_bounds__(MT_THREADS)
 hamming_topk_kernel(const MatchArgs a, uint32_t *topk, uint32_t *nseen_out) {
     __shared__ uint4 Bs[B_CHUNK * 2];
@@ -209,9 +212,9 @@ hamming_topk_kernel(const MatchArgs a, uint32_t *topk, uint32_t *nseen_out) {
         const uint4 *pa = reinterpret_cast<const uint4 *>(a.desc + 8 * (oa + row));
         a0 = __ldg(pa); a1 = __ldg(pa + 1);
     }
-    unsigned t[TOPK];
+    unsigned t[K];
 #pragma unroll
-    for (int i = 0; i < TOPK; ++i) t[i] = EMPTY_KEY;
+    for (int i = 0; i < K; ++i) t[i] = EMPTY_KEY;
     unsigned nseen = 0;
     const unsigned C = a.cutoff;
     const uint4 *pb = reinterpret_cast<const uint4 *>(a.desc + 8 * ob);
@@ -233,35 +236,47 @@ hamming_topk_kernel(const MatchArgs a, uint32_t *topk, uint32_t *nseen_out) {
                 if (d <= C) {
                     ++nseen;
                     const unsigned key = (d << 16) | (a.last_wins ? 0xffffu - (unsigned)(j0 + j) : (unsigned)(j0 + j));
-                    if (key < t[TOPK - 1]) topk_insert(t, key);
+                    if (key < t[K - 1]) topk_insert(t, key);
                 }
             }
         }
     }
     if (live) {
         const size_t r = (size_t)blockIdx.z * a.split_rows + (size_t)p * a.row_stride + row;
-        reinterpret_cast<uint4 *>(topk)[r] = make_uint4(t[0], t[1], t[2], t[3]);
+#pragma unroll
+        for (int q = 0; q < K / 4; ++q)
+            reinterpret_cast<uint4 *>(topk)[r * (K / 4) + q] = make_uint4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
         nseen_out[r] = nseen;
     }
 }
 
 // Merge of the per-split lists into split 0: the 4 smallest keys (keys are unique: they carry the B index) and the
 // sum of the counts.  Rows no split wrote (row >= nA) hold stale keys that the resolve kernel never reads.
+template <int K>
 __global__ void topk_merge_kernel(uint32_t *topk, uint32_t *nseen, int splits, long long split_rows) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= split_rows) return;
-    uint4 v = reinterpret_cast<uint4 *>(topk)[i];
-    unsigned t[TOPK] = {v.x, v.y, v.z, v.w};
+    unsigned t[K];
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q) {
+        const uint4 v = reinterpret_cast<const uint4 *>(topk)[i * (K / 4) + q];
+        t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+    }
     unsigned n = nseen[i];
     for (int sp = 1; sp < splits; ++sp) {
-        v = reinterpret_cast<const uint4 *>(topk)[sp * split_rows + i];
-        if (v.x < t[TOPK - 1]) topk_insert(t, v.x);
-        if (v.y < t[TOPK - 1]) topk_insert(t, v.y);
-        if (v.z < t[TOPK - 1]) topk_insert(t, v.z);
-        if (v.w < t[TOPK - 1]) topk_insert(t, v.w);
+#pragma unroll
+        for (int q = 0; q < K / 4; ++q) {
+            const uint4 v = reinterpret_cast<const uint4 *>(topk)[(sp * split_rows + i) * (K / 4) + q];
+            if (v.x < t[K - 1]) topk_insert(t, v.x);
+            if (v.y < t[K - 1]) topk_insert(t, v.y);
+            if (v.z < t[K - 1]) topk_insert(t, v.z);
+            if (v.w < t[K - 1]) topk_insert(t, v.w);
+        }
         n += nseen[sp * split_rows + i];
     }
-    reinterpret_cast<uint4 *>(topk)[i] = make_uint4(t[0], t[1], t[2], t[3]);
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q)
+        reinterpret_cast<uint4 *>(topk)[i * (K / 4) + q] = make_uint4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
     nseen[i] = n;
 }
 
@@ -272,13 +287,14 @@ static int pick_splits(int ctas, int max_set) {
     return std::max(1, std::min(std::min(want, 8), max_set / 128));
 }
 
+template <int K>
 static int launch_topk(sg_ctx *ctx, MatchArgs &a, int tiles, int np, int splits, uint32_t *d_topk, uint32_t *d_nseen) {
     a.splits = splits;
     a.split_rows = (long long)np * a.row_stride;
-    hamming_topk_kernel<<<dim3(tiles, np, splits), MT_THREADS, 0, ctx->stream>>>(a, d_topk, d_nseen);
+    hamming_topk_kernel<K><<<dim3(tiles, np, splits), MT_THREADS, 0, ctx->stream>>>(a, d_topk, d_nseen);
     SG_LAUNCH_CHECK(ctx);
     if (splits > 1) {
-        topk_merge_kernel<<<(unsigned)((a.split_rows + 255) / 256), 256, 0, ctx->stream>>>(d_topk, d_nseen, splits, a.split_rows);
+        topk_merge_kernel<K><<<(unsigned)((a.split_rows + 255) / 256), 256, 0, ctx->stream>>>(d_topk, d_nseen, splits, a.split_rows);
         SG_LAUNCH_CHECK(ctx);
     }
     return SG_OK;
@@ -291,6 +307,7 @@ __device__ __forceinline__ bool ratio_rejects(float ratio, unsigned second, unsi
     return __fmul_rn(ratio, (float)second) < (float)best;
 }
 
+template <int K>
 __global__ void __launch_bounds__(RES_WARPS * 32)
 match_resolve_kernel(const MatchArgs a, int n_pairs, const uint32_t *topk, const uint32_t *nseen_in,
                      int taken_words, int *matches, uint32_t *n_matches, unsigned long long *rescans) {
@@ -321,12 +338,20 @@ match_resolve_kernel(const MatchArgs a, int n_pairs, const uint32_t *topk, const
     // buffer or the context's scratch (run_match)
     for (int base = 0; base < nA; base += 32) {
         const int i = base + lane;
-        uint4 keys = make_uint4(EMPTY_KEY, EMPTY_KEY, EMPTY_KEY, EMPTY_KEY);
+        unsigned kk[K];
+#pragma unroll
+        for (int e = 0; e < K; ++e) kk[e] = EMPTY_KEY;
         unsigned ns = 0;
         if (i < nA) {
             const size_t r = (size_t)p * a.row_stride + i;
             ns = nseen_in[r];
-            if (ns) keys = reinterpret_cast<const uint4 *>(topk)[r];
+            if (ns) {
+#pragma unroll
+                for (int q = 0; q < K / 4; ++q) {
+                    const uint4 v = reinterpret_cast<const uint4 *>(topk)[r * (K / 4) + q];
+                    kk[4 * q] = v.x; kk[4 * q + 1] = v.y; kk[4 * q + 2] = v.z; kk[4 * q + 3] = v.w;
+                }
+            }
             mrow[i] = -1;
         }
         // Optimistic batch: every lane evaluates its own row against the current `taken` bits; accepted rows
@@ -335,8 +360,7 @@ match_resolve_kernel(const MatchArgs a, int n_pairs, const uint32_t *topk, const
         // first unsafe row is re-evaluated in the next round (it is then first and therefore safe) or, when its
         // truncated list cannot decide, rescanned exactly by the whole warp.
         unsigned pending = __ballot_sync(0xffffffffu, ns > 0);
-        const bool complete = ns <= TOPK;
-        const unsigned kk[TOPK] = {keys.x, keys.y, keys.z, keys.w};
+        const bool complete = ns <= (unsigned)K;
         while (pending) {
             ++round_tag;
             int decision = 0;   // 0 reject, 1 accept u0, 2 rescan
@@ -345,7 +369,7 @@ match_resolve_kernel(const MatchArgs a, int n_pairs, const uint32_t *topk, const
             if (mine) {
                 unsigned u0 = EMPTY_KEY, u1 = EMPTY_KEY, last = EMPTY_KEY;
 #pragma unroll
-                for (int e = 0; e < TOPK; ++e) {
+                for (int e = 0; e < K; ++e) {
                     if (kk[e] == EMPTY_KEY) continue;
                     last = kk[e];
                     const unsigned idx = kk[e] & 0xffffu;
@@ -371,7 +395,7 @@ match_resolve_kernel(const MatchArgs a, int n_pairs, const uint32_t *topk, const
             bool unsafe = mine && decision == 2;
             if (mine && !unsafe) {
 #pragma unroll
-                for (int e = 0; e < TOPK; ++e) {
+                for (int e = 0; e < K; ++e) {
                     if (kk[e] == EMPTY_KEY) continue;
                     const unsigned c = claim[kk[e] & (CLAIM_SLOTS - 1)];
                     if ((c >> 8) == round_tag && 31 - (int)(c & 0xffu) < lane) unsafe = true;   // claimed by an earlier row
@@ -523,6 +547,51 @@ int match_chunk_pairs(const sg_db *db, bool own_matches) {
     return (int)std::max<size_t>(1, ((size_t)256 << 20) / per_pair);
 }
 
+// Top-K scratch: `rows` rows of `K` keys + one count per row, from the stream-ordered pool.
+static int ensure_topk(sg_ctx *ctx, size_t rows, int K) {
+    if (rows <= ctx->topk_rows && rows * K <= ctx->topk_words) return SG_OK;
+    rows = std::max(rows, ctx->topk_rows);
+    const size_t words = std::max(rows * K, ctx->topk_words);
+    if (ctx->d_topk) cudaFreeAsync(ctx->d_topk, ctx->main_stream);
+    if (ctx->d_nseen) cudaFreeAsync(ctx->d_nseen, ctx->main_stream);
+    ctx->d_topk = nullptr; ctx->d_nseen = nullptr; ctx->topk_rows = 0; ctx->topk_words = 0;
+    SG_CUDA(ctx, cudaMallocAsync((void **)&ctx->d_topk, words * 4, ctx->main_stream));
+    SG_CUDA(ctx, cudaMallocAsync((void **)&ctx->d_nseen, rows * 4, ctx->main_stream));
+    ctx->topk_rows = rows; ctx->topk_words = words;
+    return SG_OK;
+}
+
+template <int K>
+static int run_match_k(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, const sg_match_params &mp,
+                       int *d_matches, int match_stride, uint32_t *d_n_matches, int chunk, int tiles, int splits) {
+    const int stride = db->max_set;
+    MatchArgs a{};
+    a.desc = db->d_desc; a.angle = db->d_angle; a.offsets = db->d_offsets;
+    a.cutoff = match_cutoff(mp); a.thr = mp.thr; a.ratio = mp.ratio;
+    a.ratio_is_double = mp.ratio_is_double; a.check_orientation = mp.check_orientation;
+    const int taken_words = (db->max_set + 31) / 32;
+    const size_t rsmem = (size_t)RES_WARPS * (taken_words + 32 + CLAIM_SLOTS) * 4;
+    if (rsmem > 48 * 1024)
+        SG_CUDA(ctx, cudaFuncSetAttribute(match_resolve_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+    for (int p0 = 0; p0 < n_pairs; p0 += chunk) {
+        const int np = std::min(chunk, n_pairs - p0);
+        if (p0 == 0) mark(ctx, EV_MATCH0, true);
+        a.pairs = d_pairs + 2 * (size_t)p0;
+        a.row_stride = stride;
+        int sp = np == chunk ? splits : pick_splits(tiles * np, db->max_set);
+        sp = (int)std::max<size_t>(1, std::min<size_t>(sp, ctx->topk_rows / ((size_t)np * stride)));   // never beyond the scratch
+        if (int r = launch_topk<K>(ctx, a, tiles, np, sp, ctx->d_topk, ctx->d_nseen)) return r;
+        if (p0 == 0) mark(ctx, EV_TOPK1);
+        a.match_stride = d_matches ? match_stride : stride;
+        int *mout = d_matches ? d_matches + (size_t)p0 * match_stride : ctx->d_matches;
+        match_resolve_kernel<K><<<(np + RES_WARPS - 1) / RES_WARPS, RES_WARPS * 32, rsmem, ctx->stream>>>(
+            a, np, ctx->d_topk, ctx->d_nseen, taken_words, mout, d_n_matches + p0, ctx->d_rescans);
+        SG_LAUNCH_CHECK(ctx);
+        if (p0 == 0) mark(ctx, EV_RESOLVE1);
+    }
+    return SG_OK;
+}
+
 int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, const sg_match_params &mp,
               int *d_matches, int match_stride, uint32_t *d_n_matches, bool reset_rescans) {
     if (n_pairs <= 0) return SG_OK;
@@ -533,51 +602,21 @@ int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, con
     const int chunk = std::min(n_pairs, match_chunk_pairs(db, d_matches == nullptr));
     const int tiles = (stride + MT_THREADS - 1) / MT_THREADS;
     const int splits = pick_splits(tiles * chunk, db->max_set);
-    {
-        size_t need = (size_t)chunk * stride;
-        if (need * splits > ctx->topk_rows) {
-            need *= splits;
-            if (ctx->d_topk) cudaFreeAsync(ctx->d_topk, ctx->main_stream);
-            if (ctx->d_nseen) cudaFreeAsync(ctx->d_nseen, ctx->main_stream);
-            ctx->d_topk = nullptr; ctx->d_nseen = nullptr; ctx->topk_rows = 0;
-            SG_CUDA(ctx, cudaMallocAsync((void **)&ctx->d_topk, need * TOPK * 4, ctx->main_stream));
-            SG_CUDA(ctx, cudaMallocAsync((void **)&ctx->d_nseen, need * 4, ctx->main_stream));
-            ctx->topk_rows = need;
-            need /= splits;
-        }
-        if (!d_matches) {
-            size_t cap = ctx->matches_cap;
-            int r = grow(ctx, (void **)&ctx->d_matches, &cap, need, sizeof(int));
-            ctx->matches_cap = cap;
-            if (r) return r;
-        }
+    // Few pairs (single-call matchers, stereo stream): latency matters and the grid is small anyway, so the lists are
+    // 16 entries long -- clusters of near-identical descriptors (repeated structure) then hardly ever exhaust a list,
+    // which would cost an exact rescan by a single warp.  Many pairs: 4 entries, the throughput configuration.
+    const bool wide = tiles * chunk < 2 * 148;
+    const size_t need = (size_t)chunk * stride;
+    if (int r = ensure_topk(ctx, need * splits, wide ? TOPK_WIDE : TOPK)) return r;
+    if (!d_matches) {
+        size_t cap = ctx->matches_cap;
+        int r = grow(ctx, (void **)&ctx->d_matches, &cap, need, sizeof(int));
+        ctx->matches_cap = cap;
+        if (r) return r;
     }
     if (reset_rescans) SG_CUDA(ctx, cudaMemsetAsync(ctx->d_rescans, 0, sizeof(unsigned long long), ctx->stream));
-    MatchArgs a{};
-    a.desc = db->d_desc; a.angle = db->d_angle; a.offsets = db->d_offsets;
-    a.cutoff = match_cutoff(mp); a.thr = mp.thr; a.ratio = mp.ratio;
-    a.ratio_is_double = mp.ratio_is_double; a.check_orientation = mp.check_orientation;
-    const int taken_words = (db->max_set + 31) / 32;
-    const size_t rsmem = (size_t)RES_WARPS * (taken_words + 32 + CLAIM_SLOTS) * 4;
-    if (rsmem > 48 * 1024)
-        SG_CUDA(ctx, cudaFuncSetAttribute(match_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-    for (int p0 = 0; p0 < n_pairs; p0 += chunk) {
-        const int np = std::min(chunk, n_pairs - p0);
-        if (p0 == 0) mark(ctx, EV_MATCH0, true);
-        a.pairs = d_pairs + 2 * (size_t)p0;
-        a.row_stride = stride;
-        int sp = np == chunk ? splits : pick_splits(tiles * np, db->max_set);
-        sp = (int)std::max<size_t>(1, std::min<size_t>(sp, ctx->topk_rows / ((size_t)np * stride)));   // never beyond the scratch
-        if (int r = launch_topk(ctx, a, tiles, np, sp, ctx->d_topk, ctx->d_nseen)) return r;
-        if (p0 == 0) mark(ctx, EV_TOPK1);
-        a.match_stride = d_matches ? match_stride : stride;
-        int *mout = d_matches ? d_matches + (size_t)p0 * match_stride : ctx->d_matches;
-        match_resolve_kernel<<<(np + RES_WARPS - 1) / RES_WARPS, RES_WARPS * 32, rsmem, ctx->stream>>>(
-            a, np, ctx->d_topk, ctx->d_nseen, taken_words, mout, d_n_matches + p0, ctx->d_rescans);
-        SG_LAUNCH_CHECK(ctx);
-        if (p0 == 0) mark(ctx, EV_RESOLVE1);
-    }
-    return SG_OK;
+    return wide ? run_match_k<TOPK_WIDE>(ctx, db, d_pairs, n_pairs, mp, d_matches, match_stride, d_n_matches, chunk, tiles, splits)
+                : run_match_k<TOPK>(ctx, db, d_pairs, n_pairs, mp, d_matches, match_stride, d_n_matches, chunk, tiles, splits);
 }
 
 // ---- candidate lists for matchForTriangulationDBoW (keyframe_matcher.cpp:160-293) ----------------------------------
@@ -591,19 +630,11 @@ int run_topk_lists(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs
     const int stride = std::max(db->max_set, 1);
     const int tiles = (stride + MT_THREADS - 1) / MT_THREADS;
     const int splits = pick_splits(tiles * n_pairs, db->max_set);
-    const size_t need = (size_t)n_pairs * stride * splits;
-    if (need > ctx->topk_rows) {
-        if (ctx->d_topk) cudaFreeAsync(ctx->d_topk, ctx->main_stream);
-        if (ctx->d_nseen) cudaFreeAsync(ctx->d_nseen, ctx->main_stream);
-        ctx->d_topk = nullptr; ctx->d_nseen = nullptr; ctx->topk_rows = 0;
-        SG_CUDA(ctx, cudaMallocAsync((void **)&ctx->d_topk, need * TOPK * 4, ctx->main_stream));
-        SG_CUDA(ctx, cudaMallocAsync((void **)&ctx->d_nseen, need * 4, ctx->main_stream));
-        ctx->topk_rows = need;
-    }
+    if (int r = ensure_topk(ctx, (size_t)n_pairs * stride * splits, TOPK)) return r;
     MatchArgs a{};
     a.desc = db->d_desc; a.angle = db->d_angle; a.offsets = db->d_offsets; a.pairs = d_pairs;
     a.cutoff = thr; a.thr = thr; a.row_stride = stride; a.last_wins = 1;
-    if (int r = launch_topk(ctx, a, tiles, n_pairs, splits, ctx->d_topk, ctx->d_nseen)) return r;
+    if (int r = launch_topk<TOPK>(ctx, a, tiles, n_pairs, splits, ctx->d_topk, ctx->d_nseen)) return r;
     *d_topk = ctx->d_topk; *d_nseen = ctx->d_nseen; *row_stride = stride;
     return SG_OK;
 }
