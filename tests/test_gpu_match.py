@@ -53,6 +53,30 @@ def test_match_duplicates_force_rescans(ctx, oracle):
     assert ctx.rescans() > 0
 
 
+def test_match_duplicates_force_rescans_in_large_launches(ctx, slamgpu, oracle):
+    """The same clustered sets through a launch with many pairs: that path keeps 4-entry lists (few pairs get 16), so
+    its exact rescans must be exercised separately."""
+    rng = np.random.default_rng(12)
+    base = rng.integers(0, 2 ** 32, (30, 8), dtype=np.uint32)
+    sets_d, sets_a = [], []
+    for s in range(3):
+        d = np.repeat(base, 20, axis=0)[rng.permutation(600)]
+        for i, k in enumerate(rng.integers(0, 3, len(d))):
+            for b in rng.integers(0, 256, k):
+                d[i, b >> 5] ^= np.uint32(1 << (int(b) & 31))
+        sets_d.append(d)
+        sets_a.append(rng.uniform(0, 360, len(d)).astype(np.float32))
+    db = slamgpu.DescriptorDB(ctx, np.stack(sets_d), np.stack(sets_a))
+    pairs = np.array([(i % 3, (i // 3) % 3) for i in range(180)], np.int32)       # 180 pairs x 3 row tiles: the 4-entry path
+    n, m = db.match_pairs(pairs, check_orientation=False)
+    assert ctx.rescans() > 0
+    ref = {(i, j): oracle.match_bruteforce(sets_d[i], sets_a[i], sets_d[j], sets_a[j], check_orientation=False)
+           for i in range(3) for j in range(3)}
+    for k, (i, j) in enumerate(pairs.tolist()):
+        assert n[k] == ref[(i, j)][0] and np.array_equal(m[k], ref[(i, j)][1]), k
+    db.close()
+
+
 def test_match_ragged_and_empty(ctx, oracle, synth):
     dA, aA, dB, aB = synth.correlated_descriptors(700, 21)
     for na, nb in [(700, 300), (300, 700), (700, 1), (1, 700), (257, 1025), (0, 10), (10, 0)]:
