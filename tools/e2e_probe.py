@@ -30,7 +30,7 @@ print("raw D2H %.1f MB: %.3f ms  %.1f GB/s" % (arrs["desc"].nbytes / 1e6, dt * 1
 dt = t(lambda: ctx.extract_device(dbuf.ptr, W, W * H, F))
 print("device-resident extract: %.3f ms" % (dt * 1e3))
 none = slamgpu.Keypoints(None, None, None, None, None, None, None, None, arrs["count"].ctypes.data, None)
-for chunk in (8, 16, 32, 64, 128, 256):
+for chunk in (16, 24, 32, 40, 48, 64, 128):
     ctx.set_pipeline_chunk(chunk)
     a = t(lambda: ctx._check(lib.sg_extract(ctx._h, pin.array.ctypes.data, W, W * H, F, None, None, None, C.byref(ks))))
     b = t(lambda: ctx._check(lib.sg_extract(ctx._h, pin.array.ctypes.data, W, W * H, F, None, None, None, C.byref(none))))
