@@ -345,6 +345,11 @@ def extra_configs(slamgpu, sm, sh, rank, world, local, barrier_max_, td):
         t_mbow, (n_mbow, _) = timed(lambda: c6.match_bow(qdesc, ang_q, nodes_q, kdesc, ang_k, nodes_k, check_orientation=False))
         bword, bweight, _ = voc.transform(kdesc, 2)
         t_bvec, (vw, vv) = timed(lambda: voc.bow_vector(bword, bweight))
+        NB = 256                                                        # one extraction batch worth of keyframes per call
+        bdesc = np.tile(kdesc, (NB, 1)) ^ np.repeat(rng.integers(0, 2 ** 32, (NB, 1), dtype=np.uint32), nk, axis=0)
+        t_btr, (bw_all, bwt_all, _) = timed(lambda: voc.transform(bdesc, 2), n=3)
+        boffs = (np.arange(NB + 1, dtype=np.int64) * nk)
+        t_bvb, vecs_b = timed(lambda: voc.bow_vector_batch(bw_all, bwt_all, boffs), n=3)
         voc.close()
         NKF = 10000
         vecs = sm.synth.random_bow_vectors(NKF, 100000, 1500, 9, n_topics=40)
@@ -364,6 +369,9 @@ def extra_configs(slamgpu, sm, sh, rank, world, local, barrier_max_, td):
                               "ms_per_call_host_buffers": t_bow * 1e3, "distinct_words": int(len(np.unique(bw)))},
             "bow_vector": {"workload": "BowVector of %d features: per-word sums in feature order + L1 norm, doubles (DBoW2 transform / normalize)" % nk,
                            "ms_per_call_host_buffers": t_bvec * 1e3, "words": int(len(vw))},
+            "bow_batch": {"workload": "%d keyframes x %d features per call: tree descent, then BowVectors (one CTA per keyframe)" % (NB, nk),
+                          "transform_ms_per_call_host_buffers": t_btr * 1e3, "vector_ms_per_call_host_buffers": t_bvb * 1e3,
+                          "keyframes_per_s": NB / (t_btr + t_bvb)},
             "bow_similar": {"workload": "getBowSimilar (bow_index.cpp:95-176): one query against %d stored keyframes of 750..1700 words" % NKF,
                             "ms_per_call_host_buffers": t_sim * 1e3, "keyframes_scored_per_s": NKF / t_sim, "candidates": int(len(sim_kf))},
             "match_for_loop_closures_bow": {"workload": "%d x %d features in DBoW2 node buckets (keyframe_matcher.cpp:65-146)" % (nq, nk),

@@ -277,6 +277,10 @@ int sg_bow_transform_device(sg_ctx *ctx, const sg_vocab *vocab, const uint32_t *
                             int32_t *d_word, double *d_weight, int32_t *d_node);
 int sg_bow_vector(sg_ctx *ctx, const int32_t *h_word, const double *h_weight, int n, uint32_t *h_vec_word,
                   double *h_vec_value, int *n_words);
+/* Batched form (one CTA per keyframe): keyframe k owns features [h_offsets[k], h_offsets[k+1]) of h_word / h_weight (at
+ * most 4096 each); its BowVector is written to h_vec_word / h_vec_value starting at h_offsets[k], n_words[k] entries. */
+int sg_bow_vector_batch(sg_ctx *ctx, const int32_t *h_word, const double *h_weight, const int64_t *h_offsets, int n_keyframes,
+                        uint32_t *h_vec_word, double *h_vec_value, int32_t *n_words);
 /* Device-resident BowVectors of up to max_keyframes keyframes (max_words_per_keyframe each), keyed by
  * (map id, keyframe id) like the reference's MapKf.  add = BowIndex::add, remove = BowIndex::remove (unknown
  * keyframe: no-op).  sg_bow_similar = getBowSimilar: every stored keyframe except (self_map, self_kf) that shares a

@@ -84,11 +84,16 @@ bow_transform_kernel(const VocabDev v, const uint32_t *desc, int n, int levels_u
 // v.addWeight(word, w) for every feature with w > 0, in feature order: the value of a word is the left-to-right sum
 // of its features' weights; normalize: norm = sum of |value| in ascending word order, value /= norm when norm > 0.
 __global__ void __launch_bounds__(BOWV_THREADS)
-bow_vector_kernel(const int *word, const double *weight, int n, uint32_t *vec_word, double *vec_value, int *n_words) {
+bow_vector_kernel(const int *word, const double *weight, const long long *offsets, uint32_t *vec_word, double *vec_value,
+                  int *n_words) {
     __shared__ unsigned long long key[BOWV_MAX];
     __shared__ int warp_tot[BOWV_THREADS / 32];
     __shared__ double s_norm;
     const int t = threadIdx.x;
+    // keyframe blockIdx.x owns features [offsets[k], offsets[k + 1]); its BowVector goes to the same offset
+    const long long o = offsets[blockIdx.x];
+    const int n = (int)(offsets[blockIdx.x + 1] - o);
+    word += o; weight += o; vec_word += o; vec_value += o; n_words += blockIdx.x;
     for (int i = t; i < BOWV_MAX; i += BOWV_THREADS)
         key[i] = (i < n && weight[i] > 0.0) ? ((unsigned long long)(unsigned)word[i] << 32 | (unsigned)i) : ~0ull;
     __syncthreads();
@@ -285,31 +290,50 @@ extern "C" int sg_bow_transform_device(sg_ctx *ctx, const sg_vocab *vocab, const
 }
 
 // ---- BowVector, keyframe database, similarity query ----------------------------------------------------------
-extern "C" int sg_bow_vector(sg_ctx *ctx, const int32_t *h_word, const double *h_weight, int n, uint32_t *h_vec_word,
-                             double *h_vec_value, int *n_words) {
+extern "C" int sg_bow_vector_batch(sg_ctx *ctx, const int32_t *h_word, const double *h_weight, const int64_t *h_offsets,
+                                   int n_keyframes, uint32_t *h_vec_word, double *h_vec_value, int32_t *n_words) {
     cudaSetDevice(ctx->device);
-    if (!n_words) return fail(ctx, SG_ERR_INVALID, "null argument");
-    *n_words = 0;
-    if (n <= 0) return SG_OK;
+    if (n_keyframes <= 0) return SG_OK;
+    if (!h_offsets || !n_words) return fail(ctx, SG_ERR_INVALID, "null argument");
+    if (h_offsets[0] != 0) return fail(ctx, SG_ERR_INVALID, "offsets[0] must be 0");
+    for (int k = 0; k < n_keyframes; ++k) {
+        const long long n = h_offsets[k + 1] - h_offsets[k];
+        if (n < 0 || n > BOWV_MAX) return fail(ctx, SG_ERR_INVALID, "keyframe %d has %lld features (supported: 0..%d)", k, n, BOWV_MAX);
+        n_words[k] = 0;
+    }
+    const size_t total = (size_t)h_offsets[n_keyframes];
+    if (total == 0) return SG_OK;
     if (!h_word || !h_weight || !h_vec_word || !h_vec_value) return fail(ctx, SG_ERR_INVALID, "null argument");
-    if (n > BOWV_MAX) return fail(ctx, SG_ERR_INVALID, "%d features (supported: up to %d per keyframe)", n, BOWV_MAX);
     Scratch sc(ctx);
-    sc.want(4 * (size_t)n); sc.want(8 * (size_t)n); sc.want(4 * (size_t)n); sc.want(8 * (size_t)n); sc.want(4);
+    sc.want(4 * total); sc.want(8 * total); sc.want(4 * total); sc.want(8 * total);
+    sc.want(8 * ((size_t)n_keyframes + 1)); sc.want(4 * (size_t)n_keyframes);
     if (int r = sc.commit()) return r;
     int *d_word;
     double *d_weight;
-    if (int r = sc.put(&d_word, (const int *)h_word, (size_t)n)) return r;
-    if (int r = sc.put(&d_weight, h_weight, (size_t)n)) return r;
-    uint32_t *d_vw = sc.take<uint32_t>(n);
-    double *d_vv = sc.take<double>(n);
-    int *d_n = sc.take<int>(1);
-    bow_vector_kernel<<<1, BOWV_THREADS, 0, ctx->stream>>>(d_word, d_weight, n, d_vw, d_vv, d_n);
+    long long *d_off;
+    if (int r = sc.put(&d_word, (const int *)h_word, total)) return r;
+    if (int r = sc.put(&d_weight, h_weight, total)) return r;
+    uint32_t *d_vw = sc.take<uint32_t>(total);
+    double *d_vv = sc.take<double>(total);
+    if (int r = sc.put(&d_off, (const long long *)h_offsets, (size_t)n_keyframes + 1)) return r;
+    int *d_n = sc.take<int>(n_keyframes);
+    bow_vector_kernel<<<n_keyframes, BOWV_THREADS, 0, ctx->stream>>>(d_word, d_weight, d_off, d_vw, d_vv, d_n);
     SG_LAUNCH_CHECK(ctx);
-    SG_CUDA(ctx, cudaMemcpyAsync(n_words, d_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    SG_CUDA(ctx, cudaMemcpyAsync(h_vec_word, d_vw, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    SG_CUDA(ctx, cudaMemcpyAsync(h_vec_value, d_vv, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(n_words, d_n, 4 * (size_t)n_keyframes, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(h_vec_word, d_vw, 4 * total, cudaMemcpyDeviceToHost, ctx->stream));
+    SG_CUDA(ctx, cudaMemcpyAsync(h_vec_value, d_vv, 8 * total, cudaMemcpyDeviceToHost, ctx->stream));
     SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SG_OK;
+}
+
+extern "C" int sg_bow_vector(sg_ctx *ctx, const int32_t *h_word, const double *h_weight, int n, uint32_t *h_vec_word,
+                             double *h_vec_value, int *n_words) {
+    if (!n_words) return fail(ctx, SG_ERR_INVALID, "null argument");
+    *n_words = 0;
+    if (n <= 0) return SG_OK;
+    if (n > BOWV_MAX) return fail(ctx, SG_ERR_INVALID, "%d features (supported: up to %d per keyframe)", n, BOWV_MAX);
+    const int64_t offsets[2] = {0, n};
+    return sg_bow_vector_batch(ctx, h_word, h_weight, offsets, 1, h_vec_word, h_vec_value, n_words);
 }
 
 struct sg_bowdb {

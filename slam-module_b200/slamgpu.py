@@ -69,7 +69,7 @@ ABI_SYMBOLS = [
     "sg_set_pipeline_chunk", "sg_search_candidates", "sg_feature_index", "sg_medoid", "sg_set_overlap", "sg_match_bow", "sg_vocab_create", "sg_vocab_destroy",
     "sg_bow_transform", "sg_bow_transform_device", "sg_match_triangulation", "sg_bow_vector", "sg_bowdb_create",
     "sg_bowdb_destroy", "sg_bowdb_size", "sg_bowdb_add", "sg_bowdb_remove", "sg_bow_similar", "sg_extract_submit",
-    "sg_extract_wait", "sg_db_wrap_device",
+    "sg_extract_wait", "sg_db_wrap_device", "sg_bow_vector_batch",
 ]
 
 _lib = None
@@ -165,6 +165,8 @@ def lib():
         L.sg_bow_transform_device.restype = C.c_int
         L.sg_bow_vector.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sg_bow_vector.restype = C.c_int
+        L.sg_bow_vector_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sg_bow_vector_batch.restype = C.c_int
         L.sg_bowdb_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.sg_bowdb_create.restype = C.c_int
         L.sg_bowdb_destroy.argtypes = [C.c_void_p]
@@ -646,6 +648,17 @@ class Vocabulary:
         self.ctx._check(lib().sg_bow_vector(self.ctx._h, word.ctypes.data, weight.ctypes.data, n, vw.ctypes.data, vv.ctypes.data,
                                             C.byref(k)))
         return vw[:k.value].copy(), vv[:k.value].copy()
+
+    def bow_vector_batch(self, word, weight, offsets):
+        """BowVectors of many keyframes in one launch: keyframe k owns features offsets[k]..offsets[k+1].
+        -> list of (words, values) per keyframe."""
+        word = np.ascontiguousarray(word, np.int32); weight = np.ascontiguousarray(weight, np.float64)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        nk = len(offsets) - 1
+        vw = np.empty(max(len(word), 1), np.uint32); vv = np.empty(max(len(word), 1), np.float64); cnt = np.zeros(max(nk, 1), np.int32)
+        self.ctx._check(lib().sg_bow_vector_batch(self.ctx._h, word.ctypes.data, weight.ctypes.data, offsets.ctypes.data, nk,
+                                                  vw.ctypes.data, vv.ctypes.data, cnt.ctypes.data))
+        return [(vw[offsets[k]:offsets[k] + cnt[k]].copy(), vv[offsets[k]:offsets[k] + cnt[k]].copy()) for k in range(nk)]
 
     def close(self):
         if self._h:

@@ -337,6 +337,29 @@ def test_gpu_bow_vector_bit_exact(slamgpu, oracle, synth):
 
 
 @pytest.mark.gpu
+def test_gpu_bow_vector_batch_bit_exact(slamgpu, oracle, synth):
+    """Many keyframes per launch (ragged, with empty and all-stopped keyframes): each equals the single-keyframe result."""
+    rng = np.random.default_rng(43)
+    v = synth.random_vocabulary(10, 3, 5)
+    sizes = [0, 1, 2000, 37, 4096, 512, 0, 1999, 300]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    word = rng.integers(0, 700, int(offs[-1])).astype(np.int32)
+    weight = np.where(rng.random(len(word)) < 0.1, 0.0, rng.uniform(1e-3, 9.0, len(word)))
+    weight[offs[3]:offs[4]] = 0.0                                     # keyframe 3: every word stopped
+    with slamgpu.Context(640, 480, max_frames=1) as ctx:
+        voc = slamgpu.Vocabulary(ctx, v)
+        got = voc.bow_vector_batch(word, weight, offs)
+        assert len(got) == len(sizes)
+        for k in range(len(sizes)):
+            rw, rx = oracle.bow_vector(word[offs[k]:offs[k + 1]], weight[offs[k]:offs[k + 1]])
+            assert np.array_equal(got[k][0], rw) and np.array_equal(got[k][1], rx), k
+        assert len(got[3][0]) == 0 and len(got[2][0]) > 500
+        with pytest.raises(slamgpu.SlamGpuError):
+            voc.bow_vector_batch(np.zeros(4097, np.int32), np.ones(4097), np.array([0, 4097], np.int64))
+        voc.close()
+
+
+@pytest.mark.gpu
 def test_gpu_bow_similar_bit_exact(slamgpu, oracle, synth):
     vocab_size = 5000
     vecs = synth.random_bow_vectors(400, vocab_size, 300, 55)
