@@ -493,6 +493,7 @@ static int extract_launches(sg_ctx *ctx, int n_frames) {
 int sg_extract_download(sg_ctx *ctx, int n_frames, sg_keypoints *o) {
     cudaSetDevice(ctx->device);
     if (!o || n_frames < 1 || n_frames > ctx->frames_ready) return fail(ctx, SG_ERR_INVALID, "bad n_frames / output");
+    if (int r = slots_free(ctx, 0, n_frames)) return r;     // a batch in flight is still writing these slots
     const size_t n = (size_t)n_frames * ctx->geom.out_cap;
     if (int r = d2h(ctx, o->x, ctx->d_x, n)) return r;
     if (int r = d2h(ctx, o->y, ctx->d_y, n)) return r;
