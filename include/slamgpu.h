@@ -60,6 +60,8 @@ typedef struct sg_ctx sg_ctx;
 /* Replaces OrbExtractor::build / ImagePyramid::build / FeatureDetector::build
  * (orb_extractor.cpp:356-358, image_pyramid.cpp:209-219, feature_detector.cpp:138-140). */
 int sg_create(int device, const sg_params *params, sg_ctx **out);
+/* Objects created from a context (sg_db, sg_vocab, sg_bowdb) use its device, streams and memory pool: destroy them
+ * before the context. */
 void sg_destroy(sg_ctx *ctx);
 const char *sg_last_error(const sg_ctx *ctx); /* ctx may be NULL: error of the failed sg_create */
 int sg_abi_version(void);

@@ -28,7 +28,7 @@ int grow(sg_ctx *ctx, void **ptr, size_t *cap, size_t need, size_t elem) {
     // device-wide cudaFree / cudaMalloc, which takes milliseconds to seconds on virtualised hosts
     if (*ptr) cudaFreeAsync(*ptr, ctx->main_stream);
     *ptr = nullptr; *cap = 0;
-    SG_CUDA(ctx, cudaMallocAsync(ptr, need * elem, ctx->main_stream));
+    SG_CUDA(ctx, cudaMallocFromPoolAsync(ptr, need * elem, ctx->pool, ctx->main_stream));
     *cap = need;
     return SG_OK;
 }
@@ -308,12 +308,16 @@ int sg_create(int device, const sg_params *params, sg_ctx **out) {
         return bail(SG_ERR_CUDA);
     }
     ctx->main_stream = ctx->stream;
-    {   // keep what the stream-ordered allocator (database offsets) has freed: no trimming at synchronisation points
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
+    {   // the context's own stream-ordered memory pool (scratch buffers, descriptor databases): it keeps what is freed
+        // -- no trimming at synchronisation points -- and leaves the process-wide default pool alone
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&ctx->pool, &props) != cudaSuccess) { ctx->err = "cudaMemPoolCreate failed"; return bail(SG_ERR_CUDA); }
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     if (const char *e = getenv("SG_PIPE_STREAMS")) ctx->pipe_streams = std::min((int)sg_ctx::N_CMP, std::max(1, atoi(e)));   // tuning knob
     if (cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) != cudaSuccess
@@ -356,6 +360,7 @@ void sg_destroy(sg_ctx *ctx) {
     for (cudaStream_t q : {ctx->s_in, ctx->s_out}) if (q) cudaStreamDestroy(q);
     for (cudaStream_t q : ctx->s_cmp) if (q) cudaStreamDestroy(q);
     if (cudaStream_t m = ctx->main_stream ? ctx->main_stream : ctx->stream) cudaStreamDestroy(m);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
 }
 
@@ -719,7 +724,7 @@ static int db_finish(sg_ctx *ctx, sg_db *db, const int64_t *h_offsets, int n_set
     }
     // stream-ordered allocation from the device's memory pool: creating / destroying a database (per step in the
     // extract -> match flow) must not pay a device-wide cudaMalloc / cudaFree
-    SG_CUDA(ctx, cudaMallocAsync((void **)&db->d_offsets, sizeof(long long) * (n_sets + 1), ctx->stream));
+    SG_CUDA(ctx, cudaMallocFromPoolAsync((void **)&db->d_offsets, sizeof(long long) * (n_sets + 1), ctx->pool, ctx->stream));
     SG_CUDA(ctx, cudaMemcpyAsync(db->d_offsets, db->offsets.data(), sizeof(long long) * (n_sets + 1), cudaMemcpyHostToDevice, ctx->stream));
     SG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // db->offsets is pageable host memory that outlives the call, but keep the create synchronous
     return SG_OK;
@@ -733,8 +738,8 @@ static int db_create(sg_ctx *ctx, const uint32_t *desc, const float *angle, cons
     sg_db *db = new sg_db();
     const size_t total = (size_t)h_offsets[n_sets];
     int r = db_finish(ctx, db, h_offsets, n_sets);
-    if (!r && cudaMallocAsync((void **)&db->d_desc, std::max<size_t>(total, 1) * 32 + 32, ctx->stream) != cudaSuccess) r = fail(ctx, SG_ERR_CUDA, "cudaMallocAsync failed");
-    if (!r && cudaMallocAsync((void **)&db->d_angle, std::max<size_t>(total, 1) * 4, ctx->stream) != cudaSuccess) r = fail(ctx, SG_ERR_CUDA, "cudaMallocAsync failed");
+    if (!r && cudaMallocFromPoolAsync((void **)&db->d_desc, std::max<size_t>(total, 1) * 32 + 32, ctx->pool, ctx->stream) != cudaSuccess) r = fail(ctx, SG_ERR_CUDA, "pool allocation failed");
+    if (!r && cudaMallocFromPoolAsync((void **)&db->d_angle, std::max<size_t>(total, 1) * 4, ctx->pool, ctx->stream) != cudaSuccess) r = fail(ctx, SG_ERR_CUDA, "pool allocation failed");
     if (!r && total) {
         if (cudaMemcpyAsync(db->d_desc, desc, total * 32, kind, ctx->stream) != cudaSuccess
             || cudaMemcpyAsync(db->d_angle, angle, total * 4, kind, ctx->stream) != cudaSuccess

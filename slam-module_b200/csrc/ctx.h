@@ -103,6 +103,7 @@ struct sg_ctx {
     struct Ticket { bool busy = false; int base = 0, n = 0; } ticket[N_TICKETS];
     int next_ticket = 0;
     int stream_chunk = 128;              // chunk of sg_extract_submit (no fill / drain ramp)
+    cudaMemPool_t pool = nullptr;        // stream-ordered pool of this context (scratch, descriptor databases)
     bool bow_attr_set = false;           // dynamic shared memory limit of bow_score_kernel raised on this device
     unsigned pipe_rr = 0;                // round-robin position over the compute streams
     int pipe_chunk = 32;                // frames per pipeline chunk of sg_extract

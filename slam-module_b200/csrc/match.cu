@@ -555,8 +555,8 @@ static int ensure_topk(sg_ctx *ctx, size_t rows, int K) {
     if (ctx->d_topk) cudaFreeAsync(ctx->d_topk, ctx->main_stream);
     if (ctx->d_nseen) cudaFreeAsync(ctx->d_nseen, ctx->main_stream);
     ctx->d_topk = nullptr; ctx->d_nseen = nullptr; ctx->topk_rows = 0; ctx->topk_words = 0;
-    SG_CUDA(ctx, cudaMallocAsync((void **)&ctx->d_topk, words * 4, ctx->main_stream));
-    SG_CUDA(ctx, cudaMallocAsync((void **)&ctx->d_nseen, rows * 4, ctx->main_stream));
+    SG_CUDA(ctx, cudaMallocFromPoolAsync((void **)&ctx->d_topk, words * 4, ctx->pool, ctx->main_stream));
+    SG_CUDA(ctx, cudaMallocFromPoolAsync((void **)&ctx->d_nseen, rows * 4, ctx->pool, ctx->main_stream));
     ctx->topk_rows = rows; ctx->topk_words = words;
     return SG_OK;
 }

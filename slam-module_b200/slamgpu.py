@@ -290,8 +290,15 @@ class Context:
 
     def close(self):
         if self._h:
+            # objects created from the context (databases, vocabularies) use its device, streams and pool: they go first
+            for child in list(self.__dict__.get("_children", ())):
+                child.close()
             lib().sg_destroy(self._h)
             self._h = None
+
+    def _adopt(self, child):
+        import weakref
+        self.__dict__.setdefault("_children", weakref.WeakSet()).add(child)
 
     def __enter__(self):
         return self
@@ -590,6 +597,7 @@ class DescriptorDB:
             ctx._check(lib().sg_db_create(ctx._h, desc.ctypes.data, angle.ctypes.data, offsets.ctypes.data,
                                           len(offsets) - 1, C.byref(h)))
         self._h = h
+        ctx._adopt(self)
         self.offsets = offsets
         self.max_set = int(np.max(np.diff(offsets))) if len(offsets) > 1 else 0
 
@@ -631,6 +639,7 @@ class Vocabulary:
                                          a["node_weight"].ctypes.data, a["node_word"].ctypes.data, len(a["node_word"]),
                                          int(vocab["levels"]), C.byref(h)))
         self._h = h
+        ctx._adopt(self)
 
     def transform(self, desc, levels_up=4):
         desc = np.ascontiguousarray(desc, np.uint32).reshape(-1, 8)
@@ -674,6 +683,7 @@ class BowDatabase:
         h = C.c_void_p()
         ctx._check(lib().sg_bowdb_create(ctx._h, int(max_keyframes), int(max_words_per_keyframe), C.byref(h)))
         self._h = h
+        ctx._adopt(self)
 
     def __len__(self):
         return int(lib().sg_bowdb_size(self._h))
