@@ -115,6 +115,37 @@ def test_gpu_search_candidates_bit_exact(slamgpu, oracle, seed, nk, nq):
 
 
 @pytest.mark.gpu
+def test_gpu_search_candidates_edge_cases(slamgpu, oracle):
+    """Integer keypoint coordinates (many equal y: the Y order is libstdc++'s std::sort on both sides), 20 000 keypoints,
+    radii from 0 (strict '<': nothing inside) to most of the image, queries outside the image."""
+    rng = np.random.default_rng(21)
+    nk, nq = 20000, 600
+    kx = rng.integers(0, 640, nk).astype(np.float32); ky = rng.integers(0, 480, nk).astype(np.float32)
+    koct = rng.integers(0, 8, nk).astype(np.int32)
+    kdesc = rng.integers(0, 2 ** 32, (nk, 8), dtype=np.uint32)
+    src = rng.integers(0, nk, nq)
+    qx = (kx[src] + rng.integers(-2, 3, nq)).astype(np.float32); qy = (ky[src] + rng.integers(-2, 3, nq)).astype(np.float32)
+    qx[:20] = -500.0; qy[20:40] = 5000.0                                 # far outside
+    qr = rng.choice(np.array([0.0, 0.5, 1.0, 3.0, 25.0, 400.0], np.float32), nq)
+    qdesc = kdesc[src].copy()
+    for i in range(nq):
+        for b in rng.integers(0, 256, int(rng.integers(0, 30))):
+            qdesc[i, b >> 5] ^= np.uint32(1 << (int(b) & 31))
+    qlevel = rng.integers(0, 8, nq).astype(np.int32)
+    with slamgpu.Context(640, 480, max_frames=1) as ctx:
+        assert np.array_equal(slamgpu.feature_index(kx, ky), oracle.feature_index(kx, ky))
+        for kw in (dict(mode=0, thr=50), dict(mode=0, thr=100, qlevel=qlevel)):
+            n, idx, dist = ctx.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, **kw)
+            rn, ridx, rdist = oracle.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, **kw)
+            assert n == rn and np.array_equal(idx, ridx) and np.array_equal(dist, rdist) and n > 50, kw
+        t1, t2 = np.zeros(nk, np.uint8), np.zeros(nk, np.uint8)
+        n, idx, dist = ctx.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=1, thr=100, taken=t1)
+        rn, ridx, rdist = oracle.search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=1, thr=100, taken=t2)
+        assert n == rn and np.array_equal(idx, ridx) and np.array_equal(dist, rdist) and np.array_equal(t1, t2)
+        assert (idx[qr == 0.0] == -1).all() and (idx[:40] == -1).all()
+
+
+@pytest.mark.gpu
 def test_gpu_search_consumption_forces_rescans(slamgpu, oracle):
     """Many queries compete for few keypoints inside one radius: the truncated top-4 lists run dry and the exact
     rescan path decides."""
