@@ -153,6 +153,18 @@ def test_extract_unusual_geometries(slamgpu, oracle, synth, w, h, levels, factor
         assert got["n"] > 0
 
 
+@pytest.mark.parametrize("ini,mn", [(40, 10), (15, 15), (7, 1), (120, 30), (254, 200)])
+def test_extract_other_fast_thresholds(slamgpu, oracle, synth, ini, mn):
+    """FAST thresholds other than the upstream 20 / 7: equal thresholds (no fallback pass), very low ones (almost every
+    pixel scores: the scored-pixel list overflows into the map scan), very high ones (few or no corners)."""
+    img = synth.frame(640, 480, 3100 + ini)
+    with slamgpu.Context(640, 480, max_keypoints=1500, ini_fast_thr=ini, min_fast_thr=mn, max_frames=1) as ctx:
+        got = ctx.detect_and_extract(img)[0]
+    ref = oracle.extract(oracle.make_params(640, 480, max_keypoints=1500, ini_fast_thr=ini, min_fast_thr=mn), img)
+    _assert_same_extraction(got, ref)
+    assert (got["n"] > 0) == (ini < 254)
+
+
 def test_extract_batch_matches_single_frames(slamgpu, oracle, synth):
     imgs = synth.frames(640, 480, 6, 2100)
     with slamgpu.Context(640, 480, max_frames=6) as ctx:
