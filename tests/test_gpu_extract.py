@@ -140,7 +140,7 @@ def test_extract_bit_exact(slamgpu, oracle, synth, w, h, seed, maxkp):
                                                      (320, 240, 1, 1.2, 300), (800, 600, 6, 1.3, 5000), (1920, 1080, 8, 1.2, 4000),
                                                      (96, 64, 8, 1.2, 100), (64, 64, 4, 1.2, 50), (3840, 2160, 8, 1.2, 8000),
                                                      (1920, 480, 8, 1.2, 1500), (480, 1920, 8, 1.2, 1500), (4096, 64, 8, 1.2, 500),
-                                                     (64, 4096, 8, 1.2, 500)])
+                                                     (64, 4096, 8, 1.2, 500), (640, 480, 8, 1.2, 1), (640, 480, 8, 1.2, 8), (640, 480, 8, 1.2, 30)])
 def test_extract_unusual_geometries(slamgpu, oracle, synth, w, h, levels, factor, maxkp):
     """Image sizes that are not multiples of the tile / cell sizes, a single-level pyramid, another scale factor,
     budgets above and below the usual 2000, a 4K frame, 4:1 and 64:1 aspect ratios (more initial quadtree nodes than
