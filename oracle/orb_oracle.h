@@ -156,6 +156,14 @@ int orc_search_candidates(const float *kx, const float *ky, const int *koct, con
                           const uint32_t *qdesc, const int *q_pred_level, int nQ, int mode, unsigned thr,
                           int *out_idx, unsigned *out_dist);
 
+/* matchMapPointsSim3 (keyframe_matcher.cpp:633-686): both findMatchesTranformedMps directions + the agreement filter;
+ * q12 / q21: per keypoint the projected query into the other keyframe (r < 0: no query); see oracle/src/search.cpp. */
+int orc_match_sim3(const float *x1, const float *y1, const int *oct1, const uint32_t *d1, int n1,
+                   const float *x2, const float *y2, const int *oct2, const uint32_t *d2, int n2,
+                   const float *q12x, const float *q12y, const float *q12r, const uint32_t *q12desc, const int *q12lvl,
+                   const float *q21x, const float *q21y, const float *q21r, const uint32_t *q21desc, const int *q21lvl,
+                   int *out_pairs);
+
 /* Bag of words behind BowIndex (bow_index.cpp:44-176); DBoW2 itself is absent: restated from its published
  * algorithm, PARITY UNPINNED.  See oracle/src/bow.cpp. */
 void orc_bow_transform(const int *child_off, const int *child_ids, const uint32_t *node_desc, const double *node_weight,

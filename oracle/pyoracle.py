@@ -341,6 +341,27 @@ def search_candidates(kx, ky, koct, kdesc, qx, qy, qr, qdesc, mode=0, thr=50, ta
     return int(n), idx[:len(qx)], dist[:len(qx)]
 
 
+def match_sim3(x1, y1, oct1, d1, x2, y2, oct2, d2, q12, q12desc, q12lvl, q21, q21desc, q21lvl):
+    """matchMapPointsSim3 (keyframe_matcher.cpp:633-686) on projected queries: q12 [n1, 3] = (x, y, r) of keyframe 1's map
+    points in keyframe 2 (r < 0: no query), q21 [n2, 3] the reverse.  Returns the agreed (i, j) pairs [n, 2]."""
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    i = lambda a: np.ascontiguousarray(a, np.int32)
+    u = lambda a: np.ascontiguousarray(a, np.uint32).reshape(-1, 8)
+    x1, y1, x2, y2 = f(x1), f(y1), f(x2), f(y2)
+    oct1, oct2, q12lvl, q21lvl = i(oct1), i(oct2), i(q12lvl), i(q21lvl)
+    d1, d2, q12desc, q21desc = u(d1), u(d2), u(q12desc), u(q21desc)
+    q12 = f(q12).reshape(-1, 3); q21 = f(q21).reshape(-1, 3)
+    a = [np.ascontiguousarray(q12[:, k]) for k in range(3)] + [np.ascontiguousarray(q21[:, k]) for k in range(3)]
+    out = np.zeros((max(min(len(x1), len(x2)), 1), 2), np.int32)
+    vp = lambda v: C.c_void_p(v.ctypes.data)
+    L = lib()
+    L.orc_match_sim3.restype = C.c_int
+    n = L.orc_match_sim3(vp(x1), vp(y1), vp(oct1), vp(d1), len(x1), vp(x2), vp(y2), vp(oct2), vp(d2), len(x2),
+                         vp(a[0]), vp(a[1]), vp(a[2]), vp(q12desc), vp(q12lvl), vp(a[3]), vp(a[4]), vp(a[5]), vp(q21desc),
+                         vp(q21lvl), vp(out))
+    return out[:n].copy()
+
+
 def bow_transform(vocab, desc, levels_up=4):
     """vocab: dict(child_off, child_ids, node_desc, node_weight, node_word, levels) (see synth.random_vocabulary)."""
     desc = np.ascontiguousarray(desc, np.uint32).reshape(-1, 8)

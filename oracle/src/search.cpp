@@ -121,3 +121,43 @@ extern "C" int orc_search_candidates(const float *kx, const float *ky, const int
     }
     return count;
 }
+
+// matchMapPointsSim3 (keyframe_matcher.cpp:633-686): findMatchesTranformedMps (:552-631) in both directions, then only
+// the pairs on which the two directions agree (:672-685).  The Sim3 geometry (transform, reprojection, viewing
+// distance, scale prediction) stays with the caller: q12_* is, per keypoint i of keyframe 1, the projection of its
+// map point into keyframe 2 with the search radius margin * scaleFactor[level] and the predicted level; r < 0 marks
+// a keypoint that issues no query (no map point, seeded as already matched :643-649, not TRIANGULATED, outside the
+// image or the viewing-distance range).  q21_* likewise per keypoint of keyframe 2.  out_pairs: (i, j) in i order.
+extern "C" int orc_match_sim3(const float *x1, const float *y1, const int *oct1, const uint32_t *d1, int n1,
+                              const float *x2, const float *y2, const int *oct2, const uint32_t *d2, int n2,
+                              const float *q12x, const float *q12y, const float *q12r, const uint32_t *q12desc, const int *q12lvl,
+                              const float *q21x, const float *q21y, const float *q21r, const uint32_t *q21desc, const int *q21lvl,
+                              int *out_pairs) {
+    auto direction = [](const float *kx, const float *ky, const int *koct, const uint32_t *kdesc, int nK, const float *qx,
+                        const float *qy, const float *qr, const uint32_t *qdesc, const int *qlvl, int nQ) {
+        const auto index = build_index(kx, ky, nK);
+        std::vector<int> match(nQ, -1), cand;
+        for (int q = 0; q < nQ; ++q) {
+            if (qr[q] < 0) continue;
+            around(index, qx[q], qy[q], qr[q], cand);
+            unsigned best = 256;
+            int best_idx = -1;
+            for (int i : cand) {
+                if (koct[i] < qlvl[q] - 1 || koct[i] > qlvl[q]) continue;          // :611
+                const unsigned d = hamming(qdesc + 8 * q, kdesc + 8 * i);
+                if (d < best) { best = d; best_idx = i; }
+            }
+            if (best <= 100) match[q] = best_idx;                                   // :625 HAMMING_DIST_THR_HIGH
+        }
+        return match;
+    };
+    const std::vector<int> m12 = direction(x2, y2, oct2, d2, n2, q12x, q12y, q12r, q12desc, q12lvl, n1);
+    const std::vector<int> m21 = direction(x1, y1, oct1, d1, n1, q21x, q21y, q21r, q21desc, q21lvl, n2);
+    int n = 0;
+    for (int i = 0; i < n1; ++i) {
+        const int j = m12[i];
+        if (j < 0) continue;
+        if (m21[j] == i) { out_pairs[2 * n] = i; out_pairs[2 * n + 1] = j; ++n; }
+    }
+    return n;
+}
