@@ -251,6 +251,19 @@ int sg_search_candidates(sg_ctx *ctx, const float *h_kx, const float *h_ky, cons
                          const float *h_qx, const float *h_qy, const float *h_qr, const uint32_t *h_qdesc,
                          const int32_t *h_qlevel, int nQ, int mode, uint32_t thr, int32_t *h_idx, uint32_t *h_dist,
                          uint32_t *n_matched);
+/* matchMapPointsSim3 (keyframe_matcher.cpp:633-686; findMatchesTranformedMps :552-631 in both directions + the
+ * agreement filter :672-685).  The Sim3 geometry stays with the caller like in sg_search_candidates: per keypoint i of
+ * keyframe 1, (h_q12x, h_q12y, h_q12r)[i] is the projection of its map point into keyframe 2 with the search radius
+ * margin * scaleFactors[level], h_q12desc its descriptor and h_q12level the predicted level; r < 0 marks a keypoint that
+ * issues no query (no map point, seeded as already matched :643-649, not TRIANGULATED, outside the image or the
+ * viewing-distance range).  h_q21* likewise per keypoint of keyframe 2.  h_order1 / h_order2: FeatureSearch order or NULL.
+ * h_pairs receives 2 * n_pairs indices (keypoint of kf1, keypoint of kf2), capacity 2 * min(n1, n2), in kf1 order. */
+int sg_match_sim3(sg_ctx *ctx, const float *h_x1, const float *h_y1, const int32_t *h_oct1, const uint32_t *h_desc1, int n1,
+                  const int32_t *h_order1, const float *h_x2, const float *h_y2, const int32_t *h_oct2, const uint32_t *h_desc2,
+                  int n2, const int32_t *h_order2, const float *h_q12x, const float *h_q12y, const float *h_q12r,
+                  const uint32_t *h_q12desc, const int32_t *h_q12level, const float *h_q21x, const float *h_q21y,
+                  const float *h_q21r, const uint32_t *h_q21desc, const int32_t *h_q21level, int32_t *h_pairs,
+                  uint32_t *n_pairs);
 /* FeatureSearch constructor (feature_search.cpp:22-31): keypoint indices sorted by y (host code, no GPU). */
 int sg_feature_index(const float *h_x, const float *h_y, int n, int32_t *h_order);
 /* MapPoint::updateDescriptor (map_point.cpp:75-116), batched: segment s owns descriptors

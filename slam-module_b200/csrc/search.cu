@@ -406,6 +406,59 @@ extern "C" int sg_search_candidates(sg_ctx *ctx, const float *h_kx, const float 
     return SG_OK;
 }
 
+// matchMapPointsSim3 (keyframe_matcher.cpp:633-686): findMatchesTranformedMps (:552-631) in both directions -- two
+// mode-0 candidate searches with the octave window and HAMMING_DIST_THR_HIGH -- and the agreement filter of :672-685.
+static int sim3_direction(sg_ctx *ctx, const float *kx, const float *ky, const int32_t *koct, const uint32_t *kdesc, int nK,
+                          const int32_t *order, const float *qx, const float *qy, const float *qr, const uint32_t *qdesc,
+                          const int32_t *qlevel, int nQ, std::vector<int32_t> &match) {
+    match.assign(std::max(nQ, 0), -1);
+    std::vector<int> live;
+    for (int q = 0; q < nQ; ++q)
+        if (qr[q] >= 0.f) live.push_back(q);          // r < 0: the keypoint issues no query (:566-590)
+    if (live.empty() || nK == 0) return SG_OK;
+    const size_t L = live.size();
+    std::vector<float> x(L), y(L), r(L);
+    std::vector<int32_t> lvl(L), idx(L);
+    std::vector<uint32_t> desc(8 * L), dist(L);
+    for (size_t i = 0; i < L; ++i) {
+        const int q = live[i];
+        x[i] = qx[q]; y[i] = qy[q]; r[i] = qr[q]; lvl[i] = qlevel[q];
+        std::copy(qdesc + 8 * (size_t)q, qdesc + 8 * (size_t)q + 8, desc.begin() + 8 * i);
+    }
+    if (int rc = sg_search_candidates(ctx, kx, ky, koct, kdesc, nK, order, nullptr, x.data(), y.data(), r.data(), desc.data(),
+                                      lvl.data(), (int)L, 0, 100u, idx.data(), dist.data(), nullptr))
+        return rc;
+    for (size_t i = 0; i < L; ++i) match[live[i]] = idx[i];
+    return SG_OK;
+}
+
+extern "C" int sg_match_sim3(sg_ctx *ctx, const float *h_x1, const float *h_y1, const int32_t *h_oct1, const uint32_t *h_desc1,
+                             int n1, const int32_t *h_order1, const float *h_x2, const float *h_y2, const int32_t *h_oct2,
+                             const uint32_t *h_desc2, int n2, const int32_t *h_order2, const float *h_q12x, const float *h_q12y,
+                             const float *h_q12r, const uint32_t *h_q12desc, const int32_t *h_q12level, const float *h_q21x,
+                             const float *h_q21y, const float *h_q21r, const uint32_t *h_q21desc, const int32_t *h_q21level,
+                             int32_t *h_pairs, uint32_t *n_pairs) {
+    if (n_pairs) *n_pairs = 0;
+    if (n1 < 0 || n2 < 0) return fail(ctx, SG_ERR_INVALID, "negative keypoint count");
+    if (n1 == 0 || n2 == 0) return SG_OK;
+    if (!h_q12x || !h_q12y || !h_q12r || !h_q12desc || !h_q12level || !h_q21x || !h_q21y || !h_q21r || !h_q21desc || !h_q21level
+        || !h_pairs)
+        return fail(ctx, SG_ERR_INVALID, "null argument");
+    std::vector<int32_t> m12, m21;
+    if (int rc = sim3_direction(ctx, h_x2, h_y2, h_oct2, h_desc2, n2, h_order2, h_q12x, h_q12y, h_q12r, h_q12desc, h_q12level, n1, m12))
+        return rc;
+    if (int rc = sim3_direction(ctx, h_x1, h_y1, h_oct1, h_desc1, n1, h_order1, h_q21x, h_q21y, h_q21r, h_q21desc, h_q21level, n2, m21))
+        return rc;
+    uint32_t n = 0;
+    for (int i = 0; i < n1; ++i) {
+        const int j = m12[i];
+        if (j < 0) continue;
+        if (m21[j] == i) { h_pairs[2 * n] = i; h_pairs[2 * n + 1] = j; ++n; }   // 1 -> 2 and 2 -> 1 agree (:680)
+    }
+    if (n_pairs) *n_pairs = n;
+    return SG_OK;
+}
+
 extern "C" int sg_feature_index(const float *h_x, const float *h_y, int n, int32_t *h_order) {
     struct Node { float x, y; int idx; };
     std::vector<Node> v(std::max(n, 0));

@@ -66,7 +66,7 @@ ABI_SYMBOLS = [
     "sg_angle_bin_order", "sg_angle_bin_order_depth", "sg_angle_bin", "sg_device_count", "sg_malloc", "sg_free",
     "sg_memcpy_h2d", "sg_memcpy_d2h", "sg_host_alloc_pinned", "sg_host_free_pinned", "sg_timer_start",
     "sg_timer_stop", "sg_flush_l2", "sg_microbench_popc", "sg_set_profiling", "sg_get_stage_ms",
-    "sg_set_pipeline_chunk", "sg_search_candidates", "sg_feature_index", "sg_medoid", "sg_set_overlap", "sg_match_bow", "sg_vocab_create", "sg_vocab_destroy",
+    "sg_set_pipeline_chunk", "sg_search_candidates", "sg_match_sim3", "sg_feature_index", "sg_medoid", "sg_set_overlap", "sg_match_bow", "sg_vocab_create", "sg_vocab_destroy",
     "sg_bow_transform", "sg_bow_transform_device", "sg_match_triangulation", "sg_bow_vector", "sg_bowdb_create",
     "sg_bowdb_destroy", "sg_bowdb_size", "sg_bowdb_add", "sg_bowdb_remove", "sg_bow_similar", "sg_extract_submit",
     "sg_extract_wait", "sg_db_wrap_device", "sg_bow_vector_batch",
@@ -147,6 +147,9 @@ def lib():
         L.sg_feature_index.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.sg_feature_index.restype = C.c_int
         L.sg_medoid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sg_match_sim3.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p] + \
+                                   [C.c_void_p] * 10 + [C.c_void_p, C.c_void_p]
+        L.sg_match_sim3.restype = C.c_int
         L.sg_medoid.restype = C.c_int
         L.sg_set_pipeline_chunk.restype = C.c_int
         L.sg_set_overlap.argtypes = [C.c_void_p, C.c_int]
@@ -566,6 +569,27 @@ class Context:
             qx.ctypes.data, qy.ctypes.data, qr.ctypes.data, qdesc.ctypes.data, None if ql is None else ql.ctypes.data,
             len(qx), int(mode), int(thr), idx.ctypes.data, dist.ctypes.data, C.byref(n)))
         return int(n.value), idx[:len(qx)], dist[:len(qx)]
+
+    def match_sim3(self, x1, y1, oct1, d1, x2, y2, oct2, d2, q12, q12desc, q12lvl, q21, q21desc, q21lvl, order1=None, order2=None):
+        """matchMapPointsSim3 on projected queries (q12 [n1, 3] = x, y, r of keyframe 1's map points in keyframe 2, r < 0: no
+        query; q21 [n2, 3] the reverse); returns the agreed (i, j) keypoint pairs [n, 2]."""
+        f = lambda a: np.ascontiguousarray(a, np.float32)
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        u = lambda a: np.ascontiguousarray(a, np.uint32).reshape(-1, 8)
+        x1, y1, x2, y2 = f(x1), f(y1), f(x2), f(y2)
+        oct1, oct2, q12lvl, q21lvl = i32(oct1), i32(oct2), i32(q12lvl), i32(q21lvl)
+        d1, d2, q12desc, q21desc = u(d1), u(d2), u(q12desc), u(q21desc)
+        q12 = f(q12).reshape(-1, 3); q21 = f(q21).reshape(-1, 3)
+        a = [np.ascontiguousarray(q12[:, k]) for k in range(3)] + [np.ascontiguousarray(q21[:, k]) for k in range(3)]
+        o1 = None if order1 is None else i32(order1)
+        o2 = None if order2 is None else i32(order2)
+        pairs = np.zeros((max(min(len(x1), len(x2)), 1), 2), np.int32)
+        n = C.c_uint32()
+        p = lambda v: None if v is None else v.ctypes.data
+        self._check(lib().sg_match_sim3(self._h, p(x1), p(y1), p(oct1), p(d1), len(x1), p(o1), p(x2), p(y2), p(oct2), p(d2), len(x2),
+                                        p(o2), p(a[0]), p(a[1]), p(a[2]), p(q12desc), p(q12lvl), p(a[3]), p(a[4]), p(a[5]),
+                                        p(q21desc), p(q21lvl), p(pairs), C.byref(n)))
+        return pairs[:n.value].copy()
 
     def medoid(self, desc, offsets):
         desc = np.ascontiguousarray(desc, np.uint32).reshape(-1, 8)

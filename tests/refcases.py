@@ -12,6 +12,95 @@ from oracle import pyoracle as po
 from oracle import pyref as pr
 
 
+class OracleImpl:
+    """The CPU oracle behind the method names the cases call."""
+    name = "oracle"
+    match_bow = staticmethod(po.match_bow)
+    match_bruteforce = staticmethod(po.match_bruteforce)
+    match_triangulation = staticmethod(po.match_triangulation)
+    search_candidates = staticmethod(po.search_candidates)
+    match_sim3 = staticmethod(po.match_sim3)
+    medoid = staticmethod(po.medoid)
+
+    def geometry(self, lv, sf, mk):
+        s, _, _, b = po.geometry(po.make_params(640, 480, levels=lv, scale_factor=sf, max_keypoints=mk))
+        return s, b
+
+    def feature_order(self, x, y):
+        return po.feature_index(x, y)
+
+    def extract(self, p, img, tracks, ids, level):
+        return po.extract(p, img, tracks, ids, level)
+
+    def pyramid(self, p, img):
+        return po.pyramid(p, img)
+
+    def bow(self, vocab, desc, kfs, removed, queries, n_words):
+        word, weight, node = po.bow_transform(vocab, desc, levels_up=4)
+        w, v = po.bow_vector(word, weight)
+        ix = po.BowIndex(n_words)
+        for k, (ww, vv) in enumerate(kfs):
+            ix.add(1000, k, ww, vv)
+        for k in removed:
+            ix.remove(1000, k)
+        sims = [ix.similar(kfs[k][0], kfs[k][1], self_key=(1000, k))[1:] for k in queries]
+        ix.close()
+        return word, weight, node, w, v, sims
+
+
+class GpuImpl:
+    """libslamgpu.so through its C ABI (slam_module_b200.slamgpu): the product under test."""
+    name = "gpu"
+
+    def __init__(self, slamgpu):
+        self.sg = slamgpu
+        self.ctx = slamgpu.Context(640, 480, max_frames=1)
+        for m in ("match_bow", "match_bruteforce", "match_triangulation", "search_candidates", "match_sim3", "medoid"):
+            setattr(self, m, getattr(self.ctx, m))
+
+    def close(self):
+        self.ctx.close()
+
+    def geometry(self, lv, sf, mk):
+        with self.sg.Context(640, 480, levels=lv, scale_factor=sf, max_keypoints=mk, max_frames=1) as c:
+            return c.scales.copy(), c.budgets.copy()
+
+    def feature_order(self, x, y):
+        return self.sg.feature_index(x, y)
+
+    def _ctx(self, p, max_tracks=0, level=0):
+        return self.sg.Context(p.width, p.height, levels=p.levels, scale_factor=p.scale_factor, max_keypoints=p.max_keypoints,
+                               ini_fast_thr=p.ini_fast_thr, min_fast_thr=p.min_fast_thr, max_frames=1, max_tracks=max_tracks,
+                               track_level=level)
+
+    def extract(self, p, img, tracks, ids, level):
+        nt = 0 if tracks is None else len(tracks)
+        with self._ctx(p, nt, level) as c:
+            return c.detect_and_extract(img, None if tracks is None else [tracks], None if ids is None else [ids])[0]
+
+    def pyramid(self, p, img):
+        with self._ctx(p) as c:
+            c.pyramid_update(img)
+            return ([c.get_level(0, l) for l in range(p.levels)], [c.get_blurred_level(0, l) for l in range(p.levels)])
+
+    def bow(self, vocab, desc, kfs, removed, queries, n_words):
+        voc = self.sg.Vocabulary(self.ctx, vocab)
+        word, weight, node = voc.transform(desc, levels_up=4)
+        w, v = voc.bow_vector(word, weight)
+        db = self.sg.BowDatabase(self.ctx, len(kfs) + 4)
+        for k, (ww, vv) in enumerate(kfs):
+            db.add(1000, k, ww, vv)
+        for k in removed:
+            db.remove(1000, k)
+        sims = [db.similar(kfs[k][0], kfs[k][1], self_key=(1000, k))[1:] for k in queries]
+        db.close(); voc.close()
+        return word, weight, node, w, v, sims
+
+
+def _impl(backend):
+    return OracleImpl() if backend == "oracle" else backend
+
+
 def _flip(rng, d, nbits):
     d = d.copy()
     for b in rng.integers(0, 256, nbits):
@@ -29,7 +118,7 @@ def case_settings(backend):
         if backend == "ref":
             s, _, b = pr.settings(lv, sf, mk)
         else:
-            s, _, _, b = po.geometry(po.make_params(640, 480, levels=lv, scale_factor=sf, max_keypoints=mk))
+            s, b = _impl(backend).geometry(lv, sf, mk)
         out["scale%d" % i] = s
         out["budget%d" % i] = b
     return out
@@ -42,6 +131,8 @@ def case_feature_search(backend):
     x = rng.uniform(0, 640, n).astype(np.float32)
     y = np.round(rng.uniform(0, 480, n)).astype(np.float32)       # integer y: many ties in the Y sort
     x[::9] = np.round(x[::9])
+    if backend not in ("oracle", "ref"):     # the C ABI exposes the index order (queries: sg_search_candidates cases below)
+        return {"order": backend.feature_order(x, y)}
     f = po.features_around if backend == "oracle" else pr.features_around
     out = {"order": f(x, y, 320.0, 240.0, 2000.0)}                 # huge radius: the whole Y-sorted order
     qs = [(10.0, 10.0, 30.0), (320.0, 240.0, 0.0), (320.5, 100.0, 1.0), (600.0, 470.0, 55.5), (-20.0, 200.0, 40.0),
@@ -77,8 +168,7 @@ def _extract_inputs(name):
 
 def case_extract(backend, name):
     p, img, tracks, ids, level = _extract_inputs(name)
-    f = po.extract if backend == "oracle" else pr.extract
-    r = f(p, img, tracks, ids, level)
+    r = pr.extract(p, img, tracks, ids, level) if backend == "ref" else _impl(backend).extract(p, img, tracks, ids, level)
     return {k: r[k] for k in ("x", "y", "angle", "octave", "desc", "track_id")}
 
 
@@ -86,7 +176,7 @@ def case_pyramid_crc(backend):
     import zlib
     p = po.make_params(640, 480)
     img = sm.synth.frame(640, 480, 1000)
-    lv, bl = (po.pyramid if backend == "oracle" else pr.pyramid)(p, img)
+    lv, bl = pr.pyramid(p, img) if backend == "ref" else _impl(backend).pyramid(p, img)
     return {"pyr": np.array([zlib.crc32(a.tobytes()) for a in lv], np.int64),
             "blur": np.array([zlib.crc32(a.tobytes()) for a in bl], np.int64)}
 
@@ -122,7 +212,7 @@ def case_loop_closures(backend, seed, require):
     else:
         eA = ((sA == 1) | ((sA == 2) & (not require))).astype(np.uint8)       # keyframe_matcher.cpp:79-84
         eB = (sB == 1).astype(np.uint8)                                        # :94-96
-        n, m = po.match_bow(dA, aA, nodeA, dB, aB, nodeB, eA, eB, ratio=0.8, thr=50, check_orientation=True)
+        n, m = _impl(backend).match_bow(dA, aA, nodeA, dB, aB, nodeB, eA, eB, ratio=0.8, thr=50, check_orientation=True)
     return {"n": np.array([n]), "matches": m}
 
 
@@ -134,7 +224,7 @@ def case_loop_closures_bruteforce(backend, seed):
     if backend == "ref":
         n, m = pr.match_loop_closures(dA, aA, zA, dB, aB, zB)
     else:
-        n, m = po.match_bruteforce(dA, aA, dB, aB, ratio=0.8, thr=50, check_orientation=True)
+        n, m = _impl(backend).match_bruteforce(dA, aA, dB, aB, ratio=0.8, thr=50, check_orientation=True)
     return {"n": np.array([n]), "matches": m}
 
 
@@ -182,8 +272,8 @@ def case_triangulation(backend, seed, thr_deg):
         return {"n": np.array([n]), "matches": m, "E": E}
     E = essential_from_poses(poseA, poseB)
     sf = po.geometry(po.make_params(640, 480))[0]
-    n, m = po.match_triangulation(dA, aA, octA, bA, nodeA, dB, aB, bB, nodeB, E, sf, (1 - hA).astype(np.uint8),
-                                  (1 - hB).astype(np.uint8), residual_deg_thr=thr_deg)
+    n, m = _impl(backend).match_triangulation(dA, aA, octA, bA, nodeA, dB, aB, bB, nodeB, E, sf, (1 - hA).astype(np.uint8),
+                                              (1 - hB).astype(np.uint8), residual_deg_thr=thr_deg)
     return {"n": np.array([n]), "matches": m, "E": E}
 
 
@@ -261,8 +351,8 @@ def case_search_by_projection(backend, seed, golden=None):
     live = g["qr"] >= 0
     t = taken.copy()
     idx = np.full(len(qdesc), -1, np.int32)
-    n, i2, _ = po.search_candidates(kx, ky, koct, kdesc, g["qx"][live], g["qy"][live], g["qr"][live], qdesc[live], mode=1,
-                                    thr=100, taken=t)
+    n, i2, _ = _impl(backend).search_candidates(kx, ky, koct, kdesc, g["qx"][live], g["qy"][live], g["qr"][live], qdesc[live],
+                                                mode=1, thr=100, taken=t)
     idx[live] = i2
     return {"n": np.array([n]), "idx": idx, "qx": g["qx"], "qy": g["qy"], "qr": g["qr"], "ql": g["ql"]}
 
@@ -280,7 +370,8 @@ def case_replace_duplication(backend, seed, golden=None):
     g = golden
     live = g["qr"] >= 0
     best = np.full(len(qdesc), -1, np.int32)
-    _, b2, _ = po.search_candidates(kx, ky, koct, kdesc, g["qx"][live], g["qy"][live], g["qr"][live], qdesc[live], mode=0, thr=50)
+    _, b2, _ = _impl(backend).search_candidates(kx, ky, koct, kdesc, g["qx"][live], g["qy"][live], g["qr"][live], qdesc[live],
+                                                mode=0, thr=50)
     best[live] = b2
     # keyframe_matcher.cpp:500-524 on observation counts: owner[k] >= 0 query index, -2 original map point, -1 none
     owner = np.where(kp_mp > 0, -2, -1).astype(np.int64)
@@ -350,7 +441,7 @@ def case_sim3(backend, seed, golden=None):
     g = golden
     qd12 = desc[np.maximum(mp1, 0)]
     qd21 = desc[np.maximum(mp2, 0)]
-    pairs = po.match_sim3(x1, y1, oct1, d1, x2, y2, oct2, d2, g["q12"], qd12, g["l12"], g["q21"], qd21, g["l21"])
+    pairs = _impl(backend).match_sim3(x1, y1, oct1, d1, x2, y2, oct2, d2, g["q12"], qd12, g["l12"], g["q21"], qd21, g["l21"])
     return {"pairs": pairs, "q12": g["q12"], "l12": g["l12"], "q21": g["q21"], "l21": g["l21"]}
 
 
@@ -364,7 +455,7 @@ def case_medoid(backend):
     desc[offs[5] + 3] = desc[offs[5] + 1]                           # twins: first index wins
     if backend == "ref":
         return {"desc": pr.medoid(desc, offs)}
-    best = po.medoid(desc, offs)
+    best = _impl(backend).medoid(desc, offs)
     return {"desc": np.stack([desc[offs[s] + best[s]] for s in range(len(sizes))])}
 
 
@@ -410,19 +501,11 @@ def case_bow(backend, tmpdir):
             out["sim%d_score" % qi] = sc
         ix.close()
         return out
-    word, weight, node = po.bow_transform(vocab, desc, levels_up=4)
-    w, v = po.bow_vector(word, weight)
+    word, weight, node, w, v, sims = _impl(backend).bow(vocab, desc, kfs, (3, 50, 51), (0, 7, 99, 3), n_words)
     # DBoW2 drops weight-0 features from the feature vector; the reference tree is numbered by its text file (node id ==
     # line order == breadth-first id of synth.random_vocabulary), so node ids compare directly
     out.update(node=np.where(weight > 0, node, -1).astype(np.int32), word=w, value=v)
-    ix = po.BowIndex(n_words)
-    for k, (ww, vv) in enumerate(kfs):
-        ix.add(1000, k, ww, vv)
-    for k in (3, 50, 51):
-        ix.remove(1000, k)
-    for qi, k in enumerate((0, 7, 99, 3)):
-        _, kf, sc = ix.similar(kfs[k][0], kfs[k][1], self_key=(1000, k))
+    for qi, (kf, sc) in enumerate(sims):
         out["sim%d_kf" % qi] = kf
         out["sim%d_score" % qi] = sc
-    ix.close()
     return out
