@@ -159,8 +159,11 @@ static int build_context(sg_ctx *ctx) {
     if (int r = dev_alloc(ctx, &ctx->d_kp_xy, F * g.det_cap)) return r;
     if (int r = dev_alloc(ctx, &ctx->d_kp_resp, F * g.det_cap)) return r;
     if (int r = dev_alloc(ctx, &ctx->d_kp_count, F * p.levels)) return r;
-    if (int r = dev_alloc(ctx, &ctx->d_err, 1)) return r;
-    SG_CUDA(ctx, cudaMemset(ctx->d_err, 0, sizeof(int)));
+    // one overflow word for the synchronous calls + one per batch in flight (sg_extract_submit ticket)
+    if (int r = dev_alloc(ctx, &ctx->d_err, 1 + sg_ctx::N_TICKETS)) return r;
+    SG_CUDA(ctx, cudaMemset(ctx->d_err, 0, sizeof(int) * (1 + sg_ctx::N_TICKETS)));
+    SG_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_err, sizeof(int) * (1 + sg_ctx::N_TICKETS), cudaHostAllocDefault));
+    for (int i = 0; i <= sg_ctx::N_TICKETS; ++i) ctx->h_err[i] = 0;
     SG_CUDA(ctx, cudaMemset(ctx->d_kp_count, 0, sizeof(int) * F * p.levels));
     const size_t T = std::max(p.max_tracks, 1);
     if (int r = dev_alloc(ctx, &ctx->d_trk_xy, F * T)) return r;
@@ -217,6 +220,8 @@ static int upload_frames(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t f
 static int upload_tracks(sg_ctx *ctx, const float *h_xy, const int32_t *h_ids, const int32_t *n_tracks, int n_frames) {
     ctx->have_tracks = false;
     if (!h_xy || !n_tracks || ctx->p.max_tracks <= 0) return SG_OK;
+    if (n_frames < 1 || n_frames > ctx->p.max_frames)   // the device arrays hold max_frames * max_tracks entries
+        return fail(ctx, SG_ERR_INVALID, "n_frames %d outside [1, %d]", n_frames, ctx->p.max_frames);
     const int T = ctx->p.max_tracks, lvl = ctx->p.track_level;
     if (lvl < 0 || lvl >= ctx->p.levels) return fail(ctx, SG_ERR_INVALID, "track_level outside the pyramid");
     const Level &L = ctx->lv[lvl];
@@ -350,6 +355,7 @@ void sg_destroy(sg_ctx *ctx) {
                     ctx->d_rescans, ctx->d_tmp, ctx->d_dbtmp, ctx->d_cell_table};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_err) cudaFreeHost(ctx->h_err);
     for (auto &slot : ctx->ev_stage)
         for (auto &e : slot) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -611,6 +617,8 @@ static int pipeline_wait_all(sg_ctx *ctx, int rc) {
 int sg_extract(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames,
                const float *h_track_xy, const int32_t *h_track_ids, const int32_t *n_tracks, sg_keypoints *h_out) {
     cudaSetDevice(ctx->device);
+    if (n_frames < 1 || n_frames > ctx->p.max_frames)   // before anything is sized by it (track staging, device copies)
+        return fail(ctx, SG_ERR_INVALID, "n_frames %d outside [1, %d]", n_frames, ctx->p.max_frames);
     if (int r = slots_free(ctx, 0, n_frames)) return r;
     if (int r = upload_tracks(ctx, h_track_xy, h_track_ids, n_tracks, n_frames)) return r;
     return pipeline_wait_all(ctx, pipeline_submit(ctx, h_imgs, pitch, frame_stride, n_frames, 0, h_out));
@@ -621,17 +629,29 @@ int sg_extract_submit(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t fram
                       const sg_keypoints *h_out, int *ticket) {
     cudaSetDevice(ctx->device);
     if (!ticket) return fail(ctx, SG_ERR_INVALID, "null ticket");
-    const int t = ctx->next_ticket % sg_ctx::N_TICKETS;
-    if (ctx->ticket[t].busy) return fail(ctx, SG_ERR_INVALID, "%d batches are in flight: wait for one first", (int)sg_ctx::N_TICKETS);
+    if (n_frames < 1 || n_frames > ctx->p.max_frames)
+        return fail(ctx, SG_ERR_INVALID, "n_frames %d outside [1, %d]", n_frames, ctx->p.max_frames);
+    int t = -1;                                   // any free ticket: waits may come back out of order
+    for (int i = 0; i < sg_ctx::N_TICKETS && t < 0; ++i) {
+        const int c = (ctx->next_ticket + i) % sg_ctx::N_TICKETS;
+        if (!ctx->ticket[c].busy) t = c;
+    }
+    if (t < 0) return fail(ctx, SG_ERR_INVALID, "%d batches are in flight: wait for one first", (int)sg_ctx::N_TICKETS);
     if (int r = slots_free(ctx, base_frame, n_frames)) return r;
     ctx->have_tracks = false;
-    if (int r = pipeline_submit(ctx, h_imgs, pitch, frame_stride, n_frames, base_frame, h_out, true)) {
-        pipeline_wait_all(ctx, r);
-        return r;
+    ctx->err_slot = 1 + t;                        // this batch's own overflow word
+    const int rs = pipeline_submit(ctx, h_imgs, pitch, frame_stride, n_frames, base_frame, h_out, true);
+    ctx->err_slot = 0;
+    if (rs) {
+        pipeline_wait_all(ctx, rs);
+        return rs;
     }
-    ++ctx->next_ticket;
+    ctx->next_ticket = t + 1;
     ctx->ticket[t].busy = true; ctx->ticket[t].base = base_frame; ctx->ticket[t].n = n_frames;
     if (!ctx->ticket_ev[t]) SG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ticket_ev[t], cudaEventDisableTiming));
+    // s_out runs behind every kernel of the batch: read the batch's overflow word there and clear it for the next user
+    SG_CUDA(ctx, cudaMemcpyAsync(ctx->h_err + 1 + t, ctx->d_err + 1 + t, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_out));
+    SG_CUDA(ctx, cudaMemsetAsync(ctx->d_err + 1 + t, 0, sizeof(int), ctx->s_out));
     SG_CUDA(ctx, cudaEventRecord(ctx->ticket_ev[t], ctx->s_out));      // every D2H of the batch is on s_out, after its kernels
     *ticket = t;
     return SG_OK;
@@ -642,7 +662,10 @@ int sg_extract_wait(sg_ctx *ctx, int ticket) {
     if (ticket < 0 || ticket >= sg_ctx::N_TICKETS || !ctx->ticket[ticket].busy) return fail(ctx, SG_ERR_INVALID, "ticket %d is not in flight", ticket);
     SG_CUDA(ctx, cudaEventSynchronize(ctx->ticket_ev[ticket]));
     ctx->ticket[ticket].busy = false;
-    return check_device_error(ctx);
+    const int e = ctx->h_err[1 + ticket];
+    ctx->h_err[1 + ticket] = 0;
+    if (e) return fail(ctx, e, "device-side capacity exceeded (candidate list or quadtree node table) in the batch of ticket %d", ticket);
+    return SG_OK;
 }
 
 int sg_set_pipeline_chunk(sg_ctx *ctx, int frames) {

@@ -138,7 +138,9 @@ struct sg_ctx {
     int *d_kp_xy = nullptr;                // [max_frames][det_cap]  x | y<<16 (level coords)
     int *d_kp_resp = nullptr;
     int *d_kp_count = nullptr;             // [max_frames][levels]
-    int *d_err = nullptr;                  // device-side overflow flag
+    int *d_err = nullptr;                  // device-side overflow flags: [0] synchronous calls, [1 + t] batch of ticket t
+    int *h_err = nullptr;                  // pinned mirror read back behind each streamed batch
+    int err_slot = 0;                      // which flag the stage launchers hand to the kernels
     int4 *d_cell_table = nullptr;          // FAST cells: level, cell row / column, origin, extent (fast_cell_table)
 
     // tracker points (host-filtered, orb_extractor.cpp:89-104)

@@ -570,7 +570,7 @@ int launch_detect(sg_ctx *ctx, int n_frames) {
         FastMaps maps;
         for (int l = 0; l < g.levels; ++l) maps.m[l] = ctx->lv[l].map_fast;
         fast_cells_kernel<<<dim3(total_cells, n_frames), FAST_THREADS, 0, ctx->stream>>>(
-            g, maps, ctx->d_cell_table, ctx->d_cand, ctx->d_cand_count, ctx->d_err);
+            g, maps, ctx->d_cell_table, ctx->d_cand, ctx->d_cand_count, ctx->d_err + ctx->err_slot);
         SG_LAUNCH_CHECK(ctx);
     }
     mark(ctx, EV_FAST1);
@@ -578,7 +578,7 @@ int launch_detect(sg_ctx *ctx, int n_frames) {
     if (smem > 48 * 1024)
         SG_CUDA(ctx, cudaFuncSetAttribute(distribute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     distribute_kernel<<<dim3(g.levels, n_frames), DIST_THREADS, smem, ctx->stream>>>(
-        g, nc_max, ctx->d_cand, ctx->d_cand_node, ctx->d_cand_count, ctx->d_kp_xy, ctx->d_kp_resp, ctx->d_kp_count, ctx->d_err);
+        g, nc_max, ctx->d_cand, ctx->d_cand_node, ctx->d_cand_count, ctx->d_kp_xy, ctx->d_kp_resp, ctx->d_kp_count, ctx->d_err + ctx->err_slot);
     SG_LAUNCH_CHECK(ctx);
     mark(ctx, EV_DIST1);
     ctx->detected = true;

@@ -544,7 +544,8 @@ __global__ void popc_bench_kernel(unsigned *out, int iters, unsigned seed) {
 // Pairs per launch: bounds the top-K (and match-row) scratch to ~256 MB.
 int match_chunk_pairs(const sg_db *db, bool own_matches) {
     const size_t per_pair = (size_t)std::max(db->max_set, 1) * (TOPK * 4 + 4 + (own_matches ? 4 : 0));
-    return (int)std::max<size_t>(1, ((size_t)256 << 20) / per_pair);
+    // grid.y of hamming_topk_kernel is the pair index: at most 65535 pairs per launch whatever the scratch allows
+    return (int)std::min<size_t>(65535, std::max<size_t>(1, ((size_t)256 << 20) / per_pair));
 }
 
 // Top-K scratch: `rows` rows of `K` keys + one count per row, from the stream-ordered pool.
@@ -599,6 +600,12 @@ int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, con
     if (mp.thr > 256) return fail(ctx, SG_ERR_INVALID, "thr must be <= 256");
     const int stride = db->max_set;
     if (d_matches && match_stride < stride) return fail(ctx, SG_ERR_INVALID, "match_stride smaller than the largest set");
+    if (stride == 0) {   // every set is empty: zero matches for every pair, no launch
+        SG_CUDA(ctx, cudaMemsetAsync(d_n_matches, 0, sizeof(uint32_t) * (size_t)n_pairs, ctx->stream));
+        if (d_matches && match_stride > 0)
+            SG_CUDA(ctx, cudaMemsetAsync(d_matches, 0xff, sizeof(int) * (size_t)n_pairs * match_stride, ctx->stream));
+        return SG_OK;
+    }
     const int chunk = std::min(n_pairs, match_chunk_pairs(db, d_matches == nullptr));
     const int tiles = (stride + MT_THREADS - 1) / MT_THREADS;
     const int splits = pick_splits(tiles * chunk, db->max_set);

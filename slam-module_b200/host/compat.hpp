@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include "linalg.hpp"
+
 namespace accelerated {
 // accelerated::Image as the hot path uses it: width / height / storageType (image_pyramid.cpp:211,
 // feature_detector.cpp:79) plus, for CPU images, what accelerated::opencv::ref() would expose.
@@ -45,11 +47,23 @@ struct Image {
     accelerated::Image &getAccImage() { return acc; }
 };
 
-// tracker::Camera: only isValidPixel is used on the path (orb_extractor.cpp:101,231)
+// tracker::Camera: isValidPixel on the extraction path (orb_extractor.cpp:101,231); rayToPixel / pixelToRay for the
+// projection matchers (keyframe.cpp:408-444).  The default is a pinhole model over all pixels.
 class Camera {
 public:
+    double fx = 1, fy = 1, cx = 0, cy = 0;
     virtual ~Camera() = default;
     virtual bool isValidPixel(double x, double y) const { (void)x; (void)y; return true; }
+    bool isValidPixel(const slam::la::Vector2d &p) const { return isValidPixel(p(0), p(1)); }
+    virtual bool rayToPixel(const slam::la::Vector3d &ray, slam::la::Vector2d &pix) const {
+        if (!(ray(2) > 0)) return false;
+        pix = slam::la::Vector2d(fx * (ray(0) / ray(2)) + cx, fy * (ray(1) / ray(2)) + cy);
+        return true;
+    }
+    virtual bool pixelToRay(const slam::la::Vector2d &pix, slam::la::Vector3d &ray) const {
+        ray = slam::la::Vector3d((pix(0) - cx) / fx, (pix(1) - cy) / fy, 1.0).normalized();
+        return true;
+    }
 };
 }  // namespace tracker
 
@@ -64,6 +78,8 @@ struct ParametersSlam {
     std::string slamFeatureDetector = "FAST"; // feature_detector.cpp:38-41
     float loopClosureFeatureMatchLoweRatio = 0.8f;     // keyframe_matcher.cpp:120
     bool requireTringulationForLoopClosures = true;    // keyframe_matcher.cpp:82 (sic)
+    float epipolarCheckThresholdDegrees = 0.2f;        // keyframe_matcher.cpp:168
+    std::string vocabularyPath;                        // bow_index.cpp:35 (DBoW2 text vocabulary, see loadVocabularyText)
     float bowMinInCommonRatio = 0.8f;         // bow_index.cpp:144
     float bowScoreRatio = 0.75f;              // bow_index.cpp:170
     // upstream OpenVSLAM FAST thresholds of the detector the north star names

@@ -15,6 +15,7 @@
 #include <tuple>
 
 #include "../../include/slamgpu.h"
+#include "slam_matchers.hpp"
 
 namespace slam {
 namespace {
@@ -221,6 +222,8 @@ public:
         keypts.clear();
         keyptTrackIds.clear();
         // tracker points: the camera test of orb_extractor.cpp:101 is applied here, the margin test in the library
+        // the context's track capacity is fixed at creation: grow it (a new context) rather than drop tracker points
+        if ((int)tracks.size() > fe->params.max_tracks) regrow((int)tracks.size(), img);
         const int T = fe->params.max_tracks;
         int nTracks = 0;
         trackXy.clear(); trackIds.clear();
@@ -274,6 +277,24 @@ private:
             imagePyramid = ImagePyramid::build(settings, img);
         }
         assert(img.width == fe->params.width && img.height == fe->params.height);
+    }
+    // more tracker points than the context was sized for (the reference keeps every valid track, orb_extractor.cpp:89-124):
+    // a private context with room for them replaces the shared one for this extractor
+    void regrow(int nTracks, tracker::Image &img) {
+        int cap = std::max(64, fe->params.max_tracks);
+        while (cap < nTracks) cap *= 2;
+        std::fprintf(stderr, "slam-b200: %d tracker points exceed cudaMaxTracks = %d: re-creating the extractor's context for %d\n",
+                     nTracks, fe->params.max_tracks, cap);
+        auto grown = std::make_shared<CudaFrontend>();
+        grown->params = fe->params;
+        grown->params.max_tracks = cap;
+        const int rc = sg_create(settings.parameters.slam.cudaDevice, &grown->params, &grown->ctx);
+        if (rc != SG_OK) die(nullptr, "sg_create", rc);
+        grown->levels = fe->levels;
+        grown->cap = sg_keypoint_capacity(grown->ctx);
+        grown->scales = fe->scales; grown->widths = fe->widths; grown->heights = fe->heights;
+        fe = grown;
+        (void)img;
     }
     sg_keypoints outputs(int n) {
         const size_t m = (size_t)n * fe->cap;
@@ -360,21 +381,18 @@ unsigned int matchForLoopClosures(const Keyframe &kf1, const Keyframe &kf2, cons
     for (size_t i = 0; i < kps1.size(); ++i) {
         const MpId id = kf1.mapPoints.at(i);
         if (id.v == -1) continue;
-        if (parameters.requireTringulationForLoopClosures && mapDB1.mapPoints.at(id.v).status != MapPointStatus::TRIANGULATED) continue;
+        if (parameters.requireTringulationForLoopClosures && mapDB1.mapPoints.at(id).status != MapPointStatus::TRIANGULATED) continue;
         elig1[i] = 1;
     }
     for (size_t i = 0; i < kps2.size(); ++i) {
         const MpId id = kf2.mapPoints.at(i);
-        if (id.v == -1 || mapDB2.mapPoints.at(id.v).status != MapPointStatus::TRIANGULATED) continue;
+        if (id.v == -1 || mapDB2.mapPoints.at(id).status != MapPointStatus::TRIANGULATED) continue;
         elig2[i] = 1;
     }
     const auto &fv1 = kf1.shared->bowFeatureVec, &fv2 = kf2.shared->bowFeatureVec;
-    if (fv1.empty() && fv2.empty()) {                               // no vocabulary: one node holds everything
-        std::vector<int> idx1, idx2;
-        for (size_t i = 0; i < kps1.size(); ++i) if (elig1[i]) idx1.push_back((int)i);
-        for (size_t i = 0; i < kps2.size(); ++i) if (elig2[i]) idx2.push_back((int)i);
-        return matchSubset(kps1, idx1, kps2, idx2, matchedMapPoints, parameters.loopClosureFeatureMatchLoweRatio, true, ctx);
-    }
+    // keyframe_matcher.cpp:65-147 walks the two feature vectors: with empty vectors the reference finds nothing.  (The
+    // single-node brute-force form of the north star is bruteForceMatch below, an explicit call.)
+    if (fv1.empty() || fv2.empty()) return 0;
     // node of every feature; DBoW2 lists the features of a node in index order (bow_index.cpp:59-93), which is
     // the order the library assumes inside a node
     auto nodes = [](const std::map<unsigned, std::vector<unsigned>> &fv, size_t n) {
@@ -407,6 +425,196 @@ unsigned int bruteForceMatch(const KeyPointVector &kps1, const KeyPointVector &k
     for (size_t i = 0; i < idx1.size(); ++i) idx1[i] = (int)i;
     for (size_t i = 0; i < idx2.size(); ++i) idx2[i] = (int)i;
     return matchSubset(kps1, idx1, kps2, idx2, matches, loweRatio, checkOrientation, ctx);
+}
+
+// ---- data-model slice (map_point.cpp:11-17,65-73,117-184; keyframe.cpp:248-307,408-424) -------------------------
+MapPoint::MapPoint(MpId id, KfId keyframeId, KpId keyPointId) : id(id), referenceKeyframe(keyframeId) {
+    assert(keyframeId.v != -1);
+    addObservation(keyframeId, keyPointId);
+}
+void MapPoint::addObservation(KfId keyframeId, KpId keyPointId) {
+    assert(!observations.count(keyframeId));
+    observations.emplace(keyframeId, keyPointId);
+}
+void MapPoint::eraseObservation(KfId keyframeId) {
+    assert(observations.count(keyframeId));
+    observations.erase(keyframeId);
+}
+// map_point.cpp:117-158: every observation of this point moves to `otherMp` (or is dropped where otherMp is seen too)
+void MapPoint::replaceWith(MapDB &mapDB, MapPoint &otherMp) {
+    assert(id.v != -1 && otherMp.id.v != -1 && mapDB.mapPoints.count(id) && mapDB.mapPoints.count(otherMp.id));
+    if (otherMp.id == id) return;
+    if (trackId.v != -1) {
+        if (otherMp.trackId.v == -1) {
+            mapDB.trackIdToMapPoint.at(trackId) = otherMp.id;
+            otherMp.trackId = trackId;
+        } else {
+            mapDB.trackIdToMapPoint.erase(trackId);
+        }
+    }
+    for (const auto &obs : observations) {
+        Keyframe &kf = *mapDB.keyframes.at(obs.first);
+        kf.keyPointToTrackId.erase(obs.second);
+        if (!otherMp.observations.count(obs.first)) {
+            kf.mapPoints[obs.second.v] = otherMp.id;
+            otherMp.addObservation(obs.first, obs.second);
+        } else {
+            kf.mapPoints[obs.second.v] = MpId(-1);
+        }
+    }
+    status = MapPointStatus::BAD;
+    mapDB.mapPoints.erase(id);     // `this` dies here, exactly as in the reference
+}
+// map_point.cpp:174-183
+int MapPoint::predictScaleLevel(float dist, const StaticSettings &settings) const {
+    const float ratio = maxViewingDistance / dist;
+    const int scale = std::ceil(std::log(ratio) / std::log(settings.parameters.slam.orbScaleFactor));
+    return std::min(std::max(scale, 0), static_cast<int>(settings.scaleFactors.size() - 1));
+}
+
+void Keyframe::addObservation(MpId mapPointId, KpId keyPointId) {
+    assert(mapPoints[keyPointId.v].v == -1);
+    mapPoints[keyPointId.v] = mapPointId;
+}
+void Keyframe::eraseObservation(MpId mapPointId) {
+    const auto it = std::find(mapPoints.begin(), mapPoints.end(), mapPointId);
+    assert(it != mapPoints.end());
+    it->v = -1;
+    keyPointToTrackId.erase(KpId((int)std::distance(mapPoints.begin(), it)));
+}
+Vector3d Keyframe::cameraCenter() const {   // keyframe.hpp:23-25: -R^T t
+    return -poseCW.topLeftCorner<3, 3>().transpose() * poseCW.block<3, 1>(0, 3);
+}
+bool Keyframe::reproject(const Vector3d &pointW, Vector2f &reprojected) const {
+    float unused = 0;
+    Vector2d pix;
+    const bool visible = reprojectToImage(*shared->camera, poseCW.topLeftCorner<3, 3>(), poseCW.block<3, 1>(0, 3), pointW, pix, unused);
+    reprojected = Vector2f((float)pix(0), (float)pix(1));
+    return visible;
+}
+void Keyframe::getFeaturesAround(const Vector2f &point, float r, std::vector<size_t> &output) {
+    assert(shared->featureSearch);
+    shared->featureSearch->getFeaturesAround(point(0), point(1), r, output);
+}
+bool reprojectToImage(const tracker::Camera &camera, const Matrix3d &rot_cw, const Vector3d &trans_cw, const Vector3d &pos_w,
+                      Vector2d &reproj, float &x_right) {
+    const Vector3d pos_c = rot_cw * pos_w + trans_cw;
+    x_right = 0.0;
+    if (!camera.rayToPixel(pos_c, reproj)) return false;
+    if (!camera.isValidPixel(reproj)) return false;
+    x_right = (float)reproj(0);
+    return true;
+}
+
+// ---- FeatureSearch (feature_search.cpp:22-48): index order from the library, the radius walk over it ---------------
+namespace {
+class IndexedFeatureSearch : public FeatureSearch {
+public:
+    explicit IndexedFeatureSearch(const KeyPointVector &kps) : x(kps.size()), y(kps.size()), order(kps.size()) {
+        for (size_t i = 0; i < kps.size(); ++i) { x[i] = kps[i].pt.x; y[i] = kps[i].pt.y; }
+        if (!kps.empty()) sg_feature_index(x.data(), y.data(), (int)kps.size(), order.data());
+        sortedY.resize(kps.size());
+        for (size_t p = 0; p < order.size(); ++p) sortedY[p] = y[(size_t)order[p]];
+    }
+    void getFeaturesAround(float qx, float qy, float r, std::vector<size_t> &output) const final {
+        output.clear();
+        for (auto it = std::lower_bound(sortedY.begin(), sortedY.end(), qy - r); it != sortedY.end() && *it <= qy + r; ++it) {
+            const size_t i = (size_t)order[(size_t)(it - sortedY.begin())];
+            const float dx = qx - x[i], dy = qy - y[i];
+            if (dx * dx + dy * dy < r * r) output.push_back(i);
+        }
+    }
+private:
+    std::vector<float> x, y, sortedY;
+    std::vector<std::int32_t> order;
+};
+
+// essential_solver.cc:139-162 (create_E_21) on the adapter's matrix types
+struct AdapterTypes {
+    using Vector2f = slam::Vector2f;
+    using Vector2d = slam::Vector2d;
+    using Vector3d = slam::Vector3d;
+    using Matrix3d = slam::Matrix3d;
+    using Matrix4d = slam::Matrix4d;
+    static Matrix3d createE21(const Matrix3d &rot_1w, const Vector3d &trans_1w, const Matrix3d &rot_2w, const Vector3d &trans_2w) {
+        const Matrix3d rot_21 = rot_2w * rot_1w.transpose();
+        const Vector3d t = -rot_21 * trans_1w + trans_2w;
+        Matrix3d skew;
+        skew << 0, -t(2), t(1), t(2), 0, -t(0), -t(1), t(0), 0;
+        return skew * rot_21;
+    }
+};
+}  // namespace
+
+std::unique_ptr<FeatureSearch> FeatureSearch::create(const KeyPointVector &kps) {
+    return std::unique_ptr<FeatureSearch>(new IndexedFeatureSearch(kps));
+}
+
+// ---- the candidate-list matchers: slam_matchers.hpp instantiated for the types of this header -----------------------
+std::vector<std::pair<KpId, KpId>> matchForTriangulationDBoW(Keyframe &kf1, Keyframe &kf2, const StaticSettings &settings, sg_ctx *ctx) {
+    return cuda_matchers::matchForTriangulationDBoW<AdapterTypes, KpId>(kf1, kf2, settings, ctx);
+}
+int searchByProjection(Keyframe &kf, const std::vector<MpId> &mps, MapDB &mapDB, ViewerDataPublisher *, const float threshold,
+                       const StaticSettings &settings, sg_ctx *ctx) {
+    return cuda_matchers::searchByProjection<AdapterTypes>(kf, mps, mapDB, threshold, settings, ctx);
+}
+template <typename T>
+unsigned int replaceDuplication(Keyframe &kf, const T &mapPoints, const float margin, MapDB &mapDB, const StaticSettings &settings,
+                                sg_ctx *ctx) {
+    return cuda_matchers::replaceDuplication<AdapterTypes>(kf, mapPoints, margin, mapDB, settings, ctx);
+}
+template unsigned int replaceDuplication<std::vector<MpId>>(Keyframe &, const std::vector<MpId> &, const float, MapDB &,
+                                                            const StaticSettings &, sg_ctx *);
+template unsigned int replaceDuplication<std::set<MpId>>(Keyframe &, const std::set<MpId> &, const float, MapDB &,
+                                                         const StaticSettings &, sg_ctx *);
+void matchMapPointsSim3(Keyframe &kf1, Keyframe &kf2, const Matrix4d &transform12, MapDB &mapDB,
+                        std::vector<std::pair<MpId, MpId>> &matches, const StaticSettings &settings, sg_ctx *ctx) {
+    cuda_matchers::matchMapPointsSim3<AdapterTypes>(kf1, kf2, transform12, mapDB, matches, settings, ctx);
+}
+void updateDescriptors(MapDB &mapDB, const std::vector<MpId> &mapPoints, sg_ctx *ctx) {
+    cuda_matchers::updateDescriptors(mapDB, mapPoints, ctx);
+}
+
+// ---- DBoW2 text vocabulary (bow_index.cpp:11-19 -> TemplatedVocabulary::loadFromTextFile) ---------------------------
+bool loadVocabularyText(const std::string &path, BowVocabulary &out) {
+    std::FILE *f = std::fopen(path.c_str(), "r");
+    if (!f) return false;
+    int k = 0, L = 0, scoring = 0, weighting = 0;
+    if (std::fscanf(f, "%d %d %d %d", &k, &L, &scoring, &weighting) != 4 || k < 0 || k > 20 || L < 1 || L > 10 || scoring < 0
+        || scoring > 5 || weighting < 0 || weighting > 3) { std::fclose(f); return false; }
+    // node ids are the line numbers (root = 0); children keep file order, which is DBoW2's tie order in the descent
+    std::vector<std::vector<std::int32_t>> children(1);
+    std::vector<std::uint32_t> desc(8, 0);
+    std::vector<double> weight(1, 0.0);
+    std::vector<std::int32_t> word(1, -1);
+    int pid = 0, leaf = 0, nWords = 0;
+    while (std::fscanf(f, "%d %d", &pid, &leaf) == 2) {
+        const std::int32_t nid = (std::int32_t)children.size();
+        if (pid < 0 || pid >= nid) { std::fclose(f); return false; }
+        children.emplace_back();
+        children[(size_t)pid].push_back(nid);
+        std::uint8_t bytes[32];
+        for (int i = 0; i < 32; ++i) { int v = 0; if (std::fscanf(f, "%d", &v) != 1) { std::fclose(f); return false; } bytes[i] = (std::uint8_t)v; }
+        std::uint32_t w8[8];
+        std::memcpy(w8, bytes, 32);
+        desc.insert(desc.end(), w8, w8 + 8);
+        double w = 0;
+        if (std::fscanf(f, "%lf", &w) != 1) { std::fclose(f); return false; }
+        weight.push_back(w);
+        word.push_back(leaf > 0 ? nWords++ : -1);
+    }
+    std::fclose(f);
+    out = BowVocabulary();
+    out.levels = L;
+    out.childOff.push_back(0);
+    for (const auto &c : children) {
+        out.childIds.insert(out.childIds.end(), c.begin(), c.end());
+        out.childOff.push_back((std::int32_t)out.childIds.size());
+    }
+    out.nodeWord = word;
+    out.nodeDescriptor = desc;
+    out.nodeWeight = weight;
+    return nWords > 0;
 }
 
 // ---- BowIndex (bow_index.cpp:31-188) ----------------------------------------------------------------------

@@ -2,13 +2,16 @@
 // libslamgpu.so (include/slamgpu.h).  Same names, argument meaning and error behaviour as the
 // reference (asserts, no exceptions, outputs cleared then filled), so that code written against
 //   image_pyramid.hpp:16-30, feature_detector.hpp:15-24, orb_extractor.hpp:11-30,
-//   static_settings.hpp:8-22, key_point.hpp:11-28, keyframe_matcher.hpp:33-40
+//   static_settings.hpp:8-22, key_point.hpp:11-28, keyframe_matcher.hpp:33-91, feature_search.hpp:16-21,
+//   bow_index.hpp:21-65, map_point.cpp:75-116
 // compiles against this header after swapping the include.
 #pragma once
 #include <array>
 #include <cstdint>
 #include <map>
 #include <memory>
+#include <set>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -34,12 +37,19 @@ struct StaticSettings {
     std::vector<std::size_t> maxNumberOfKeypointsPerLevel() const;
 };
 
-// key_point.hpp:11-28 (Eigen::Vector3d bearing -> three doubles; filled later by keyframe.cpp:67)
+using Vector2f = la::Vector2f;
+using Vector2d = la::Vector2d;
+using Vector3f = la::Vector3f;
+using Vector3d = la::Vector3d;
+using Matrix3d = la::Matrix3d;
+using Matrix4d = la::Matrix4d;
+
+// key_point.hpp:11-28 (bearing: filled later by keyframe.cpp:67)
 struct KeyPoint {
     tracker::Feature::Point pt{0, 0};
     float angle = 0;
     int octave = 0;
-    std::array<double, 3> bearing{{0, 0, 0}};
+    Vector3d bearing;
     using Descriptor = std::array<std::uint32_t, 8>;
     Descriptor descriptor{};
 };
@@ -103,26 +113,94 @@ constexpr unsigned int HAMMING_DIST_THR_LOW = 50;
 constexpr unsigned int HAMMING_DIST_THR_HIGH = 100;
 constexpr unsigned int MAX_HAMMING_DIST = 256;
 
-// The slice of Keyframe / MapDB that matchForLoopClosures reads (keyframe_matcher.cpp:50-158):
-// keypoints with descriptors and angles, the map point id of every keypoint and its status.
-enum class MapPointStatus { NOT_TRIANGULATED, TRIANGULATED, BAD };
-struct MpId { int v = -1; };
-struct KfId { int v = -1; };    // id.hpp:48-51
-struct MapId { int v = -1; };
-struct MapPoint { MapPointStatus status = MapPointStatus::NOT_TRIANGULATED; };
-struct MapDB { std::vector<MapPoint> mapPoints; };   // indexed by MpId::v
+// ---- the slice of the reference's data model the matchers touch (id.hpp, map_point.hpp, keyframe.hpp, mapdb.hpp) ----
+struct Id { int v = -1; Id() {} explicit Id(int v) : v(v) {} };                    // id.hpp:14-22
+struct KfId : Id { KfId() {} explicit KfId(int v) : Id(v) {} };
+struct MpId : Id { MpId() {} explicit MpId(int v) : Id(v) {} };
+struct KpId : Id { KpId() {} explicit KpId(int v) : Id(v) {} };
+struct TrackId : Id { TrackId() {} explicit TrackId(int v) : Id(v) {} };
+struct MapId : Id { MapId() {} explicit MapId(int v) : Id(v) {} };
+inline bool operator<(const KfId &a, const KfId &b) { return a.v < b.v; }
+inline bool operator<(const MpId &a, const MpId &b) { return a.v < b.v; }
+inline bool operator<(const KpId &a, const KpId &b) { return a.v < b.v; }
+inline bool operator<(const TrackId &a, const TrackId &b) { return a.v < b.v; }
+inline bool operator==(const MpId &a, const MpId &b) { return a.v == b.v; }
+inline bool operator==(const KfId &a, const KfId &b) { return a.v == b.v; }
+
+enum class MapPointStatus { TRIANGULATED, NOT_TRIANGULATED, UNSURE, BAD };          // map_point.hpp:20
+class MapDB;
+class Keyframe;
+
+// feature_search.hpp:16-21: the Y-sorted index comes from the library (sg_feature_index, the reference's std::sort)
+class FeatureSearch {
+public:
+    static std::unique_ptr<FeatureSearch> create(const KeyPointVector &keypoints);
+    virtual ~FeatureSearch() = default;
+    virtual void getFeaturesAround(float x, float y, float r, std::vector<size_t> &output) const = 0;
+};
+
+// map_point.hpp:22-94 (members the matchers read or update)
+class MapPoint {
+public:
+    MapPoint() {}
+    MapPoint(MpId id, KfId keyframeId, KpId keyPointId);
+    void addObservation(KfId keyframeId, KpId keyPointId);
+    void eraseObservation(KfId keyframeId);
+    void replaceWith(MapDB &mapDB, MapPoint &otherMp);
+    int predictScaleLevel(float dist, const StaticSettings &settings) const;
+
+    MpId id;
+    TrackId trackId = TrackId(-1);
+    MapPointStatus status = MapPointStatus::NOT_TRIANGULATED;
+    Vector3d position;
+    Vector3f norm;
+    float minViewingDistance = 0;
+    float maxViewingDistance = 30;
+    KeyPoint::Descriptor descriptor{};
+    std::map<KfId, KpId> observations;
+    KfId referenceKeyframe;
+};
+
 // bowFeatureVec: DBoW2::FeatureVector = std::map<NodeId, std::vector<unsigned>> (keyframe.hpp, bow_index.cpp:59-93)
 // bowVec: DBoW2::BowVector = std::map<WordId, WordValue (double)>
 struct KeyframeShared {
+    std::shared_ptr<const tracker::Camera> camera;
     KeyPointVector keyPoints;
+    std::unique_ptr<FeatureSearch> featureSearch;
     std::map<unsigned, double> bowVec;
     std::map<unsigned, std::vector<unsigned>> bowFeatureVec;
 };
-struct Keyframe {
+
+// keyframe.hpp:107-213
+class Keyframe {
+public:
+    bool hasFeatureDescriptors() const { return hasFullFeatures; }
+    void addObservation(MpId mapPointId, KpId keyPointId);
+    void eraseObservation(MpId mapPointId);
+    bool reproject(const Vector3d &point, Vector2f &reprojected) const;
+    Vector3d cameraCenter() const;
+    void getFeaturesAround(const Vector2f &point, float r, std::vector<size_t> &output);
+
     KfId id;
     std::shared_ptr<KeyframeShared> shared;
+    std::map<KpId, TrackId> keyPointToTrackId;
     std::vector<MpId> mapPoints;   // per keypoint, v == -1: none
+    Matrix4d poseCW = Matrix4d::Identity();
+    bool hasFullFeatures = true;
 };
+
+// mapdb.hpp:17-26
+class MapDB {
+public:
+    std::map<KfId, std::shared_ptr<Keyframe>> keyframes;
+    std::map<MpId, MapPoint> mapPoints;
+    std::map<TrackId, MpId> trackIdToMapPoint;
+};
+
+// keyframe.hpp:216-222 / keyframe.cpp:408-424
+bool reprojectToImage(const tracker::Camera &camera, const Matrix3d &rot_cw, const Vector3d &trans_cw, const Vector3d &pos_w,
+                      Vector2d &reproj, float &x_right);
+struct ViewerDataPublisher;   // debug hook of the reference's searchByProjection: accepted and ignored
 
 /** keyframe_matcher.hpp:33-40.  With bowFeatureVec filled in on both keyframes: the reference's node-bucketed
  *  comparison (keyframe_matcher.cpp:65-146); with empty feature vectors every feature is in ONE node (brute force,
@@ -131,6 +209,21 @@ struct Keyframe {
 unsigned int matchForLoopClosures(const Keyframe &kf1, const Keyframe &kf2, const MapDB &mapDB1, const MapDB &mapDB2,
                                   std::vector<int> &matchedMapPoints, const odometry::ParametersSlam &parameters,
                                   sg_ctx *ctx);
+
+/** keyframe_matcher.hpp:53 (matchForTriangulationDBoW), :59-66 (searchByProjection), :72-78 (replaceDuplication, for
+ *  std::vector<MpId> and std::set<MpId>), :85-91 (matchMapPointsSim3): the reference's signatures plus the context.
+ *  Instantiations of the templates in slam_matchers.hpp for the types above. */
+std::vector<std::pair<KpId, KpId>> matchForTriangulationDBoW(Keyframe &kf1, Keyframe &kf2, const StaticSettings &settings, sg_ctx *ctx);
+int searchByProjection(Keyframe &kf, const std::vector<MpId> &mps, MapDB &mapDB, ViewerDataPublisher *dataPublisher,
+                       const float threshold, const StaticSettings &settings, sg_ctx *ctx);
+template <typename T>
+unsigned int replaceDuplication(Keyframe &kf, const T &mapPoints, const float margin, MapDB &mapDB, const StaticSettings &settings,
+                                sg_ctx *ctx);
+void matchMapPointsSim3(Keyframe &kf1, Keyframe &kf2, const Matrix4d &transform12, MapDB &mapDB,
+                        std::vector<std::pair<MpId, MpId>> &matches, const StaticSettings &settings, sg_ctx *ctx);
+/** MapPoint::updateDescriptor (map_point.cpp:75-116) for a list of map points in one launch (the reference calls it per
+ *  touched map point: mapper_helpers.cpp:122,132,312,811,1069). */
+void updateDescriptors(MapDB &mapDB, const std::vector<MpId> &mapPoints, sg_ctx *ctx);
 
 /** The same loop on bare keypoint vectors (every feature eligible). */
 unsigned int bruteForceMatch(const KeyPointVector &kps1, const KeyPointVector &kps2, std::vector<int> &matches,
@@ -142,10 +235,16 @@ using BowVector = std::map<unsigned, double>;                       // WordId ->
 using FeatureVector = std::map<unsigned, std::vector<unsigned>>;    // NodeId -> feature indices
 }  // namespace DBoW2
 using Atlas = std::vector<MapDB>;
-struct MapKf { MapId mapId; KfId kfId; };
+struct MapKf { MapId mapId; KfId kfId; };   // bow_index.hpp:26-29
 bool operator==(const MapKf &lhs, const MapKf &rhs);
 bool operator<(const MapKf &lhs, const MapKf &rhs);
 struct BowSimilar { MapKf mapKf; float score; };
+
+struct BowVocabulary;
+/** DBoW2 text vocabulary ("k L scoring weighting", then one line per node: parent is_leaf 32 descriptor bytes weight;
+ *  the format bow_index.cpp:11-19 loads with loadFromTextFile) -> the flattened tree the library takes.
+ *  @return false when the file cannot be read or is malformed */
+bool loadVocabularyText(const std::string &path, BowVocabulary &out);
 
 /** The loaded DBoW2 vocabulary tree, flattened: node 0 = root, the children of node i are
  *  childIds[childOff[i] .. childOff[i+1]) (breadth first, larger ids than i). */

@@ -3,9 +3,11 @@
 // every artefact as raw binary; tests/test_gpu_host_adapters.py compares the dumps with the CPU oracle.
 //
 //   host_adapter_main <w> <h> <imgA.raw> <imgB.raw> <outdir> <maxKeypoints>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -128,18 +130,26 @@ int main(int argc, char **argv) {
     MapDB db1, db2;
     for (size_t i = 0; i < kf1.shared->keyPoints.size(); ++i) {
         MpId id; id.v = (i % 5 == 4) ? -1 : (int)db1.mapPoints.size();
-        if (id.v >= 0) { MapPoint mp; mp.status = (i % 7 == 6) ? MapPointStatus::NOT_TRIANGULATED : MapPointStatus::TRIANGULATED; db1.mapPoints.push_back(mp); }
+        if (id.v >= 0) { MapPoint mp; mp.id = id; mp.status = (i % 7 == 6) ? MapPointStatus::NOT_TRIANGULATED : MapPointStatus::TRIANGULATED; db1.mapPoints.emplace(id, mp); }
         kf1.mapPoints.push_back(id);
     }
     for (size_t i = 0; i < kf2.shared->keyPoints.size(); ++i) {
         MpId id; id.v = (int)db2.mapPoints.size();
-        MapPoint mp; mp.status = (i % 3 == 2) ? MapPointStatus::NOT_TRIANGULATED : MapPointStatus::TRIANGULATED;
-        db2.mapPoints.push_back(mp);
+        MapPoint mp; mp.id = id; mp.status = (i % 3 == 2) ? MapPointStatus::NOT_TRIANGULATED : MapPointStatus::TRIANGULATED;
+        db2.mapPoints.emplace(id, mp);
         kf2.mapPoints.push_back(id);
     }
     auto fe = cudaFrontend(settings, w, h);
     std::vector<int> matched;
+    // empty feature vectors: the reference's node walk finds nothing (keyframe_matcher.cpp:70)
+    if (matchForLoopClosures(kf1, kf2, db1, db2, matched, params.slam, cudaContext(fe)) != 0) return 6;
+    // one node holding every feature: the brute-force degenerate case
+    for (size_t i = 0; i < kf1.shared->keyPoints.size(); ++i) kf1.shared->bowFeatureVec[0].push_back((unsigned)i);
+    for (size_t i = 0; i < kf2.shared->keyPoints.size(); ++i) kf2.shared->bowFeatureVec[0].push_back((unsigned)i);
+    matched.clear();
     const unsigned n = matchForLoopClosures(kf1, kf2, db1, db2, matched, params.slam, cudaContext(fe));
+    kf1.shared->bowFeatureVec.clear();
+    kf2.shared->bowFeatureVec.clear();
     std::vector<std::int32_t> m(matched.begin(), matched.end());
     m.push_back((int)n);
     dump(out + "/loop_matches.i32", m);
@@ -215,6 +225,122 @@ int main(int argc, char **argv) {
         }
         dump(out + "/bow_similar_ids.i32", simIds);
         dump(out + "/bow_similar_scores.f32", simScores);
+    }
+    // ---- candidate-list matchers on the adapter's own Keyframe / MapPoint / MapDB types ------------------------------
+    // (exact parity of these templates is checked against the reference's functions in tests/cpp/ref_adapter_main.cpp;
+    //  here: the instantiations exported by libslam_frontend.so run and their results satisfy the matchers' invariants)
+    {
+        auto cam = std::make_shared<tracker::Camera>();          // f = 1, c = 0: pixel = position.xy / position.z
+        auto mkKf = [&](int id, const KeyPointVector &kps) {
+            auto kf = std::make_shared<Keyframe>();
+            kf->id = KfId(id);
+            kf->shared = std::make_shared<KeyframeShared>();
+            kf->shared->camera = cam;
+            kf->shared->keyPoints = kps;
+            kf->shared->featureSearch = FeatureSearch::create(kps);
+            kf->mapPoints.assign(kps.size(), MpId(-1));
+            return kf;
+        };
+        MapDB db;
+        auto k1 = mkKf(1, batch[1]), k2 = mkKf(2, batch[1]);      // two views of the same keypoints
+        db.keyframes.emplace(k1->id, k1);
+        db.keyframes.emplace(k2->id, k2);
+        std::vector<MpId> ids;
+        const auto &kps = k2->shared->keyPoints;
+        for (size_t i = 0; i < kps.size(); i += 2) {               // kf2 owns a map point on every second keypoint
+            MapPoint mp(MpId((int)ids.size()), k2->id, KpId((int)i));
+            mp.status = MapPointStatus::TRIANGULATED;
+            mp.position = Vector3d(kps[i].pt.x * 2.0, kps[i].pt.y * 2.0, 2.0);
+            mp.norm = (-mp.position).normalized().cast<float>();
+            const double d = mp.position.norm();
+            mp.maxViewingDistance = (float)(d * std::pow(1.2, kps[i].octave + 0.5));
+            mp.minViewingDistance = (float)(d * 0.1);
+            mp.descriptor = kps[i].descriptor;
+            mp.descriptor[3] ^= 0x00010010u;                        // two flipped bits
+            db.mapPoints.emplace(mp.id, mp);
+            k2->mapPoints[i] = mp.id;
+            ids.push_back(mp.id);
+        }
+        sg_ctx *c = cudaContext(fe);
+        const int found = searchByProjection(*k1, ids, db, nullptr, 15.0f, settings, c);
+        int good = 0;
+        for (size_t i = 0; i < kps.size(); ++i) {
+            const MpId id = k1->mapPoints[i];
+            if (id.v < 0) continue;
+            const MapPoint &mp = db.mapPoints.at(id);
+            if (!mp.observations.count(k1->id) || mp.observations.at(k1->id).v != (int)i) return 7;
+            unsigned dist = 0;
+            for (int wd = 0; wd < 8; ++wd) dist += (unsigned)__builtin_popcount(mp.descriptor[wd] ^ kps[i].descriptor[wd]);
+            if (dist > HAMMING_DIST_THR_HIGH) return 8;
+            ++good;
+        }
+        if (good != found || found < (int)ids.size() / 2) return 9;
+        // every point is now seen by kf1: replaceDuplication must skip them all (keyframe_matcher.cpp:429-431) ...
+        if (replaceDuplication(*k1, ids, 3.0f, db, settings, c) != 0) return 10;
+        // ... and fuse them again after kf1 forgets them
+        for (const MpId id : ids) {
+            MapPoint &mp = db.mapPoints.at(id);
+            if (mp.observations.count(k1->id)) { k1->mapPoints[mp.observations.at(k1->id).v] = MpId(-1); mp.eraseObservation(k1->id); }
+        }
+        const unsigned fused = replaceDuplication(*k1, std::set<MpId>(ids.begin(), ids.end()), 3.0f, db, settings, c);
+        if ((int)fused < found / 2) return 11;
+        // Sim3 with the identity guess: every point seen by both keyframes at the same pixel agrees in both directions
+        std::vector<std::pair<MpId, MpId>> pairs;
+        MapDB db2;
+        auto s1 = mkKf(1, batch[1]), s2 = mkKf(2, batch[1]);
+        db2.keyframes.emplace(s1->id, s1);
+        db2.keyframes.emplace(s2->id, s2);
+        int next = 0;
+        for (size_t i = 0; i < kps.size(); i += 3)
+            for (auto *kf : {s1.get(), s2.get()}) {
+                MapPoint mp(MpId(next++), kf->id, KpId((int)i));
+                mp.status = MapPointStatus::TRIANGULATED;
+                mp.position = Vector3d(kps[i].pt.x * 2.0, kps[i].pt.y * 2.0, 2.0);
+                const double d = mp.position.norm();
+                mp.maxViewingDistance = (float)(d * std::pow(1.2, kps[i].octave + 0.5));
+                mp.minViewingDistance = (float)(d * 0.1);
+                mp.descriptor = kps[i].descriptor;
+                db2.mapPoints.emplace(mp.id, mp);
+                kf->mapPoints[i] = mp.id;
+            }
+        matchMapPointsSim3(*s1, *s2, Matrix4d::Identity(), db2, pairs, settings, c);
+        if (pairs.size() < (size_t)next / 4) return 12;
+        for (const auto &pr : pairs)
+            if (db2.mapPoints.at(pr.first).observations.at(s1->id).v != db2.mapPoints.at(pr.second).observations.at(s2->id).v) {
+                // a twin keypoint (same pixel row, identical descriptor) may legitimately win: distances must then be equal
+                const auto &a = kps[(size_t)db2.mapPoints.at(pr.first).observations.at(s1->id).v], &b = kps[(size_t)db2.mapPoints.at(pr.second).observations.at(s2->id).v];
+                if (a.descriptor != b.descriptor) return 13;
+            }
+        // triangulation matcher between the two views (identical bearings, translated camera): runs and returns pairs
+        for (auto *kf : {s1.get(), s2.get()})
+            for (size_t i = 0; i < kps.size(); ++i) {
+                Vector3d ray;
+                cam->pixelToRay(Vector2d(kps[i].pt.x, kps[i].pt.y), ray);
+                kf->shared->keyPoints[i].bearing = ray;
+                kf->shared->bowFeatureVec[kps[i].descriptor[0] % 5u].push_back((unsigned)i);
+            }
+        s2->poseCW(0, 3) = 0.3;
+        const auto tri = matchForTriangulationDBoW(*s1, *s2, settings, c);
+        for (const auto &pr : tri)
+            if (s1->mapPoints[(size_t)pr.first.v].v != -1 || s2->mapPoints[(size_t)pr.second.v].v != -1) return 14;
+        // batched MapPoint::updateDescriptor: a point seen once keeps that observation's descriptor
+        std::vector<MpId> all;
+        for (const auto &e : db2.mapPoints) all.push_back(e.first);
+        updateDescriptors(db2, all, c);
+        for (const auto &e : db2.mapPoints) {
+            const auto &obs = *e.second.observations.begin();
+            if (e.second.descriptor != db2.keyframes.at(obs.first)->shared->keyPoints[(size_t)obs.second.v].descriptor) return 15;
+        }
+        std::printf("matchers ok: %d projected, %u fused, %zu sim3 pairs, %zu triangulation pairs\n", found, fused, pairs.size(), tri.size());
+    }
+    // ---- DBoW2 text vocabulary loader (bow_index.cpp:11-19) on the file the test wrote -------------------------------
+    {
+        BowVocabulary tv;
+        if (loadVocabularyText(out + "/voc.txt", tv)) {
+            if (tv.childOff != voc.childOff || tv.childIds != voc.childIds || tv.nodeWord != voc.nodeWord
+                || tv.nodeDescriptor != voc.nodeDescriptor || tv.nodeWeight != voc.nodeWeight || tv.levels != voc.levels) return 16;
+            std::printf("vocabulary text loader ok: %zu nodes\n", tv.nodeWord.size());
+        } else if (!voc.childOff.empty()) return 17;
     }
     std::printf("ok %zu %zu %u %u\n", kpsA.size(), kpsB.size(), n, nb);
     return 0;

@@ -62,7 +62,8 @@ class GpuImpl:
         self.ctx.close()
 
     def geometry(self, lv, sf, mk):
-        with self.sg.Context(640, 480, levels=lv, scale_factor=sf, max_keypoints=mk, max_frames=1) as c:
+        side = max(64, int(48 * sf ** (lv - 1)) + 1)      # the library refuses pyramids whose top level cannot hold a patch
+        with self.sg.Context(side, side, levels=lv, scale_factor=sf, max_keypoints=mk, max_frames=1) as c:
             return c.scales.copy(), c.budgets.copy()
 
     def feature_order(self, x, y):

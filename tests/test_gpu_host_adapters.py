@@ -22,7 +22,10 @@ def test_host_adapter_library_builds_and_exports():
     _build()
     syms = subprocess.check_output(["nm", "-DC", str(HOST / "libslam_frontend.so")], text=True)
     for s in ("slam::ImagePyramid::build(", "slam::FeatureDetector::build(", "slam::OrbExtractor::build(",
-              "slam::matchForLoopClosures(", "slam::BowIndex::transform(", "slam::BowIndex::getBowSimilar(", "slam::StaticSettings::maxNumberOfKeypointsPerLevel()",
+              "slam::matchForLoopClosures(", "slam::matchForTriangulationDBoW(", "slam::searchByProjection(",
+              "slam::replaceDuplication<std::vector<slam::MpId", "slam::replaceDuplication<std::set<slam::MpId",
+              "slam::matchMapPointsSim3(", "slam::updateDescriptors(", "slam::FeatureSearch::create(",
+              "slam::loadVocabularyText(", "slam::BowIndex::transform(", "slam::BowIndex::getBowSimilar(", "slam::StaticSettings::maxNumberOfKeypointsPerLevel()",
               "slam::match::compute_descriptor_distance_32("):
         assert s in syms, s
 
@@ -53,9 +56,12 @@ def test_host_adapters_match_oracle(tmp_path, oracle, synth):
                          ("node_weight.f64", "node_weight", np.float64)):
         np.ascontiguousarray(voc[key], t).tofile(tmp_path / ("voc_" + name))
     np.array([voc["levels"]], np.int32).tofile(tmp_path / "voc_levels.i32")
+    import refcases
+    refcases.write_vocabulary_txt(voc, str(tmp_path / "voc.txt"), 4)     # the DBoW2 text format bow_index.cpp:11-19 loads
     r = subprocess.run([str(exe), str(w), str(h), str(tmp_path / "a.raw"), str(tmp_path / "b.raw"), str(tmp_path), str(maxkp)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+    assert "matchers ok" in r.stdout and "vocabulary text loader ok" in r.stdout, r.stdout
     p = oracle.make_params(w, h, max_keypoints=maxkp)
     _, _, _, budgets = oracle.geometry(p)
 
@@ -152,3 +158,17 @@ def test_host_adapters_match_oracle(tmp_path, oracle, synth):
     assert not ids and not scores
     idx.close()
 
+
+
+@pytest.mark.gpu
+def test_matcher_adapters_on_reference_classes():
+    """slam_matchers.hpp instantiated with the REFERENCE'S OWN Keyframe / MapPoint / MapDB classes, run next to the
+    reference's own searchByProjection / replaceDuplication / matchMapPointsSim3 / matchForTriangulationDBoW /
+    MapPoint::updateDescriptor on identical scenes (tests/cpp/ref_adapter_main.cpp, built by `make -C oracle ref_adapter`
+    where /root/reference exists; the binary travels to the GPU box under oracle/_ref/)."""
+    exe = ROOT / "oracle" / "_ref" / "ref_adapter_main"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/ref_adapter_main was not built (no reference tree at build time)")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 mismatches" in r.stdout, r.stdout
