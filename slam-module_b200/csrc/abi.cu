@@ -356,6 +356,8 @@ void sg_destroy(sg_ctx *ctx) {
     for (void *q : ptrs) if (q) cudaFree(q);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    if (ctx->h_pack) cudaFreeHost(ctx->h_pack);
+    if (ctx->d_pack) cudaFree(ctx->d_pack);
     for (auto &slot : ctx->ev_stage)
         for (auto &e : slot) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -614,6 +616,88 @@ static int pipeline_wait_all(sg_ctx *ctx, int rc) {
     return check_device_error(ctx);
 }
 
+// ---- small batches (the reference's own call pattern: one keyframe per call, keyframe.cpp:95-116) ---------------------
+// Latency path: one stream, and ONE device->host copy.  A pack kernel gathers what the call returns for a frame --
+// keypoint count, per-level counts, the overflow word and the `count` live entries of every output array -- into one
+// block of a staging buffer; the host scatters the block into the caller's arrays.  (The pipelined path issues up to
+// ten copies per chunk plus a separate read of the overflow word: ~35 us of a ~200 us call.)
+constexpr int LEAN_MAX_FRAMES = 4;
+constexpr int PACK_HEADER_WORDS = 32;    // count, err, level counts (<= SG_MAX_LEVELS), padding: 128 bytes
+
+__global__ void __launch_bounds__(256)
+pack_outputs_kernel(const float *x, const float *y, const float *angle, const int *octave, const int *track_id, const int *lvl_x,
+                    const int *lvl_y, const uint32_t *desc, const int *count, const int *kp_count, const int *err, int levels,
+                    int out_cap, int cap, uint32_t *pack) {
+    // out_cap: slots per frame of the source arrays; cap: out_cap rounded up to 4 (16-byte aligned fields in the block)
+    const int f = blockIdx.x;
+    const size_t block_words = PACK_HEADER_WORDS + (size_t)cap * 15;
+    uint32_t *out = pack + (size_t)f * block_words;
+    const int n = min(count[f], out_cap);
+    if (threadIdx.x == 0) { out[0] = (uint32_t)count[f]; out[1] = (uint32_t)*err; }
+    if ((int)threadIdx.x < levels) out[2 + threadIdx.x] = (uint32_t)kp_count[f * levels + threadIdx.x];
+    uint32_t *o = out + PACK_HEADER_WORDS;
+    const size_t base = (size_t)f * out_cap;
+    const uint32_t *src[7] = {reinterpret_cast<const uint32_t *>(x), reinterpret_cast<const uint32_t *>(y),
+                              reinterpret_cast<const uint32_t *>(angle), reinterpret_cast<const uint32_t *>(octave),
+                              reinterpret_cast<const uint32_t *>(track_id), reinterpret_cast<const uint32_t *>(lvl_x),
+                              reinterpret_cast<const uint32_t *>(lvl_y)};
+#pragma unroll
+    for (int a = 0; a < 7; ++a)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) o[(size_t)a * cap + i] = src[a][base + i];
+    const uint4 *d4 = reinterpret_cast<const uint4 *>(desc + 8 * base);
+    uint4 *o4 = reinterpret_cast<uint4 *>(o + (size_t)7 * cap);
+    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) o4[i] = d4[i];
+}
+
+static int extract_lean(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames, sg_keypoints *o) {
+    const Level &L0 = ctx->lv[0];
+    if (!h_imgs || pitch < L0.w) return fail(ctx, SG_ERR_INVALID, "bad image pointer / pitch");
+    if (!o) return fail(ctx, SG_ERR_INVALID, "null output");
+    const int out_cap = ctx->geom.out_cap, cap = (out_cap + 3) & ~3, levels = ctx->p.levels;
+    const size_t block_words = PACK_HEADER_WORDS + (size_t)cap * 15, bytes = (size_t)n_frames * block_words * 4;
+    if (!ctx->d_pack) {
+        SG_CUDA(ctx, cudaMalloc((void **)&ctx->d_pack, (size_t)LEAN_MAX_FRAMES * block_words * 4));
+        SG_CUDA(ctx, cudaHostAlloc((void **)&ctx->h_pack, (size_t)LEAN_MAX_FRAMES * block_words * 4, cudaHostAllocDefault));
+    }
+    cudaStream_t st = ctx->main_stream;
+    if (pitch == L0.pitch && (n_frames == 1 || frame_stride == L0.frame_stride)) {
+        SG_CUDA(ctx, cudaMemcpyAsync(L0.pyr, h_imgs, (size_t)(n_frames - 1) * L0.frame_stride + (size_t)L0.pitch * L0.h,
+                                     cudaMemcpyHostToDevice, st));
+    } else {
+        for (int f = 0; f < n_frames; ++f)
+            SG_CUDA(ctx, cudaMemcpy2DAsync(L0.pyr + (size_t)f * L0.frame_stride, L0.pitch, h_imgs + (size_t)f * frame_stride, pitch,
+                                           L0.w, L0.h, cudaMemcpyHostToDevice, st));
+    }
+    if (int r = set_level0(ctx, L0.pyr, L0.pitch, L0.frame_stride, n_frames)) return r;
+    ctx->stream = st; ctx->frame0 = 0;
+    if (int r = extract_launches(ctx, n_frames)) return r;
+    pack_outputs_kernel<<<n_frames, 256, 0, st>>>(ctx->d_x, ctx->d_y, ctx->d_angle, ctx->d_octave, ctx->d_track_id, ctx->d_lvl_x,
+                                                  ctx->d_lvl_y, ctx->d_desc, ctx->d_count, ctx->d_kp_count, ctx->d_err, levels, out_cap,
+                                                  cap, ctx->d_pack);
+    SG_LAUNCH_CHECK(ctx);
+    SG_CUDA(ctx, cudaMemcpyAsync(ctx->h_pack, ctx->d_pack, bytes, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(ctx, cudaStreamSynchronize(st));
+    int err = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        const uint32_t *b = ctx->h_pack + (size_t)f * block_words, *a = b + PACK_HEADER_WORDS;
+        const int n = std::min((int)b[0], out_cap);
+        err |= (int)b[1];
+        if (o->count) o->count[f] = (int)b[0];
+        if (o->level_count) std::memcpy(o->level_count + (size_t)f * levels, b + 2, sizeof(int) * (size_t)levels);
+        const size_t at = (size_t)f * out_cap;
+        auto put = [&](auto *dst, int field, size_t words_per) {
+            if (dst) std::memcpy(dst + at * words_per, a + (size_t)field * cap, (size_t)n * words_per * 4);
+        };
+        put(o->x, 0, 1); put(o->y, 1, 1); put(o->angle, 2, 1); put(o->octave, 3, 1); put(o->track_id, 4, 1);
+        put(o->lvl_x, 5, 1); put(o->lvl_y, 6, 1); put(o->desc, 7, 8);
+    }
+    if (err) {
+        cudaMemsetAsync(ctx->d_err, 0, sizeof(int), st);
+        return fail(ctx, err, "device-side capacity exceeded (candidate list or quadtree node table)");
+    }
+    return SG_OK;
+}
+
 int sg_extract(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_stride, int n_frames,
                const float *h_track_xy, const int32_t *h_track_ids, const int32_t *n_tracks, sg_keypoints *h_out) {
     cudaSetDevice(ctx->device);
@@ -621,6 +705,7 @@ int sg_extract(sg_ctx *ctx, const uint8_t *h_imgs, int pitch, size_t frame_strid
         return fail(ctx, SG_ERR_INVALID, "n_frames %d outside [1, %d]", n_frames, ctx->p.max_frames);
     if (int r = slots_free(ctx, 0, n_frames)) return r;
     if (int r = upload_tracks(ctx, h_track_xy, h_track_ids, n_tracks, n_frames)) return r;
+    if (n_frames <= LEAN_MAX_FRAMES && !ctx->profiling) return extract_lean(ctx, h_imgs, pitch, frame_stride, n_frames, h_out);
     return pipeline_wait_all(ctx, pipeline_submit(ctx, h_imgs, pitch, frame_stride, n_frames, 0, h_out));
 }
 
@@ -681,11 +766,13 @@ int sg_extract_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t fram
     if (int r = check_device_images(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
     if (int r = set_level0(ctx, d_imgs, pitch, frame_stride, n_frames)) return r;
     ctx->have_tracks = false;
-    const int parts = std::min(ctx->overlap_parts, (int)sg_ctx::N_CMP);
-    if (parts <= 1 || n_frames < 16 * parts || ctx->profiling) return extract_launches(ctx, n_frames);
+    // (more slices than streams: the slices rotate over the streams; small slices keep a slice's planes inside the L2)
+    const int parts = std::max(1, std::min(ctx->overlap_parts, n_frames / 8));
+    if (parts <= 1 || ctx->profiling) return extract_launches(ctx, n_frames);
     // Independent slices of the batch on separate streams: the latency-bound quadtree kernel and the kernel tails
     // of one slice run under the issue-bound pyramid / FAST kernels of another.  Joined back on the main stream.
-    while ((int)ctx->pipe_ev.size() < parts) {
+    const int streams = std::min(parts, ctx->overlap_streams);
+    while ((int)ctx->pipe_ev.size() < streams) {
         cudaEvent_t e;
         SG_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->pipe_ev.push_back(e);
@@ -694,22 +781,29 @@ int sg_extract_device(sg_ctx *ctx, const uint8_t *d_imgs, int pitch, size_t fram
     int rc = SG_OK, f0 = 0;
     for (int c = 0; c < parts && rc == SG_OK; ++c) {
         const int n = (n_frames - f0) / (parts - c);
-        cudaStream_t cmp = ctx->s_cmp[c];
-        SG_CUDA(ctx, cudaStreamWaitEvent(cmp, ctx->ev_fork, 0));
+        cudaStream_t cmp = ctx->s_cmp[c % streams];
+        if (c < streams) SG_CUDA(ctx, cudaStreamWaitEvent(cmp, ctx->ev_fork, 0));
         ctx->stream = cmp; ctx->frame0 = f0; ctx->in_pipeline = true;
         rc = extract_launches(ctx, n);
         ctx->stream = ctx->main_stream; ctx->frame0 = 0; ctx->in_pipeline = false;
         if (rc) break;
-        SG_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[c], cmp));
-        SG_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->pipe_ev[c], 0));
         f0 += n;
+    }
+    for (int c = 0; c < streams && rc == SG_OK; ++c) {     // join every stream back on the main stream
+        SG_CUDA(ctx, cudaEventRecord(ctx->pipe_ev[c], ctx->s_cmp[c]));
+        SG_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->pipe_ev[c], 0));
     }
     return rc;
 }
 
 int sg_set_overlap(sg_ctx *ctx, int parts) {
-    if (parts < 1 || parts > sg_ctx::N_CMP) return fail(ctx, SG_ERR_INVALID, "parts must be 1..%d", (int)sg_ctx::N_CMP);
+    // parts: slices of the batch (1..64); values above 1000 encode "streams * 1000 + parts" (tuning aid)
+    int streams = ctx->overlap_streams;
+    if (parts >= 1000) { streams = parts / 1000; parts %= 1000; }
+    if (parts < 1 || parts > 64 || streams < 1 || streams > sg_ctx::N_CMP)
+        return fail(ctx, SG_ERR_INVALID, "parts must be 1..64 and streams 1..%d", (int)sg_ctx::N_CMP);
     ctx->overlap_parts = parts;
+    ctx->overlap_streams = streams;
     return SG_OK;
 }
 

@@ -96,7 +96,8 @@ struct sg_ctx {
     static constexpr int N_CMP = 8;
     cudaStream_t main_stream = nullptr, s_in = nullptr, s_out = nullptr, s_cmp[N_CMP] = {};
     int pipe_streams = 4;               // compute streams the chunks rotate over (up to N_CMP; more than 4 measured no gain)
-    int overlap_parts = 4;              // sg_extract_device: independent slices of the batch on separate streams
+    int overlap_parts = 4;              // sg_extract_device: independent slices of the batch ...
+    int overlap_streams = 4;            // ... rotating over this many compute streams
     std::vector<cudaEvent_t> pipe_ev;   // [2 * chunks]: H2D done, compute done
     static constexpr int N_TICKETS = 8;  // sg_extract_submit: completion events of the batches in flight
     cudaEvent_t ticket_ev[N_TICKETS] = {};
@@ -157,6 +158,7 @@ struct sg_ctx {
     int *d_count = nullptr;                // [max_frames]
 
     // staging
+    uint32_t *d_pack = nullptr, *h_pack = nullptr;   // packed outputs of the small-batch latency path (extract_lean)
     uint8_t *h_stage = nullptr;            // pinned, one batch of images
     size_t h_stage_bytes = 0;
     void *d_flush = nullptr;

@@ -114,7 +114,7 @@ struct DescMaps { CUtensorMap mom[SG_MAX_LEVELS], blur[SG_MAX_LEVELS]; };   // 4
 __global__ void __launch_bounds__(DESC_WARPS * 32)
 describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescMaps maps, const int *kp_xy, const int *kp_count,
                 const int *trk_xy, const float *trk_pt, const int *trk_id, const int *trk_count,
-                int track_level, int n_frames, DescOut o) {
+                int track_level, int n_frames, int split, DescOut o) {
     __shared__ uint32_t s_wu[4][16][MOM_WORDS];    // u weights (signed bytes) per (alignment, |v|, word)
     __shared__ uint32_t s_wm[4][16][MOM_WORDS];    // disc mask (0 / 1 bytes)
     __shared__ __align__(128) uint8_t s_patch[DESC_WARPS][2 * PATCH_BYTES];   // two TMA destinations per warp
@@ -158,7 +158,11 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
     uint8_t *patch = s_patch[warp];
     uint64_t *bars = s_bar[warp];
 
-    for (int grp = blockIdx.x * DESC_WARPS + warp; grp < n_groups; grp += gridDim.x * DESC_WARPS) {
+    // small batches (single-frame calls): a group is cut into `split` parts of 32 / split keypoints, one warp each, so
+    // that the grid still fills the chip; every warp of a group does the (cheap) slot lookup for all 32 lanes
+    const int per_part = 32 / split;
+    for (int vg = blockIdx.x * DESC_WARPS + warp; vg < n_groups * split; vg += gridDim.x * DESC_WARPS) {
+        const int grp = vg / split, part = vg - grp * split;
         const int f = g.frame0 + grp / groups_per_frame;
         const int slot0 = (grp % groups_per_frame) << 5;
         const int n_trk = trk_count ? trk_count[f] : 0;
@@ -171,9 +175,11 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
             if (lane >= d) incl += t;
         }
         const int total = n_trk + __shfl_sync(0xffffffffu, incl, SG_MAX_LEVELS - 1);
-        if (slot0 == 0 && lane == 0) o.count[f] = total;
+        if (slot0 == 0 && lane == 0 && part == 0) o.count[f] = total;
         if (slot0 >= total) continue;
         const int n_here = min(32, total - slot0);
+        const int jlo = part * per_part, jhi = min(n_here, jlo + per_part);
+        if (jlo >= jhi) continue;
 
         // ---- lane j looks up keypoint slot0 + j -------------------------------------------------------------
         KpInfo k{0, 0, 0, -1, 0.f, 0.f};
@@ -228,10 +234,10 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
                 }
             };
             __syncwarp();   // every lane is done with both buffers (previous group)
-            issue(0);
-            for (int j = 0; j < n_here; ++j) {
+            issue(jlo);
+            for (int j = jlo; j < jhi; ++j) {
                 const int b = j & 1;
-                if (j + 1 < n_here) issue(j + 1);     // buffer b ^ 1 was last read for keypoint j - 1 (syncwarp below)
+                if (j + 1 < jhi) issue(j + 1);        // buffer b ^ 1 was last read for keypoint j - 1 (syncwarp below)
                 const int ix = __shfl_sync(0xffffffffu, k.ix, j);
                 const int off16 = (ix - HALF_PATCH) & (XALIGN - 1), off = off16 & 3;
                 mbar_wait(bars + b, (bar_phase >> b) & 1u);
@@ -261,7 +267,7 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
         const float rad = (float)((double)angle * 3.14159265358979323846 / 180.0);
         const float cs = util_cos(rad), sn = util_sin(rad);
         const size_t oi0 = (size_t)f * g.out_cap + slot0;
-        if (lane < n_here) {
+        if (lane >= jlo && lane < jhi) {
             const size_t oi = oi0 + lane;
             o.x[oi] = k.ox; o.y[oi] = k.oy; o.angle[oi] = angle; o.octave[oi] = k.l;
             o.track_id[oi] = k.tid; o.lvl_x[oi] = k.ix; o.lvl_y[oi] = k.iy;
@@ -279,11 +285,11 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
             }
         };
         __syncwarp();       // phase A's reads are complete
-        issue_blur(0);
-        for (int j = 0; j < n_here; ++j) {
+        issue_blur(jlo);
+        for (int j = jlo; j < jhi; ++j) {
             const int b = j & 1;
             __syncwarp();   // keypoint j - 1 has been sampled by every lane: its buffer may be refilled
-            if (j + 1 < n_here) issue_blur(j + 1);
+            if (j + 1 < jhi) issue_blur(j + 1);
             const int ix = __shfl_sync(0xffffffffu, k.ix, j);
             const float c_ = __shfl_sync(0xffffffffu, cs, j), s_ = __shfl_sync(0xffffffffu, sn, j);
             const int off = (ix - BLUR_R) & (XALIGN - 1);
@@ -331,13 +337,16 @@ int launch_describe(sg_ctx *ctx, int n_frames) {
         SG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, describe_kernel, DESC_WARPS * 32, 0));
         ctx->describe_ctas_per_sm = std::max(per_sm, 1);
     }
-    const int blocks = std::max(1, std::min((groups + DESC_WARPS - 1) / DESC_WARPS, ctx->sm_count * ctx->describe_ctas_per_sm));
+    const int resident_warps = ctx->sm_count * ctx->describe_ctas_per_sm * DESC_WARPS;
+    int split = 1;
+    while (split < 8 && groups * split * 2 <= resident_warps) split *= 2;
+    const int blocks = std::max(1, std::min((groups * split + DESC_WARPS - 1) / DESC_WARPS, ctx->sm_count * ctx->describe_ctas_per_sm));
     DescMaps maps;
     for (int l = 0; l < g.levels; ++l) { maps.mom[l] = ctx->lv[l].map_mom; maps.blur[l] = ctx->lv[l].map_blur; }
     describe_kernel<<<blocks, DESC_WARPS * 32, 0, ctx->stream>>>(
         g, maps, ctx->d_kp_xy, ctx->d_kp_count,
         trk ? ctx->d_trk_xy : nullptr, trk ? ctx->d_trk_pt : nullptr, trk ? ctx->d_trk_id : nullptr,
-        trk ? ctx->d_trk_count : nullptr, ctx->p.track_level, n_frames, o);
+        trk ? ctx->d_trk_count : nullptr, ctx->p.track_level, n_frames, split, o);
     SG_LAUNCH_CHECK(ctx);
     mark(ctx, EV_DESC1);
     return SG_OK;
