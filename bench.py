@@ -51,13 +51,17 @@ def peaks():
 
 
 def traffic_of(stage):
-    """ncu-measured DRAM bytes per launch of the stage's dominant kernel (profiles/traffic_r1.json), or None."""
-    f = ROOT / "profiles" / "traffic_r1.json"
-    if not f.exists():
-        return None
-    t = json.loads(f.read_text())
-    key = {"fast": "fast_cells_kernel", "pyramid": "pyr_fast_kernel<1> level 1"}.get(stage)
-    return t.get(key, {}).get("bytes_per_launch") if key else None
+    """ncu-measured DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the stage's kernel(s) for one full
+    256-frame step, from the newest profiles/traffic_r*.json (written by tools/summarize_profiles.py from full-batch
+    `ncu --set full` captures of the shipped kernels); returns (bytes, tag) or (None, None)."""
+    files = sorted((ROOT / "profiles").glob("traffic_r*.json"))
+    if not files:
+        return None, None
+    t = json.loads(files[-1].read_text())
+    e = t.get({"fast": "fast_cells_kernel", "pyramid": "pyr_fast_kernel (all 8 launches)"}.get(stage, ""), None)
+    if e is None and stage == "pyramid":
+        e = t.get("pyr_fast_kernel<1> level 1")
+    return (e.get("bytes_per_launch"), t.get("tag", files[-1].stem)) if e else (None, None)
 
 
 def make_frames(n, seed0):
@@ -160,52 +164,131 @@ def barrier_max(td, local, value):
     return float(t.item())
 
 
-def cpu_extract_baseline(po, frames, threads):
-    p = po.make_params(W, H, levels=LEVELS, scale_factor=FACTOR, max_keypoints=MAXKP)
-    secs, total = po.bench_extract(p, frames, threads)
+def cpu_extract_baseline(be, frames, threads):
+    from oracle import pyoracle
+    p = pyoracle.make_params(W, H, levels=LEVELS, scale_factor=FACTOR, max_keypoints=MAXKP)
+    secs, total = be.bench_extract(p, frames, threads)
     return len(frames) / secs, secs, total
 
 
+def reference_backend():
+    """(module, kind, description): oracle/_ref/libref_slam.so -- the reference's own orb_extractor.cpp / image_pyramid.cpp /
+    feature_detector.cpp / keyframe_matcher.cpp compiled verbatim (OpenCV primitives and the absent corner detector from
+    the oracle port, see oracle/ref_slam.cpp) -- when it was built, else the oracle port."""
+    from oracle import pyoracle as po
+    po.build()
+    try:
+        from oracle import pyref as pr
+        if pr.available():
+            return pr, po, "reference", ("the reference's own sources compiled verbatim (oracle/_ref/libref_slam.so: orb_extractor.cpp, "
+                                         "image_pyramid.cpp, feature_detector.cpp, keyframe_matcher.cpp; OpenCV primitives and the absent corner "
+                                         "detector from the oracle port)")
+    except Exception:
+        pass
+    return po, po, "port", "oracle port of the reference CPU path (oracle/_ref was not built: no reference tree at build time)"
+
+
+def cv2_baseline(frames, desc_sets, pairs, threads):
+    """'Best available CPU library' column: OpenCV's own optimised kernels on all host cores.
+    Not the reference and not bit-comparable with it -- cv2.ORB is OpenCV's ORB (Harris-ranked, no cell grid / quadtree);
+    reported so that the GPU numbers can be read against SIMD CPU code rather than against a scalar port only."""
+    try:
+        import cv2
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": str(e)}
+    from concurrent.futures import ThreadPoolExecutor
+    cv2.setNumThreads(1)
+    local = threading.local()
+
+    def orb_frame(i):
+        if not hasattr(local, "orb"):
+            local.orb = cv2.ORB_create(nfeatures=MAXKP, scaleFactor=FACTOR, nlevels=LEVELS, edgeThreshold=19, patchSize=31, fastThreshold=20)
+        kp, _ = local.orb.detectAndCompute(frames[i], None)
+        return len(kp)
+
+    def stage_frame(i):
+        # the OpenCV calls the reference itself makes (image_pyramid.cpp:75-85) + cv::FAST(20, nms) on every level
+        if not hasattr(local, "fast"):
+            local.fast = cv2.FastFeatureDetector_create(threshold=20, nonmaxSuppression=True)
+        img, n = frames[i], 0
+        scale = np.float32(1.0)
+        for l in range(LEVELS):
+            if l:
+                scale = np.float32(FACTOR) * scale
+                size = (int(round(W / float(scale))), int(round(H / float(scale))))
+                img = cv2.resize(img, size, interpolation=cv2.INTER_LINEAR)
+            cv2.GaussianBlur(img, (7, 7), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101)
+            n += len(local.fast.detect(img, None))
+        return n
+
+    def match_pair(k):
+        if not hasattr(local, "bf"):
+            local.bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+        a, b = pairs[k]
+        m = local.bf.knnMatch(desc_sets[a], desc_sets[b], k=2)
+        return sum(1 for x in m if len(x) == 2 and x[0].distance <= 50 and x[0].distance <= 0.8 * x[1].distance)
+
+    out = {"cores": threads, "opencv": cv2.__version__}
+    with ThreadPoolExecutor(threads) as ex:
+        for name, fn, n, unit in (("orb", orb_frame, len(frames), "frames/s"), ("pyramid_fast", stage_frame, len(frames), "frames/s"),
+                                  ("bfmatcher", match_pair, len(pairs), "keyframe pairs/s")):
+            list(ex.map(fn, range(min(n, threads))))                    # warm-up: per-thread objects
+            t0 = time.perf_counter()
+            r = list(ex.map(fn, range(n)))
+            dt = time.perf_counter() - t0
+            out[name] = {"value": n / dt, "unit": unit, "items": n, "seconds": dt, "mean_result": float(np.mean(r))}
+    out["orb"]["what"] = "cv2.ORB_create(2000, 1.2, 8).detectAndCompute per frame (OpenCV's complete ORB)"
+    out["pyramid_fast"]["what"] = "cv2.resize chain + cv2.GaussianBlur(7x7, sigma 2) + cv2.FAST(20, nms) on all 8 levels per frame"
+    out["bfmatcher"]["what"] = "cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2) + ratio 0.8 on 2000 x 2000 descriptors per pair"
+    out["bfmatcher"]["descriptor_pair_distances_per_s"] = out["bfmatcher"]["value"] * MATCH_N * MATCH_N
+    return out
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port: the reference itself cannot be built
-    here) on the host cores, frames sharded over all threads; rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (oracle/_ref when the
+    reference compiled at build time, else the oracle port), frames sharded over all threads; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import pyoracle as po
-    po.build()
+    be, po, kind, what = reference_backend()
     cores = os.cpu_count() or 1
-    sample = FRAMES            # the whole step: 256 frames (about 1-2 s on a 16-core host)
+    sample = FRAMES            # the whole step: 256 frames
     frames = make_frames(sample, 9000)
-    for _ in range(args.warmup):
-        cpu_extract_baseline(po, frames[:max(cores, 4)], cores)
+    for _ in range(max(1, args.warmup)):
+        cpu_extract_baseline(be, frames[:max(2 * cores, 8)], cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_extract_baseline(po, frames, cores)
+        cpu_extract_baseline(be, frames, cores)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     # matching leg on a few pairs
     import slam_module_b200 as sm
     d, a = sm.synth.random_descriptors(8, MATCH_N, 5)
-    pairs = np.array([(i % 8, (i + 1) % 8) for i in range(16 * max(8, cores))], np.int32)
-    msec, _ = po.bench_match(d, a, pairs, cores)
-    desc = "oracle port of the reference CPU path, %d frames per step sharded over %d host threads" % (sample, cores)
+    pairs = np.array([(i % 8, (i + 1) % 8) for i in range(4 * max(8, cores))], np.int32)
+    be.bench_match(d, a, pairs[:cores], cores)
+    msec, _ = be.bench_match(d, a, pairs, cores)
+    cv2_cols = None
+    if not args.skip_cv2:
+        cv2_cols = cv2_baseline(frames[:max(64, 4 * cores)], [np.ascontiguousarray(x).view(np.uint8).reshape(MATCH_N, 32) for x in d],
+                                pairs[:2 * cores], cores)
+    desc = "%s, %d frames per step sharded over %d host threads" % (what, sample, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": sample, "levels": LEVELS, "scale_factor": FACTOR,
                    "max_keypoints": MAXKP},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": desc, "cv2": cv2_cols},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "matching": {"value": len(pairs) * MATCH_N * MATCH_N / msec, "unit": "descriptor-pair distances/s",
                      "keyframe_pairs_per_s": len(pairs) / msec, "cores": cores},
+        "matching_value": len(pairs) * MATCH_N * MATCH_N / msec,
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def extra_configs(slamgpu, sm, sh, rank, world, local, barrier_max_, td):
+def extra_configs(slamgpu, sm, sh, rank, world, local, barrier_max_, td, config5_full=False):
     """The remaining BASELINE.json configs, each on a bounded sample, reported beside the headline
     (configs[1]) and the matching leg (configs[2]):
       configs[0]  one 640x480 frame, 1000 keypoints: latency of sg_extract (host buffers) and of the kernels;
@@ -311,6 +394,40 @@ def extra_configs(slamgpu, sm, sh, rank, world, local, barrier_max_, td):
             "keyframe_pairs_per_s": rate, "descriptor_pair_distances_per_s": rate * N * N,
             "projected_full_job_s": total / rate, "pairs_in_rank_block": int(hi - lo),
             "pairs_with_matches_in_sample": int((cnt > 0).sum())}
+        if config5_full:
+            # the whole job: every rank matches its complete block of the all-pairs list (counts only), wall time from the
+            # barrier before the first launch to the slowest rank's last count; 256 random pairs of rank 0 re-done by the oracle
+            full = sh.pair_block(KF, rank, world)
+            d_full = c5.device_buffer(full.nbytes).upload(full)
+            d_fcnt = c5.device_buffer(4 * len(full))
+            c5.synchronize()
+            barrier_max_(td, local, 0.0)
+            t0 = time.perf_counter()
+            db.match_pairs_device(d_full.ptr, len(full), d_fcnt.ptr)
+            c5.synchronize()
+            wall = barrier_max_(td, local, time.perf_counter() - t0)
+            fcnt = d_fcnt.download(np.uint32, len(full))
+            tot_matches = barrier_max_(td, local, 0.0)   # (barrier) ; matches are summed below through the max trick per rank
+            sums = [barrier_max_(td, local, float(fcnt.sum()) if r == rank else 0.0) for r in range(world)]
+            checked, bad = 0, 0
+            if rank == 0:
+                from oracle import pyoracle as po
+                po.build()
+                pick = np.random.default_rng(5).choice(len(full), size=min(256, len(full)), replace=False)
+                # every 64th pair revisits a place: make sure matching pairs are among the checked ones
+                hot = np.flatnonzero(fcnt > 0)
+                if len(hot):
+                    pick[:min(64, len(hot))] = hot[np.random.default_rng(6).choice(len(hot), size=min(64, len(hot)), replace=False)]
+                for k in pick:
+                    i, j = int(full[k, 0]), int(full[k, 1])
+                    n_ref, _ = po.match_bruteforce(desc[i], ang[i], desc[j], ang[j])
+                    checked += 1
+                    bad += int(n_ref != int(fcnt[k]))
+            out["config4_loop_closure_scale"]["full_job"] = {
+                "pairs": int(total), "pairs_this_rank": int(len(full)), "wall_s": wall, "keyframe_pairs_per_s": total / wall,
+                "descriptor_pair_distances_per_s": total / wall * N * N, "matches_total": float(sum(sums)),
+                "pairs_with_matches_rank0": int((fcnt > 0).sum()), "oracle_spot_check": {"pairs": checked, "count_mismatches": bad}}
+            del tot_matches
         db.close()
     # ---- candidate-list matchers and descriptor medoid (host-buffer calls) -------------
     with slamgpu.Context(W, H, max_frames=1, device=local) as c6:
@@ -386,6 +503,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-cv2", action="store_true", help="leave out the cv2 (OpenCV SIMD) columns of the CPU baseline")
+    ap.add_argument("--config5-full", action="store_true",
+                    help="run BASELINE configs[4] in full: all 49 995 000 keyframe pairs of 10 000 keyframes, block-sharded over the ranks")
     ap.add_argument("--skip-extra-configs", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: leave out the host-buffer (chunked) pass")
     ap.add_argument("--pipe-chunk", type=int, default=0, help="frames per pipeline chunk of sg_extract (0: library default)")
@@ -457,6 +577,18 @@ def main():
         hb = host_batches[i % N_BATCHES].array
         ctx._check(lib.sg_extract(ctx._h, hb.ctypes.data, W, frame_bytes, FRAMES, None, None, None, C.byref(out_struct)))
 
+    # raw pinned host->device copy of one batch (one cudaMemcpyAsync, all ranks at once): the ceiling of any host-buffer path
+    h2d_gbs = None
+    if not args.skip_e2e:
+        scratch = ctx.device_buffer(FRAMES * frame_bytes)
+        scratch.upload(host_batches[0].array)
+        barrier_max(td, local, 0.0)
+        t0 = time.perf_counter()
+        for i in range(20):
+            scratch.upload(host_batches[i % N_BATCHES].array)
+        h2d_s = barrier_max(td, local, time.perf_counter() - t0)
+        h2d_gbs = 20 * FRAMES * frame_bytes / h2d_s / 1e9        # per rank, while every rank copies
+        scratch.free()
     e2e_steps = min(max(args.steps, 20), 200)      # its own step count (reported in e2e.steps): long enough to amortise the fill / drain of the batches in flight
     e2e_value = None
     if not args.skip_e2e:
@@ -549,21 +681,31 @@ def main():
     extras = None
     if not args.skip_extra_configs:
         from slam_module_b200 import sharding as sh
-        extras = extra_configs(slamgpu, sm, sh, rank, world, local, barrier_max, td)
+        extras = extra_configs(slamgpu, sm, sh, rank, world, local, barrier_max, td, config5_full=args.config5_full)
 
     # ---- CPU baseline beside it (rank 0, N == 1 only) ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
-        from oracle import pyoracle as po
-        po.build()
+        be, po, cpu_kind, cpu_what = reference_backend()
         cores = os.cpu_count() or 1
         sample = FRAMES
-        v, secs, _ = cpu_extract_baseline(po, host_batches[0].array[:sample], cores)
-        v2, secs2, _ = cpu_extract_baseline(po, host_batches[1].array[:sample], cores)   # second pass: warm caches, take the better
+        cpu_extract_baseline(be, host_batches[0].array[:2 * cores], cores)                # warm-up: heap growth, thread start
+        v, secs, _ = cpu_extract_baseline(be, host_batches[0].array[:sample], cores)
+        v2, secs2, _ = cpu_extract_baseline(be, host_batches[1].array[:sample], cores)   # second pass: take the better
         if v2 > v:
             v, secs = v2, secs2
-        n_cpu_pairs = 16 * max(8, cores)
-        msec, _ = po.bench_match(np.stack(sets_d[:8]), np.stack(sets_a[:8]), pairs[:n_cpu_pairs] % 8, cores)
+        port_v = None
+        if be is not po:                                                                  # the scalar port beside it
+            cpu_extract_baseline(po, host_batches[0].array[:2 * cores], cores)
+            port_v, _, _ = cpu_extract_baseline(po, host_batches[0].array[:sample], cores)
+        n_cpu_pairs = 4 * max(8, cores)
+        be.bench_match(np.stack(sets_d[:8]), np.stack(sets_a[:8]), pairs[:cores] % 8, cores)
+        msec, _ = be.bench_match(np.stack(sets_d[:8]), np.stack(sets_a[:8]), pairs[:n_cpu_pairs] % 8, cores)
+        cv2_cols = None
+        if not args.skip_cv2:
+            cv2_cols = cv2_baseline(host_batches[0].array[:max(64, 4 * cores)],
+                                    [np.ascontiguousarray(x).view(np.uint8).reshape(MATCH_N, 32) for x in sets_d[:8]],
+                                    pairs[:2 * cores] % 8, cores)
         # parity of this very run against the oracle (checker role): keypoint sets, angles, descriptors, match indices
         N_CHECK = 8
         pp = po.make_params(W, H, levels=LEVELS, scale_factor=FACTOR, max_keypoints=MAXKP)
@@ -592,9 +734,10 @@ def main():
                   "max_angle_diff_rad": max_dang, "descriptor_mismatches": int(desc_bad),
                   "keyframe_pairs_checked": N_CHECK // 2, "match_index_mismatches": int(match_bad),
                   "checker": "oracle port (oracle/), same frames as the timed batch"}
-        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "parity": parity,
-               "sample": "oracle port of the reference CPU path on the %d frames of one step, sharded over %d host "
-                         "threads (%.1f s per pass, best of 2)" % (sample, cores, secs),
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": cpu_kind, "parity": parity,
+               "sample": "%s on the %d frames of one step, sharded over %d host threads (%.1f s per pass, best of 2)"
+                         % (cpu_what, sample, cores, secs),
+               "port_value": port_v, "cv2": cv2_cols,
                "matching_value": n_cpu_pairs * MATCH_N * MATCH_N / msec, "matching_unit": "descriptor-pair distances/s",
                "matching_sample": "%d keyframe pairs over %d threads (%.1f s)" % (n_cpu_pairs, cores, msec)}
 
@@ -612,9 +755,10 @@ def main():
         roof_stage = dom if dom in stage_bytes else "pyramid"
         roofline = {"kernel": {"pyramid": "pyr_fast_kernel (8 launches: blur of level 0 + 7 fused resize+blur levels; traffic: the level-1 launch)",
                                "fast": "fast_cells_kernel (1 launch per step)"}[roof_stage],
-                    "note": "integer-issue bound, not HBM bound: ALU pipe ~69% busy, issue slots ~67% (profiles/ncu_full_r1h.md)",
+                    "note": "integer-issue bound, not HBM bound: ALU pipe ~69% busy, issue slots ~67% (profiles/, newest ncu_full_*.md)",
                     "bound": "hbm", "achieved": stages[roof_stage]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": stages[roof_stage]["frac_of_hbm"], "traffic": traffic_of(roof_stage), "peak_source": peak_src,
+                    "frac": stages[roof_stage]["frac_of_hbm"], "traffic": traffic_of(roof_stage)[0], "traffic_source": traffic_of(roof_stage)[1],
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch_group": stage_bytes[roof_stage], "dominant_stage_by_time": dom}
         topk_ms = m_stage["match_topk"]
         popc_achieved = 8.0 * min(MATCH_PAIRS, MATCH_PAIRS) * MATCH_N * MATCH_N / (topk_ms * 1e-3) if topk_ms > 0 else None
@@ -630,9 +774,18 @@ def main():
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
                     "api": "sg_extract_submit / sg_extract_wait (pinned host buffers; every batch is copied H2D, processed and copied "
                            "D2H; %d batches in flight, chunked H2D / kernels / D2H pipeline inside each)" % IN_FLIGHT,
+                    "h2d_ceiling": None if h2d_gbs is None else {
+                        "gbs_per_gpu_while_all_ranks_copy": h2d_gbs, "aggregate_gbs": h2d_gbs * world,
+                        "frames_per_s": world * h2d_gbs * 1e9 / frame_bytes,
+                        "frac": (e2e_stream / (world * h2d_gbs * 1e9 / frame_bytes)) if e2e_stream else None,
+                        "what": "20 raw pinned host->device copies of one 78.6 MB batch per rank, all ranks concurrently: the "
+                                "ceiling of any path that takes host frames (307 KB per frame over PCIe)"},
                     "single_call_value": e2e_value,
                     "single_call_api": "sg_extract (one synchronous call per batch, same pipeline, nothing in flight across calls)"},
             "gpu_launches": int(launches),
+            "matching_value": match_value, "matching_unit": "descriptor-pair distances/s", "matching_e2e_value": match_e2e,
+            "stereo_pairs_per_s": (extras or {}).get("config3_stereo_stream", {}).get("stereo_pairs_per_s"),
+            "single_frame_latency_us": (extras or {}).get("config0_single_frame", {}).get("latency_us_host_call_median"),
             "stages": stages,
             "roofline": roofline,
             "matching": {"metric": "Hamming matches/sec (2000x2000 per keyframe pair, ratio 0.8, angle histogram; configs[2])",

@@ -178,6 +178,8 @@ int orc_bowindex_similar(void *index, const unsigned *q_word, const double *q_va
                          float bowMinInCommonRatio, float bowScoreRatio, int *out_map, int *out_kf, float *out_score,
                          int capacity);
 
+/* malloc settings of the timed CPU baselines: freed temporaries stay in the heap (see oracle/src/extract.cpp). */
+void orc_tune_malloc(void);
 double orc_bench_extract(const orc_params *p, const uint8_t *imgs, int n_frames, int threads, long *total_kp);
 double orc_bench_match(const uint32_t *desc, const float *ang, int n_sets, int n_per_set,
                        const int *pairs, int n_pairs, float ratio, unsigned thr, int threads, long *total_matches);

@@ -33,6 +33,8 @@ def lib():
         L.ref_match_triangulation.restype = C.c_uint
         L.ref_replace_duplication.restype = C.c_uint
         L.ref_bow_create.restype = C.c_void_p
+        L.ref_bench_extract.restype = C.c_double
+        L.ref_bench_match.restype = C.c_double
         _lib = L
     return _lib
 
@@ -230,3 +232,20 @@ class BowIndex:
         if self.h:
             lib().ref_bow_destroy(self.h)
             self.h = None
+
+
+def bench_extract(p, imgs, threads):
+    """The reference's OrbExtractor::detectAndExtract over a stack of frames, sharded over `threads` host threads."""
+    imgs = np.ascontiguousarray(imgs, np.uint8)
+    total = C.c_long(0)
+    s = lib().ref_bench_extract(C.byref(p), _p(imgs), imgs.shape[0], int(threads), C.byref(total))
+    return float(s), total.value
+
+
+def bench_match(desc, ang, pairs, threads, ratio=0.8):
+    """The reference's matchForLoopClosures (single node, every feature eligible) over keyframe pairs."""
+    desc = _u32(desc); ang = _f32(ang); pairs = _i32(pairs)
+    total = C.c_long(0)
+    s = lib().ref_bench_match(_p(desc), _p(ang), desc.shape[0], desc.shape[1], _p(pairs), len(pairs), C.c_float(ratio),
+                              int(threads), C.byref(total))
+    return float(s), total.value

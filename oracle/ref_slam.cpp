@@ -15,10 +15,13 @@
 //     members): restated below; MapDB helpers of mapdb.cpp (needs ../odometry/util.hpp): getMapWithId restated below.
 // This file contains scenario builders only: it fills Keyframe / MapPoint / MapDB objects from flat arrays, calls
 // the reference function, and flattens the result.
+#include <atomic>
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <memory>
 #include <set>
+#include <thread>
 #include <vector>
 
 #include "orb_oracle.h"
@@ -218,6 +221,20 @@ void add_query_points(MapDB &db, int id0, const double *pos, const float *norm, 
         std::memcpy(mp.descriptor.data(), desc + 8 * (size_t)q, 32);
         db.mapPoints.emplace(mp.id, mp);
     }
+}
+}  // namespace
+
+namespace {
+template <class F> double run_threads(int n_items, int threads, F fn) {
+    orc_tune_malloc();
+    threads = std::max(1, threads);
+    std::atomic<int> next{0};
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&] { for (int i; (i = next.fetch_add(1)) < n_items;) fn(i); });
+    for (auto &th : pool) th.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 }  // namespace
 
@@ -586,6 +603,64 @@ int ref_bow_similar(void *h, const unsigned *q_word, const double *q_value, int 
     const auto sim = b->index->getBowSimilar(b->db, b->atlas, *kf);
     for (size_t i = 0; i < sim.size() && (int)i < cap; ++i) { out_kf[i] = sim[i].mapKf.kfId.v; out_score[i] = sim[i].score; }
     return (int)sim.size();
+}
+
+// ---- timed drivers for bench.py's reference arm (`"kind": "reference"`): frames / keyframe pairs sharded over host
+//      threads; the reference itself is single threaded, one OrbExtractor per thread like one per Mapper (mapper.cpp:145)
+
+double ref_bench_extract(const orc_params *p, const uint8_t *imgs, int n_frames, int threads, long *total_kp) {
+    orc_tune_malloc();
+    const odometry::Parameters q = make_parameters(p);
+    const StaticSettings s(q);
+    std::atomic<long> total{0};
+    const size_t fsz = (size_t)p->width * p->height;
+    threads = std::max(1, threads);
+    std::atomic<int> next{0};
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&] {
+            auto orb = OrbExtractor::build(s);
+            tracker::Camera cam;
+            KeyPointVector kps;
+            std::vector<int> ids;
+            for (int i; (i = next.fetch_add(1)) < n_frames;) {
+                GrayImage im(imgs + fsz * (size_t)i, p->width, p->height, p->width);
+                orb->detectAndExtract(im, cam, {}, kps, ids);
+                total += (long)kps.size();
+            }
+        });
+    for (auto &th : pool) th.join();
+    if (total_kp) *total_kp = total;
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+double ref_bench_match(const uint32_t *desc, const float *ang, int n_sets, int n_per_set, const int *pairs, int n_pairs,
+                       float ratio, int threads, long *total_matches) {
+    std::vector<std::shared_ptr<Keyframe>> kfs;
+    MapDB db;
+    std::vector<int> node(n_per_set, 0);
+    for (int i = 0; i < n_per_set; ++i) {
+        MapPoint mp;
+        mp.id = MpId(i);
+        mp.status = MapPointStatus::TRIANGULATED;
+        db.mapPoints.emplace(mp.id, mp);
+    }
+    for (int sidx = 0; sidx < n_sets; ++sidx) {
+        auto kf = make_keyframe(sidx, nullptr, nullptr, ang + (size_t)sidx * n_per_set, nullptr, desc + (size_t)sidx * n_per_set * 8, nullptr, n_per_set);
+        fill_feature_vector(kf->shared->bowFeatureVec, node.data(), n_per_set);
+        for (int i = 0; i < n_per_set; ++i) kf->mapPoints[i] = MpId(i);
+        kfs.push_back(kf);
+    }
+    odometry::ParametersSlam ps;
+    ps.loopClosureFeatureMatchLoweRatio = ratio;
+    std::atomic<long> total{0};
+    const double secs = run_threads(n_pairs, threads, [&](int i) {
+        std::vector<int> m;
+        total += matchForLoopClosures(*kfs[pairs[2 * i]], *kfs[pairs[2 * i + 1]], db, db, m, ps);
+    });
+    if (total_matches) *total_matches = total;
+    return secs;
 }
 
 }  // extern "C"

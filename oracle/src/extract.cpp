@@ -3,6 +3,7 @@
 // orientation :132-134, descriptors + output assembly :139-163) and feature_detector.cpp:103-133.
 #include "common.h"
 #include <chrono>
+#include <malloc.h>
 #include <thread>
 #include <atomic>
 
@@ -16,7 +17,10 @@ extern "C" int orc_extract(const orc_params *p, const uint8_t *img, int stride,
                            float *x, float *y, float *angle, int *octave, uint32_t *desc, int *track_id,
                            int *lvl_x, int *lvl_y, int cap, int *level_counts) {
     const Geometry g = make_geometry(*p);
-    std::vector<uint8_t> pyr(g.off[g.levels]), blur(g.off[g.levels]);
+    // per-thread planes, kept across calls like the reference's cached pyramid (orb_extractor.cpp:201-203): allocating
+    // and faulting in 2 x 0.95 MB per frame serialises the threads of the CPU baseline on the kernel's mmap lock
+    thread_local std::vector<uint8_t> pyr, blur;
+    if (pyr.size() < g.off[g.levels]) { pyr.resize(g.off[g.levels]); blur.resize(g.off[g.levels]); }
     orc_pyramid(p, img, stride, pyr.data(), blur.data());
     int n = 0;
     auto emit = [&](float fx, float fy, float a, int oct, const uint32_t *d, int tid, int lx, int ly) {
@@ -68,8 +72,18 @@ extern "C" int orc_extract(const orc_params *p, const uint8_t *img, int stride,
     return n;
 }
 
+// glibc returns every freed block above 128 KB to the kernel (munmap) and maps the next one afresh: the per-call
+// temporaries of the pyramid / FAST code (0.3 - 2 MB) then cost a page-fault storm per frame and the threads of the
+// baseline serialise on the process's mmap lock (measured: 8 threads 4.3x slower).  Keep such blocks in the heap.
+extern "C" void orc_tune_malloc(void) {
+    mallopt(M_MMAP_THRESHOLD, 32 << 20);
+    mallopt(M_TRIM_THRESHOLD, 512 << 20);
+    mallopt(M_TOP_PAD, 64 << 20);
+}
+
 template <class F>
 static double run_threads(int n_items, int threads, F fn) {
+    orc_tune_malloc();
     threads = std::max(1, threads);
     std::atomic<int> next{0};
     const auto t0 = std::chrono::steady_clock::now();
