@@ -18,6 +18,7 @@
 #include "compat.hpp"
 
 struct sg_ctx;
+struct sg_db;
 struct sg_vocab;
 struct sg_bowdb;
 
@@ -159,14 +160,18 @@ public:
     KeyPoint::Descriptor descriptor{};
     std::map<KfId, KpId> observations;
     KfId referenceKeyframe;
+    std::array<std::uint8_t, 3> color{{0, 0, 0}};   // cv::Vec3b, visualisation only (kept for the archive round trip)
 };
 
 // bowFeatureVec: DBoW2::FeatureVector = std::map<NodeId, std::vector<unsigned>> (keyframe.hpp, bow_index.cpp:59-93)
 // bowVec: DBoW2::BowVector = std::map<WordId, WordValue (double)>
 struct KeyframeShared {
     std::shared_ptr<const tracker::Camera> camera;
+    std::string cameraModel;                          // camera->serialize() as stored in a map archive (keyframe.hpp:82)
     KeyPointVector keyPoints;
     std::unique_ptr<FeatureSearch> featureSearch;
+    std::vector<std::array<std::uint8_t, 3>> colors;  // keyframe.hpp:55
+    std::shared_ptr<std::vector<Vector3f>> stereoPointCloud;
     std::map<unsigned, double> bowVec;
     std::map<unsigned, std::vector<unsigned>> bowFeatureVec;
 };
@@ -182,12 +187,20 @@ public:
     void getFeaturesAround(const Vector2f &point, float r, std::vector<size_t> &output);
 
     KfId id;
+    KfId previousKfId, nextKfId;
     std::shared_ptr<KeyframeShared> shared;
     std::map<KpId, TrackId> keyPointToTrackId;
     std::vector<MpId> mapPoints;   // per keypoint, v == -1: none
+    std::vector<float> keyPointDepth;
     Matrix4d poseCW = Matrix4d::Identity();
+    Matrix4d origPoseCW = Matrix4d::Identity();
+    la::Matrix<double, 3, 6> uncertainty;
+    double t = 0;
     bool hasFullFeatures = true;
 };
+
+// loop_closer.hpp:35-46
+struct LoopClosureEdge { KfId kfId1, kfId2; Matrix4d poseDiff = Matrix4d::Identity(); };
 
 // mapdb.hpp:17-26
 class MapDB {
@@ -195,6 +208,14 @@ public:
     std::map<KfId, std::shared_ptr<Keyframe>> keyframes;
     std::map<MpId, MapPoint> mapPoints;
     std::map<TrackId, MpId> trackIdToMapPoint;
+    // serialised state the matchers never touch (mapdb.hpp:83-98), kept for the archive round trip
+    std::vector<LoopClosureEdge> loopClosureEdges;
+    Matrix4d prevPose = Matrix4d::Identity(), prevInputPose = Matrix4d::Identity();
+    std::vector<double> discardedUncertainty = std::vector<double>(18, 0.0);   // Eigen::MatrixXd, column major
+    int discardedUncertaintyRows = 3, discardedUncertaintyCols = 6;
+    double firstKfTimestamp = -1.0;
+    int nextMp = 0;
+    KfId lastKfCandidateId, lastKfId;
 };
 
 // keyframe.hpp:216-222 / keyframe.cpp:408-424
@@ -279,6 +300,28 @@ private:
     ::sg_bowdb *db = nullptr;
     int capacity;
 };
+
+// ---- map archives: the cereal binary files Mapper::end writes and loadMapDB reads ----------------
+// (mapper.cpp:504-512, mapper_helpers.cpp:958-993; MapDB::serialize mapdb.hpp:83-98, Keyframe::serialize keyframe.hpp:199-213,
+//  KeyframeShared::save / load keyframe.hpp:80-105, MapPoint::serialize map_point.hpp:78-93, KeyPoint::serialize
+//  key_point.hpp:22-25 -- `octave` is written twice).  cereal itself and the parent project's Eigen / cv::Vec3b adapters
+//  (../util/serialization.hpp) are not in the reference tree: the byte layout follows cereal's published binary archive
+//  rules and the two adapter layouts named in MapArchiveOptions -- PARITY UNPINNED, no example archive exists offline.
+struct MapArchiveOptions {
+    // Eigen matrices: raw column-major coefficients; dynamic dimensions are preceded by their extent as 64-bit integers
+    // (the widely used cereal adapter).  fixedSizeHeader = true additionally writes rows / cols (int32) before fixed-size
+    // matrices (the other common adapter).
+    bool fixedSizeHeader = false;
+};
+/** @return false (with `error` set) on a truncated or inconsistent archive */
+bool loadMapArchive(const std::string &path, MapDB &mapDB, std::string *error = nullptr, const MapArchiveOptions &opt = MapArchiveOptions());
+bool saveMapArchive(const std::string &path, const MapDB &mapDB, std::string *error = nullptr, const MapArchiveOptions &opt = MapArchiveOptions());
+
+/** The rebuild hook next to loadMapDB's (mapper_helpers.cpp:972-988 rebuilds the BoW vectors and FeatureSearch of every
+ *  loaded keyframe): a device-resident descriptor database with one set per keyframe, in std::map (KfId) order, for
+ *  sg_match_pairs -- BASELINE configs[4] on a real atlas.  `keyframeIds` receives the KfId of every set.
+ *  Also refreshes shared->featureSearch of every keyframe.  The caller owns the database (sg_db_destroy). */
+struct ::sg_db *buildDescriptorDatabase(MapDB &mapDB, sg_ctx *ctx, std::vector<KfId> &keyframeIds);
 
 namespace match {
 /** openvslam/match_base.h:18-39, evaluated on the GPU for n descriptor pairs. */
