@@ -268,14 +268,14 @@ constexpr int DIST_THREADS = 256;
 
 struct NodeBox { short bx, by, ex, ey; };
 
-// Exclusive scan of data[0..n) in place (block-wide); returns the total.  tmp: 33 ints of smem.
-__device__ int block_exclusive_scan(int *data, int n, int *tmp) {
+// Exclusive scan of data[0..n) in place (block-wide); returns the total.  tmp: 2 x 8 ints of smem, used alternately
+// (`flip` toggles per call), so that one barrier between the warp totals and their use and one behind the scan suffice.
+__device__ int block_exclusive_scan(int *data, int n, int *tmp, int &flip) {
     const int tid = threadIdx.x, nt = DIST_THREADS;   // every caller runs DIST_THREADS threads: a shift, not a division
     const int per = (n + nt - 1) / nt;
     const int b = min(tid * per, n), e = min(b + per, n);
     int sum = 0;
     for (int i = b; i < e; ++i) sum += data[i];
-    // scan of the per-thread sums
     int v = sum;
     const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
@@ -283,24 +283,30 @@ __device__ int block_exclusive_scan(int *data, int n, int *tmp) {
         const int u = __shfl_up_sync(0xffffffffu, v, o);
         if (lane >= o) v += u;
     }
-    __syncthreads();   // previous users of tmp are done
-    if (lane == 31) tmp[wid] = v;
+    int *t = tmp + 8 * flip;
+    flip ^= 1;
+    if (lane == 31) t[wid] = v;
     __syncthreads();
-    if (wid == 0) {
-        int w = lane < (nt >> 5) ? tmp[lane] : 0;
+    int base = 0, total = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += u;
-        }
-        tmp[lane] = w;   // inclusive warp totals
-        if (lane == 31) tmp[32] = w;
+    for (int w = 0; w < DIST_THREADS / 32; ++w) {
+        const int x = t[w];
+        base += w < wid ? x : 0;
+        total += x;
     }
-    __syncthreads();
-    int run = v - sum + (wid ? tmp[wid - 1] : 0);
+    int run = v - sum + base;
     for (int i = b; i < e; ++i) { const int x = data[i]; data[i] = run; run += x; }
-    const int total = tmp[(nt >> 5) - 1];
     __syncthreads();
+    return total;
+}
+
+// Number of j < n with pred(j) (block-wide), one barrier per DIST_THREADS elements.
+template <class F> __device__ int block_count(int n, F pred) {
+    int total = 0;
+    for (int j0 = 0; j0 < n; j0 += DIST_THREADS) {
+        const int j = j0 + threadIdx.x;
+        total += __syncthreads_count(j < n && pred(j));
+    }
     return total;
 }
 
@@ -315,43 +321,40 @@ __device__ __forceinline__ int quadrant(const NodeBox &b, int x, int y) {
     return (mx <= x ? 1 : 0) + (my <= y ? 2 : 0);
 }
 
-__global__ void __launch_bounds__(DIST_THREADS)
-distribute_kernel(const __grid_constant__ GeomDev g, int node_cap_max, const unsigned long long *cand_all,
-                  uint32_t *cand_node_all, const int *cand_count, int *kp_xy, int *kp_resp, int *kp_count,
-                  int *err) {
-    extern __shared__ __align__(16) uint8_t dsm[];
-    const int NC = node_cap_max;
-    // shared arrays
-    unsigned long long *best = reinterpret_cast<unsigned long long *>(dsm);        // [NC]
-    NodeBox *box0 = reinterpret_cast<NodeBox *>(best + NC);                        // [NC]
-    NodeBox *box1 = box0 + NC;                                                     // [NC]
-    int *cnt0 = reinterpret_cast<int *>(box1 + NC);                                // [NC]
-    int *cnt1 = cnt0 + NC;                                                         // [NC]
-    int *ccnt = cnt1 + NC;                                                         // [4 NC] child counts
-    int *cpos = ccnt + 4 * NC;                                                     // [4 NC] child positions
-    int *ord = cpos + 4 * NC;                                                      // [NC] processing index
-    int *byord = ord + NC;                                                         // [NC]
-    int *ps = byord + NC;                                                          // [NC + 1] scan over order
-    int *kpos = ps + NC + 1;                                                       // [NC] position of kept nodes
-    __shared__ int tmp[33];
-    __shared__ int s_m;
-
-    const int tid = threadIdx.x, l = blockIdx.x, f = blockIdx.y + g.frame0;
-    const LevelDev &L = g.lv[l];
-    const int N = L.budget;
-    int ncand = cand_count[f * g.levels + l];
-    if (ncand > L.cand_cap) ncand = 0;   // overflow already flagged by the FAST kernel
-    const unsigned long long *cand = cand_all + (size_t)f * g.cand_per_frame + L.cand_off;
-    uint32_t *cnode = cand_node_all + (size_t)f * g.cand_per_frame + L.cand_off;
-    int *out_xy = kp_xy + (size_t)f * g.det_cap + L.kp_off;
-    int *out_resp = kp_resp + (size_t)f * g.det_cap + L.kp_off;
-    if (ncand == 0 || L.area_w <= 0 || L.area_h <= 0) {
-        if (tid == 0) kp_count[f * g.levels + l] = 0;
-        return;
+// Candidates of one (frame, level): position and current node, either cached in shared memory (levels with at most
+// CAND_SMEM candidates: every level of the VGA / 720p configurations) or in the global arrays.
+constexpr int CAND_SMEM = 3072;
+template <bool CACHED> struct CandStore {
+    const unsigned long long *cand;
+    uint32_t *cnode;
+    uint32_t *s_xy;
+    unsigned short *s_node;
+    __device__ __forceinline__ void xy(int i, int &x, int &y) const {
+        if (CACHED) { const uint32_t p = s_xy[i]; x = p & 0xffff; y = p >> 16; }
+        else cand_xy((unsigned)cand[i], x, y);
     }
+    __device__ __forceinline__ int node(int i) const { return CACHED ? (int)s_node[i] : (int)cnode[i]; }
+    __device__ __forceinline__ void set_node(int i, int v) const { if (CACHED) s_node[i] = (unsigned short)v; else cnode[i] = v; }
+};
 
-    NodeBox *box = box0, *nbox = box1;
-    int *cnt = cnt0, *ncnt = cnt1;
+struct DistShared {
+    unsigned long long *best;
+    NodeBox *box0, *box1;
+    int *cnt0, *cnt1, *ccnt0, *ccnt1, *ord, *byord, *ps, *kpos;
+    unsigned short *cpos;
+};
+
+template <bool CACHED>
+__device__ void distribute_level(const LevelDev &L, int NC, int ncand, const CandStore<CACHED> &cs, const DistShared &sh, int *tmp,
+                                 int *s_m, int *out_xy, int *out_resp, int *kp_count_out, int *err) {
+    const int tid = threadIdx.x;
+    const int N = L.budget;
+    int flip = 0;
+    NodeBox *box = sh.box0, *nbox = sh.box1;
+    int *cnt = sh.cnt0, *ncnt = sh.cnt1;
+    int *ccnt = sh.ccnt0, *nccnt = sh.ccnt1;    // quadrant populations of the current / the next node list
+    unsigned short *cpos = sh.cpos;
+    int *ord = sh.ord, *byord = sh.byord, *ps = sh.ps, *kpos = sh.kpos;
 
     // ---- initial nodes: round(aspect) patches along the longer side -----------------------------------
     const int nx = L.init_nx, ny = L.init_ny;
@@ -369,61 +372,79 @@ distribute_kernel(const __grid_constant__ GeomDev g, int node_cap_max, const uns
     __syncthreads();
     for (int i = tid; i < ncand; i += DIST_THREADS) {
         int x, y;
-        cand_xy((unsigned)cand[i], x, y);
-        const unsigned ix = (unsigned)(x / dx), iy = (unsigned)(y / dy);
-        const int nd = min((int)(ix + iy * nx), n - 1);
-        cnode[i] = nd;
-        atomicAdd(&ncnt[nd], 1);
+        cand_xy((unsigned)cs.cand[i], x, y);
+        if (CACHED) cs.s_xy[i] = (uint32_t)x | ((uint32_t)y << 16);
+        int nd = 0;
+        if (n > 1) {
+            const unsigned ix = (unsigned)(x / dx), iy = (unsigned)(y / dy);
+            nd = min((int)(ix + iy * nx), n - 1);
+        }
+        cs.set_node(i, nd);
+        if (n > 1) atomicAdd(&ncnt[nd], 1);
     }
+    if (n == 1 && tid == 0) ncnt[0] = ncand;
     __syncthreads();
     // drop empty initial nodes, keeping their order
-    for (int i = tid; i < n; i += DIST_THREADS) kpos[i] = ncnt[i] > 0 ? 1 : 0;
-    __syncthreads();
-    {
-        const int kept = block_exclusive_scan(kpos, n, tmp);
+    if (n > 1) {
+        for (int i = tid; i < n; i += DIST_THREADS) kpos[i] = ncnt[i] > 0 ? 1 : 0;
+        __syncthreads();
+        const int kept = block_exclusive_scan(kpos, n, tmp, flip);
         for (int i = tid; i < n; i += DIST_THREADS)
             if (ncnt[i] > 0) { box[kpos[i]] = nbox[i]; cnt[kpos[i]] = ncnt[i]; }
+        for (int i = tid; i < 4 * kept; i += DIST_THREADS) ccnt[i] = 0;
         __syncthreads();
-        for (int i = tid; i < ncand; i += DIST_THREADS) cnode[i] = kpos[cnode[i]];
+        // (quadrant populations of the first round are counted on the way)
+        for (int i = tid; i < ncand; i += DIST_THREADS) {
+            const int nd = kpos[cs.node(i)];
+            cs.set_node(i, nd);
+            if (cnt[nd] > 1) {
+                int x, y;
+                cs.xy(i, x, y);
+                atomicAdd(&ccnt[4 * nd + quadrant(box[nd], x, y)], 1);
+            }
+        }
         n = kept;
+        __syncthreads();
+    } else {
+        { NodeBox *tb = box; box = nbox; nbox = tb; int *tc = cnt; cnt = ncnt; ncnt = tc; }
+        if (tid < 4) ccnt[tid] = 0;
+        __syncthreads();
+        if (ncand > 1) {
+            const NodeBox b0 = box[0];
+            for (int i = tid; i < ncand; i += DIST_THREADS) {
+                int x, y;
+                cs.xy(i, x, y);
+                atomicAdd(&ccnt[quadrant(b0, x, y)], 1);
+            }
+        }
         __syncthreads();
     }
 
     // ---- rounds ----------------------------------------------------------------------------------------
     bool partial = false;
     while (true) {
-        // A/B: quadrant populations of every dividable node
-        for (int i = tid; i < 4 * n; i += DIST_THREADS) ccnt[i] = 0;
-        __syncthreads();
-        for (int i = tid; i < ncand; i += DIST_THREADS) {
-            const int nd = cnode[i];
-            if (cnt[nd] > 1) {
-                int x, y;
-                cand_xy((unsigned)cand[i], x, y);
-                atomicAdd(&ccnt[4 * nd + quadrant(box[nd], x, y)], 1);
-            }
-        }
-        __syncthreads();
+        // (A/B, the quadrant populations of every dividable node, were counted while the candidates moved: ccnt)
         // C: processing order of the dividable nodes
         int P;
-        if (!partial) {
-            for (int j = tid; j < n; j += DIST_THREADS) ord[j] = cnt[j] > 1 ? 1 : 0;
-            __syncthreads();
-            P = block_exclusive_scan(ord, n, tmp);
-        } else {
+        for (int j = tid; j < n; j += DIST_THREADS) ord[j] = cnt[j] > 1 ? 1 : 0;
+        __syncthreads();
+        P = block_exclusive_scan(ord, n, tmp, flip);       // whole round: list order
+        if (partial) {
             // most populated first; equal counts: the node nearer the list front (the newer one) first
             if (n <= 4096 && ncand < (1 << 19)) {
-                // rank = number of splittable nodes with a larger (count, -position) key: one compare per node pair
-                for (int j = tid; j < n; j += DIST_THREADS) kpos[j] = cnt[j] > 1 ? (cnt[j] << 12) | (4095 - j) : 0;
+                // rank = number of dividable nodes with a larger (count, -position) key; the keys of the P dividable
+                // nodes are compacted first (ps as scratch), so the loop runs over P, not n, entries
+                for (int j = tid; j < n; j += DIST_THREADS)
+                    if (cnt[j] > 1) ps[ord[j]] = (cnt[j] << 12) | (4095 - j);
                 __syncthreads();
                 for (int j = tid; j < n; j += DIST_THREADS) {
-                    const int kj = kpos[j];
-                    int r = 0;
-                    if (kj)
-                        for (int k = 0; k < n; ++k) r += kpos[k] > kj ? 1 : 0;
-                    ord[j] = r;
+                    if (cnt[j] > 1) {
+                        const int kj = (cnt[j] << 12) | (4095 - j);
+                        int r = 0;
+                        for (int k = 0; k < P; ++k) r += ps[k] > kj ? 1 : 0;
+                        ord[j] = r;                           // only thread j reads or writes ord[j] here
+                    }
                 }
-                __syncthreads();
             } else {                                            // keys would not fit 31 bits
                 for (int j = tid; j < n; j += DIST_THREADS) {
                     const int cj = cnt[j];
@@ -433,12 +454,10 @@ distribute_kernel(const __grid_constant__ GeomDev g, int node_cap_max, const uns
                             const int ck = cnt[k];
                             r += (ck > 1 && (ck > cj || (ck == cj && k < j))) ? 1 : 0;
                         }
-                    ord[j] = r;
+                    if (cj > 1) ord[j] = r;
                 }
             }
-            for (int j = tid; j < n; j += DIST_THREADS) kpos[j] = cnt[j] > 1 ? 1 : 0;
             __syncthreads();
-            P = block_exclusive_scan(kpos, n, tmp);
         }
         for (int j = tid; j < n; j += DIST_THREADS)
             if (cnt[j] > 1) byord[ord[j]] = j;
@@ -448,27 +467,31 @@ distribute_kernel(const __grid_constant__ GeomDev g, int node_cap_max, const uns
             const int *c = ccnt + 4 * byord[i];
             ps[i] = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
         }
-        if (tid == 0) { ps[P] = 0; s_m = P; }
+        if (tid == 0) { ps[P] = 0; *s_m = P; }
         __syncthreads();
-        block_exclusive_scan(ps, P + 1, tmp);   // ps[i] = children created before order index i; ps[P] = all
+        block_exclusive_scan(ps, P + 1, tmp, flip);   // ps[i] = children created before order index i; ps[P] = all
         if (partial) {
             // list size after processing order index i:  n + (ps[i+1] - (i+1))
             for (int i = tid; i < P; i += DIST_THREADS) {
                 const bool reached = N <= n + ps[i + 1] - (i + 1);
                 const bool before = i > 0 && N <= n + ps[i] - i;
-                if (reached && !before) s_m = i + 1;
+                if (reached && !before) *s_m = i + 1;
             }
             __syncthreads();
         }
-        const int m = s_m;
+        const int m = *s_m;
         const int total_new = ps[m];
         const int n_new = total_new + (n - m);
-        if (n_new > NC) { if (tid == 0) { atomicExch(err, SG_ERR_OVERFLOW); kp_count[f * g.levels + l] = 0; } return; }
-        // E: survivors keep their relative order behind the new children
-        for (int j = tid; j < n; j += DIST_THREADS) kpos[j] = (cnt[j] > 1 && ord[j] < m) ? 0 : 1;
-        __syncthreads();
-        block_exclusive_scan(kpos, n, tmp);
-        // F: new node table
+        if (n_new > NC) { if (tid == 0) { atomicExch(err, SG_ERR_OVERFLOW); *kp_count_out = 0; } return; }
+        // E: survivors keep their relative order behind the new children.  Whole round: every dividable node is processed,
+        //    so the survivors before j are j minus the dividable nodes before j (ord holds exactly that count).
+        if (partial) {
+            for (int j = tid; j < n; j += DIST_THREADS) kpos[j] = (cnt[j] > 1 && ord[j] < m) ? 0 : 1;
+            __syncthreads();
+            block_exclusive_scan(kpos, n, tmp, flip);
+        }
+        // F: new node table (and cleared quadrant populations for it)
+        for (int i = tid; i < 4 * n_new; i += DIST_THREADS) nccnt[i] = 0;
         for (int j = tid; j < n; j += DIST_THREADS) {
             if (cnt[j] > 1 && ord[j] < m) {
                 const NodeBox b = box[j];
@@ -484,48 +507,49 @@ distribute_kernel(const __grid_constant__ GeomDev g, int node_cap_max, const uns
                     nb.by = (q & 2) ? (short)my : b.by; nb.ey = (q & 2) ? b.ey : (short)my;
                     nbox[pos] = nb;
                     ncnt[pos] = c;
-                    cpos[4 * j + q] = pos;
+                    cpos[4 * j + q] = (unsigned short)pos;
                 }
             } else {
-                const int pos = total_new + kpos[j];
+                const int pos = total_new + (partial ? kpos[j] : j - ord[j]);
                 nbox[pos] = box[j];
                 ncnt[pos] = cnt[j];
                 kpos[j] = pos;
             }
         }
         __syncthreads();
-        // G: move the candidates
+        // G: move the candidates; a candidate that lands in a dividable node is counted in that node's quadrant right
+        //    away (A/B of the next round: no second pass over the candidates)
+        const bool more = n_new < N && n_new != n;          // another round follows
         for (int i = tid; i < ncand; i += DIST_THREADS) {
-            const int nd = cnode[i];
-            if (cnt[nd] > 1 && ord[nd] < m) {
-                int x, y;
-                cand_xy((unsigned)cand[i], x, y);
-                cnode[i] = cpos[4 * nd + quadrant(box[nd], x, y)];
-            } else {
-                cnode[i] = kpos[nd];
-            }
+            const int nd = cs.node(i);
+            const bool moved = cnt[nd] > 1 && ord[nd] < m;
+            if (!moved && !more) { cs.set_node(i, kpos[nd]); continue; }
+            int x, y;
+            cs.xy(i, x, y);
+            const int nn = moved ? cpos[4 * nd + quadrant(box[nd], x, y)] : kpos[nd];
+            cs.set_node(i, nn);
+            if (more && ncnt[nn] > 1) atomicAdd(&nccnt[4 * nn + quadrant(nbox[nn], x, y)], 1);
         }
         __syncthreads();
         // H: termination (uniform)
         const int n_old = n;
         n = n_new;
-        { NodeBox *tb = box; box = nbox; nbox = tb; int *tc = cnt; cnt = ncnt; ncnt = tc; }
+        { NodeBox *tb = box; box = nbox; nbox = tb; int *tc = cnt; cnt = ncnt; ncnt = tc; tc = ccnt; ccnt = nccnt; nccnt = tc; }
         if (N <= n || n == n_old) break;
         if (!partial) {
             // dividable nodes of the new list (all of them are children made in this round)
-            for (int j = tid; j < n; j += DIST_THREADS) kpos[j] = cnt[j] > 1 ? 1 : 0;
-            __syncthreads();
-            const int pool = block_exclusive_scan(kpos, n, tmp);
+            const int pool = block_count(n, [&](int j) { return cnt[j] > 1; });
             if (N < n + 3 * pool) partial = true;
         }
     }
 
     // ---- strongest candidate of every node; earlier candidate wins ties --------------------------------
+    unsigned long long *best = sh.best;
     for (int j = tid; j < n; j += DIST_THREADS) best[j] = 0ull;
     __syncthreads();
     for (int i = tid; i < ncand; i += DIST_THREADS) {
-        const unsigned long long c = cand[i];
-        atomicMax(&best[cnode[i]], (c & 0xffffffff00000000ull) | (0xffffffffu - (unsigned)c));
+        const unsigned long long c = cs.cand[i];
+        atomicMax(&best[cs.node(i)], (c & 0xffffffff00000000ull) | (0xffffffffu - (unsigned)c));
     }
     __syncthreads();
     for (int j = tid; j < n; j += DIST_THREADS) {
@@ -535,7 +559,52 @@ distribute_kernel(const __grid_constant__ GeomDev g, int node_cap_max, const uns
         out_xy[j] = (x + PATCH_RADIUS) | ((y + PATCH_RADIUS) << 16);
         out_resp[j] = (int)(b >> 32);
     }
-    if (tid == 0) kp_count[f * g.levels + l] = n;
+    if (tid == 0) *kp_count_out = n;
+}
+
+__global__ void __launch_bounds__(DIST_THREADS)
+distribute_kernel(const __grid_constant__ GeomDev g, int node_cap_max, const unsigned long long *cand_all,
+                  uint32_t *cand_node_all, const int *cand_count, int *kp_xy, int *kp_resp, int *kp_count,
+                  int *err) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    const int NC = node_cap_max;
+    DistShared sh;
+    sh.box0 = reinterpret_cast<NodeBox *>(dsm);                                    // [NC]
+    sh.box1 = sh.box0 + NC;                                                        // [NC]
+    sh.cnt0 = reinterpret_cast<int *>(sh.box1 + NC);                               // [NC]
+    sh.cnt1 = sh.cnt0 + NC;                                                        // [NC]
+    sh.ccnt0 = sh.cnt1 + NC;                                                       // [4 NC] child counts (this round)
+    sh.ccnt1 = sh.ccnt0 + 4 * NC;                                                  // [4 NC] child counts (next round)
+    sh.best = reinterpret_cast<unsigned long long *>(sh.ccnt0);                    // [NC] after the rounds, over the child counts
+    sh.ord = sh.ccnt1 + 4 * NC;                                                    // [NC] processing index
+    sh.byord = sh.ord + NC;                                                        // [NC]
+    sh.ps = sh.byord + NC;                                                         // [NC + 1] scan over order
+    sh.kpos = sh.ps + NC + 1;                                                      // [NC] position of kept nodes
+    sh.cpos = reinterpret_cast<unsigned short *>(sh.kpos + NC + 1);                // [4 NC] child positions (NC < 65536)
+    uint32_t *s_xy = reinterpret_cast<uint32_t *>(sh.cpos + 4 * NC + 4);           // [CAND_SMEM] x | y << 16
+    unsigned short *s_node = reinterpret_cast<unsigned short *>(s_xy + CAND_SMEM); // [CAND_SMEM]
+    __shared__ int tmp[16];
+    __shared__ int s_m;
+
+    const int tid = threadIdx.x, l = blockIdx.x, f = blockIdx.y + g.frame0;
+    const LevelDev &L = g.lv[l];
+    int ncand = cand_count[f * g.levels + l];
+    if (ncand > L.cand_cap) ncand = 0;   // overflow already flagged by the FAST kernel
+    const unsigned long long *cand = cand_all + (size_t)f * g.cand_per_frame + L.cand_off;
+    uint32_t *cnode = cand_node_all + (size_t)f * g.cand_per_frame + L.cand_off;
+    int *out_xy = kp_xy + (size_t)f * g.det_cap + L.kp_off;
+    int *out_resp = kp_resp + (size_t)f * g.det_cap + L.kp_off;
+    if (ncand == 0 || L.area_w <= 0 || L.area_h <= 0) {
+        if (tid == 0) kp_count[f * g.levels + l] = 0;
+        return;
+    }
+    if (ncand <= CAND_SMEM && NC < 65536) {
+        const CandStore<true> cs{cand, cnode, s_xy, s_node};
+        distribute_level<true>(L, NC, ncand, cs, sh, tmp, &s_m, out_xy, out_resp, kp_count + f * g.levels + l, err);
+    } else {
+        const CandStore<false> cs{cand, cnode, s_xy, s_node};
+        distribute_level<false>(L, NC, ncand, cs, sh, tmp, &s_m, out_xy, out_resp, kp_count + f * g.levels + l, err);
+    }
 }
 
 // {level | cell row << 8 | cell column << 20, first evaluated x, y, width | height << 16} of every FAST cell (host, sg_create)
@@ -554,7 +623,7 @@ void fast_cell_table(const GeomDev &g, std::vector<int4> &cells) {
 
 size_t distribute_smem_bytes(int node_cap_max) {
     const size_t NC = node_cap_max;
-    return NC * (8 + 2 * sizeof(NodeBox) + 2 * 4 + 4 * 4 + 4 * 4 + 4 + 4 + 4 + 4) + 16;
+    return NC * (2 * sizeof(NodeBox) + 2 * 4 + 2 * 4 * 4 + 4 * 2 + 4 + 4 + 4 + 4) + 64 + (size_t)CAND_SMEM * 6;
 }
 
 int launch_detect(sg_ctx *ctx, int n_frames) {
@@ -574,6 +643,7 @@ int launch_detect(sg_ctx *ctx, int n_frames) {
         SG_LAUNCH_CHECK(ctx);
     }
     mark(ctx, EV_FAST1);
+    if (nc_max >= 65536) return fail(ctx, SG_ERR_INVALID, "more than 65535 quadtree nodes per level are not supported");
     const size_t smem = distribute_smem_bytes(nc_max);
     if (smem > 48 * 1024)
         SG_CUDA(ctx, cudaFuncSetAttribute(distribute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

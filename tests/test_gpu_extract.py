@@ -281,6 +281,48 @@ def test_extract_device_resident_full_batch(slamgpu, oracle, synth):
         assert np.array_equal(g["x"], r["x"]) and np.array_equal(g["y"], r["y"])
 
 
+def test_extract_256_distinct_frames_all_against_oracle(slamgpu, oracle):
+    """The timed batch of bench.py (BASELINE configs[1]: 256 DISTINCT 640x480 frames, 2000 keypoints) through the three entry
+    points -- device resident, host buffers, streaming -- every frame compared with the oracle, every field bit for bit."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    import bench
+    imgs = bench.make_frames(256, 10000)
+    assert len({imgs[f].tobytes() for f in range(256)}) == 256
+    p = oracle.make_params(640, 480, max_keypoints=2000)
+    with ThreadPoolExecutor(os.cpu_count() or 4) as ex:
+        refs = list(ex.map(lambda f: oracle.extract(p, imgs[f]), range(256)))
+    with slamgpu.Context(640, 480, max_keypoints=2000, max_frames=256) as ctx:
+        buf = ctx.device_buffer(imgs.nbytes).upload(imgs)
+        ctx.extract_device(buf.ptr, 640, 640 * 480, 256)
+        dev = ctx.extract_download(256)
+        host = ctx.detect_and_extract(imgs)
+        arrs, ks = ctx.alloc_outputs(256, pinned=True)
+        ctx.extract_wait(ctx.extract_submit(imgs, 0, ks))
+        buf.free()
+        cap = ctx.cap
+        for f in range(256):
+            _assert_same_extraction(dev[f], refs[f])
+            _assert_same_extraction(host[f], refs[f])
+            n = refs[f]["n"]
+            assert int(arrs["count"][f]) == n
+            for k in ("x", "y", "angle", "octave", "desc"):
+                assert np.array_equal(arrs[k][f, :n], refs[f][k]), (f, k)
+            assert cap >= n
+    assert sum(r["n"] for r in refs) > 256 * 1900
+
+
+def test_extract_rejects_bad_frame_counts_with_tracks(slamgpu):
+    """n_frames is validated before anything is sized by it (tracker-point staging included)."""
+    with slamgpu.Context(640, 480, max_frames=2, max_tracks=8) as ctx:
+        imgs = np.zeros((3, 480, 640), np.uint8)
+        tracks = [np.array([[100.0, 100.0]], np.float32)] * 3
+        with pytest.raises(slamgpu.SlamGpuError):
+            ctx.detect_and_extract(imgs, tracks=tracks)
+        ok = ctx.detect_and_extract(imgs[:2], tracks=tracks[:2])      # the context still works afterwards
+        assert len(ok) == 2
+
+
 def test_errors(slamgpu):
     with pytest.raises(slamgpu.SlamGpuError):
         slamgpu.Context(32, 32)

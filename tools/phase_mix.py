@@ -1,0 +1,49 @@
+#!/usr/bin/env python3
+"""Executed warp instructions of one captured launch, aggregated over SOURCE-LINE RANGES (phases) of a .cu file:
+    python tools/phase_mix.py <rep> <file.cu> name:lo-hi [name:lo-hi ...] [--px N] [--launch K]
+Lines outside every range are reported as 'other'.  Inlined helper lines (tma.cuh, ...) are attributed to 'helpers'."""
+import csv, subprocess, sys
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+rep, cu = args[0], args[1]
+px = float(sys.argv[sys.argv.index("--px") + 1]) if "--px" in sys.argv else None
+launch = int(sys.argv[sys.argv.index("--launch") + 1]) if "--launch" in sys.argv else 0
+if px is not None:
+    args = [a for a in args if a != str(int(px)) and a != sys.argv[sys.argv.index("--px") + 1]]
+if "--launch" in sys.argv:
+    args = [a for a in args if a != sys.argv[sys.argv.index("--launch") + 1]]
+ranges = []
+for a in args[2:]:
+    name, r = a.rsplit(":", 1)
+    lo, hi = r.split("-")
+    ranges.append((name, int(lo), int(hi)))
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+blocks, hdr, cur = [], None, None
+for r in rows:
+    if r and r[0] == "Line No":
+        hdr = r
+        cur = []
+        blocks.append(cur)
+        continue
+    if hdr and cur is not None and len(r) == len(hdr) and r[0].isdigit():
+        cur.append(r)
+blk = blocks[launch]
+ci = hdr.index("Instructions Executed")
+fi = hdr.index("File Path") if "File Path" in hdr else None
+tot = sum(int(r[ci] or 0) for r in blk)
+agg = {}
+for r in blk:
+    n = int(r[ci] or 0)
+    line = int(r[0])
+    where = "other"
+    if fi is not None and r[fi] and not r[fi].endswith(cu.split("/")[-1]):
+        where = "helpers (%s)" % r[fi].split("/")[-1]
+    else:
+        for name, lo, hi in ranges:
+            if lo <= line <= hi:
+                where = name
+                break
+    agg[where] = agg.get(where, 0) + n
+print("launch %d: %d warp instructions%s" % (launch, tot, (" = %.1f thread-instructions per px" % (tot * 32 / px)) if px else ""))
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1]):
+    print("  %-34s %12d  %5.1f%%%s" % (k, v, 100.0 * v / tot, ("  %5.1f /px" % (v * 32 / px)) if px else ""))

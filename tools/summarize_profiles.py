@@ -82,3 +82,76 @@ with open(dst / ("ncu_full_%s.md" % tag), "w") as f:
                     i = hdr.index(w)
                     f.write("| %s | %s | %s |\n" % (w, r[i], units[i]))
 print("wrote", dst / ("ncu_full_%s.md" % tag))
+
+
+# ---- full-batch evidence (tools/profile_r2.sh): DRAM traffic per step, opcode mix, instructions per pixel by phase ----
+import json
+
+W8, H8 = [640, 533, 444, 370, 309, 257, 214, 179], [480, 400, 333, 278, 231, 193, 161, 134]
+PX = [w * h * 256 for w, h in zip(W8, H8)]
+SUM_PX = sum(PX)
+KP = 513000
+PHASES = {
+    "fast_cells_kernel": ("detect.cu", SUM_PX, ["setup+TMA:70-101", "pair words:102-117", "stage 1 (antipodal test, queue):118-155",
+                                                "stage 2 (exact score):156-219", "NMS:220-247", "output:248-262"]),
+    "pyr_fast_kernel": ("pyramid.cu", None, ["setup, taps, TMA wait:223-271", "resize:272-302", "plane store:303-315", "reflect-101:316-341",
+                                             "blur horizontal:342-377", "blur vertical:378-421"]),
+    "describe_kernel": ("describe.cu", None, ["tables, pattern:118-160", "slot lookup:161-220", "moments (TMA + IDP.4A):221-263",
+                                              "angle, trig, outputs:264-275", "rBRIEF (TMA + sampling):276-322"]),
+    "distribute_kernel": ("detect.cu", None, ["initial nodes:356-391", "quadrant counts:392-406", "processing order:407-445",
+                                              "scans, stop point:446-471", "new node table:472-496", "move candidates:497-508",
+                                              "termination:509-521", "strongest per node:522-539"]),
+}
+traffic = {"tag": tag, "how": "ncu --set full --clock-control none on tools/full_batch_pass.py (256-frame single launches, profiling "
+                              "layout of bench.py's stage timing); dram__bytes_read.sum + dram__bytes_write.sum per launch"}
+mix_md = ["# SASS opcode mix and per-phase instruction budget, %s\n\nFull-batch launches (256 frames of 640x480, 8 levels, 2000 keypoints; "
+          "2048 keyframe pairs), `ncu --set full --import-source on`, read with `tools/sass_mix.py` / `tools/phase_mix.py`.  "
+          "Thread-instructions per pixel = 32 x warp instructions / pixels of the level(s) the launch covers.\n" % tag]
+for rep in sorted(OUT.glob("prof_*_%s.ncu-rep" % tag)):
+    kern = rep.name[len("prof_"):-len("_%s.ncu-rep" % tag)]
+    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    if len(rows) < 3:
+        continue
+    hdr = rows[0]
+    ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+    units = rows[1]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = []
+    for r in rows[2:]:
+        b = float(r[ir].replace(",", "")) * scale.get(units[ir], 1) + float(r[iw].replace(",", "")) * scale.get(units[iw], 1)
+        per.append({"bytes": b, "duration_us": float(r[it].replace(",", "")) * {"ns": 1e-3, "us": 1, "ms": 1e3}.get(units[it], 1)})
+    if kern == "pyr_fast_kernel":
+        traffic["pyr_fast_kernel (all 8 launches)"] = {"bytes_per_launch": sum(p["bytes"] for p in per), "launches": len(per),
+                                                       "per_launch": per, "algorithmic_bytes": 2208264 * 256}
+    else:
+        traffic[kern] = {"bytes_per_launch": per[0]["bytes"], "duration_us": per[0]["duration_us"]}
+        if kern == "fast_cells_kernel":
+            traffic[kern]["algorithmic_bytes"] = 950532 * 256
+    # opcode mix
+    px_arg = ",".join(str(v) for v in PX) if kern == "pyr_fast_kernel" else (str(SUM_PX) if kern == "fast_cells_kernel" else None)
+    cmd = [sys.executable, str(ROOT / "tools" / "sass_mix.py"), str(rep)] + ([px_arg] if px_arg else [])
+    mix = subprocess.run(cmd, capture_output=True, text=True).stdout
+    blocks = mix.split("== ")[1:]
+    keep = blocks[:2] if kern == "pyr_fast_kernel" else blocks[:1]      # level 0 (blur only) and level 1 (resize + blur)
+    mix_md.append("\n## %s\n" % kern)
+    if kern == "pyr_fast_kernel":
+        mix_md.append("Warp instructions of the 8 launches of one step (level 0 = blur only, levels 1-7 = resize + blur):\n")
+        for n, b in enumerate(blocks):
+            mix_md.append("* level %d: %s" % (n, b.splitlines()[0].split(": ", 1)[1]))
+        mix_md.append("")
+    for b in keep:
+        lines = b.splitlines()
+        mix_md.append("```\n" + lines[0] + "\n" + "\n".join(lines[1:19]) + "\n```")
+    if kern in PHASES:
+        cu, px, ranges = PHASES[kern]
+        launches = [(1, PX[1])] if kern == "pyr_fast_kernel" else [(0, px)]
+        for launch, lpx in launches:
+            cmd = [sys.executable, str(ROOT / "tools" / "phase_mix.py"), str(rep), cu] + ranges + ["--launch", str(launch)]
+            if lpx:
+                cmd += ["--px", str(lpx)]
+            ph = subprocess.run(cmd, capture_output=True, text=True).stdout
+            mix_md.append("Per phase (source-line ranges of `csrc/%s`)%s:\n\n```\n%s```" % (cu, " of the level-1 launch" if kern == "pyr_fast_kernel" else "", ph))
+(dst / ("traffic_%s.json" % tag)).write_text(json.dumps(traffic, indent=1))
+(dst / ("sass_mix_%s.md" % tag)).write_text("\n".join(mix_md) + "\n")
+print("wrote", dst / ("traffic_%s.json" % tag), dst / ("sass_mix_%s.md" % tag))
