@@ -319,6 +319,15 @@ def extra_configs(slamgpu, sm, sh, rank, world, local, barrier_max_, td, config5
         out["config0_single_frame"] = {"workload": "1 frame 640x480, 8 levels, 1000 keypoints", "keypoints": int(arrs["count"][0]),
                                        "latency_us_host_call_median": 1e6 * statistics.median(lat[5:]),
                                        "latency_us_kernels_only": dev_us}
+        if rank == 0 and world == 1:
+            # the same frame through the reference's CPU path on ONE host thread
+            be, po_, kind, _ = reference_backend()
+            p1 = po_.make_params(W, H, levels=LEVELS, scale_factor=FACTOR, max_keypoints=1000)
+            one = np.ascontiguousarray(pin.array[:1])
+            be.bench_extract(p1, np.repeat(one, 2, axis=0), 1)
+            secs, _ = be.bench_extract(p1, np.repeat(one, 8, axis=0), 1)
+            out["config0_single_frame"]["cpu_single_thread_ms_per_frame"] = 1e3 * secs / 8
+            out["config0_single_frame"]["cpu_kind"] = kind
     # ---- configs[3]: 1280x720 stereo stream --------------------------------------------------------------
     SW, SH, PAIRS = 1280, 720, 16
     with slamgpu.Context(SW, SH, levels=LEVELS, scale_factor=FACTOR, max_keypoints=MAXKP, max_frames=2 * PAIRS, device=local) as c4:
@@ -568,6 +577,11 @@ def main():
 
     # ---- end to end through the host-buffer entry point (H2D + kernels + D2H) -----------------------------
     out_arrs, out_struct = ctx._alloc_out(FRAMES, pinned=True)   # pinned: the D2H copies overlap the kernels
+    # what detectAndExtract returns (orb_extractor.hpp:16-20): position, angle, octave, descriptor, track id per keypoint.
+    # The integer level coordinates are a test convenience of the library: not requested, not copied.
+    E2E_SKIP = ("lvl_x", "lvl_y")
+    for k in E2E_SKIP:
+        setattr(out_struct, k, None)
     if args.pipe_chunk:
         ctx.set_pipeline_chunk(args.pipe_chunk)
     lib = slamgpu.lib()
@@ -601,13 +615,16 @@ def main():
         ctx.synchronize()
         e2e_s = barrier_max(td, local, time.perf_counter() - t0)
         e2e_value = world * FRAMES * e2e_steps / e2e_s
-    d2h_bytes = sum(int(a.nbytes) for a in out_arrs.values())
+    d2h_bytes = sum(int(a.nbytes) for k, a in out_arrs.items() if k not in E2E_SKIP)
     # ... and the streaming form of the same call: IN_FLIGHT batches in flight on disjoint ranges of the context's frame
     # slots, so the copies of batch i+1 run under the kernels and the copy-out of batch i.  Every step still moves
     # its inputs H2D and its results D2H inside the timed region; the region ends when the last batch is on the host.
     e2e_stream = None
     if not args.skip_e2e:
         out2 = [(out_arrs, out_struct)] + [ctx.alloc_outputs(FRAMES, pinned=True) for _ in range(IN_FLIGHT - 1)]
+        for _, ks_ in out2[1:]:
+            for k in E2E_SKIP:
+                setattr(ks_, k, None)
         tickets = [None] * IN_FLIGHT
 
         def run_stream(n, first):

@@ -7,23 +7,20 @@
  * Nothing in the product path (slam-module_b200/, include/) may include, link or call it.
  *
  * Parity status (see DESIGN.md "Oracle"):
- *   - pyramid pixels, fastAtan2, FAST-9/16: restated from OpenCV, pinned against cv2 4.13.0
- *     outputs generated in the build container (tests/golden/, tools/gen_golden.py).
- *   - util::cos/sin, Hamming distance, angle histogram, rBRIEF table: pinned against the
- *     reference's own headers compiled verbatim (oracle/_ref, oracle/Makefile target `ref`).
- *   - FAST cell grid + quadtree distribution: the reference delegates this stage to an absent
- *     parent-project class (feature_detector.cpp:89-98); the oracle follows the upstream
- *     OpenVSLAM scheme named by the north star with a documented tie-break.  PARITY UNPINNED
- *     for that stage: the oracle is the specification.
- *   - matchForLoopClosures brute-force degenerate case: restated from keyframe_matcher.cpp:50-158;
- *     the reference ships no test vectors for it (parity pinned only through the verbatim
- *     leaf headers it is built from).
- *   - candidate-list matchers, matchForTriangulationDBoW, MapPoint::updateDescriptor, FeatureSearch: restated from
- *     keyframe_matcher.cpp / feature_search.cpp / map_point.cpp; the reference has no vectors for them, so they are
- *     checked against plain-python restatements in tests/test_search.py only -- PARITY UNPINNED.  The epipolar test uses
- *     Eigen's summation order from memory (Eigen is not in the tree).
- *   - BoW transform / BowVector / L1 score / getBowSimilar: DBoW2 is an absent dependency; its published tree descent,
- *     addWeight / normalize and L1Scoring::score are restated -- PARITY UNPINNED.
+ *   - PINNED against the reference's own sources compiled verbatim (oracle/_ref/libref_slam.so: static_settings.cpp,
+ *     feature_search.cpp, orb_extractor.cpp, image_pyramid.cpp, feature_detector.cpp, keyframe_matcher.cpp,
+ *     map_point.cpp, keyframe.cpp, bow_index.cpp, and the four openvslam/ header leaves; oracle/Makefile target `ref`,
+ *     oracle/ref_slam.cpp), live and through tests/golden/golden_ref_slam.npz: scale factors and budgets, FeatureSearch
+ *     order and radius queries, the chained pyramid, detectAndExtract end to end (border filter, tracker branch,
+ *     ic_angle, rBRIEF, output order), matchForLoopClosures, matchForTriangulationDBoW, searchByProjection,
+ *     replaceDuplication, matchMapPointsSim3, MapPoint::updateDescriptor, BowIndex (tests/test_reference_parity.py).
+ *   - OpenCV arithmetic (resize, GaussianBlur, fastAtan2, FAST-9/16, cvRound): restated from OpenCV, pinned against
+ *     cv2 4.13.0 outputs generated in the build container (tests/golden/golden_cv2.npz, tools/gen_golden.py).
+ *   - PARITY UNPINNED: the FAST cell grid + quadtree distribution -- the reference delegates that stage to an absent
+ *     parent-project class (feature_detector.cpp:89-98); the oracle follows the upstream OpenVSLAM scheme named by the
+ *     north star with a documented tie-break and IS the specification.  DBoW2 itself (absent): its published tree descent,
+ *     addWeight / normalize and L1Scoring::score are restated.  The summation order of Eigen's 3-term sums in the
+ *     epipolar test is recalled (Eigen is not in the tree).
  */
 #ifndef ORB_ORACLE_H
 #define ORB_ORACLE_H

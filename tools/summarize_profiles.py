@@ -98,9 +98,10 @@ PHASES = {
                                              "blur horizontal:342-377", "blur vertical:378-421"]),
     "describe_kernel": ("describe.cu", None, ["tables, pattern:118-160", "slot lookup:161-220", "moments (TMA + IDP.4A):221-263",
                                               "angle, trig, outputs:264-275", "rBRIEF (TMA + sampling):276-322"]),
-    "distribute_kernel": ("detect.cu", None, ["initial nodes:356-391", "quadrant counts:392-406", "processing order:407-445",
-                                              "scans, stop point:446-471", "new node table:472-496", "move candidates:497-508",
-                                              "termination:509-521", "strongest per node:522-539"]),
+    "distribute_kernel": ("detect.cu", None, ["scan helpers:271-352", "initial nodes:353-421", "processing order (rank loop):422-461",
+                                              "children scan, stop point:462-490", "new node table:491-517",
+                                              "move candidates + next quadrant counts:518-534", "termination:535-546",
+                                              "strongest per node:547-566", "kernel entry:567-620"]),
 }
 traffic = {"tag": tag, "how": "ncu --set full --clock-control none on tools/full_batch_pass.py (256-frame single launches, profiling "
                               "layout of bench.py's stage timing); dram__bytes_read.sum + dram__bytes_write.sum per launch"}
