@@ -221,6 +221,8 @@ int sg_db_create_device(sg_ctx *ctx, const uint32_t *d_desc, const float *d_angl
  * sg_extract_device_views qualify).  The extract -> match flow of one GPU then moves no descriptor at all. */
 int sg_db_wrap_device(sg_ctx *ctx, const uint32_t *d_desc, const float *d_angle, const int64_t *h_offsets,
                       int n_sets, sg_db **out);
+/* Releases a database.  Normally called before sg_destroy of its context; a database that outlives its context has had
+ * its device memory released by sg_destroy and only the handle is freed here. */
 void sg_db_destroy(sg_db *db);
 /* Batched matching of keyframe pairs (h_pairs: n_pairs x {setA, setB}).  h_matches may be NULL;
  * otherwise row p holds `match_stride` ints (>= size of the largest A set), -1 padded.

@@ -347,6 +347,13 @@ void sg_destroy(sg_ctx *ctx) {
     // batches may still be in flight on the pipeline streams (sg_extract_submit without its wait)
     for (cudaStream_t q : {ctx->main_stream, ctx->s_in, ctx->s_out}) if (q) cudaStreamSynchronize(q);
     for (cudaStream_t q : ctx->s_cmp) if (q) cudaStreamSynchronize(q);
+    // databases still alive: their device memory goes with the context (pool); the handles stay valid for sg_db_destroy
+    for (sg_db *db : ctx->dbs) {
+        if (db->owns_data) { if (db->d_desc) cudaFree(db->d_desc); if (db->d_angle) cudaFree(db->d_angle); }
+        if (db->d_offsets) cudaFree(db->d_offsets);
+        db->d_desc = nullptr; db->d_angle = nullptr; db->d_offsets = nullptr; db->ctx = nullptr;
+    }
+    ctx->dbs.clear();
     for (auto &L : ctx->lv) { cudaFree(L.pyr); cudaFree(L.blur); cudaFree(L.xtab); cudaFree(L.ytab); }
     void *ptrs[] = {ctx->d_cand, ctx->d_cand_node, ctx->d_cand_count, ctx->d_kp_xy, ctx->d_kp_resp, ctx->d_kp_count,
                     ctx->d_err, ctx->d_trk_xy, ctx->d_trk_pt, ctx->d_trk_id, ctx->d_trk_count, ctx->d_x, ctx->d_y,
@@ -832,6 +839,7 @@ int sg_hamming(sg_ctx *ctx, const uint32_t *h_a, const uint32_t *h_b, int n, uin
 
 static int db_finish(sg_ctx *ctx, sg_db *db, const int64_t *h_offsets, int n_sets) {
     db->ctx = ctx;
+    ctx->dbs.push_back(db);      // sg_destroy releases the device memory of databases that outlive their context
     db->n_sets = n_sets;
     db->offsets.assign(h_offsets, h_offsets + n_sets + 1);
     db->max_set = 0;
@@ -914,7 +922,11 @@ int sg_db_wrap_device(sg_ctx *ctx, const uint32_t *d_desc, const float *d_angle,
 }
 void sg_db_destroy(sg_db *db) {
     if (!db) return;
-    if (db->ctx) cudaSetDevice(db->ctx->device);
+    if (db->ctx) {
+        cudaSetDevice(db->ctx->device);
+        auto &v = db->ctx->dbs;
+        v.erase(std::remove(v.begin(), v.end(), db), v.end());
+    }
     auto release = [&](void *p) {      // stream-ordered, after everything queued on the context's stream so far
         if (!p) return;
         if (db->ctx) cudaFreeAsync(p, db->ctx->main_stream);

@@ -123,6 +123,7 @@ struct sg_ctx {
     int sm_count = 148;
     int describe_ctas_per_sm = 0;      // occupancy of the persistent describe kernel (queried on first use)
 
+    std::vector<sg_db *> dbs;           // descriptor databases created on this context and not yet destroyed
     std::vector<sg::Level> lv;
     sg::GeomDev geom{};
     const uint8_t *level0 = nullptr;   // current level-0 planes (own buffer or caller's device images)

@@ -314,30 +314,41 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
         }
     }
     // ---- reflect-101: halo entries outside the image mirror resized pixels inside it ------------
-    // only the (up to) four 3-wide strips outside the image are visited; sources are always inside
+    // Rows first (whole words of the up to three rows above / below the image, copied from their mirror rows), then,
+    // behind a barrier, the up to three columns left / right of the image for EVERY window row (the halo rows now hold
+    // their mirrors, so a corner gets the pixel mirrored in both directions).  One thread per word / per row and side.
     {
         const bool left = x0 == 0, right = x0 + tw + 3 > a.w, top = y0 == 0, bottom = y0 + th + 3 > a.h;
-        if (left || right || top || bottom) {
-            if (left || right)
-                for (int i = tid; i < FRH * 6; i += PYR_THREADS) {
-                    const int ry = i / 6, k = i - ry * 6;
-                    const int x = k < 3 ? k - 3 : a.w + k - 3, y = y0 - 3 + ry;
-                    if ((k < 3 ? left : right) && y < a.h + 3 && x - x0 < TW + 4) {
-                        const int mx = reflect101(x, a.w), my = reflect101(y, a.h);
-                        R[ry * FW + (x - x0 + X0)] = R[(my - (y0 - 3)) * FW + (mx - x0 + X0)];
-                    }
+        if (top || bottom) {
+            constexpr int WORDS = 18;                               // window columns x0 - 4 .. x0 + 67
+            if (tid < 6 * WORDS) {
+                const int k = tid / WORDS, wd = tid - k * WORDS;    // k < 3: row -1 - k ; else row a.h + (k - 3)
+                const int y = k < 3 ? -1 - k : a.h + k - 3;
+                const int ry = y - (y0 - 3);
+                if ((k < 3 ? top : bottom) && ry < FRH) {
+                    const int my = k < 3 ? -y : 2 * (a.h - 1) - y;   // reflect-101; inside the window: |y - my| <= 6
+                    uint32_t *row = reinterpret_cast<uint32_t *>(R + ry * FW + X0 - 4) + wd;
+                    *row = *(reinterpret_cast<const uint32_t *>(R + (my - (y0 - 3)) * FW + X0 - 4) + wd);
                 }
-            if (top || bottom)
-                for (int i = tid; i < 6 * 72; i += PYR_THREADS) {
-                    const int k = i / 72, rx = i - k * 72;
-                    const int y = k < 3 ? k - 3 : a.h + k - 3, x = x0 - 4 + rx;
-                    if ((k < 3 ? top : bottom) && x >= 0 && x < a.w && y - (y0 - 3) < FRH) {
-                        const int my = reflect101(y, a.h);
-                        R[(y - (y0 - 3)) * FW + rx + X0 - 4] = R[(my - (y0 - 3)) * FW + rx + X0 - 4];
-                    }
-                }
-            __syncthreads();
+            }
+            if (left || right) __syncthreads();
         }
+        if (left || right) {
+            const int ry = tid & 127, side = tid >> 7;              // threads 0..69: left strip, 128..197: right strip
+            if (ry < FRH && (side == 0 ? left : right)) {
+                uint8_t *row = R + ry * FW + X0 - x0;               // row[x] = window pixel x
+                if (side == 0) {
+                    row[-1] = row[1]; row[-2] = row[2]; row[-3] = row[3];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int x = a.w + k;
+                        if (x - x0 < TW + 4) row[x] = row[2 * (a.w - 1) - x];
+                    }
+                }
+            }
+        }
+        if (left || right || top || bottom) __syncthreads();
     }
 
     // ---- horizontal pass: 4 columns x 2 rows per item, stored as vertical u16 pairs ---------------

@@ -331,3 +331,21 @@ def test_match_triangulation_exhausted_lists_are_rescanned(ctx, oracle):
     ref = oracle.match_triangulation(dA, aA, octA, b1, node, dB, aB, b2, node, E, sf)
     assert got[0] == ref[0] == 20 and np.array_equal(got[1], ref[1])
     assert ctx.rescans() > 0
+
+
+def test_database_may_outlive_its_context(slamgpu):
+    """C callers may destroy the context before a database created on it (only the Python wrapper orders this):
+    sg_destroy releases the database's device memory and detaches it, sg_db_destroy afterwards only frees the handle."""
+    import ctypes as C
+    L = slamgpu.lib()
+    ctx = slamgpu.Context(640, 480, max_frames=1)
+    d, a = np.zeros((2, 64, 8), np.uint32), np.zeros((2, 64), np.float32)
+    offs = np.array([0, 64, 128], np.int64)
+    db = C.c_void_p()
+    assert L.sg_db_create(ctx._h, d.ctypes.data, a.ctypes.data, offs.ctypes.data, 2, C.byref(db)) == 0
+    h, ctx._h = ctx._h, None          # destroy the context behind the wrapper's back, database still alive
+    L.sg_destroy(h)
+    L.sg_db_destroy(db)               # must not touch the dead context
+    with slamgpu.Context(640, 480, max_frames=1) as c2:      # the device is still healthy
+        n, m = c2.match_bruteforce(d[0], a[0], d[1], a[1])
+        assert n >= 0
