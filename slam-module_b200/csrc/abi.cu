@@ -36,6 +36,8 @@ int grow(sg_ctx *ctx, void **ptr, size_t *cap, size_t need, size_t elem) {
 void pyramid_source_extent(const std::vector<ResizeTap> &xt, const std::vector<ResizeTap> &yt, int w, int h,
                            bool area2x, int sw, int sh, int *tile_w, int *tile_h);
 int pyramid_fast_source_rows(const std::vector<ResizeTap> &yt, int h);
+void pyramid_tile_tables(const std::vector<ResizeTap> &xt, const std::vector<ResizeTap> &yt, int w, int h, int src_pitch,
+                         std::vector<uint4> &xtile, std::vector<uint4> &ytile);
 int run_match(sg_ctx *ctx, const sg_db *db, const int *d_pairs, int n_pairs, const sg_match_params &mp,
               int *d_matches, int match_stride, uint32_t *d_n_matches, bool reset_rescans = true);
 int match_chunk_pairs(const sg_db *db, bool own_matches);
@@ -113,6 +115,16 @@ static int build_context(sg_ctx *ctx) {
             }
             for (int i = 0; i + 1 < L.w; ++i)
                 if (xt[i + 1].s0 - xt[i].s0 > 2 || xt[i + 1].s0 < xt[i].s0) L.fast_resize = false;
+            if (L.fast_resize) {
+                // Everything the fast resize kernel derives from the taps depends on (level, tile column, window column) or
+                // (level, tile row, window row) only -- never on the frame: precomputed here, one 16-byte load per thread there.
+                std::vector<uint4> xtile, ytile;
+                pyramid_tile_tables(xt, yt, L.w, L.h, L.tma_src_w, xtile, ytile);
+                if (int r = dev_alloc(ctx, &L.xtile, xtile.size())) return r;
+                if (int r = dev_alloc(ctx, &L.ytile, ytile.size())) return r;
+                SG_CUDA(ctx, cudaMemcpy(L.xtile, xtile.data(), xtile.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+                SG_CUDA(ctx, cudaMemcpy(L.ytile, ytile.data(), ytile.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+            }
             if (int r = dev_alloc(ctx, &L.xtab, xt.size())) return r;
             if (int r = dev_alloc(ctx, &L.ytab, yt.size())) return r;
             SG_CUDA(ctx, cudaMemcpy(L.xtab, xt.data(), xt.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
@@ -354,7 +366,7 @@ void sg_destroy(sg_ctx *ctx) {
         db->d_desc = nullptr; db->d_angle = nullptr; db->d_offsets = nullptr; db->ctx = nullptr;
     }
     ctx->dbs.clear();
-    for (auto &L : ctx->lv) { cudaFree(L.pyr); cudaFree(L.blur); cudaFree(L.xtab); cudaFree(L.ytab); }
+    for (auto &L : ctx->lv) { cudaFree(L.pyr); cudaFree(L.blur); cudaFree(L.xtab); cudaFree(L.ytab); cudaFree(L.xtile); cudaFree(L.ytile); }
     void *ptrs[] = {ctx->d_cand, ctx->d_cand_node, ctx->d_cand_count, ctx->d_kp_xy, ctx->d_kp_resp, ctx->d_kp_count,
                     ctx->d_err, ctx->d_trk_xy, ctx->d_trk_pt, ctx->d_trk_id, ctx->d_trk_count, ctx->d_x, ctx->d_y,
                     ctx->d_angle, ctx->d_octave, ctx->d_track_id, ctx->d_lvl_x, ctx->d_lvl_y, ctx->d_desc, ctx->d_count,

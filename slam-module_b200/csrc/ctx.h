@@ -33,6 +33,8 @@ struct Level {
     uint8_t *blur = nullptr;
     ResizeTap *xtab = nullptr;      // [w]   (levels >= 1)
     ResizeTap *ytab = nullptr;      // [h]
+    uint4 *xtile = nullptr;         // fast resize kernel: per (tile column, window column pair) {coef a, coef b, byte offset of the 8-byte source window, PRMT selector}
+    uint4 *ytile = nullptr;         // ... per (tile row, window row) {offset of source row 0, of source row 1, b0 << 12, b1 << 12}
     bool area2x = false;            // cv::resize switches to INTER_AREA for an exact 2x decimation
     bool fast_resize = false;       // adjacent taps at most 2 source pixels apart: the IDP.2A kernel applies
     int tma_src_w = 0, tma_src_h = 0;    // TMA box of the source tile of the fast resize kernel

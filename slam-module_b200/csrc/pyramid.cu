@@ -31,6 +31,7 @@ struct PyrArgs {
     int w, h, pitch;
     unsigned long long dstride;
     const ResizeTap *xtab, *ytab;
+    const uint4 *xtile, *ytile;  // fast kernel: per-tile tap tables (pyramid_tile_tables)
     int src_tile_w, src_tile_h;  // smem extent of the source tile (bytes per row multiple of 4)
     int area2x;
     int f0;               // first frame of the launch
@@ -241,31 +242,21 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
     if (RESIZE) {
         // one thread pulls the source tile with TMA while the others stage the taps
         const int sx_lo = a.xtab[xlo].s0 & ~15, sy_lo = a.ytab[ylo].s0;   // 16-byte aligned box origin
-        const int sp = a.src_tile_w, spw = sp >> 2;
+        const int sp = a.src_tile_w;
         if (tid == 0) {
             mbar_init(bar, 1);
             mbar_expect_tx(bar, (uint32_t)(sp * a.src_tile_h));
             tma_load_3d(S, &tmap, sx_lo, sy_lo, f, bar);
         }
-        // taps of every window column / row; outside the image the nearest valid tap (value unused)
-        if (tid >= 32 && tid < 32 + 2 * COLP) {
-            const int c = tid - 32;
-            const ResizeTap t = a.xtab[min(max(x0 - 4 + c, xlo), xhi - 1)];
-            xt[c] = XTap{(uint32_t)(uint16_t)t.a0 | ((uint32_t)(uint16_t)t.a1 << 16), t.s0 - sx_lo};
-        } else if (tid >= 128 && tid < 128 + FRH) {
-            const ResizeTap t = a.ytab[min(max(y0 - 3 + tid - 128, ylo), yhi - 1)];
-            yt[tid - 128] = YTap{(uint32_t)((t.s0 - sy_lo) * sp), (uint32_t)((t.s1 - sy_lo) * sp),
-                                 (uint32_t)(uint16_t)t.a0 << 12, (uint32_t)(uint16_t)t.a1 << 12};
-        }
-        __syncthreads();          // taps staged, barrier initialised
+        // taps: the window rows' entries go to shared memory (read once per row by every thread), the thread's own column
+        // pair comes straight from the per-tile table (pyramid_tile_tables: nothing here depends on the frame)
+        if (tid >= 128 && tid < 128 + FRH) reinterpret_cast<uint4 *>(yt)[tid - 128] = __ldg(a.ytile + blockIdx.y * FRH + (tid - 128));
         const int cp = tid % COLP, rg = tid / COLP;
-        // column taps of this thread's pair: loop invariants
-        const uint4 tx = *reinterpret_cast<const uint4 *>(xt + 2 * cp);   // {coef_a, s0_a, coef_b, s0_b}
-        const int base = (int)tx.y >> 2;
-        const unsigned oa = tx.y & 3u, ob = tx.w - 4u * (unsigned)base;     // byte offsets in the 8-byte window
-        // one PRMT gathers {S[a], S[a+1], S[b], S[b+1]} of a source row from its aligned 8-byte window
-        const unsigned sel = (oa * 0x11u + 0x10u) | ((ob * 0x11u + 0x10u) << 8);
-        const uint32_t s_col = smem_u32(S) + 4u * (unsigned)base;          // shared-space address of the window column
+        // {coef a, coef b, byte offset of the aligned 8-byte source window, PRMT selector gathering {S[a], S[a+1], S[b], S[b+1]}}
+        const uint4 tx = __ldg(a.xtile + blockIdx.x * COLP + cp);
+        const unsigned sel = tx.w;
+        __syncthreads();          // taps staged, barrier initialised
+        const uint32_t s_col = smem_u32(S) + tx.z;                          // shared-space address of the window column
         uint32_t r_addr = smem_u32(R) + 2u * cp + (unsigned)(rg * ROWS_PER_G) * FW;
         const uint32_t yt_addr = smem_u32(yt) + (unsigned)(rg * ROWS_PER_G) * (unsigned)sizeof(YTap);
         mbar_wait(bar, 0);        // source tile landed
@@ -276,8 +267,8 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
                 const uint4 ty = lds128(yt_addr + k * (unsigned)sizeof(YTap));
                 const uint32_t a0 = s_col + ty.x, a1 = s_col + ty.y;
                 const uint32_t g0 = __byte_perm(lds32(a0), lds32(a0 + 4), sel), g1 = __byte_perm(lds32(a1), lds32(a1 + 4), sel);
-                const unsigned ha0 = __dp2a_lo(tx.x, g0, 0u), hb0 = __dp2a_hi(tx.z, g0, 0u);
-                const unsigned ha1 = __dp2a_lo(tx.x, g1, 0u), hb1 = __dp2a_hi(tx.z, g1, 0u);
+                const unsigned ha0 = __dp2a_lo(tx.x, g0, 0u), hb0 = __dp2a_hi(tx.y, g0, 0u);
+                const unsigned ha1 = __dp2a_lo(tx.x, g1, 0u), hb1 = __dp2a_hi(tx.y, g1, 0u);
                 // ((b * (h >> 4)) >> 16) == umulhi(b << 12, h & ~15): one LOP3 + one IMAD.HI per product
                 const unsigned va = (__umulhi(ty.w, ha1 & ~15u) + __umulhi(ty.z, ha0 & ~15u) + 2u) >> 2;
                 const unsigned vb = (__umulhi(ty.w, hb1 & ~15u) + __umulhi(ty.z, hb0 & ~15u) + 2u) >> 2;
@@ -304,13 +295,19 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
 
     // ---- pyramid plane: interior of R, 32-bit stores ----------------------------------------------
     if (RESIZE) {
-        uint8_t *dst = a.dst + (size_t)f * a.dstride + (size_t)y0 * a.pitch + x0;
-        const int wd = tid & 15;
+        const int wd = tid & 15, r0 = tid >> 4;                     // 16 words x 16 rows per sweep
         if (4 * wd < tw) {
-#pragma unroll 4
-            for (int r = tid >> 4; r < th; r += PYR_THREADS / 16)
-                *reinterpret_cast<uint32_t *>(dst + (size_t)r * a.pitch + 4 * wd) =
-                    *reinterpret_cast<const uint32_t *>(R + (r + 3) * FW + X0 + 4 * wd);
+            uint8_t *dst = a.dst + (size_t)f * a.dstride + (size_t)(y0 + r0) * a.pitch + x0 + 4 * wd;
+            const size_t step = (size_t)(PYR_THREADS / 16) * a.pitch;
+            uint32_t src = smem_u32(R) + (unsigned)((r0 + 3) * FW + X0 + 4 * wd);
+            if (th == FTH) {
+#pragma unroll
+                for (int i = 0; i < FTH / (PYR_THREADS / 16); ++i, dst += step, src += (PYR_THREADS / 16) * FW)
+                    *reinterpret_cast<uint32_t *>(dst) = lds32(src);
+            } else {
+                for (int r = r0; r < th; r += PYR_THREADS / 16, dst += step, src += (PYR_THREADS / 16) * FW)
+                    *reinterpret_cast<uint32_t *>(dst) = lds32(src);
+            }
         }
     }
     // ---- reflect-101: halo entries outside the image mirror resized pixels inside it ------------
@@ -449,6 +446,43 @@ int pyramid_fast_source_rows(const std::vector<ResizeTap> &yt, int h) {
 }
 int pyramid_fast_tile_rows() { return FTH; }
 
+// Per-tile tap tables of the fast resize kernel (host, at sg_create): what the kernel used to derive per CTA from xtab /
+// ytab.  xtile[tile column][COLP]: for the window column pair (x0 - 4 + 2cp, + 1), clamped to the in-image window like the
+// kernel's halo handling: {a0 | a1 << 16 of column a, of column b, byte offset of the aligned 8-byte source window inside
+// the TMA tile, PRMT selector gathering {S[a], S[a+1], S[b], S[b+1]} from it}.  ytile[tile row][FRH]: {byte offset of the
+// two source rows in the tile, b0 << 12, b1 << 12}.  The TMA box origin (xtab[xlo].s0 & ~15, ytab[ylo].s0) stays in the kernel.
+void pyramid_tile_tables(const std::vector<ResizeTap> &xt, const std::vector<ResizeTap> &yt, int w, int h, int src_pitch,
+                         std::vector<uint4> &xtile, std::vector<uint4> &ytile) {
+    xtile.clear(); ytile.clear();
+    for (int x0 = 0; x0 < w; x0 += TW) {
+        const int tw = std::min(TW, w - x0), xlo = std::max(x0 - 3, 0), xhi = std::min(x0 + tw + 3, w);
+        const int sx_lo = xt[xlo].s0 & ~15;
+        for (int cp = 0; cp < COLP; ++cp) {
+            const ResizeTap ta = xt[std::min(std::max(x0 - 4 + 2 * cp, xlo), xhi - 1)];
+            const ResizeTap tb = xt[std::min(std::max(x0 - 4 + 2 * cp + 1, xlo), xhi - 1)];
+            const int sa = ta.s0 - sx_lo, sb = tb.s0 - sx_lo, base = sa >> 2;
+            const unsigned oa = (unsigned)(sa & 3), ob = (unsigned)(sb - 4 * base);
+            uint4 e;
+            e.x = (uint32_t)(uint16_t)ta.a0 | ((uint32_t)(uint16_t)ta.a1 << 16);
+            e.y = (uint32_t)(uint16_t)tb.a0 | ((uint32_t)(uint16_t)tb.a1 << 16);
+            e.z = 4u * (unsigned)base;
+            e.w = (oa * 0x11u + 0x10u) | ((ob * 0x11u + 0x10u) << 8);
+            xtile.push_back(e);
+        }
+    }
+    for (int y0 = 0; y0 < h; y0 += FTH) {
+        const int th = std::min(FTH, h - y0), ylo = std::max(y0 - 3, 0), yhi = std::min(y0 + th + 3, h);
+        const int sy_lo = yt[ylo].s0;
+        for (int r = 0; r < FRH; ++r) {
+            const ResizeTap t = yt[std::min(std::max(y0 - 3 + r, ylo), yhi - 1)];
+            uint4 e;
+            e.x = (uint32_t)((t.s0 - sy_lo) * src_pitch); e.y = (uint32_t)((t.s1 - sy_lo) * src_pitch);
+            e.z = (uint32_t)(uint16_t)t.a0 << 12; e.w = (uint32_t)(uint16_t)t.a1 << 12;
+            ytile.push_back(e);
+        }
+    }
+}
+
 static size_t pyr_smem_bytes(const PyrArgs &a, bool resize) {
     size_t b = RH * RW + RH * TW * 2;
     if (resize) b += (size_t)a.src_tile_h * a.src_tile_w + sizeof(ResizeTap) * (TW + 6 + TH + 6);
@@ -497,6 +531,7 @@ int launch_pyramid(sg_ctx *ctx, int n_frames) {
             a.sstride = l == 1 ? ctx->level0_stride : P.frame_stride;
             a.dst = L.pyr;
             a.xtab = L.xtab; a.ytab = L.ytab;
+            a.xtile = L.xtile; a.ytile = L.ytile;
             a.src_tile_w = L.src_tile_w; a.src_tile_h = L.src_tile_h;
             a.area2x = L.area2x ? 1 : 0;
             PyrArgs fa = a;

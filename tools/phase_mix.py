@@ -7,10 +7,13 @@ args = [a for a in sys.argv[1:] if not a.startswith("--")]
 rep, cu = args[0], args[1]
 px = float(sys.argv[sys.argv.index("--px") + 1]) if "--px" in sys.argv else None
 launch = int(sys.argv[sys.argv.index("--launch") + 1]) if "--launch" in sys.argv else 0
+n_launches = int(sys.argv[sys.argv.index("--launches") + 1]) if "--launches" in sys.argv else 1   # launches captured in the report
 if px is not None:
     args = [a for a in args if a != str(int(px)) and a != sys.argv[sys.argv.index("--px") + 1]]
 if "--launch" in sys.argv:
     args = [a for a in args if a != sys.argv[sys.argv.index("--launch") + 1]]
+if "--launches" in sys.argv:
+    args = [a for a in args if a != sys.argv[sys.argv.index("--launches") + 1]]
 ranges = []
 for a in args[2:]:
     name, r = a.rsplit(":", 1)
@@ -27,7 +30,9 @@ for r in rows:
         continue
     if hdr and cur is not None and len(r) == len(hdr) and r[0].isdigit():
         cur.append(r)
-blk = blocks[launch]
+# the source page lists, per captured launch, one block per source file (the .cu first, then inlined headers)
+per = max(1, len(blocks) // n_launches)
+blk = [r for b in blocks[launch * per:(launch + 1) * per] for r in b]
 ci = hdr.index("Instructions Executed")
 fi = hdr.index("File Path") if "File Path" in hdr else None
 tot = sum(int(r[ci] or 0) for r in blk)

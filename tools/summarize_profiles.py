@@ -149,6 +149,8 @@ for rep in sorted(OUT.glob("prof_*_%s.ncu-rep" % tag)):
         launches = [(1, PX[1])] if kern == "pyr_fast_kernel" else [(0, px)]
         for launch, lpx in launches:
             cmd = [sys.executable, str(ROOT / "tools" / "phase_mix.py"), str(rep), cu] + ranges + ["--launch", str(launch)]
+            if kern == "pyr_fast_kernel":
+                cmd += ["--launches", "8"]
             if lpx:
                 cmd += ["--px", str(lpx)]
             ph = subprocess.run(cmd, capture_output=True, text=True).stdout
