@@ -213,14 +213,15 @@ __global__ void __launch_bounds__(PYR_THREADS) pyr_level_kernel(const PyrArgs a)
 constexpr int FTH = 64, FRH = FTH + 6;       // output tile rows, window rows (incl. the 3-px blur halo)
 constexpr int FR_BYTES = 6784;               // >= FRH * 96, multiple of 128
 constexpr int COLP = 36;                     // window column pairs (72 columns: x0 - 4 .. x0 + 67)
-constexpr int ROWG = 7, ROWS_PER_G = FRH / ROWG;   // 7 row groups x 10 rows; 7 * 36 = 252 threads busy
-static_assert(ROWG * ROWS_PER_G == FRH && ROWG * COLP <= PYR_THREADS, "resize work split");
+constexpr int TAILP = COLP - 32;             // column pairs beyond a warp's 32 lanes
+constexpr int MAIN_ROWS = 9;                 // warps 0..5: 9 window rows each, warps 6 and 7: 8 (54 + 16 = 70)
+static_assert(TAILP == 4 && PYR_THREADS == 256 && 6 * MAIN_ROWS + 2 * (MAIN_ROWS - 1) == FRH, "resize work split");
 template <bool RESIZE> struct RGeom { static constexpr int FW = RESIZE ? 80 : 96, X0 = RESIZE ? 4 : 16; };
 struct XTap { uint32_t coef; int32_t s0; };          // a0 | a1 << 16, source column relative to the tile
 struct YTap { uint32_t o0, o1, b0s, b1s; };          // byte offsets of the two source rows in S, coefficients << 12
 
 template <bool RESIZE>
-__global__ void __launch_bounds__(PYR_THREADS)
+__global__ void __launch_bounds__(PYR_THREADS, 8)
 pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
     // [TMA destination: source tile S (RESIZE) or R itself] [R] [Hp] [xt] [yt] [mbarrier]
     extern __shared__ __align__(128) uint8_t smem[];
@@ -241,44 +242,63 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
 
     if (RESIZE) {
         // one thread pulls the source tile with TMA while the others stage the taps
-        const int sx_lo = a.xtab[xlo].s0 & ~15, sy_lo = a.ytab[ylo].s0;   // 16-byte aligned box origin
-        const int sp = a.src_tile_w;
         if (tid == 0) {
+            const int sx_lo = a.xtab[xlo].s0 & ~15, sy_lo = a.ytab[ylo].s0;   // 16-byte aligned box origin
             mbar_init(bar, 1);
-            mbar_expect_tx(bar, (uint32_t)(sp * a.src_tile_h));
+            mbar_expect_tx(bar, (uint32_t)(a.src_tile_w * a.src_tile_h));
             tma_load_3d(S, &tmap, sx_lo, sy_lo, f, bar);
         }
         // taps: the window rows' entries go to shared memory (read once per row by every thread), the thread's own column
         // pair comes straight from the per-tile table (pyramid_tile_tables: nothing here depends on the frame)
         if (tid >= 128 && tid < 128 + FRH) reinterpret_cast<uint4 *>(yt)[tid - 128] = __ldg(a.ytile + blockIdx.y * FRH + (tid - 128));
-        const int cp = tid % COLP, rg = tid / COLP;
+        if (tid >= 128 + FRH && tid < 128 + FRH + TAILP)
+            reinterpret_cast<uint4 *>(xt)[tid - 128 - FRH] = __ldg(a.xtile + blockIdx.x * COLP + 32 + (tid - 128 - FRH));
+        // Work split: a warp never spans two window rows in one instruction of the main pass (lane = column pair 0..31 of ONE
+        // row, so the gathered source words and the 16-bit stores of a warp fall into distinct banks); the remaining
+        // TAILP column pairs are done 8 rows x TAILP pairs per warp instruction.  Per warp: 9 (8) main rows + 1 (2) tail passes.
+        const int lane = tid & 31, wp = tid >> 5;
         // {coef a, coef b, byte offset of the aligned 8-byte source window, PRMT selector gathering {S[a], S[a+1], S[b], S[b+1]}}
-        const uint4 tx = __ldg(a.xtile + blockIdx.x * COLP + cp);
-        const unsigned sel = tx.w;
+        const uint4 tx = __ldg(a.xtile + blockIdx.x * COLP + lane);
         __syncthreads();          // taps staged, barrier initialised
-        const uint32_t s_col = smem_u32(S) + tx.z;                          // shared-space address of the window column
-        uint32_t r_addr = smem_u32(R) + 2u * cp + (unsigned)(rg * ROWS_PER_G) * FW;
-        const uint32_t yt_addr = smem_u32(yt) + (unsigned)(rg * ROWS_PER_G) * (unsigned)sizeof(YTap);
+        const uint32_t s_base = smem_u32(S), r_base = smem_u32(R), yt_base = smem_u32(yt);
+        auto resize_px = [&](const uint4 &t, int row) {     // window row `row`, the column pair t describes -> two R bytes
+            const uint4 ty = lds128(yt_base + (unsigned)row * (unsigned)sizeof(YTap));
+            const uint32_t a0 = s_base + t.z + ty.x, a1 = s_base + t.z + ty.y;
+            const uint32_t g0 = __byte_perm(lds32(a0), lds32(a0 + 4), t.w), g1 = __byte_perm(lds32(a1), lds32(a1 + 4), t.w);
+            const unsigned ha0 = __dp2a_lo(t.x, g0, 0u), hb0 = __dp2a_hi(t.y, g0, 0u);
+            const unsigned ha1 = __dp2a_lo(t.x, g1, 0u), hb1 = __dp2a_hi(t.y, g1, 0u);
+            // ((b * (h >> 4)) >> 16) == umulhi(b << 12, h & ~15): one LOP3 + one IMAD.HI per product
+            const unsigned va = (__umulhi(ty.w, ha1 & ~15u) + __umulhi(ty.z, ha0 & ~15u) + 2u) >> 2;
+            const unsigned vb = (__umulhi(ty.w, hb1 & ~15u) + __umulhi(ty.z, hb0 & ~15u) + 2u) >> 2;
+            return va | (vb << 8);
+        };
         mbar_wait(bar, 0);        // source tile landed
         // partial tiles (right / bottom image edge): only the window columns / rows the blur of the tile reads
-        if (rg < ROWG && 2 * cp < tw + 8) {
-            const int rows = min(ROWS_PER_G, th + 6 - rg * ROWS_PER_G);   // full tiles: ROWS_PER_G, no per-row test
-            auto resize_row = [&](int k) {
-                const uint4 ty = lds128(yt_addr + k * (unsigned)sizeof(YTap));
-                const uint32_t a0 = s_col + ty.x, a1 = s_col + ty.y;
-                const uint32_t g0 = __byte_perm(lds32(a0), lds32(a0 + 4), sel), g1 = __byte_perm(lds32(a1), lds32(a1 + 4), sel);
-                const unsigned ha0 = __dp2a_lo(tx.x, g0, 0u), hb0 = __dp2a_hi(tx.y, g0, 0u);
-                const unsigned ha1 = __dp2a_lo(tx.x, g1, 0u), hb1 = __dp2a_hi(tx.y, g1, 0u);
-                // ((b * (h >> 4)) >> 16) == umulhi(b << 12, h & ~15): one LOP3 + one IMAD.HI per product
-                const unsigned va = (__umulhi(ty.w, ha1 & ~15u) + __umulhi(ty.z, ha0 & ~15u) + 2u) >> 2;
-                const unsigned vb = (__umulhi(ty.w, hb1 & ~15u) + __umulhi(ty.z, hb0 & ~15u) + 2u) >> 2;
-                sts16(r_addr + k * FW, va | (vb << 8));
-            };
-            if (rows == ROWS_PER_G) {
+        const int rows_needed = min(FRH, th + 6);
+        {
+            const int row0 = wp < 6 ? MAIN_ROWS * wp : 6 * MAIN_ROWS + (MAIN_ROWS - 1) * (wp - 6);
+            const int n = min(wp < 6 ? MAIN_ROWS : MAIN_ROWS - 1, rows_needed - row0);
+            if (2 * lane < tw + 8) {
+                const uint32_t r_addr = r_base + 2u * lane + (unsigned)row0 * FW;
+                if (n >= MAIN_ROWS - 1) {
 #pragma unroll
-                for (int k = 0; k < ROWS_PER_G; ++k) resize_row(k);
-            } else {
-                for (int k = 0; k < rows; ++k) resize_row(k);
+                    for (int k = 0; k < MAIN_ROWS - 1; ++k) sts16(r_addr + k * FW, resize_px(tx, row0 + k));
+                    if (n == MAIN_ROWS) sts16(r_addr + (MAIN_ROWS - 1) * FW, resize_px(tx, row0 + MAIN_ROWS - 1));
+                } else {
+                    for (int k = 0; k < n; ++k) sts16(r_addr + k * FW, resize_px(tx, row0 + k));
+                }
+            }
+        }
+        {
+            const int cq = lane & (TAILP - 1), rq = lane >> 2;
+            if (2 * (32 + cq) < tw + 8) {
+                const uint4 tt = lds128(smem_u32(xt) + (unsigned)cq * 16u);
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {                          // warp 6 also takes window rows 64 .. 69
+                    if (pass == 1 && wp != 6) break;
+                    const int row = (pass ? 64 : 8 * wp) + rq;
+                    if (row < rows_needed) sts16(r_base + 2u * (32 + cq) + (unsigned)row * FW, resize_px(tt, row));
+                }
             }
         }
     } else {
@@ -293,23 +313,8 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
     }
     __syncthreads();
 
-    // ---- pyramid plane: interior of R, 32-bit stores ----------------------------------------------
-    if (RESIZE) {
-        const int wd = tid & 15, r0 = tid >> 4;                     // 16 words x 16 rows per sweep
-        if (4 * wd < tw) {
-            uint8_t *dst = a.dst + (size_t)f * a.dstride + (size_t)(y0 + r0) * a.pitch + x0 + 4 * wd;
-            const size_t step = (size_t)(PYR_THREADS / 16) * a.pitch;
-            uint32_t src = smem_u32(R) + (unsigned)((r0 + 3) * FW + X0 + 4 * wd);
-            if (th == FTH) {
-#pragma unroll
-                for (int i = 0; i < FTH / (PYR_THREADS / 16); ++i, dst += step, src += (PYR_THREADS / 16) * FW)
-                    *reinterpret_cast<uint32_t *>(dst) = lds32(src);
-            } else {
-                for (int r = r0; r < th; r += PYR_THREADS / 16, dst += step, src += (PYR_THREADS / 16) * FW)
-                    *reinterpret_cast<uint32_t *>(dst) = lds32(src);
-            }
-        }
-    }
+    // (the pyramid plane itself -- the interior of R -- is stored by the vertical blur pass below: same rows, same words,
+    //  same address arithmetic as the blurred plane)
     // ---- reflect-101: halo entries outside the image mirror resized pixels inside it ------------
     // Rows first (whole words of the up to three rows above / below the image, copied from their mirror rows), then,
     // behind a barrier, the up to three columns left / right of the image for EVERY window row (the halo rows now hold
@@ -366,7 +371,11 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
         constexpr uint32_t D2 = K2 | (K1 << 8) | (K0 << 16);                        //        w2 bytes 0..2
         const int g = tid & 15;
         const int rp_end = min(FRH / 2, (th + 7) >> 1);     // partial tiles: rows / columns of the tile only
-        for (int rp = tid >> 4; rp < rp_end && 4 * g < tw; rp += PYR_THREADS / 16) {
+        // the two half warps take row pairs rp and rp + 2 (bits 0 and 1 of tid >> 4 swapped): their R rows are 4 apart,
+        // 4 * FW / 4 = 80 or 96 words = 16 banks mod 32 for FW = 80 (0 for 96, where the 24-word rows already interleave)
+        const int q = tid >> 4;
+        const int rp_first = RESIZE ? ((q & ~3) | ((q & 1) << 1) | ((q >> 1) & 1)) : q;
+        for (int rp = rp_first; rp < rp_end && 4 * g < tw; rp += PYR_THREADS / 16) {
             uint32_t o[2][4];
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
@@ -391,6 +400,8 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
         const int r0 = 4 * strip;
         if (r0 < th && 4 * g < tw) {
             uint8_t *bl = a.blur + (size_t)f * a.dstride + (size_t)(y0 + r0) * a.pitch + x0 + 4 * g;
+            const ptrdiff_t plane_delta = RESIZE ? a.dst - a.blur : 0;       // same layout, other plane
+            const uint32_t r_word = smem_u32(R) + (unsigned)((r0 + 3) * FW + X0 + 4 * g);
             uint4 P[5];
 #pragma unroll
             for (int j = 0; j < 5; ++j) P[j] = *reinterpret_cast<const uint4 *>(Hp + (2 * strip + j) * TW + 4 * g);
@@ -422,8 +433,16 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
                 const uint32_t even = __byte_perm(__byte_perm(ve[0], ve[1], 0x0062), __byte_perm(ve[2], ve[3], 0x0062), 0x5410);
                 const uint32_t odd = __byte_perm(__byte_perm(vo[0], vo[1], 0x0062), __byte_perm(vo[2], vo[3], 0x0062), 0x5410);
                 const int r = r0 + 2 * h;
-                if (r < th) *reinterpret_cast<uint32_t *>(bl + (size_t)(2 * h) * a.pitch) = even;
-                if (r + 1 < th) *reinterpret_cast<uint32_t *>(bl + (size_t)(2 * h + 1) * a.pitch) = odd;
+                if (r < th) {
+                    uint8_t *o = bl + (size_t)(2 * h) * a.pitch;
+                    *reinterpret_cast<uint32_t *>(o) = even;
+                    if (RESIZE) *reinterpret_cast<uint32_t *>(o + plane_delta) = lds32(r_word + (unsigned)(2 * h) * FW);
+                }
+                if (r + 1 < th) {
+                    uint8_t *o = bl + (size_t)(2 * h + 1) * a.pitch;
+                    *reinterpret_cast<uint32_t *>(o) = odd;
+                    if (RESIZE) *reinterpret_cast<uint32_t *>(o + plane_delta) = lds32(r_word + (unsigned)(2 * h + 1) * FW);
+                }
             }
         }
     }

@@ -30,9 +30,13 @@ for r in rows:
         continue
     if hdr and cur is not None and len(r) == len(hdr) and r[0].isdigit():
         cur.append(r)
-# the source page lists, per captured launch, one block per source file (the .cu first, then inlined headers)
-per = max(1, len(blocks) // n_launches)
-blk = [r for b in blocks[launch * per:(launch + 1) * per] for r in b]
+# the source page lists, per captured launch, one block per source file: the kernel's .cu first (many lines), then a few
+# short blocks for the inlined helpers (tma.cuh, crt headers) -- a launch starts at every block of 20 or more lines
+starts = [i for i, b in enumerate(blocks) if len(b) >= 20]
+lo = starts[launch]
+hi = starts[launch + 1] if launch + 1 < len(starts) else len(blocks)
+main_rows = set(id(r) for r in blocks[lo])
+blk = [r for b in blocks[lo:hi] for r in b]
 ci = hdr.index("Instructions Executed")
 fi = hdr.index("File Path") if "File Path" in hdr else None
 tot = sum(int(r[ci] or 0) for r in blk)
@@ -41,8 +45,8 @@ for r in blk:
     n = int(r[ci] or 0)
     line = int(r[0])
     where = "other"
-    if fi is not None and r[fi] and not r[fi].endswith(cu.split("/")[-1]):
-        where = "helpers (%s)" % r[fi].split("/")[-1]
+    if id(r) not in main_rows:
+        where = "inlined helpers (tma.cuh, ...)"
     else:
         for name, lo, hi in ranges:
             if lo <= line <= hi:
