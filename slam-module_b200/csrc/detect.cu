@@ -586,7 +586,9 @@ distribute_kernel(const __grid_constant__ GeomDev g, int node_cap_max, const uns
     __shared__ int tmp[16];
     __shared__ int s_m;
 
-    const int tid = threadIdx.x, l = blockIdx.x, f = blockIdx.y + g.frame0;
+    // grid (frames, levels): CTAs are issued frame-fastest, so the long level-0 CTAs of all frames start first and the
+    // short top-level ones fill the tail of the launch
+    const int tid = threadIdx.x, l = blockIdx.y, f = blockIdx.x + g.frame0;
     const LevelDev &L = g.lv[l];
     int ncand = cand_count[f * g.levels + l];
     if (ncand > L.cand_cap) ncand = 0;   // overflow already flagged by the FAST kernel
@@ -647,7 +649,7 @@ int launch_detect(sg_ctx *ctx, int n_frames) {
     const size_t smem = distribute_smem_bytes(nc_max);
     if (smem > 48 * 1024)
         SG_CUDA(ctx, cudaFuncSetAttribute(distribute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    distribute_kernel<<<dim3(g.levels, n_frames), DIST_THREADS, smem, ctx->stream>>>(
+    distribute_kernel<<<dim3(n_frames, g.levels), DIST_THREADS, smem, ctx->stream>>>(
         g, nc_max, ctx->d_cand, ctx->d_cand_node, ctx->d_cand_count, ctx->d_kp_xy, ctx->d_kp_resp, ctx->d_kp_count, ctx->d_err + ctx->err_slot);
     SG_LAUNCH_CHECK(ctx);
     mark(ctx, EV_DIST1);

@@ -94,8 +94,7 @@ KP = 513000
 PHASES = {
     "fast_cells_kernel": ("detect.cu", SUM_PX, ["setup+TMA:70-101", "pair words:102-117", "stage 1 (antipodal test, queue):118-155",
                                                 "stage 2 (exact score):156-219", "NMS:220-247", "output:248-262"]),
-    "pyr_fast_kernel": ("pyramid.cu", None, ["setup, taps, TMA wait:223-271", "resize:272-302", "plane store:303-315", "reflect-101:316-341",
-                                             "blur horizontal:342-377", "blur vertical:378-421"]),
+    "pyr_fast_kernel": ("pyramid.cu", None, None),      # ranges located by the kernel's own section comments, see pyramid_phases()
     "describe_kernel": ("describe.cu", None, ["tables, pattern:118-160", "slot lookup:161-220", "moments (TMA + IDP.4A):221-263",
                                               "angle, trig, outputs:264-275", "rBRIEF (TMA + sampling):276-322"]),
     "distribute_kernel": ("detect.cu", None, ["scan helpers:271-352", "initial nodes:353-421", "processing order (rank loop):422-461",
@@ -103,6 +102,26 @@ PHASES = {
                                               "move candidates + next quadrant counts:518-534", "termination:535-546",
                                               "strongest per node:547-566", "kernel entry:567-620"]),
 }
+def pyramid_phases():
+    """Source-line ranges of pyr_fast_kernel's phases, found by its section markers (so edits do not stale them)."""
+    lines = (ROOT / "slam-module_b200" / "csrc" / "pyramid.cu").read_text().splitlines()
+    def at(text, after=0):
+        for i in range(after, len(lines)):
+            if text in lines[i]:
+                return i + 1
+        raise SystemExit("pyramid.cu: marker %r not found" % text)
+    k = at("pyr_fast_kernel(const PyrArgs a")
+    rz = at("auto resize_px", k)
+    bo = at("// blur only: the", rz) - 1
+    rf = at("// ---- reflect-101", bo)
+    bh = at("// ---- horizontal pass", rf)
+    bv = at("// ---- vertical pass", bh)
+    end = next(i + 1 for i in range(bv, len(lines)) if lines[i] == "}")       # closing brace of the kernel
+    return ["setup, taps, TMA wait:%d-%d" % (k, rz - 1), "resize:%d-%d" % (rz, bo - 1), "blur-only load:%d-%d" % (bo, rf - 1),
+            "reflect-101:%d-%d" % (rf, bh - 1), "blur horizontal:%d-%d" % (bh, bv - 1), "blur vertical + plane store:%d-%d" % (bv, end)]
+
+
+PHASES["pyr_fast_kernel"] = ("pyramid.cu", None, pyramid_phases())
 traffic = {"tag": tag, "how": "ncu --set full --clock-control none on tools/full_batch_pass.py (256-frame single launches, profiling "
                               "layout of bench.py's stage timing); dram__bytes_read.sum + dram__bytes_write.sum per launch"}
 mix_md = ["# SASS opcode mix and per-phase instruction budget, %s\n\nFull-batch launches (256 frames of 640x480, 8 levels, 2000 keypoints; "
