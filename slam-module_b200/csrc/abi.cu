@@ -142,7 +142,7 @@ static int build_context(sg_ctx *ctx) {
     describe_box_dims(&mom_w, &mom_h, &blur_w, &blur_h);
     for (int l = 0; l < p.levels; ++l) {
         Level &L = ctx->lv[l];
-        if (int r = encode_plane_map(ctx, &L.map_blur, L.blur, L.w, L.h, L.pitch, L.frame_stride, p.max_frames, blur_w, blur_h)) return r;
+        if (int r = encode_plane_map(ctx, &L.map_blur, L.blur, L.w, L.h, L.pitch, L.frame_stride, p.max_frames, blur_w, blur_h, true)) return r;
         if (l > 0)
             if (int r = encode_plane_map(ctx, &L.map_mom, L.pyr, L.w, L.h, L.pitch, L.frame_stride, p.max_frames, mom_w, mom_h)) return r;
     }

@@ -237,7 +237,7 @@ struct Scratch {
 };
 // TMA descriptor of an 8-bit plane stack {w, h, frames} with a fixed box (tma.cpp).
 int encode_plane_map(sg_ctx *ctx, CUtensorMap *out, const uint8_t *base, int w, int h, int pitch, size_t frame_stride,
-                     int frames, int box_w, int box_h);
+                     int frames, int box_w, int box_h, bool swizzle64 = false);
 int encode_level0_maps(sg_ctx *ctx);
 // Record stage event i on the context's stream when profiling is on.
 inline void mark(sg_ctx *ctx, int i, bool first = false) {

@@ -95,7 +95,7 @@ constexpr int BLUR_R = 18;              // max |rotated pattern coordinate| (pat
 // (48 x 37 / 32 x 31 boxes, 28% fewer bytes) raises "illegal instruction" on sm_100a / driver 580 -- measured twice.
 constexpr int XALIGN = 16, BLUR_PITCH = 64, MOM_PITCH = 48;
 constexpr int BLUR_ROWS = 2 * BLUR_R + 1, MOM_ROWS = 2 * HALF_PATCH + 1;
-constexpr int PATCH_BYTES = 2432;                            // per buffer: >= 37 * 64 and >= 31 * 48, multiple of 128
+constexpr int PATCH_BYTES = 2560;                            // per buffer: >= 37 * 64 and >= 31 * 48, multiple of 512 (swizzle period)
 constexpr float ROUND_MAGIC = 12582912.f;        // 1.5 * 2^23
 constexpr int ROUND_MAGIC_BITS = 0x4B400000;
 
@@ -107,7 +107,24 @@ __device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
-__device__ __forceinline__ int rint_magic_bits(float v) { return __float_as_int(__fadd_rn(v, ROUND_MAGIC)); }
+// packed fp32 pairs of sm_100 (FMUL2 / FADD2): every element is an IEEE round-to-nearest operation of its own
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo_f32(unsigned long long v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi_f32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 
 struct DescMaps { CUtensorMap mom[SG_MAX_LEVELS], blur[SG_MAX_LEVELS]; };   // 48 x 31 boxes over the pyramid planes, 64 x 37 over the blurred ones
 
@@ -117,7 +134,7 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
                 int track_level, int n_frames, int split, DescOut o) {
     __shared__ uint32_t s_wu[4][16][MOM_WORDS];    // u weights (signed bytes) per (alignment, |v|, word)
     __shared__ uint32_t s_wm[4][16][MOM_WORDS];    // disc mask (0 / 1 bytes)
-    __shared__ __align__(128) uint8_t s_patch[DESC_WARPS][2 * PATCH_BYTES];   // two TMA destinations per warp
+    __shared__ __align__(512) uint8_t s_patch[DESC_WARPS][2 * PATCH_BYTES];   // two TMA destinations per warp, 512-byte aligned
     __shared__ __align__(8) uint64_t s_bar[DESC_WARPS][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -134,7 +151,8 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
         (&s_wm[0][0][0])[i] = wm;
     }
     // ---- this lane's 8 point pairs (descriptor byte = lane), as floats in registers -------------------------
-    float px0[8], py0[8], px1[8], py1[8];
+    // Both points of a pair share one packed register: {x0, x1} and {y0, y1} (FMUL2 / FADD2 work on two floats at once).
+    unsigned long long pxx[8], pyy[8];
     {
         const int4 *pat = reinterpret_cast<const int4 *>(d_pattern) + 2 * lane;
 #pragma unroll
@@ -143,8 +161,8 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
             const int ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                px0[4 * h + k] = (float)(int8_t)(ws[k] & 0xff); py0[4 * h + k] = (float)(int8_t)((ws[k] >> 8) & 0xff);
-                px1[4 * h + k] = (float)(int8_t)((ws[k] >> 16) & 0xff); py1[4 * h + k] = (float)(int8_t)((ws[k] >> 24) & 0xff);
+                pxx[4 * h + k] = pack_f32x2((float)(int8_t)(ws[k] & 0xff), (float)(int8_t)((ws[k] >> 16) & 0xff));
+                pyy[4 * h + k] = pack_f32x2((float)(int8_t)((ws[k] >> 8) & 0xff), (float)(int8_t)((ws[k] >> 24) & 0xff));
             }
         }
     }
@@ -293,21 +311,35 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
             const int ix = __shfl_sync(0xffffffffu, k.ix, j);
             const float c_ = __shfl_sync(0xffffffffu, cs, j), s_ = __shfl_sync(0xffffffffu, sn, j);
             const int off = (ix - BLUR_R) & (XALIGN - 1);
-            const uint8_t *patch_j = patch + b * PATCH_BYTES;
             mbar_wait(bars + b, (bar_phase >> b) & 1u);
             bar_phase ^= 1u << b;
-            // sample index = (r + 18) * 64 + (c + 18 + off); r, c arrive as MAGIC_BITS + integer
+            // The blurred box is stored with TMA's 64-byte swizzle: byte i = row * 64 + column of the box lives at
+            // i ^ ((i >> 3) & 0x30) (16-byte chunk index XOR bits 7-8 of the offset; the buffer is 512-byte aligned, so the
+            // shared address itself can be swizzled).  Un-swizzled, bank = 16 * (row & 1) + column / 4 and the 32 samples of a
+            // warp instruction pile up on the few banks under the patch centre (5.5 wavefronts per LDS measured); swizzled,
+            // eight consecutive rows of one column chunk use eight different bank groups.
+            // sample offset = (r + 18) * 64 + (c + 18 + off); r, c arrive as MAGIC_BITS + integer
             // (unsigned arithmetic: the magic offsets cancel modulo 2^32)
-            const unsigned bias = (unsigned)(BLUR_R * BLUR_PITCH + BLUR_R + off) - (unsigned)ROUND_MAGIC_BITS * (unsigned)(BLUR_PITCH + 1);
+            const unsigned bias = smem_u32(patch + b * PATCH_BYTES) + (unsigned)(BLUR_R * BLUR_PITCH + BLUR_R + off)
+                                  - (unsigned)ROUND_MAGIC_BITS * (unsigned)(BLUR_PITCH + 1);
+            auto sample = [&](unsigned r_bits, unsigned c_bits) {
+                const unsigned i = r_bits * BLUR_PITCH + c_bits + bias;
+                return (int)lds_u8(i ^ ((i >> 3) & 0x30u));
+            };
+            // rotation (orb_extractor.cpp:31-45): row = x * sin + y * cos, column = x * cos - y * sin, every product and sum
+            // rounded to float on its own.  The products of both points run as packed FMUL2; the sums stay scalar FADDs
+            // (ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 -- one rounding too few -- even with --fmad=false);
+            // x * cos - y * sin is computed as x * cos + y * (-sin), the same value bit for bit.
+            const unsigned long long cc = pack_f32x2(c_, c_), ss = pack_f32x2(s_, s_), ns = pack_f32x2(-s_, -s_);
+            const unsigned long long magic2 = pack_f32x2(ROUND_MAGIC, ROUND_MAGIC);
             unsigned bits = 0;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const int r0 = rint_magic_bits(__fadd_rn(__fmul_rn(px0[q], s_), __fmul_rn(py0[q], c_)));
-                const int c0 = rint_magic_bits(__fsub_rn(__fmul_rn(px0[q], c_), __fmul_rn(py0[q], s_)));
-                const int r1 = rint_magic_bits(__fadd_rn(__fmul_rn(px1[q], s_), __fmul_rn(py1[q], c_)));
-                const int c1 = rint_magic_bits(__fsub_rn(__fmul_rn(px1[q], c_), __fmul_rn(py1[q], s_)));
-                const int v0 = patch_j[(unsigned)r0 * BLUR_PITCH + (unsigned)c0 + bias];
-                const int v1 = patch_j[(unsigned)r1 * BLUR_PITCH + (unsigned)c1 + bias];
+                const unsigned long long xs = mul_f32x2(pxx[q], ss), yc = mul_f32x2(pyy[q], cc);
+                const unsigned long long xc = mul_f32x2(pxx[q], cc), yn = mul_f32x2(pyy[q], ns);
+                const unsigned long long rr = add_f32x2(pack_f32x2(__fadd_rn(lo_f32(xs), lo_f32(yc)), __fadd_rn(hi_f32(xs), hi_f32(yc))), magic2);
+                const unsigned long long cl = add_f32x2(pack_f32x2(__fadd_rn(lo_f32(xc), lo_f32(yn)), __fadd_rn(hi_f32(xc), hi_f32(yn))), magic2);
+                const int v0 = sample((unsigned)rr, (unsigned)cl), v1 = sample((unsigned)(rr >> 32), (unsigned)(cl >> 32));
                 bits |= (v0 < v1 ? 1u : 0u) << q;
             }
             unsigned word = bits << (8 * (lane & 3));

@@ -21,17 +21,18 @@ static EncodeTiledFn encode_fn() {
 }
 
 int encode_plane_map(sg_ctx *ctx, CUtensorMap *out, const uint8_t *base, int w, int h, int pitch, size_t frame_stride,
-                     int frames, int box_w, int box_h) {
+                     int frames, int box_w, int box_h, bool swizzle64) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(ctx, SG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     if (((uintptr_t)base & 15) || (pitch & 15) || (frame_stride & 15) || (box_w & 15) || box_w > 256 || box_h > 256)
         return fail(ctx, SG_ERR_INVALID, "plane not addressable by TMA (base/pitch/stride must be 16-byte multiples, box <= 256)");
+    if (swizzle64 && box_w != 64) return fail(ctx, SG_ERR_INVALID, "the 64-byte swizzle needs a 64-byte box row");
     const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
     const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
     const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, SG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return SG_OK;
