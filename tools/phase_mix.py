@@ -50,8 +50,8 @@ for addr, n, ln in blocks[lo]["sass"]:
         if a <= ln <= b:
             where[addr] = name
             break
-    else:
-        where.setdefault(addr, "other")
+    # (a line of the .cu outside every range -- a __device__ helper defined above the kernel -- is treated like an
+    #  inlined header helper: the phase of its neighbours)
 for b in blocks[lo + 1:hi]:
     for addr, n, ln in b["sass"]:
         count.setdefault(addr, n)

@@ -91,37 +91,41 @@ W8, H8 = [640, 533, 444, 370, 309, 257, 214, 179], [480, 400, 333, 278, 231, 193
 PX = [w * h * 256 for w, h in zip(W8, H8)]
 SUM_PX = sum(PX)
 KP = 513000
-PHASES = {
-    "fast_cells_kernel": ("detect.cu", SUM_PX, ["setup+TMA:70-101", "pair words:102-117", "stage 1 (antipodal test, queue):118-155",
-                                                "stage 2 (exact score):156-219", "NMS:220-247", "output:248-262"]),
-    "pyr_fast_kernel": ("pyramid.cu", None, None),      # ranges located by the kernel's own section comments, see pyramid_phases()
-    "describe_kernel": ("describe.cu", None, ["tables, pattern:118-160", "slot lookup:161-220", "moments (TMA + IDP.4A):221-263",
-                                              "angle, trig, outputs:264-275", "rBRIEF (TMA + sampling):276-322"]),
+PHASES = {      # kernel -> (source file, pixels of the launch or None, ["phase:lo-hi", ...]); the first three are filled below
     "distribute_kernel": ("detect.cu", None, ["scan helpers:271-352", "initial nodes:353-421", "processing order (rank loop):422-461",
                                               "children scan, stop point:462-490", "new node table:491-517",
                                               "move candidates + next quadrant counts:518-534", "termination:535-546",
-                                              "strongest per node:547-566", "kernel entry:567-620"]),
+                                              "strongest per node:547-566", "kernel entry:567-626"]),
 }
-def pyramid_phases():
-    """Source-line ranges of pyr_fast_kernel's phases, found by its section markers (so edits do not stale them)."""
-    lines = (ROOT / "slam-module_b200" / "csrc" / "pyramid.cu").read_text().splitlines()
-    def at(text, after=0):
+def marker_phases(cu, start, sections):
+    """Source-line ranges of a kernel's phases, located by its own section comments (so edits do not stale them):
+    `start` = text on the kernel's signature line, sections = [(phase name, text that opens it), ...] in file order; a
+    phase runs to the line before the next one, the last to the closing brace of the kernel."""
+    lines = (ROOT / "slam-module_b200" / "csrc" / cu).read_text().splitlines()
+    def at(text, after):
         for i in range(after, len(lines)):
             if text in lines[i]:
                 return i + 1
-        raise SystemExit("pyramid.cu: marker %r not found" % text)
-    k = at("pyr_fast_kernel(const PyrArgs a")
-    rz = at("auto resize_px", k)
-    bo = at("// blur only: the", rz) - 1
-    rf = at("// ---- reflect-101", bo)
-    bh = at("// ---- horizontal pass", rf)
-    bv = at("// ---- vertical pass", bh)
-    end = next(i + 1 for i in range(bv, len(lines)) if lines[i] == "}")       # closing brace of the kernel
-    return ["setup, taps, TMA wait:%d-%d" % (k, rz - 1), "resize:%d-%d" % (rz, bo - 1), "blur-only load:%d-%d" % (bo, rf - 1),
-            "reflect-101:%d-%d" % (rf, bh - 1), "blur horizontal:%d-%d" % (bh, bv - 1), "blur vertical + plane store:%d-%d" % (bv, end)]
+        raise SystemExit("%s: marker %r not found" % (cu, text))
+    k = at(start, 0)
+    pos, cur = [], k
+    for name, text in sections:
+        cur = at(text, cur) if text else k
+        pos.append((name, cur))
+    end = next(i + 1 for i in range(pos[-1][1], len(lines)) if lines[i] == "}")
+    return ["%s:%d-%d" % (name, lo, (pos[i + 1][1] - 1) if i + 1 < len(pos) else end) for i, (name, lo) in enumerate(pos)]
 
 
-PHASES["pyr_fast_kernel"] = ("pyramid.cu", None, pyramid_phases())
+PHASES["pyr_fast_kernel"] = ("pyramid.cu", None, marker_phases("pyramid.cu", "pyr_fast_kernel(const PyrArgs a", [
+    ("setup, taps, TMA wait", None), ("resize", "auto resize_px"), ("blur-only load", "// blur only: the"),
+    ("reflect-101", "// ---- reflect-101"), ("blur horizontal", "// ---- horizontal pass"),
+    ("blur vertical + plane store", "// ---- vertical pass")]))
+PHASES["fast_cells_kernel"] = ("detect.cu", SUM_PX, marker_phases("detect.cu", "fast_cells_kernel(const __grid_constant__", [
+    ("setup+TMA", None), ("pair words", "// ---- pair words"), ("stage 1 (antipodal test, queue)", "// Two passes at most"),
+    ("stage 2 (exact score)", "// ---- stage 2"), ("NMS", "// ---- cell-local NMS"), ("output", "if (nkeep == 0) return;")]))
+PHASES["describe_kernel"] = ("describe.cu", None, marker_phases("describe.cu", "describe_kernel(const __grid_constant__", [
+    ("tables, pattern", None), ("slot lookup", "const int groups_per_frame"), ("moments (TMA + IDP.4A)", "// ---- phase A"),
+    ("angle, trig, outputs", "// ---- phase B"), ("rBRIEF (TMA + sampling)", "// ---- phase C")]))
 traffic = {"tag": tag, "how": "ncu --set full --clock-control none on tools/full_batch_pass.py (256-frame single launches, profiling "
                               "layout of bench.py's stage timing); dram__bytes_read.sum + dram__bytes_write.sum per launch"}
 mix_md = ["# SASS opcode mix and per-phase instruction budget, %s\n\nFull-batch launches (256 frames of 640x480, 8 levels, 2000 keypoints; "
