@@ -132,8 +132,9 @@ __global__ void __launch_bounds__(DESC_WARPS * 32)
 describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescMaps maps, const int *kp_xy, const int *kp_count,
                 const int *trk_xy, const float *trk_pt, const int *trk_id, const int *trk_count,
                 int track_level, int n_frames, int split, DescOut o) {
-    __shared__ uint32_t s_wu[4][16][MOM_WORDS];    // u weights (signed bytes) per (alignment, |v|, word)
-    __shared__ uint32_t s_wm[4][16][MOM_WORDS];    // disc mask (0 / 1 bytes)
+    // moment weights per (alignment of the window inside its word, |v|, word): the signed byte u and the byte |v| inside the
+    // disc, 0 outside, so that m10 and the two halves of m01 are two IDP.4A per pixel word with no other arithmetic
+    __shared__ uint32_t s_w[2][4][16][MOM_WORDS];      // [0]: u, [1]: |v|
     __shared__ __align__(512) uint8_t s_patch[DESC_WARPS][2 * PATCH_BYTES];   // two TMA destinations per warp, 512-byte aligned
     __shared__ __align__(8) uint64_t s_bar[DESC_WARPS][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -141,16 +142,15 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
     // ---- per-CTA tables --------------------------------------------------------------------------------
     for (int i = threadIdx.x; i < 4 * 16 * MOM_WORDS; i += DESC_WARPS * 32) {
         const int w = i % MOM_WORDS, av = (i / MOM_WORDS) % 16, off = i / (MOM_WORDS * 16);
-        uint32_t wu = 0, wm = 0;
+        uint32_t wu = 0, wv = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int u = 4 * w + j - HALF_PATCH - off;
-            if (abs(u) <= c_umax[av]) { wu |= (uint32_t)(uint8_t)(int8_t)u << (8 * j); wm |= 1u << (8 * j); }
+            if (abs(u) <= c_umax[av]) { wu |= (uint32_t)(uint8_t)(int8_t)u << (8 * j); wv |= (uint32_t)av << (8 * j); }
         }
-        (&s_wu[0][0][0])[i] = wu;
-        (&s_wm[0][0][0])[i] = wm;
+        (&s_w[0][0][0][0])[i] = wu;
+        (&s_w[1][0][0][0])[i] = wv;
     }
-    // ---- this lane's 8 point pairs (descriptor byte = lane), as floats in registers -------------------------
     // Both points of a pair share one packed register: {x0, x1} and {y0, y1} (FMUL2 / FADD2 work on two floats at once).
     unsigned long long pxx[8], pyy[8];
     {
@@ -262,17 +262,23 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
                 bar_phase ^= 1u << b;
                 int m10 = 0, m01 = 0;
                 if (lane < 3 * MOM_WORDS) {
-                    const uint8_t *c = patch + b * PATCH_BYTES + mrow * MOM_PITCH + (off16 & ~3) + 4 * mword;
+                    // lane = (row mod 3, word): window rows mrow, mrow + 3, ...; v = row - 15 is negative for i < 5 (|v| = 15 -
+                    // mrow - 3 i) and mrow + 3 (i - 5) from there on, so every load address is a lane base plus an immediate
+                    const uint32_t pix_a = smem_u32(patch + b * PATCH_BYTES + mrow * MOM_PITCH + (off16 & ~3) + 4 * mword);
+                    const uint32_t up_a = smem_u32(&s_w[0][off][HALF_PATCH - mrow][mword]), dn_a = smem_u32(&s_w[0][off][mrow][mword]);
+                    constexpr uint32_t WV = sizeof(s_w[0]);      // from a u word to the |v| word of the same (alignment, row, word)
+                    int m01n = 0;
 #pragma unroll
                     for (int i = 0; i < 11; ++i) {
-                        const int v = 3 * i + mrow - HALF_PATCH;
-                        if (v <= HALF_PATCH) {
-                            const uint32_t pix = *reinterpret_cast<const uint32_t *>(c + 3 * i * MOM_PITCH);
-                            const int av = abs(v);
-                            m10 = dp4a_us(pix, (int)s_wu[off][av][mword], m10);
-                            m01 += v * (int)__dp4a(pix, s_wm[off][av][mword], 0u);
+                        if (3 * i + mrow < MOM_ROWS) {       // false only for i = 10, mrow > 0
+                            const uint32_t pix = lds32(pix_a + 3 * i * MOM_PITCH);
+                            const uint32_t wa = i < 5 ? up_a - 3 * i * MOM_WORDS * 4 : dn_a + 3 * (i - 5) * MOM_WORDS * 4;
+                            m10 = dp4a_us(pix, (int)lds32(wa), m10);
+                            if (i < 5) m01n = (int)__dp4a(pix, lds32(wa + WV), (unsigned)m01n);
+                            else m01 = (int)__dp4a(pix, lds32(wa + WV), (unsigned)m01);
                         }
                     }
+                    m01 -= m01n;
                 }
                 m10 = __reduce_add_sync(0xffffffffu, m10);     // (also orders this keypoint's reads before the next issue)
                 m01 = __reduce_add_sync(0xffffffffu, m01);
