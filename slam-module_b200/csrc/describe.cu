@@ -242,13 +242,11 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
         // j + 1 while the warp sums keypoint j from shared memory
         int my_m10 = 0, my_m01 = 0;
         {
-            auto issue = [&](int j) {
-                const int ix = __shfl_sync(0xffffffffu, k.ix, j), iy = __shfl_sync(0xffffffffu, k.iy, j);
-                const int l = __shfl_sync(0xffffffffu, k.l, j);
-                if (lane == 0) {
+            auto issue = [&](int j) {       // lane j owns keypoint j: it issues the load itself (no shuffles of the box origin)
+                if (lane == j) {
                     uint64_t *bar = bars + (j & 1);
                     mbar_expect_tx(bar, MOM_ROWS * MOM_PITCH);
-                    tma_load_3d(patch + (j & 1) * PATCH_BYTES, &maps.mom[l], (ix - HALF_PATCH) & ~(XALIGN - 1), iy - HALF_PATCH, f, bar);
+                    tma_load_3d(patch + (j & 1) * PATCH_BYTES, &maps.mom[k.l], (k.ix - HALF_PATCH) & ~(XALIGN - 1), k.iy - HALF_PATCH, f, bar);
                 }
             };
             __syncwarp();   // every lane is done with both buffers (previous group)
@@ -300,12 +298,10 @@ describe_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ DescM
         // ---- phase C: rBRIEF on the blurred level -----------------------------------------------------------
         // same double buffering with 64 x 37 boxes of the blurred plane
         auto issue_blur = [&](int j) {
-            const int ix = __shfl_sync(0xffffffffu, k.ix, j), iy = __shfl_sync(0xffffffffu, k.iy, j);
-            const int l = __shfl_sync(0xffffffffu, k.l, j);
-            if (lane == 0) {
+            if (lane == j) {
                 uint64_t *bar = bars + (j & 1);
                 mbar_expect_tx(bar, BLUR_ROWS * BLUR_PITCH);
-                tma_load_3d(patch + (j & 1) * PATCH_BYTES, &maps.blur[l], (ix - BLUR_R) & ~(XALIGN - 1), iy - BLUR_R, f, bar);
+                tma_load_3d(patch + (j & 1) * PATCH_BYTES, &maps.blur[k.l], (k.ix - BLUR_R) & ~(XALIGN - 1), k.iy - BLUR_R, f, bar);
             }
         };
         __syncwarp();       // phase A's reads are complete
