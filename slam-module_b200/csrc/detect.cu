@@ -186,19 +186,19 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
                 const unsigned vb = (c ^ cm) | 0x01000100u;
                 // score = max over the 16 arcs of min over the arc's 9 ring pixels of e_j = vb - r'_j
                 //       = vb - min over arcs of max over the arc of r'_j   (r' = ring pixels, complemented for bright).
-                // Sliding max over windows of 9 of the circular sequence, by doubling: 2, 4, 8, then +1.
-                unsigned d[16], m2[16], m4[16];
+                // Sliding max over windows of 9 of the circular sequence as 3 x 3 with the three-input VIMNMX3:
+                // m3[j] = max(d[j..j+2]), window j = max(m3[j], m3[j+3], m3[j+6]); 16 + 16 operations, then 8 for the minimum
+                // over the 16 windows (the doubling scheme 2, 4, 8, +1 needs 56).
+                unsigned d[16], m3[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) d[j] = r[j] ^ cm;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) m2[j] = __vmaxu2(d[j], d[(j + 1) & 15]);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) m4[j] = __vmaxu2(m2[j], m2[(j + 2) & 15]);
+                for (int j = 0; j < 16; ++j) m3[j] = __vimax3_u16x2(d[j], d[(j + 1) & 15], d[(j + 2) & 15]);
                 unsigned hi = 0xffffffffu;
 #pragma unroll
-                for (int j = 0; j < 16; j += 2)           // three-input min / max (VIMNMX3): 24 instead of 48 operations
-                    hi = __vimin3_u16x2(hi, __vimax3_u16x2(m4[j], m4[(j + 4) & 15], d[(j + 8) & 15]),
-                                        __vimax3_u16x2(m4[j + 1], m4[(j + 5) & 15], d[(j + 9) & 15]));
+                for (int j = 0; j < 16; j += 2)
+                    hi = __vimin3_u16x2(hi, __vimax3_u16x2(m3[j], m3[(j + 3) & 15], m3[(j + 6) & 15]),
+                                        __vimax3_u16x2(m3[j + 1], m3[(j + 4) & 15], m3[(j + 7) & 15]));
                 const unsigned lo = vb - hi;
                 const int s0 = (int)(lo & 0xffffu) - 257, s1 = (int)(lo >> 16) - 257;
                 const bool w0 = sa && s0 >= t, w1 = sb && s1 >= t;

@@ -197,11 +197,12 @@ __global__ void __launch_bounds__(PYR_THREADS) pyr_level_kernel(const PyrArgs a)
 // -------------------------------------------------------------------------------------------------
 // Fast path (scale factor <= 2, no INTER_AREA switch): same arithmetic, restructured for the integer
 // pipes, 64 x 64 output tiles (halo work 70/64 instead of 38/32, half the per-CTA fixed cost per pixel):
-//   resize    : a thread owns one PAIR of window columns and walks down 10 window rows, so the column
-//               taps (16-bit coefficient pair, byte selectors into an aligned 8-byte source window)
-//               are loop invariants; per row: 4 LDS, 4 PRMT, 4 IDP.2A (S0*a0 + S1*a1 of both columns
-//               and both source rows), then the two truncating vertical products.  Out-of-image
-//               window entries use clamped taps (overwritten by the mirror pass): no guards in the loop
+//   resize    : a thread owns one PAIR of window columns and walks down 9 (8) window rows of its warp, so the
+//               column taps (16-bit coefficient pair, byte selectors into an aligned 8-byte source window) are
+//               loop invariants and the 32 lanes of an instruction touch ONE window row (no bank conflicts); the
+//               last 4 of the 36 column pairs run as an 8-row x 4-pair tail.  Per row: 4 LDS, 2 PRMT, 4 IDP.2A
+//               (S0*a0 + S1*a1 of both columns and both source rows), then the two truncating vertical products.
+//               Out-of-image window entries use clamped taps (overwritten by the mirror pass): no guards in the loop
 //   blur H    : IDP.4A on byte windows (two per output), two rows per item, stored as vertical u16
 //               pairs Hp[r/2][c] = H[r][c] | H[r+1][c] << 16
 //   blur V    : IDP.2A on the vertical pairs (4 per output, rounding constant in the accumulator),
@@ -223,14 +224,14 @@ struct YTap { uint32_t o0, o1, b0s, b1s; };          // byte offsets of the two 
 template <bool RESIZE>
 __global__ void __launch_bounds__(PYR_THREADS, 8)
 pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
-    // [TMA destination: source tile S (RESIZE) or R itself] [R] [Hp] [xt] [yt] [mbarrier]
+    // [TMA destination: source tile S (RESIZE) or R itself] [R] [Hp] [taps of the 4 tail column pairs] [yt] [mbarrier]
     extern __shared__ __align__(128) uint8_t smem[];
     const int s_bytes = RESIZE ? (((a.src_tile_h + 1) * a.src_tile_w + 127) & ~127) : 0;
     uint8_t *S = smem;                                                   // [src_tile_h][src_tile_w] (RESIZE)
     uint8_t *R = smem + s_bytes;                                         // [FRH][FW]
     uint32_t *Hp = reinterpret_cast<uint32_t *>(R + FR_BYTES);           // [FRH/2][TW]
-    XTap *xt = reinterpret_cast<XTap *>(R + FR_BYTES + (FRH / 2) * TW * 4);   // [72]
-    YTap *yt = reinterpret_cast<YTap *>(xt + 2 * COLP);                  // [FRH + 2]
+    uint4 *xtail = reinterpret_cast<uint4 *>(R + FR_BYTES + (FRH / 2) * TW * 4);   // [TAILP] (576 bytes reserved)
+    YTap *yt = reinterpret_cast<YTap *>(xtail + 2 * COLP * sizeof(XTap) / sizeof(uint4));   // [FRH + 2]
     uint64_t *bar = reinterpret_cast<uint64_t *>(yt + FRH + 2);
 
     constexpr int FW = RGeom<RESIZE>::FW, X0 = RGeom<RESIZE>::X0;   // R pitch; R column of x0
@@ -252,7 +253,7 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
         // pair comes straight from the per-tile table (pyramid_tile_tables: nothing here depends on the frame)
         if (tid >= 128 && tid < 128 + FRH) reinterpret_cast<uint4 *>(yt)[tid - 128] = __ldg(a.ytile + blockIdx.y * FRH + (tid - 128));
         if (tid >= 128 + FRH && tid < 128 + FRH + TAILP)
-            reinterpret_cast<uint4 *>(xt)[tid - 128 - FRH] = __ldg(a.xtile + blockIdx.x * COLP + 32 + (tid - 128 - FRH));
+            xtail[tid - 128 - FRH] = __ldg(a.xtile + blockIdx.x * COLP + 32 + (tid - 128 - FRH));
         // Work split: a warp never spans two window rows in one instruction of the main pass (lane = column pair 0..31 of ONE
         // row, so the gathered source words and the 16-bit stores of a warp fall into distinct banks); the remaining
         // TAILP column pairs are done 8 rows x TAILP pairs per warp instruction.  Per warp: 9 (8) main rows + 1 (2) tail passes.
@@ -292,7 +293,7 @@ pyr_fast_kernel(const PyrArgs a, const __grid_constant__ CUtensorMap tmap) {
         {
             const int cq = lane & (TAILP - 1), rq = lane >> 2;
             if (2 * (32 + cq) < tw + 8) {
-                const uint4 tt = lds128(smem_u32(xt) + (unsigned)cq * 16u);
+                const uint4 tt = lds128(smem_u32(xtail) + (unsigned)cq * 16u);
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {                          // warp 6 also takes window rows 64 .. 69
                     if (pass == 1 && wp != 6) break;
