@@ -166,23 +166,23 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
             r[4] = wo[4];           r[5] = wo[-WP + 4];     r[6] = we[-2 * WP + 1];  r[7] = wo[-3 * WP + 3];
             r[8] = we[-3 * WP];     r[9] = wo[-3 * WP + 2]; r[10] = we[-2 * WP - 1]; r[11] = wo[-WP + 1];
             r[12] = wo[1];          r[13] = wo[WP + 1];     r[14] = we[2 * WP - 1];  r[15] = wo[3 * WP + 2];
-            // polarity each lane can still have (bit 0 dark, bit 1 bright), from the compass pixels
-            unsigned fa, fbb;
+            // polarity each 16-bit lane can still have, from the compass pixels: bit 15 / 31 of `dark` and `bright`
+            // (dead entries and pixels outside the cell: neither)
+            unsigned dark, bright;
             {
                 const unsigned vb = c | 0x01000100u;
                 const unsigned A = __vmaxu2(__vminu2(r[0], r[8]), __vminu2(r[4], r[12]));
                 const unsigned B = __vminu2(__vmaxu2(r[0], r[8]), __vmaxu2(r[4], r[12]));
-                const unsigned fd = ~(thiH - vb + A) & 0x80008000u, fb = ~(vb - B + Hmtlo) & 0x80008000u;
-                fa = ((fd >> 15) & 1u) | ((fb >> 14) & 2u);
-                fbb = (fd >> 31) | ((fb >> 30) & 2u);
-                if (!live || 2 * k >= cw) fa = 0;
-                if (!live || 2 * k + 1 >= cw) fbb = 0;
+                const unsigned ok = (live && 2 * k < cw ? 0x00008000u : 0u) | (live && 2 * k + 1 < cw ? 0x80000000u : 0u);
+                dark = ~(thiH - vb + A) & ok;
+                bright = ~(vb - B + Hmtlo) & ok;
             }
             uint8_t *rp = resp + (y + 1) * RPW + 4 + 2 * k;
             // dark first; a lane that can have both polarities (rare) is scored a second time as bright
-            unsigned sa = (fa & 1u) ? 1u : fa, sb = (fbb & 1u) ? 1u : fbb;
+            unsigned act = dark | bright, br = bright & ~dark;     // lanes scored in this round; of those, the bright ones
+            const unsigned won_bias = (unsigned)(0x8000 - 257 - t) * 0x00010001u;
             for (int round = 0; round < 2; ++round) {
-                const unsigned cm = (sa == 2u ? 0x000000ffu : 0u) | (sb == 2u ? 0x00ff0000u : 0u);   // complement -> bright test
+                const unsigned cm = (br >> 15) * 0xffu;             // 0x000000ff / 0x00ff0000: complement -> bright test
                 const unsigned vb = (c ^ cm) | 0x01000100u;
                 // score = max over the 16 arcs of min over the arc's 9 ring pixels of e_j = vb - r'_j
                 //       = vb - min over arcs of max over the arc of r'_j   (r' = ring pixels, complemented for bright).
@@ -199,10 +199,11 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
                 for (int j = 0; j < 16; j += 2)
                     hi = __vimin3_u16x2(hi, __vimax3_u16x2(m3[j], m3[(j + 3) & 15], m3[(j + 6) & 15]),
                                         __vimax3_u16x2(m3[j + 1], m3[(j + 4) & 15], m3[(j + 7) & 15]));
-                const unsigned lo = vb - hi;
-                const int s0 = (int)(lo & 0xffffu) - 257, s1 = (int)(lo >> 16) - 257;
-                const bool w0 = sa && s0 >= t, w1 = sb && s1 >= t;
-                if (w0 || w1) {
+                const unsigned lo = vb - hi;                        // score + 257 per lane, 1 .. 511
+                const unsigned won = (lo + won_bias) & act;         // bit 15 / 31: scored in this round and score >= t
+                if (won) {
+                    const bool w0 = (won & 0x8000u) != 0u, w1 = (won >> 31) != 0u;
+                    const int s0 = (int)(lo & 0xffffu) - 257, s1 = (int)(lo >> 16) - 257;
                     if (w0) rp[0] = (uint8_t)s0;
                     if (w1) rp[1] = (uint8_t)s1;
                     // pixels with a score are the only NMS candidates (a pixel scores in at most one polarity)
@@ -211,9 +212,8 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
                     at += w0 ? 1 : 0;
                     if (w1 && at < MAX_SCORED) scored[at] = (unsigned short)((y << 6) | (2 * k + 1));
                 }
-                sa = fa == 3u ? 2u : 0u;
-                sb = fbb == 3u ? 2u : 0u;
-                if (!__any_sync(0xffffffffu, (sa | sb) != 0u)) break;
+                act = br = dark & bright;
+                if (!__any_sync(0xffffffffu, act != 0u)) break;
             }
         }
         __syncthreads();
