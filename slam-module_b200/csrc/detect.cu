@@ -67,7 +67,7 @@ __device__ __forceinline__ unsigned gt16x2(unsigned a, unsigned b) {
 
 struct FastMaps { CUtensorMap m[SG_MAX_LEVELS]; };   // 80 x 70 box over every pyramid level
 
-__global__ void __launch_bounds__(FAST_THREADS, 4)
+__global__ void __launch_bounds__(FAST_THREADS, 5)
 fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ FastMaps maps, const int4 *cells,
                   unsigned long long *cand, int *cand_count, int *err) {
     __shared__ __align__(128) uint8_t tile[TILE_ROWS * TP + 16];
@@ -638,6 +638,11 @@ int launch_detect(sg_ctx *ctx, int n_frames) {
         nc_max = std::max(nc_max, g.lv[l].node_cap);
     }
     if (total_cells > 0) {
+        static bool carveout_set = false;       // 5 CTAs x 42 KB of static shared memory per SM need the largest carve-out
+        if (!carveout_set) {
+            SG_CUDA(ctx, cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            carveout_set = true;
+        }
         FastMaps maps;
         for (int l = 0; l < g.levels; ++l) maps.m[l] = ctx->lv[l].map_fast;
         fast_cells_kernel<<<dim3(total_cells, n_frames), FAST_THREADS, 0, ctx->stream>>>(
