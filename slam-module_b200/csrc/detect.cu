@@ -70,12 +70,14 @@ struct FastMaps { CUtensorMap m[SG_MAX_LEVELS]; };   // 80 x 70 box over every p
 __global__ void __launch_bounds__(FAST_THREADS, 5)
 fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ FastMaps maps, const int4 *cells,
                   unsigned long long *cand, int *cand_count, int *err) {
-    __shared__ __align__(128) uint8_t tile[TILE_ROWS * TP + 16];
+    // the byte window is dead once the pair words are built: the stage-1 queues and the NMS winners reuse its bytes
+    __shared__ __align__(128) uint8_t tile[MAX_ENTRIES + (CELL / 2) * (CELL / 2) * 2];
+    static_assert(sizeof(tile) >= TILE_ROWS * TP + 16, "window fits under the queues");
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(16) uint32_t We[TILE_ROWS * WP], Wo[TILE_ROWS * WP];
     __shared__ __align__(16) uint8_t resp[(CELL + 2) * RPW];
-    __shared__ unsigned short ent[MAX_ENTRIES / 2];            // per-warp queues of pairs that pass stage 1: k | y << 5
-    __shared__ unsigned short keep[(CELL / 2) * (CELL / 2)];   // NMS winners (at most one per 2x2 block)
+    unsigned short *ent = reinterpret_cast<unsigned short *>(tile);   // [MAX_ENTRIES / 2] per-warp queues of pairs that pass stage 1: k | y << 5
+    unsigned short *keep = ent + MAX_ENTRIES / 2;                     // [(CELL / 2)^2] NMS winners (at most one per 2x2 block)
     __shared__ unsigned short scored[MAX_SCORED];              // y << 6 | x of the pixels with a score >= t
     __shared__ int s_nscored, s_nkeep, s_base;
 
