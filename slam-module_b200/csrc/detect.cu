@@ -31,10 +31,11 @@ namespace sg {
 constexpr int FAST_THREADS = 256;
 constexpr int TP = 80;                 // shared tile pitch: 3 px alignment slack + 70 px window, padded to words
 constexpr int TILE_ROWS = CELL + 6;    // 70
-constexpr int RPW = CELL + 8;          // response map pitch: 4-byte left pad (word-aligned rows) + 64 + right pad
+constexpr int RPW = TP;                // response map pitch: 4-byte left pad (word-aligned rows) + 64 + right pad; equal to the
+                                       // window pitch, so that one queue entry addresses the pair words AND the response bytes
 constexpr int TILE_SHIFT = 3;          // the window origin 19 + 64*j is always 3 past a word boundary
 static_assert((EVAL_ORIGIN - FAST_BORDER) % 4 == TILE_SHIFT && CELL % 4 == 0, "tile alignment");
-static_assert(((CELL + 2) * (CELL + 8)) % 16 == 0 && (CELL + 6) * 80 % 8 == 0, "vector widths of the zeroing / pair-word loops");
+static_assert(((CELL + 2) * TP) % 16 == 0 && TP == 2 * (TP / 2) && (CELL + 6) * 80 % 8 == 0, "vector widths of the zeroing / pair-word loops");
 constexpr int WP = TP / 2;             // pair-word pitch: 40 words per row
 constexpr int MAX_ENTRIES = CELL * CELL;   // 2048 pixel pairs, each at most twice (both polarities)
 constexpr int WARP_Q = MAX_ENTRIES / 2 / (FAST_THREADS / 32);   // per-warp queue: 8 rows x 32 pairs
@@ -76,9 +77,9 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(16) uint32_t We[TILE_ROWS * WP], Wo[TILE_ROWS * WP];
     __shared__ __align__(16) uint8_t resp[(CELL + 2) * RPW];
-    unsigned short *ent = reinterpret_cast<unsigned short *>(tile);   // [MAX_ENTRIES / 2] per-warp queues of pairs that pass stage 1: k | y << 5
+    unsigned short *ent = reinterpret_cast<unsigned short *>(tile);   // [MAX_ENTRIES / 2] per-warp queues of pairs that pass stage 1: y * WP + k
     unsigned short *keep = ent + MAX_ENTRIES / 2;                     // [(CELL / 2)^2] NMS winners (at most one per 2x2 block)
-    __shared__ unsigned short scored[MAX_SCORED];              // y << 6 | x of the pixels with a score >= t
+    __shared__ unsigned short scored[MAX_SCORED];              // y * RPW + x of the pixels with a score >= t
     __shared__ int s_nscored, s_nkeep, s_base;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, f = blockIdx.y + g.frame0;
@@ -150,7 +151,7 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
             // iff br < tlo.  Every 16-bit lane of both sums stays inside [0x7f00, 0x8200]: no carry between the lanes.
             const unsigned pass = ~((thiH - vb + A) & (vb - B + Hmtlo)) & okH;
             const unsigned m = __ballot_sync(0xffffffffu, pass != 0u);
-            if (pass) sts16(q_addr + 2u * (unsigned)(nq + __popc(m & lt)), (unsigned)(lane | (y << 5)));   // shared-space store: no generic address math per row
+            if (pass) sts16(q_addr + 2u * (unsigned)(nq + __popc(m & lt)), (unsigned)(lane + y * WP));   // shared-space store: no generic address math per row
             nq += __popc(m);
         }
         __syncwarp();
@@ -160,8 +161,8 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
             const int i = i0 + lane;
             const bool live = i < nq;
             const unsigned e = live ? q[i] : 0u;
-            const int k = e & 31, y = (e >> 5) & 63;
-            const uint32_t *we = We + (y + 3) * WP + k + 3, *wo = Wo + (y + 3) * WP + k;
+            // e = y * WP + k: the pair words of (y, k) and the response bytes of its two pixels are a base plus e
+            const uint32_t *we = We + 3 * WP + 3 + e, *wo = Wo + 3 * WP + e;
             unsigned r[16];
             const unsigned c = we[0];
             r[0] = we[3 * WP];      r[1] = wo[3 * WP + 3];  r[2] = we[2 * WP + 1];   r[3] = wo[WP + 4];
@@ -175,11 +176,15 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
                 const unsigned vb = c | 0x01000100u;
                 const unsigned A = __vmaxu2(__vminu2(r[0], r[8]), __vminu2(r[4], r[12]));
                 const unsigned B = __vminu2(__vmaxu2(r[0], r[8]), __vmaxu2(r[4], r[12]));
-                const unsigned ok = (live && 2 * k < cw ? 0x00008000u : 0u) | (live && 2 * k + 1 < cw ? 0x80000000u : 0u);
+                unsigned ok = live ? 0x80008000u : 0u;
+                if (cw < CELL) {                                   // last cell column: k = e mod WP (e / 40 by multiply-shift, e < 2800)
+                    const int k = (int)(e - WP * ((e * 3277u) >> 17));
+                    ok &= (2 * k < cw ? 0x00008000u : 0u) | (2 * k + 1 < cw ? 0x80000000u : 0u);
+                }
                 dark = ~(thiH - vb + A) & ok;
                 bright = ~(vb - B + Hmtlo) & ok;
             }
-            uint8_t *rp = resp + (y + 1) * RPW + 4 + 2 * k;
+            uint8_t *rp = resp + RPW + 4 + 2 * e;
             // dark first; a lane that can have both polarities (rare) is scored a second time as bright
             unsigned act = dark | bright, br = bright & ~dark;     // lanes scored in this round; of those, the bright ones
             const unsigned won_bias = (unsigned)(0x8000 - 257 - t) * 0x00010001u;
@@ -210,9 +215,9 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
                     if (w1) rp[1] = (uint8_t)s1;
                     // pixels with a score are the only NMS candidates (a pixel scores in at most one polarity)
                     int at = atomicAdd(&s_nscored, (w0 ? 1 : 0) + (w1 ? 1 : 0));
-                    if (w0 && at < MAX_SCORED) scored[at] = (unsigned short)((y << 6) | (2 * k));
+                    if (w0 && at < MAX_SCORED) scored[at] = (unsigned short)(2 * e);
                     at += w0 ? 1 : 0;
-                    if (w1 && at < MAX_SCORED) scored[at] = (unsigned short)((y << 6) | (2 * k + 1));
+                    if (w1 && at < MAX_SCORED) scored[at] = (unsigned short)(2 * e + 1);
                 }
                 act = br = dark & bright;
                 if (!__any_sync(0xffffffffu, act != 0u)) break;
@@ -225,7 +230,7 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
         if (nscored <= MAX_SCORED) {
             for (int i = tid; i < nscored; i += FAST_THREADS) {
                 const int p = scored[i];
-                const uint8_t *sp = resp + ((p >> 6) + 1) * RPW + 4 + (p & 63);
+                const uint8_t *sp = resp + RPW + 4 + p;
                 const int v = sp[0];
                 if (v > sp[-1] && v > sp[1] && v > sp[-RPW - 1] && v > sp[-RPW] && v > sp[-RPW + 1]
                     && v > sp[RPW - 1] && v > sp[RPW] && v > sp[RPW + 1])
@@ -233,8 +238,9 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
             }
         } else {
             // more scored pixels than the list holds (very dense corners): scan the response map instead
-            for (int p = tid; p < CELL * CELL; p += FAST_THREADS) {
-                const uint8_t *sp = resp + ((p >> 6) + 1) * RPW + 4 + (p & 63);
+            for (int i = tid; i < CELL * CELL; i += FAST_THREADS) {
+                const int p = (i >> 6) * RPW + (i & 63);
+                const uint8_t *sp = resp + RPW + 4 + p;
                 const int v = sp[0];
                 if (v != 0 && v > sp[-1] && v > sp[1] && v > sp[-RPW - 1] && v > sp[-RPW] && v > sp[-RPW + 1]
                     && v > sp[RPW - 1] && v > sp[RPW] && v > sp[RPW + 1])
@@ -255,8 +261,8 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
     unsigned long long *out = cand + (size_t)f * g.cand_per_frame + L.cand_off + base;
     for (int i = tid; i < nkeep; i += FAST_THREADS) {
         const int p = keep[i];
-        const int y = p >> 6, x = p & 63;
-        const int v = resp[(y + 1) * RPW + 4 + x];
+        const int y = (int)(((unsigned)p * 3277u) >> 18), x = p - y * RPW;     // p = y * 80 + x, p < 5120
+        const int v = resp[RPW + 4 + p];
         // order key == position in the sequential candidate list: cell row, cell column, y, x
         const unsigned key = ((unsigned)ci << 22) | ((unsigned)cj << 12) | ((unsigned)y << 6) | (unsigned)x;
         out[i] = ((unsigned long long)v << 32) | key;
