@@ -128,7 +128,7 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
         // ---- stage 1: compass test, one warp per row, lane = pixel pair (2k, 2k + 1) ------------------------
         // Only "does either pixel of the pair pass" is decided here (the polarity flags are recomputed for the few
         // pairs that reach stage 2).  Passing pairs go to a queue PRIVATE to the warp (ballot + prefix popc, no
-        // atomics, no CTA barrier): a warp owns rows warp, warp + 8, ... and scores its own queue right after.
+        // atomics, no CTA barrier): a warp owns 8 consecutive rows and scores its own queue right after.
         unsigned short *q = ent + warp * WARP_Q;
         const uint32_t q_addr = smem_u32(q);
         int nq = 0;
@@ -136,23 +136,48 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
         // pixels outside the cell never count
         const unsigned okH = (2 * lane < cw ? 0x00008000u : 0u) | (2 * lane + 1 < cw ? 0x80000000u : 0u);
         const unsigned thiH = thi | 0x80008000u, Hmtlo = 0x80008000u - tlo;
-        for (int y = warp; y < ch; y += FAST_THREADS / 32) {
-            const uint32_t *we = We + (y + 3) * WP + lane + 3, *wo = Wo + (y + 3) * WP + lane;
-            const unsigned vb = we[0] | 0x01000100u;
-            // e_i = vb - w_i (biased differences 256 + v - p_i, one per 16-bit lane).  Because vb is common,
-            //   dk = min_i max(e_i, e_i+8) = vb - max_i min(w_i, w_i+8),  br = max_i min(e_i, e_i+8) = vb - min_i max(w_i, w_i+8):
-            // the min / max lattice runs on the raw pair words and only two subtractions remain.
-            const unsigned w0 = we[3 * WP], w8 = we[-3 * WP], w4 = wo[4], w12 = wo[1];
-            // the two diagonal antipodal pairs (2, 2) / (-2, -2) and (2, -2) / (-2, 2) halve what reaches stage 2
-            const unsigned w2 = we[2 * WP + 1], w10 = we[-2 * WP - 1], w6 = we[-2 * WP + 1], w14 = we[2 * WP - 1];
-            const unsigned A = __vimax3_u16x2(__vminu2(w0, w8), __vminu2(w4, w12), __vmaxu2(__vminu2(w2, w10), __vminu2(w6, w14)));
-            const unsigned B = __vimin3_u16x2(__vmaxu2(w0, w8), __vmaxu2(w4, w12), __vminu2(__vmaxu2(w2, w10), __vmaxu2(w6, w14)));
-            // lane bit 15 / 31 of (thiH - dk) = thiH - vb + A is clear iff dk > thi; of (br + H) - tlo = vb - B + (H - tlo)
-            // iff br < tlo.  Every 16-bit lane of both sums stays inside [0x7f00, 0x8200]: no carry between the lanes.
-            const unsigned pass = ~((thiH - vb + A) & (vb - B + Hmtlo)) & okH;
-            const unsigned m = __ballot_sync(0xffffffffu, pass != 0u);
-            if (pass) sts16(q_addr + 2u * (unsigned)(nq + __popc(m & lt)), (unsigned)(lane + y * WP));   // shared-space store: no generic address math per row
-            nq += __popc(m);
+        // A warp walks down ROWS_PER_WARP consecutive rows and keeps the ring rows it has loaded in registers: the word of
+        // column k in row y is w0 of row y - 3, the centre of row y and w8 of row y + 3; the words of columns k - 1 / k + 1
+        // serve rows y - 2 and y + 2.  5 loads per row instead of 9 (54 per 8 rows with the fill).
+        constexpr int ROWS_PER_WARP = CELL / (FAST_THREADS / 32);
+        const int y0 = warp * ROWS_PER_WARP;
+        if (y0 < ch) {
+            const uint32_t *we = We + (y0 + 3) * WP + lane + 3, *wo = Wo + (y0 + 3) * WP + lane;
+            unsigned cc[7], cl[5], cr[5];        // rows y-3..y+3 of column k; rows y-2..y+2 of columns k-1 and k+1
+#pragma unroll
+            for (int i = 0; i < 7; ++i) cc[i] = we[(i - 3) * WP];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) { cl[i] = we[(i - 2) * WP - 1]; cr[i] = we[(i - 2) * WP + 1]; }
+#pragma unroll
+            for (int j = 0; j < ROWS_PER_WARP; ++j) {
+                const int y = y0 + j;
+                if (y < ch) {                                  // warp-uniform
+                    const unsigned vb = cc[3] | 0x01000100u;
+                    // e_i = vb - w_i (biased differences 256 + v - p_i, one per 16-bit lane).  Because vb is common,
+                    //   dk = min_i max(e_i, e_i+8) = vb - max_i min(w_i, w_i+8),  br = max_i min(e_i, e_i+8) = vb - min_i max(w_i, w_i+8):
+                    // the min / max lattice runs on the raw pair words and only two subtractions remain.
+                    const unsigned w0 = cc[6], w8 = cc[0], w4 = wo[j * WP + 4], w12 = wo[j * WP + 1];
+                    // the two diagonal antipodal pairs (2, 2) / (-2, -2) and (2, -2) / (-2, 2) halve what reaches stage 2
+                    const unsigned w2 = cr[4], w10 = cl[0], w6 = cr[0], w14 = cl[4];
+                    const unsigned A = __vimax3_u16x2(__vminu2(w0, w8), __vminu2(w4, w12), __vmaxu2(__vminu2(w2, w10), __vminu2(w6, w14)));
+                    const unsigned B = __vimin3_u16x2(__vmaxu2(w0, w8), __vmaxu2(w4, w12), __vminu2(__vmaxu2(w2, w10), __vmaxu2(w6, w14)));
+                    // lane bit 15 / 31 of (thiH - dk) = thiH - vb + A is clear iff dk > thi; of (br + H) - tlo = vb - B + (H - tlo)
+                    // iff br < tlo.  Every 16-bit lane of both sums stays inside [0x7f00, 0x8200]: no carry between the lanes.
+                    const unsigned pass = ~((thiH - vb + A) & (vb - B + Hmtlo)) & okH;
+                    const unsigned m = __ballot_sync(0xffffffffu, pass != 0u);
+                    if (pass) sts16(q_addr + 2u * (unsigned)(nq + __popc(m & lt)), (unsigned)(lane + y * WP));   // shared-space store: no generic address math per row
+                    nq += __popc(m);
+                }
+                if (j + 1 < ROWS_PER_WARP) {                   // slide the windows down one row (register renaming after unrolling)
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) cc[i] = cc[i + 1];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { cl[i] = cl[i + 1]; cr[i] = cr[i + 1]; }
+                    cc[6] = we[(j + 4) * WP];
+                    cl[4] = we[(j + 3) * WP - 1];
+                    cr[4] = we[(j + 3) * WP + 1];
+                }
+            }
         }
         __syncwarp();
 
