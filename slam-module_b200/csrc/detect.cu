@@ -148,34 +148,56 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
             for (int i = 0; i < 7; ++i) cc[i] = we[(i - 3) * WP];
 #pragma unroll
             for (int i = 0; i < 5; ++i) { cl[i] = we[(i - 2) * WP - 1]; cr[i] = we[(i - 2) * WP + 1]; }
-#pragma unroll
-            for (int j = 0; j < ROWS_PER_WARP; ++j) {
+            auto test_row = [&](int j) {
                 const int y = y0 + j;
-                if (y < ch) {                                  // warp-uniform
+                const unsigned vb = cc[3] | 0x01000100u;
+                // e_i = vb - w_i (biased differences 256 + v - p_i, one per 16-bit lane).  Because vb is common,
+                //   dk = min_i max(e_i, e_i+8) = vb - max_i min(w_i, w_i+8),  br = max_i min(e_i, e_i+8) = vb - min_i max(w_i, w_i+8):
+                // the min / max lattice runs on the raw pair words and only two subtractions remain.
+                const unsigned w0 = cc[6], w8 = cc[0], w4 = wo[j * WP + 4], w12 = wo[j * WP + 1];
+                // the two diagonal antipodal pairs (2, 2) / (-2, -2) and (2, -2) / (-2, 2) halve what reaches stage 2
+                const unsigned w2 = cr[4], w10 = cl[0], w6 = cr[0], w14 = cl[4];
+                const unsigned A = __vimax3_u16x2(__vminu2(w0, w8), __vminu2(w4, w12), __vmaxu2(__vminu2(w2, w10), __vminu2(w6, w14)));
+                const unsigned B = __vimin3_u16x2(__vmaxu2(w0, w8), __vmaxu2(w4, w12), __vminu2(__vmaxu2(w2, w10), __vmaxu2(w6, w14)));
+                // lane bit 15 / 31 of (thiH - dk) = thiH - vb + A is clear iff dk > thi; of (br + H) - tlo = vb - B + (H - tlo)
+                // iff br < tlo.  Every 16-bit lane of both sums stays inside [0x7f00, 0x8200]: no carry between the lanes.
+                const unsigned pass = ~((thiH - vb + A) & (vb - B + Hmtlo)) & okH;
+                const unsigned m = __ballot_sync(0xffffffffu, pass != 0u);
+                if (pass) sts16(q_addr + 2u * (unsigned)(nq + __popc(m & lt)), (unsigned)(lane + y * WP));   // shared-space store: no generic address math per row
+                nq += __popc(m);
+            };
+            auto slide = [&](int j) {      // the windows move down one row (register renaming after unrolling)
+#pragma unroll
+                for (int i = 0; i < 6; ++i) cc[i] = cc[i + 1];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { cl[i] = cl[i + 1]; cr[i] = cr[i + 1]; }
+                cc[6] = we[(j + 4) * WP];
+                cl[4] = we[(j + 3) * WP - 1];
+                cr[4] = we[(j + 3) * WP + 1];
+            };
+            if (y0 + ROWS_PER_WARP <= ch) {                    // all rows inside the cell (every cell but the last row of cells)
+#pragma unroll
+                for (int j = 0; j < ROWS_PER_WARP; ++j) {
+                    test_row(j);
+                    if (j + 1 < ROWS_PER_WARP) slide(j);
+                }
+            } else {
+                for (int j = 0; y0 + j < ch; ++j) {
+                    // (not unrolled: the windows really move)
+                    const int y = y0 + j;
+                    const uint32_t *wr = We + (y + 3) * WP + lane + 3;
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) cc[i] = wr[(i - 3) * WP];
+                    cl[0] = wr[-2 * WP - 1]; cl[4] = wr[2 * WP - 1]; cr[0] = wr[-2 * WP + 1]; cr[4] = wr[2 * WP + 1];
                     const unsigned vb = cc[3] | 0x01000100u;
-                    // e_i = vb - w_i (biased differences 256 + v - p_i, one per 16-bit lane).  Because vb is common,
-                    //   dk = min_i max(e_i, e_i+8) = vb - max_i min(w_i, w_i+8),  br = max_i min(e_i, e_i+8) = vb - min_i max(w_i, w_i+8):
-                    // the min / max lattice runs on the raw pair words and only two subtractions remain.
                     const unsigned w0 = cc[6], w8 = cc[0], w4 = wo[j * WP + 4], w12 = wo[j * WP + 1];
-                    // the two diagonal antipodal pairs (2, 2) / (-2, -2) and (2, -2) / (-2, 2) halve what reaches stage 2
                     const unsigned w2 = cr[4], w10 = cl[0], w6 = cr[0], w14 = cl[4];
                     const unsigned A = __vimax3_u16x2(__vminu2(w0, w8), __vminu2(w4, w12), __vmaxu2(__vminu2(w2, w10), __vminu2(w6, w14)));
                     const unsigned B = __vimin3_u16x2(__vmaxu2(w0, w8), __vmaxu2(w4, w12), __vminu2(__vmaxu2(w2, w10), __vmaxu2(w6, w14)));
-                    // lane bit 15 / 31 of (thiH - dk) = thiH - vb + A is clear iff dk > thi; of (br + H) - tlo = vb - B + (H - tlo)
-                    // iff br < tlo.  Every 16-bit lane of both sums stays inside [0x7f00, 0x8200]: no carry between the lanes.
                     const unsigned pass = ~((thiH - vb + A) & (vb - B + Hmtlo)) & okH;
                     const unsigned m = __ballot_sync(0xffffffffu, pass != 0u);
-                    if (pass) sts16(q_addr + 2u * (unsigned)(nq + __popc(m & lt)), (unsigned)(lane + y * WP));   // shared-space store: no generic address math per row
+                    if (pass) sts16(q_addr + 2u * (unsigned)(nq + __popc(m & lt)), (unsigned)(lane + y * WP));
                     nq += __popc(m);
-                }
-                if (j + 1 < ROWS_PER_WARP) {                   // slide the windows down one row (register renaming after unrolling)
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) cc[i] = cc[i + 1];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { cl[i] = cl[i + 1]; cr[i] = cr[i + 1]; }
-                    cc[6] = we[(j + 4) * WP];
-                    cl[4] = we[(j + 3) * WP - 1];
-                    cr[4] = we[(j + 3) * WP + 1];
                 }
             }
         }
