@@ -278,10 +278,10 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
             for (int i = tid; i < nscored; i += FAST_THREADS) {
                 const int p = scored[i];
                 const uint8_t *sp = resp + RPW + 4 + p;
+                // all eight neighbours first, then one comparison against their maximum (no short-circuit branches)
                 const int v = sp[0];
-                if (v > sp[-1] && v > sp[1] && v > sp[-RPW - 1] && v > sp[-RPW] && v > sp[-RPW + 1]
-                    && v > sp[RPW - 1] && v > sp[RPW] && v > sp[RPW + 1])
-                    keep[atomicAdd(&s_nkeep, 1)] = (unsigned short)p;
+                const int up = __vimax3_s32(sp[-RPW - 1], sp[-RPW], sp[-RPW + 1]), dn = __vimax3_s32(sp[RPW - 1], sp[RPW], sp[RPW + 1]);
+                if (v > __vimax3_s32(up, dn, max((int)sp[-1], (int)sp[1]))) keep[atomicAdd(&s_nkeep, 1)] = (unsigned short)p;
             }
         } else {
             // more scored pixels than the list holds (very dense corners): scan the response map instead
@@ -289,9 +289,10 @@ fast_cells_kernel(const __grid_constant__ GeomDev g, const __grid_constant__ Fas
                 const int p = (i >> 6) * RPW + (i & 63);
                 const uint8_t *sp = resp + RPW + 4 + p;
                 const int v = sp[0];
-                if (v != 0 && v > sp[-1] && v > sp[1] && v > sp[-RPW - 1] && v > sp[-RPW] && v > sp[-RPW + 1]
-                    && v > sp[RPW - 1] && v > sp[RPW] && v > sp[RPW + 1])
-                    keep[atomicAdd(&s_nkeep, 1)] = (unsigned short)p;
+                if (v != 0) {
+                    const int up = __vimax3_s32(sp[-RPW - 1], sp[-RPW], sp[-RPW + 1]), dn = __vimax3_s32(sp[RPW - 1], sp[RPW], sp[RPW + 1]);
+                    if (v > __vimax3_s32(up, dn, max((int)sp[-1], (int)sp[1]))) keep[atomicAdd(&s_nkeep, 1)] = (unsigned short)p;
+                }
             }
         }
         __syncthreads();
