@@ -694,10 +694,9 @@ int launch_detect(sg_ctx *ctx, int n_frames) {
         nc_max = std::max(nc_max, g.lv[l].node_cap);
     }
     if (total_cells > 0) {
-        static bool carveout_set = false;       // 5 CTAs x 42 KB of static shared memory per SM need the largest carve-out
-        if (!carveout_set) {
+        if (!ctx->fast_carveout_set) {          // 5 CTAs x 37 KB of static shared memory per SM need the largest carve-out
             SG_CUDA(ctx, cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            carveout_set = true;
+            ctx->fast_carveout_set = true;
         }
         FastMaps maps;
         for (int l = 0; l < g.levels; ++l) maps.m[l] = ctx->lv[l].map_fast;
