@@ -772,7 +772,7 @@ def main():
         roof_stage = dom if dom in stage_bytes else "pyramid"
         roofline = {"kernel": {"pyramid": "pyr_fast_kernel (8 launches: blur of level 0 + 7 fused resize+blur levels; traffic: the level-1 launch)",
                                "fast": "fast_cells_kernel (1 launch per step)"}[roof_stage],
-                    "note": "integer-issue bound, not HBM bound: ALU pipe ~69% busy, issue slots ~67% (profiles/, newest ncu_full_*.md)",
+                    "note": "shared-memory and integer-issue bound, not HBM bound: l1tex ~77%, ALU pipe ~69%, issue slots ~68% busy at 5 CTAs per SM (profiles/, newest ncu_full_*.md)",
                     "bound": "hbm", "achieved": stages[roof_stage]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": stages[roof_stage]["frac_of_hbm"], "traffic": traffic_of(roof_stage)[0], "traffic_source": traffic_of(roof_stage)[1],
                     "peak_source": peak_src,
