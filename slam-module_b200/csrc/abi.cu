@@ -47,7 +47,7 @@ int run_row_scan(sg_ctx *ctx, const sg_db *db, const int *d_rows, int n_rows, un
                  uint32_t *d_count);
 int run_hamming(sg_ctx *ctx, const uint32_t *d_a, const uint32_t *d_b, int n, uint32_t *d_out);
 int run_popc_bench(sg_ctx *ctx, double *popc_per_s, float *ms_out);
-size_t distribute_smem_bytes(int node_cap_max);
+size_t distribute_smem_bytes(int node_cap_max, bool pack);
 void fast_cell_table(const GeomDev &g, std::vector<int4> &cells);
 
 template <class T>
@@ -153,7 +153,7 @@ static int build_context(sg_ctx *ctx) {
             if (int r = encode_plane_map(ctx, &ctx->lv[l + 1].map_src, L.pyr, L.w, L.h, L.pitch, L.frame_stride, p.max_frames,
                                          ctx->lv[l + 1].tma_src_w, ctx->lv[l + 1].tma_src_h)) return r;
     }
-    if (distribute_smem_bytes(nc_max) > 200 * 1024)
+    if (distribute_smem_bytes(nc_max, false) > 200 * 1024)
         return fail(ctx, SG_ERR_INVALID, "max_keypoints %d needs a quadtree node table larger than shared memory", p.max_keypoints);
     g.cand_per_frame = cand_off;
     g.det_cap = kp_off;

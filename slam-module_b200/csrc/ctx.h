@@ -124,6 +124,7 @@ struct sg_ctx {
     long prof_call = -1;                             // index of the current call since profiling was switched on
     int sm_count = 148;
     int describe_ctas_per_sm = 0;      // occupancy of the persistent describe kernel (queried on first use)
+    bool dist_carveout_set = false;    // the same for distribute_kernel
     bool fast_carveout_set = false;    // fast_cells_kernel's shared-memory carve-out preference (per device: set once per context)
 
     std::vector<sg_db *> dbs;           // descriptor databases created on this context and not yet destroyed

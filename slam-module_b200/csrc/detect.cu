@@ -379,7 +379,7 @@ __device__ __forceinline__ int quadrant(const NodeBox &b, int x, int y) {
 
 // Candidates of one (frame, level): position and current node, either cached in shared memory (levels with at most
 // CAND_SMEM candidates: every level of the VGA / 720p configurations) or in the global arrays.
-constexpr int CAND_SMEM = 3072;
+constexpr int CAND_SMEM = 2688;
 template <bool CACHED> struct CandStore {
     const unsigned long long *cand;
     uint32_t *cnode;
@@ -393,14 +393,38 @@ template <bool CACHED> struct CandStore {
     __device__ __forceinline__ void set_node(int i, int v) const { if (CACHED) s_node[i] = (unsigned short)v; else cnode[i] = v; }
 };
 
+// Quadrant populations of a node list: four ints per node, or (PACK: every level holds at most 65535 candidates) four u16 in
+// two words -- 16 bytes less shared memory per node and node list, which is what lets five CTAs share an SM at VGA size.
+template <bool PACK> struct QCount {
+    uint32_t *w;
+    __device__ __forceinline__ void clear(int nodes, int tid) const {
+        for (int i = tid; i < (PACK ? 2 : 4) * nodes; i += DIST_THREADS) w[i] = 0u;
+    }
+    __device__ __forceinline__ void add(int node, int q) const {
+        if (PACK) atomicAdd(&w[2 * node + (q >> 1)], 1u << (16 * (q & 1)));
+        else atomicAdd(&w[4 * node + q], 1u);
+    }
+    __device__ __forceinline__ int get(int node, int q) const {
+        return PACK ? (int)((w[2 * node + (q >> 1)] >> (16 * (q & 1))) & 0xffffu) : (int)w[4 * node + q];
+    }
+    __device__ __forceinline__ int children(int node) const {   // quadrants that hold a candidate
+        if (PACK) {
+            const uint32_t a = w[2 * node], b = w[2 * node + 1];
+            return ((a & 0xffffu) != 0u) + ((a >> 16) != 0u) + ((b & 0xffffu) != 0u) + ((b >> 16) != 0u);
+        }
+        return (w[4 * node] > 0u) + (w[4 * node + 1] > 0u) + (w[4 * node + 2] > 0u) + (w[4 * node + 3] > 0u);
+    }
+};
+
 struct DistShared {
     unsigned long long *best;
     NodeBox *box0, *box1;
-    int *cnt0, *cnt1, *ccnt0, *ccnt1, *ord, *byord, *ps, *kpos;
+    int *cnt0, *cnt1, *ord, *byord, *ps, *kpos;
+    uint32_t *ccnt0, *ccnt1;
     unsigned short *cpos;
 };
 
-template <bool CACHED>
+template <bool CACHED, bool PACK>
 __device__ void distribute_level(const LevelDev &L, int NC, int ncand, const CandStore<CACHED> &cs, const DistShared &sh, int *tmp,
                                  int *s_m, int *out_xy, int *out_resp, int *kp_count_out, int *err) {
     const int tid = threadIdx.x;
@@ -408,7 +432,7 @@ __device__ void distribute_level(const LevelDev &L, int NC, int ncand, const Can
     int flip = 0;
     NodeBox *box = sh.box0, *nbox = sh.box1;
     int *cnt = sh.cnt0, *ncnt = sh.cnt1;
-    int *ccnt = sh.ccnt0, *nccnt = sh.ccnt1;    // quadrant populations of the current / the next node list
+    QCount<PACK> ccnt{sh.ccnt0}, nccnt{sh.ccnt1};    // quadrant populations of the current / the next node list
     unsigned short *cpos = sh.cpos;
     int *ord = sh.ord, *byord = sh.byord, *ps = sh.ps, *kpos = sh.kpos;
 
@@ -447,7 +471,7 @@ __device__ void distribute_level(const LevelDev &L, int NC, int ncand, const Can
         const int kept = block_exclusive_scan(kpos, n, tmp, flip);
         for (int i = tid; i < n; i += DIST_THREADS)
             if (ncnt[i] > 0) { box[kpos[i]] = nbox[i]; cnt[kpos[i]] = ncnt[i]; }
-        for (int i = tid; i < 4 * kept; i += DIST_THREADS) ccnt[i] = 0;
+        ccnt.clear(kept, tid);
         __syncthreads();
         // (quadrant populations of the first round are counted on the way)
         for (int i = tid; i < ncand; i += DIST_THREADS) {
@@ -456,21 +480,21 @@ __device__ void distribute_level(const LevelDev &L, int NC, int ncand, const Can
             if (cnt[nd] > 1) {
                 int x, y;
                 cs.xy(i, x, y);
-                atomicAdd(&ccnt[4 * nd + quadrant(box[nd], x, y)], 1);
+                ccnt.add(nd, quadrant(box[nd], x, y));
             }
         }
         n = kept;
         __syncthreads();
     } else {
         { NodeBox *tb = box; box = nbox; nbox = tb; int *tc = cnt; cnt = ncnt; ncnt = tc; }
-        if (tid < 4) ccnt[tid] = 0;
+        ccnt.clear(1, tid);
         __syncthreads();
         if (ncand > 1) {
             const NodeBox b0 = box[0];
             for (int i = tid; i < ncand; i += DIST_THREADS) {
                 int x, y;
                 cs.xy(i, x, y);
-                atomicAdd(&ccnt[quadrant(b0, x, y)], 1);
+                ccnt.add(0, quadrant(b0, x, y));
             }
         }
         __syncthreads();
@@ -520,8 +544,7 @@ __device__ void distribute_level(const LevelDev &L, int NC, int ncand, const Can
         __syncthreads();
         // D: children created before each processed node; in a partial round, where to stop
         for (int i = tid; i < P; i += DIST_THREADS) {
-            const int *c = ccnt + 4 * byord[i];
-            ps[i] = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
+            ps[i] = ccnt.children(byord[i]);
         }
         if (tid == 0) { ps[P] = 0; *s_m = P; }
         __syncthreads();
@@ -547,7 +570,7 @@ __device__ void distribute_level(const LevelDev &L, int NC, int ncand, const Can
             block_exclusive_scan(kpos, n, tmp, flip);
         }
         // F: new node table (and cleared quadrant populations for it)
-        for (int i = tid; i < 4 * n_new; i += DIST_THREADS) nccnt[i] = 0;
+        nccnt.clear(n_new, tid);
         for (int j = tid; j < n; j += DIST_THREADS) {
             if (cnt[j] > 1 && ord[j] < m) {
                 const NodeBox b = box[j];
@@ -555,7 +578,7 @@ __device__ void distribute_level(const LevelDev &L, int NC, int ncand, const Can
                 int created = ps[ord[j]];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int c = ccnt[4 * j + q];
+                    const int c = ccnt.get(j, q);
                     if (c == 0) continue;
                     const int pos = total_new - 1 - created++;   // pushed to the front in creation order
                     NodeBox nb;
@@ -584,13 +607,13 @@ __device__ void distribute_level(const LevelDev &L, int NC, int ncand, const Can
             cs.xy(i, x, y);
             const int nn = moved ? cpos[4 * nd + quadrant(box[nd], x, y)] : kpos[nd];
             cs.set_node(i, nn);
-            if (more && ncnt[nn] > 1) atomicAdd(&nccnt[4 * nn + quadrant(nbox[nn], x, y)], 1);
+            if (more && ncnt[nn] > 1) nccnt.add(nn, quadrant(nbox[nn], x, y));
         }
         __syncthreads();
         // H: termination (uniform)
         const int n_old = n;
         n = n_new;
-        { NodeBox *tb = box; box = nbox; nbox = tb; int *tc = cnt; cnt = ncnt; ncnt = tc; tc = ccnt; ccnt = nccnt; nccnt = tc; }
+        { NodeBox *tb = box; box = nbox; nbox = tb; int *tc = cnt; cnt = ncnt; ncnt = tc; uint32_t *tw = ccnt.w; ccnt.w = nccnt.w; nccnt.w = tw; }
         if (N <= n || n == n_old) break;
         if (!partial) {
             // dividable nodes of the new list (all of them are children made in this round)
@@ -618,6 +641,7 @@ __device__ void distribute_level(const LevelDev &L, int NC, int ncand, const Can
     if (tid == 0) *kp_count_out = n;
 }
 
+template <bool PACK>
 __global__ void __launch_bounds__(DIST_THREADS)
 distribute_kernel(const __grid_constant__ GeomDev g, int node_cap_max, const unsigned long long *cand_all,
                   uint32_t *cand_node_all, const int *cand_count, int *kp_xy, int *kp_resp, int *kp_count,
@@ -629,10 +653,11 @@ distribute_kernel(const __grid_constant__ GeomDev g, int node_cap_max, const uns
     sh.box1 = sh.box0 + NC;                                                        // [NC]
     sh.cnt0 = reinterpret_cast<int *>(sh.box1 + NC);                               // [NC]
     sh.cnt1 = sh.cnt0 + NC;                                                        // [NC]
-    sh.ccnt0 = sh.cnt1 + NC;                                                       // [4 NC] child counts (this round)
-    sh.ccnt1 = sh.ccnt0 + 4 * NC;                                                  // [4 NC] child counts (next round)
+    constexpr int QW = PACK ? 2 : 4;                                               // words of quadrant counts per node
+    sh.ccnt0 = reinterpret_cast<uint32_t *>(sh.cnt1 + NC);                         // [QW NC] child counts (this round)
+    sh.ccnt1 = sh.ccnt0 + QW * NC;                                                 // [QW NC] child counts (next round)
     sh.best = reinterpret_cast<unsigned long long *>(sh.ccnt0);                    // [NC] after the rounds, over the child counts
-    sh.ord = sh.ccnt1 + 4 * NC;                                                    // [NC] processing index
+    sh.ord = reinterpret_cast<int *>(sh.ccnt1 + QW * NC);                          // [NC] processing index
     sh.byord = sh.ord + NC;                                                        // [NC]
     sh.ps = sh.byord + NC;                                                         // [NC + 1] scan over order
     sh.kpos = sh.ps + NC + 1;                                                      // [NC] position of kept nodes
@@ -658,10 +683,10 @@ distribute_kernel(const __grid_constant__ GeomDev g, int node_cap_max, const uns
     }
     if (ncand <= CAND_SMEM && NC < 65536) {
         const CandStore<true> cs{cand, cnode, s_xy, s_node};
-        distribute_level<true>(L, NC, ncand, cs, sh, tmp, &s_m, out_xy, out_resp, kp_count + f * g.levels + l, err);
+        distribute_level<true, PACK>(L, NC, ncand, cs, sh, tmp, &s_m, out_xy, out_resp, kp_count + f * g.levels + l, err);
     } else {
         const CandStore<false> cs{cand, cnode, s_xy, s_node};
-        distribute_level<false>(L, NC, ncand, cs, sh, tmp, &s_m, out_xy, out_resp, kp_count + f * g.levels + l, err);
+        distribute_level<false, PACK>(L, NC, ncand, cs, sh, tmp, &s_m, out_xy, out_resp, kp_count + f * g.levels + l, err);
     }
 }
 
@@ -679,9 +704,20 @@ void fast_cell_table(const GeomDev &g, std::vector<int4> &cells) {
     }
 }
 
-size_t distribute_smem_bytes(int node_cap_max) {
+size_t distribute_smem_bytes(int node_cap_max, bool pack) {
     const size_t NC = node_cap_max;
-    return NC * (2 * sizeof(NodeBox) + 2 * 4 + 2 * 4 * 4 + 4 * 2 + 4 + 4 + 4 + 4) + 64 + (size_t)CAND_SMEM * 6;
+    return NC * (2 * sizeof(NodeBox) + 2 * 4 + 2 * (pack ? 2 : 4) * 4 + 4 * 2 + 4 + 4 + 4 + 4) + 64 + (size_t)CAND_SMEM * 6;
+}
+
+// Upper bound of the NMS survivors of a level: one per 2 x 2 block of every cell.
+static int max_candidates(const LevelDev &L) {
+    int total = 0;
+    for (int cj = 0; cj < L.cells_y; ++cj)
+        for (int ci = 0; ci < L.cells_x; ++ci) {
+            const int cw = std::min(CELL, L.w - 2 * EVAL_ORIGIN - CELL * ci), ch = std::min(CELL, L.h - 2 * EVAL_ORIGIN - CELL * cj);   // fast_cell_table
+            total += ((cw + 1) / 2) * ((ch + 1) / 2);
+        }
+    return total;
 }
 
 int launch_detect(sg_ctx *ctx, int n_frames) {
@@ -706,10 +742,18 @@ int launch_detect(sg_ctx *ctx, int n_frames) {
     }
     mark(ctx, EV_FAST1);
     if (nc_max >= 65536) return fail(ctx, SG_ERR_INVALID, "more than 65535 quadtree nodes per level are not supported");
-    const size_t smem = distribute_smem_bytes(nc_max);
+    // quadrant counts as packed u16 when no level can hold more than 65535 candidates (VGA: 64 964 at level 0)
+    bool pack = true;
+    for (int l = 0; l < g.levels; ++l) pack = pack && max_candidates(g.lv[l]) <= 65535;
+    const size_t smem = distribute_smem_bytes(nc_max, pack);
+    auto kernel = pack ? distribute_kernel<true> : distribute_kernel<false>;
     if (smem > 48 * 1024)
-        SG_CUDA(ctx, cudaFuncSetAttribute(distribute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    distribute_kernel<<<dim3(n_frames, g.levels), DIST_THREADS, smem, ctx->stream>>>(
+        SG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!ctx->dist_carveout_set) {
+        SG_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        ctx->dist_carveout_set = true;
+    }
+    kernel<<<dim3(n_frames, g.levels), DIST_THREADS, smem, ctx->stream>>>(
         g, nc_max, ctx->d_cand, ctx->d_cand_node, ctx->d_cand_count, ctx->d_kp_xy, ctx->d_kp_resp, ctx->d_kp_count, ctx->d_err + ctx->err_slot);
     SG_LAUNCH_CHECK(ctx);
     mark(ctx, EV_DIST1);
