@@ -91,12 +91,9 @@ W8, H8 = [640, 533, 444, 370, 309, 257, 214, 179], [480, 400, 333, 278, 231, 193
 PX = [w * h * 256 for w, h in zip(W8, H8)]
 SUM_PX = sum(PX)
 KP = 513000
-PHASES = {      # kernel -> (source file, pixels of the launch or None, ["phase:lo-hi", ...]); the first three are filled below
-    "distribute_kernel": ("detect.cu", None, ["scan helpers:271-352", "initial nodes:353-421", "processing order (rank loop):422-461",
-                                              "children scan, stop point:462-490", "new node table:491-517",
-                                              "move candidates + next quadrant counts:518-534", "termination:535-546",
-                                              "strongest per node:547-566", "kernel entry:567-626"]),
-}
+PHASES = {}     # kernel -> (source file, pixels of the launch or None, ["phase:lo-hi", ...]), filled below
+
+
 def marker_phases(cu, start, sections):
     """Source-line ranges of a kernel's phases, located by its own section comments (so edits do not stale them):
     `start` = text on the kernel's signature line, sections = [(phase name, text that opens it), ...] in file order; a
@@ -123,6 +120,12 @@ PHASES["pyr_fast_kernel"] = ("pyramid.cu", None, marker_phases("pyramid.cu", "py
 PHASES["fast_cells_kernel"] = ("detect.cu", SUM_PX, marker_phases("detect.cu", "fast_cells_kernel(const __grid_constant__", [
     ("setup+TMA", None), ("pair words", "// ---- pair words"), ("stage 1 (antipodal test, queue)", "// Two passes at most"),
     ("stage 2 (exact score)", "// ---- stage 2"), ("NMS", "// ---- cell-local NMS"), ("output", "if (nkeep == 0) return;")]))
+PHASES["distribute_kernel"] = ("detect.cu", None, marker_phases("detect.cu", "constexpr int DIST_THREADS", [
+    ("helpers (block scans, candidate store, quadrant counts)", None), ("initial nodes", "// ---- initial nodes"),
+    ("processing order (rank loop)", "// ---- rounds"), ("children scan, stop point", "// D: children created"),
+    ("new node table", "// F: new node table"), ("move candidates + next quadrant counts", "// G: move the candidates"),
+    ("termination", "// H: termination"), ("strongest per node", "// ---- strongest candidate"),
+    ("kernel entry", "distribute_kernel(const __grid_constant__")]))
 PHASES["describe_kernel"] = ("describe.cu", None, marker_phases("describe.cu", "describe_kernel(const __grid_constant__", [
     ("tables, pattern", None), ("slot lookup", "const int groups_per_frame"), ("moments (TMA + IDP.4A)", "// ---- phase A"),
     ("angle, trig, outputs", "// ---- phase B"), ("rBRIEF (TMA + sampling)", "// ---- phase C")]))
